@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py -- CTC-CRF loss+grad frames/sec on synthetic (N,T,V) log-probs (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path (numerator + denominator forward-backward, loss and (N,T,V) gradient)
+over one synthetic batch.  Workload at every N: the configuration the metric is quoted on --
+N=64 utterances per GPU, T=1500, V=218, fp32, T-compose-LM den graph H=20000/d=24 (S=39999, A~1.02M arcs)
+(SURVEY.md 8d).  Multi-GPU: every rank runs its own 64-utterance shard of a 64*N global batch (weak
+scaling, no data-path collective) plus the path's single all-reduce of [sum cost, count].
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for how each field is obtained.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "CTC-CRF loss+grad frames/sec"
+UNIT = "frames/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    # workload overrides (development only; the defaults are the headline configuration)
+    ap.add_argument("--N", type=int, default=64)
+    ap.add_argument("--T", type=int, default=1500)
+    ap.add_argument("--V", type=int, default=218)
+    ap.add_argument("--H", type=int, default=20000)
+    ap.add_argument("--d", type=int, default=24)
+    ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"])
+    ap.add_argument("--lamb", type=float, default=0.01)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-cuda", action="store_true")
+    ap.add_argument("--cpu-sample", default="auto", help="N,T of the CPU sample (default sized for ~15 s)")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, sustained copy)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def den_graph_file(H, d, V):
+    from cat_b200 import fst
+    path = os.path.join(tempfile.gettempdir(), f"ccb_den_H{H}_d{d}_V{V}_r{os.environ.get('RANK', '0')}.fst")
+    g = fst.make_synthetic_den(H, d, V, seed=7)
+    if not os.path.exists(path):
+        fst.write_fst(path + ".tmp", g)
+        os.replace(path + ".tmp", path)
+    return path, g
+
+
+def synth_labels(N, T, V, seed):
+    rng = np.random.default_rng(seed)
+    lens = np.full(N, T, np.int32)
+    ly = np.minimum(lens // 6, 400).astype(np.int32)
+    labels = rng.integers(1, V, size=int(ly.sum())).astype(np.int32)
+    return labels, lens, ly
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 8:
+                continue
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_port(graph, N, T, V, lamb, threads, seed=1234):
+    """Times the fp64 oracle (oracle/ -- the CPU restatement; the reference has no CPU path) on a bounded
+    sample of the workload.  Returns (frames/s, seconds)."""
+    from oracle import oracle
+    y, labels, lens, ly = oracle.synth_batch(N, T, V, seed=seed)
+    t0 = time.perf_counter()
+    oracle.ctc_crf(graph, y, labels, lens, ly, lamb, True, nthreads=threads)
+    dt = time.perf_counter() - t0
+    return float(lens.sum()) / dt, dt
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference path on the host cores.  The reference ships no CPU implementation
+    (src/ctc_crf/setup.py:15-16), so this is the oracle port (kind "port"), all host threads, each step a
+    bounded sample (N=cores, T=64) of the same workload: same den graph, V, label density, lamb."""
+    if rank != 0:
+        return
+    from oracle import oracle
+    oracle.build()
+    _, g = den_graph_file(args.H, args.d, args.V)
+    cores = os.cpu_count() or 1
+    sN, sT = max(1, min(args.N, cores)), 64
+    for _ in range(min(args.warmup, 1)):
+        cpu_port(g, sN, sT, args.V, args.lamb, cores)
+    t0 = time.perf_counter()
+    frames = 0
+    for k in range(args.steps):
+        cpu_port(g, sN, sT, args.V, args.lamb, cores, seed=1234 + k)
+        frames += sN * sT
+    dt = time.perf_counter() - t0
+    v = frames / dt
+    sample = f"N={sN},T={sT} slice of the workload per step (same den graph, V, lamb)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"CTC-CRF loss+grad, N={args.N},T={args.T},V={args.V}, den S={g.num_states} A={g.num_arcs}",
+                   "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch.distributed as dist
+    from cat_b200 import _C, _lib
+    import ctc_crf
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    N, T, V = args.N, args.T, args.V
+    path, graph = den_graph_file(args.H, args.d, V)
+    ctx = ctc_crf.CRFContext(path, gpus=local_rank)
+    S_plan, A_plan = _C.den_num_states(), _C.den_num_arcs()
+    dtype = torch.float32 if args.dtype == "f32" else torch.bfloat16
+    b_in = 4 if args.dtype == "f32" else 2
+
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    y = torch.log_softmax(3.0 * torch.randn(N, T, V, device=dev, generator=gen), -1).to(dtype).contiguous()
+    labels_np, lens_np, ly_np = synth_labels(N, T, V, 1234 + rank)
+    labels, lx, ly = torch.tensor(labels_np), torch.tensor(lens_np), torch.tensor(ly_np)
+    frames_per_step = int(lens_np.sum())
+    crit = ctc_crf.CTC_CRF_LOSS(lamb=args.lamb, size_average=True)
+
+    def step_resident():
+        loss, grad, _ = _C.ctc_crf_loss_fwd(y, labels, lx, ly, args.lamb, True)
+        if world > 1:
+            v = torch.stack([loss.reshape(()) * N, torch.tensor(float(N), device=dev)])
+            dist.all_reduce(v)
+        return loss
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- value: whole-job throughput, inputs resident in HBM -------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = _C.launch_count()
+    ms_total = timed(step_resident, args.steps, max(args.warmup, 3))
+    launches = _C.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = ms_total / args.steps
+    value = world * frames_per_step / (ms_per_step * 1e-3)
+
+    # ---- e2e: public API, host buffers, H2D of the step's logits + D2H of the loss inside the timed region ----
+    y_host = y.cpu().pin_memory()
+    y_dev = torch.empty_like(y)
+
+    def step_e2e():
+        y_dev.copy_(y_host, non_blocking=True)
+        loss = crit(y_dev.requires_grad_(False), labels, lx, ly)
+        if world > 1:
+            v = torch.stack([loss.reshape(()) * N, torch.tensor(float(N), device=dev)])
+            dist.all_reduce(v)
+        return float(loss.item())            # device->host read of the step's result
+
+    e2e_steps = max(3, min(args.steps, 10))
+    ms_e2e = timed(step_e2e, e2e_steps, 2) / e2e_steps
+    e2e_value = world * frames_per_step / (ms_e2e * 1e-3)
+    meta_bytes = 4 * (labels.numel() + 3 * N + 1)
+    h2d = y_host.numel() * y_host.element_size() + meta_bytes
+
+    # ---- roofline: denominator forward-backward (the dominant kernels), timed live with CUDA events ----------
+    L = _lib.lib()
+    lens_dev = lx.to(dev)
+    alpha_ws = torch.empty(int(L.ccb_den_alpha_floats(N, T)), dtype=torch.float32, device=dev)
+    aux_ws = torch.empty(int(L.ccb_den_aux_bytes(N, T)), dtype=torch.uint8, device=dev)
+    gden = torch.zeros(N, T, V, device=dev)
+    logz = torch.empty(N, device=dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    dcode = 0 if args.dtype == "f32" else 1
+
+    def den(with_bwd):
+        rc = L.ccb_den_forward_backward(y.data_ptr(), dcode, T * V, V, N, T, V, lens_dev.data_ptr(), alpha_ws.data_ptr(),
+                                        aux_ws.data_ptr(), gden.data_ptr() if with_bwd else None, T * V, V, 1.0,
+                                        logz.data_ptr(), None, stream)
+        assert rc == 0, _lib.last_error()
+
+    reps = max(2, min(args.steps, 5))
+    ms_fwd = timed(lambda: den(False), reps, 1) / reps
+    ms_fb = timed(lambda: den(True), reps, 1) / reps
+    ms_bwd = max(ms_fb - ms_fwd, 1e-6)
+    peak, peak_src = peaks()
+    graph_bytes = A_plan * 8 + S_plan * 8
+    bytes_fwd = frames_per_step * (V * b_in + 4 * S_plan) + graph_bytes
+    bytes_bwd = frames_per_step * (V * b_in + 4 * V + 4 * S_plan) + graph_bytes
+    bytes_den = frames_per_step * (2 * V * b_in + 4 * V + 8 * S_plan) + 2 * graph_bytes
+    ach = bytes_den / (ms_fb * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm", "kernel": "den_forward_kernel + den_backward_kernel (denominator forward-backward)",
+        "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+        "algorithmic_bytes_per_frame": 2 * V * b_in + 4 * V + 8 * S_plan,
+        "den_ms": ms_fb, "den_frames_per_s": frames_per_step / (ms_fb * 1e-3),
+        "kernels": {
+            "den_forward_kernel": {"ms": ms_fwd, "GB/s": bytes_fwd / (ms_fwd * 1e-3) / 1e9, "frac": bytes_fwd / (ms_fwd * 1e-3) / 1e9 / peak},
+            "den_backward_kernel": {"ms": ms_bwd, "GB/s": bytes_bwd / (ms_bwd * 1e-3) / 1e9, "frac": bytes_bwd / (ms_bwd * 1e-3) / 1e9 / peak},
+        },
+        "arc_evals_per_s": 2.0 * A_plan * frames_per_step / (ms_fb * 1e-3),
+    }
+    del alpha_ws, aux_ws, gden
+
+    out = None
+    if rank == 0:
+        # ---- reference CUDA build (B0) on the same GPU, and the CPU port on the host cores (N=1 run only) ----
+        ref_cuda_res = None
+        cpu_baseline = None
+        if world == 1:
+            if not args.no_ref_cuda:
+                try:
+                    from oracle import ref_cuda
+                    if ref_cuda.available():
+                        rN, rT = min(N, 16), min(T, 300)
+                        rctx = ref_cuda.RefContext(path, local_rank)
+                        yr = y[:rN, :rT].float().contiguous()
+                        rlab, rlens, rly = synth_labels(rN, rT, V, 99)
+                        args_ref = (rctx, yr, torch.tensor(rlab), torch.tensor(rlens), torch.tensor(rly), args.lamb, True)
+                        ref_cuda.ctc_crf_forward(*args_ref)
+                        torch.cuda.synchronize()
+                        t0 = time.perf_counter()
+                        ref_cuda.ctc_crf_forward(*args_ref)
+                        torch.cuda.synchronize()
+                        dt = time.perf_counter() - t0
+                        rctx.close()
+                        ref_cuda_res = {"value": rN * rT / dt, "unit": UNIT,
+                                        "sample": f"reference CUDA sources (oracle/_ref, sm_100a build) on this GPU, N={rN},T={rT}, same graph"}
+                except Exception as e:  # the reference arm must never take the bench down
+                    ref_cuda_res = {"error": repr(e)}
+            if not args.no_cpu_baseline:
+                from oracle import oracle
+                oracle.build()
+                cores = os.cpu_count() or 1
+                if args.cpu_sample == "auto":
+                    sN, sT = max(1, min(N, cores)), min(T, 96)
+                else:
+                    sN, sT = [int(x) for x in args.cpu_sample.split(",")]
+                v, dt = cpu_port(graph, sN, sT, V, args.lamb, cores)
+                cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "seconds": dt,
+                                "sample": f"fp64 oracle port (reference has no CPU path), N={sN},T={sT} slice, same den graph/V/lamb, {cores} threads"}
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": f"CTC-CRF loss+grad N={N}/GPU,T={T},V={V} (BASELINE configs headline)",
+                       "den_graph": f"synthetic T-compose-LM H={args.H},d={args.d}: file S={graph.num_states} A={graph.num_arcs}; plan S={S_plan} A={A_plan}",
+                       "global_batch": N * world, "parallelism": f"minibatch sharded x{world}, den graph replicated, 1 all-reduce of [cost,count]",
+                       "lamb": args.lamb,
+                       "l2": "no explicit flush: each step streams a 15.4 GB alpha spill (>> 126 MB L2)" if N * T >= 20000 else "small dev workload"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
+                    "api": "ctc_crf.CTC_CRF_LOSS.forward on pinned-host logits copied H2D inside the step, loss.item() back"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+            "reference_cuda_same_gpu": ref_cuda_res,
+        }
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    del ctx
+    if out is not None:
+        print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,204 @@
+"""``ctc_crf._C`` -- host-side mirror of the reference's pybind module (src/ctc_crf/binding.cpp:51-126).
+
+Same four entry points, same argument meaning and placement (``gpu_ctc`` takes CPU labels/lengths/costs and
+(T,N,V) activations; ``gpu_den`` takes CUDA lengths and pre-zeroed gradients), implemented by calling the C ABI
+of ``libctc_crf_b200.so`` through ctypes.  As in binding.cpp, scratch is taken from torch's caching allocator
+and the work is enqueued on the current CUDA stream of the tensors' device.  Differences: a device guard is
+installed (binding.cpp has none) and native errors raise ``RuntimeError`` instead of being
+ignored (binding.cpp:105,111) or exiting the process (den_calculate.cu:16-25).
+
+Addition: ``ctc_crf_loss_fwd`` -- the fused, synchronisation-free entry used by ``CTC_CRF_LOSS``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ctcOptions
+
+_DTYPES = {torch.float32: 0, torch.bfloat16: 1}
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise RuntimeError(f"{what} failed: {_lib.last_error() or rc}")
+
+
+def _raise_if_error(what: str) -> None:
+    msg = _lib.last_error()
+    if msg:
+        raise RuntimeError(f"{what} failed: {msg}")
+
+
+def _stream(device: torch.device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _iptr(t: torch.Tensor):
+    return C.cast(t.data_ptr(), C.POINTER(C.c_int))
+
+
+def init_env(fst_name: str, gpus: torch.Tensor) -> None:
+    """binding.cpp:51-56"""
+    assert gpus.dtype == torch.int32 and not gpus.is_cuda
+    g = gpus.contiguous()
+    _lib.lib().Init(fst_name.encode(), int(g.numel()), _iptr(g))
+    _raise_if_error("init_env")
+
+
+def release_env(gpus: torch.Tensor) -> None:
+    """binding.cpp:58-63"""
+    g = gpus.contiguous()
+    _lib.lib().Release(int(g.numel()), _iptr(g))
+
+
+def den_num_states() -> int:
+    return C.c_int.in_dll(_lib.lib(), "DEN_NUM_STATES").value
+
+
+def den_num_arcs() -> int:
+    return C.c_int.in_dll(_lib.lib(), "DEN_NUM_ARCS").value
+
+
+def gpu_den(logits: torch.Tensor, grad_net: torch.Tensor, input_lengths: torch.Tensor,
+            costs_alpha: torch.Tensor, costs_beta: torch.Tensor) -> None:
+    """binding.cpp:65-84.  logits (N,T,V) fp32 CUDA contiguous; grad_net pre-zeroed, filled in place;
+    input_lengths (N,) int32 CUDA; costs_* (N,) fp32 CUDA."""
+    L = _lib.lib()
+    assert logits.is_cuda and logits.dtype == torch.float32 and logits.is_contiguous()
+    assert grad_net.is_cuda and grad_net.dtype == torch.float32 and grad_net.is_contiguous()
+    assert input_lengths.is_cuda and input_lengths.dtype == torch.int32
+    N, T, V = logits.shape
+    dev = logits.device
+    with torch.cuda.device(dev):
+        stream = _stream(dev)
+        S = den_num_states()
+        # binding.cpp:77-79 sizes; alpha is padded to whole 32-lane groups here
+        alpha = torch.empty(max(int(L.ccb_den_alpha_floats(N, T)), (T + 1) * N * S), dtype=torch.float32, device=dev)
+        beta = torch.empty(1, dtype=torch.float32, device=dev)
+        grad_storage = torch.empty(1, dtype=torch.float32, device=dev)
+        alpha_states = alpha.numel() // ((T + 1) * N)
+        L.compute_alpha(alpha.data_ptr(), logits.data_ptr(), N, T, alpha_states, V, input_lengths.data_ptr(),
+                        costs_alpha.data_ptr(), stream)
+        _raise_if_error("gpu_den/compute_alpha")
+        L.compute_beta_and_grad(beta.data_ptr(), alpha.data_ptr(), logits.data_ptr(), costs_alpha.data_ptr(),
+                                grad_storage.data_ptr(), grad_net.data_ptr(), N, T, alpha_states, V,
+                                input_lengths.data_ptr(), costs_beta.data_ptr(), stream)
+        _raise_if_error("gpu_den/compute_beta_and_grad")
+
+
+def gpu_ctc(probs: torch.Tensor, grads: torch.Tensor, labels: torch.Tensor, label_sizes: torch.Tensor,
+            sizes: torch.Tensor, minibatch_size: int, costs: torch.Tensor, blank_label: int) -> None:
+    """binding.cpp:86-117.  probs/grads (T,N,V) fp32 CUDA (grads pre-zeroed); labels/label_sizes/sizes int32 CPU;
+    costs (N,) fp32 CPU, receives log p(l|x) per utterance."""
+    L = _lib.lib()
+    assert probs.is_cuda and probs.dtype == torch.float32 and probs.is_contiguous()
+    assert not labels.is_cuda and not label_sizes.is_cuda and not sizes.is_cuda and not costs.is_cuda
+    assert labels.dtype == torch.int32 and label_sizes.dtype == torch.int32 and sizes.dtype == torch.int32
+    assert costs.dtype == torch.float32 and costs.is_contiguous()
+    labels, label_sizes, sizes = labels.contiguous(), label_sizes.contiguous(), sizes.contiguous()
+    V = probs.size(2)
+    dev = probs.device
+    with torch.cuda.device(dev):
+        opts = ctcOptions(stream=torch.cuda.current_stream(dev).cuda_stream, blank_label=int(blank_label))
+        nbytes = C.c_size_t(0)
+        st = L.get_workspace_size(_iptr(label_sizes), _iptr(sizes), V, minibatch_size, opts, C.byref(nbytes))
+        if st != 0:
+            raise RuntimeError(f"gpu_ctc/get_workspace_size: {L.ctcGetStatusString(st).decode()}")
+        ws = torch.empty((nbytes.value + 3) // 4, dtype=torch.float32, device=dev)
+        gptr = grads.data_ptr() if grads is not None and grads.numel() > 0 else None
+        st = L.compute_ctc_loss(probs.data_ptr(), gptr, _iptr(labels), _iptr(label_sizes), _iptr(sizes), V,
+                                minibatch_size, C.cast(costs.data_ptr(), C.POINTER(C.c_float)), ws.data_ptr(), opts)
+        if st != 0:
+            raise RuntimeError(f"gpu_ctc/compute_ctc_loss: {L.ctcGetStatusString(st).decode()} {_lib.last_error()}")
+
+
+# ---------------------------------------------------------------------------------------------------
+# fused entry
+# ---------------------------------------------------------------------------------------------------
+class _PinnedRing:
+    """Small ring of pinned int32 staging buffers so the label/length upload is a true async H2D copy."""
+
+    def __init__(self, slots: int = 4):
+        self.bufs = [None] * slots
+        self.events = [None] * slots
+        self.i = 0
+
+    def stage(self, parts, device) -> torch.Tensor:
+        n = sum(int(p.numel()) for p in parts)
+        i = self.i
+        self.i = (i + 1) % len(self.bufs)
+        if self.events[i] is not None:
+            self.events[i].synchronize()
+        if self.bufs[i] is None or self.bufs[i].numel() < n:
+            self.bufs[i] = torch.empty(max(n, 1024), dtype=torch.int32, pin_memory=True)
+        buf = self.bufs[i][:n]
+        torch.cat(parts, out=buf)
+        dev = buf.to(device, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(device))
+        self.events[i] = ev
+        return dev
+
+
+_rings = {}
+
+
+def upload_meta(labels: torch.Tensor, lx: torch.Tensor, ly: torch.Tensor, device) -> Tuple[torch.Tensor, int, int]:
+    """Pack [labels | label_off(N+1) | ly | lx] into one pinned buffer and upload it asynchronously.
+    Returns (device int32 tensor, sum(ly), max(ly))."""
+    N = int(lx.numel())
+    ly64 = ly.to(torch.int64)
+    off = torch.zeros(N + 1, dtype=torch.int32)
+    off[1:].copy_(torch.cumsum(ly64, 0))
+    sum_l = int(off[-1])
+    if sum_l != int(labels.numel()):
+        raise RuntimeError(f"labels has {labels.numel()} entries but label lengths sum to {sum_l}")
+    ring = _rings.setdefault(torch.device(device).index, _PinnedRing())
+    meta = ring.stage([labels, off, ly, lx], device)
+    return meta, sum_l, int(ly.max()) if N else 0
+
+
+def ctc_crf_loss_fwd(logits: torch.Tensor, labels: torch.Tensor, lx: torch.Tensor, ly: torch.Tensor,
+                     lamb: float, size_average: bool, want_parts: bool = False
+                     ) -> Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]:
+    """Fused CTC-CRF loss.  logits (N,T,V) fp32 or bf16 CUDA contiguous log-probs; labels/lx/ly int32 CPU.
+    Returns (loss[1] fp32 CUDA, grad (N,T,V) fp32 CUDA, parts[2N] or None).  Never synchronises the host."""
+    L = _lib.lib()
+    assert logits.is_cuda and logits.dim() == 3 and logits.is_contiguous()
+    if logits.dtype not in _DTYPES:
+        raise RuntimeError(f"unsupported logits dtype {logits.dtype}")
+    N, T, V = logits.shape
+    dev = logits.device
+    if int(lx.numel()) != N or int(ly.numel()) != N:
+        raise RuntimeError("lx / ly must have one entry per utterance")
+    if N and (int(lx.max()) > T or int(lx.min()) < 0):
+        raise RuntimeError("input lengths must lie in [0, T]")
+    if labels.numel() and (int(labels.min()) < 0 or int(labels.max()) >= V):
+        raise RuntimeError("label out of range")
+    with torch.cuda.device(dev):
+        meta, sum_l, max_l = upload_meta(labels, lx, ly, dev)
+        base = meta.data_ptr()
+        p_labels, p_off = base, base + 4 * sum_l
+        p_ly, p_lx = p_off + 4 * (N + 1), p_off + 4 * (2 * N + 1)
+        alpha_ws = torch.empty(int(L.ccb_den_alpha_floats(N, T)), dtype=torch.float32, device=dev)
+        aux_ws = torch.empty(int(L.ccb_den_aux_bytes(N, T)), dtype=torch.uint8, device=dev)
+        ctc_ws = torch.empty(int(L.ccb_ctc_workspace_bytes(N, T, max_l)), dtype=torch.uint8, device=dev)
+        grad = torch.empty((N, T, V), dtype=torch.float32, device=dev)
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        parts = torch.empty(2 * N, dtype=torch.float32, device=dev) if want_parts else None
+        rc = L.ccb_ctc_crf_loss_fwd(logits.data_ptr(), _DTYPES[logits.dtype], N, T, V, p_labels, p_off, p_ly, p_lx,
+                                    max_l, float(lamb), 1 if size_average else 0, alpha_ws.data_ptr(),
+                                    aux_ws.data_ptr(), ctc_ws.data_ptr(), grad.data_ptr(), loss.data_ptr(),
+                                    parts.data_ptr() if parts is not None else None, _stream(dev))
+        _check(rc, "ctc_crf_loss_fwd")
+        # scratch is released to the caching allocator here; it is stream-ordered, so reuse is safe
+        meta.record_stream(torch.cuda.current_stream(dev))
+    return loss, grad, parts
+
+
+def launch_count() -> int:
+    return int(_lib.lib().ccb_launch_count())

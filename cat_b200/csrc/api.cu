@@ -1,0 +1,493 @@
+// C ABI of the library (include/ctc_crf_b200.h): den-graph lifetime, workspace carving, launch sequencing.
+// Mirrors the roles of the reference's binding.cpp:51-117 + den_calculate.cu:288-481 host code +
+// gpu_ctc/ctc_entrypoint.cu:29-109, without torch and without ever calling exit().
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/ctc_crf_b200.h"
+#include "common.cuh"
+
+using namespace ccb;
+
+int DEN_NUM_ARCS = 0;
+int DEN_NUM_STATES = 0;
+
+namespace {
+
+constexpr int kMaxDevices = 64;
+thread_local std::string g_err;
+std::mutex g_mu;
+DenPlan g_plan;                       // host copy (one den graph per process, like den_calculate.cu:263-273)
+bool g_plan_valid = false;
+DeviceGraph g_dev[kMaxDevices];
+std::atomic<long> g_launches{0};
+
+// scratch owned by the library for the reference-signature entry points (Section 1)
+struct LegacyScratch {
+    void *aux = nullptr; size_t aux_bytes = 0;
+    float *alpha = nullptr; size_t alpha_floats = 0;
+    void *ctc = nullptr; size_t ctc_bytes = 0;
+    int N = 0, T = 0;
+};
+LegacyScratch g_legacy[kMaxDevices];
+
+int Fail(const std::string &m) { g_err = m; return 1; }
+int FailCuda(const char *what, cudaError_t e) { g_err = std::string(what) + ": " + cudaGetErrorString(e); return (int)e ? (int)e : 1; }
+
+#define CCB_CUDA(call)                                                   \
+    do {                                                                 \
+        cudaError_t e__ = (call);                                        \
+        if (e__ != cudaSuccess) return FailCuda(#call, e__);             \
+    } while (0)
+
+template <typename T>
+int Upload(T **dst, const std::vector<T> &src) {
+    CCB_CUDA(cudaMalloc((void **)dst, std::max<size_t>(src.size(), 1) * sizeof(T)));
+    if (!src.empty()) CCB_CUDA(cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+void FreeDevice(DeviceGraph &d) {
+    if (!d.loaded) return;
+    cudaFree(d.state_label); cudaFree(d.final_lin);
+    cudaFree(d.fwd.arcs); cudaFree(d.fwd.chunk_state); cudaFree(d.fwd.chunk_arc);
+    cudaFree(d.bwd.arcs); cudaFree(d.bwd.chunk_state); cudaFree(d.bwd.chunk_arc);
+    d = DeviceGraph();
+}
+
+int UploadPass(const PassPlan &h, DevicePass *d) {
+    if (Upload(&d->arcs, h.arcs)) return 1;
+    if (Upload(&d->chunk_state, h.chunk_state)) return 1;
+    if (Upload(&d->chunk_arc, h.chunk_arc)) return 1;
+    d->num_arcs = (int)h.arcs.size();
+    d->max_tile_arcs = h.max_tile_arcs;
+    d->max_tile_labels = h.max_tile_labels;
+    return 0;
+}
+
+int CurrentGraph(DeviceGraph **out) {
+    int dev = 0;
+    CCB_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kMaxDevices || !g_dev[dev].loaded)
+        return Fail("den graph not loaded on CUDA device " + std::to_string(dev) + " (call Init / CRFContext first)");
+    *out = &g_dev[dev];
+    return 0;
+}
+
+int DenWarps() {
+    const char *e = getenv("CCB_DEN_WARPS");
+    int w = e ? atoi(e) : 16;
+    return (w == 32) ? 32 : 16;
+}
+
+int InitImpl(const char *fst_name, int n_gpus, const int *gpus) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!fst_name || n_gpus <= 0 || !gpus) return Fail("Init: bad arguments");
+    HostFst fst;
+    std::string err;
+    if (!ReadFstFile(fst_name, &fst, &err)) return Fail(err);
+    int prev = 0;
+    CCB_CUDA(cudaGetDevice(&prev));
+    int count = 0;
+    CCB_CUDA(cudaGetDeviceCount(&count));
+    for (int i = 0; i < n_gpus; ++i)
+        if (gpus[i] < 0 || gpus[i] >= count || gpus[i] >= kMaxDevices) return Fail("Init: invalid GPU id " + std::to_string(gpus[i]));
+    cudaDeviceProp prop;
+    CCB_CUDA(cudaGetDeviceProperties(&prop, gpus[0]));
+    if (!prop.cooperativeLaunch) return Fail("device does not support cooperative launch");
+    if (!BuildDenPlan(fst, prop.multiProcessorCount, DenWarps(), &g_plan, &err)) return Fail(err);
+    g_plan_valid = true;
+    DEN_NUM_STATES = g_plan.num_states;
+    DEN_NUM_ARCS = (int)g_plan.fwd.arcs.size();
+    int rc = 0;
+    for (int i = 0; i < n_gpus && rc == 0; ++i) {
+        DeviceGraph &d = g_dev[gpus[i]];
+        CCB_CUDA(cudaSetDevice(gpus[i]));
+        FreeDevice(d);
+        cudaDeviceProp p2;
+        CCB_CUDA(cudaGetDeviceProperties(&p2, gpus[i]));
+        if (p2.multiProcessorCount != prop.multiProcessorCount) { rc = Fail("Init: heterogeneous GPUs are not supported"); break; }
+        d.device = gpus[i];
+        d.S = g_plan.num_states; d.start = g_plan.start; d.num_labels = g_plan.num_labels;
+        d.n_ctas = g_plan.n_ctas; d.n_warps = g_plan.n_warps;
+        d.max_smem_optin = (int)p2.sharedMemPerBlockOptin;
+        rc = Upload(&d.state_label, g_plan.state_label) || Upload(&d.final_lin, g_plan.final_lin) ||
+             UploadPass(g_plan.fwd, &d.fwd) || UploadPass(g_plan.bwd, &d.bwd);
+        // backward-pass row of the start state (for logZ recomputed from beta)
+        {
+            // rows are contiguous: find the start row by walking chunk boundaries on the host plan
+            int a = 0, q = 0;
+            const auto &arcs = g_plan.bwd.arcs;
+            for (; q < g_plan.start; ++a) if (arcs[(size_t)a].peer & kLastFlag) ++q;
+            d.start_row_begin = a;
+            while (!(arcs[(size_t)a].peer & kLastFlag)) ++a;
+            d.start_row_end = a + 1;
+            d.start_final = g_plan.final_lin[(size_t)g_plan.start];
+        }
+        d.loaded = (rc == 0);
+    }
+    cudaSetDevice(prev);
+    return rc;
+}
+
+int ReleaseImpl(int n_gpus, const int *gpus) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int prev = 0;
+    cudaGetDevice(&prev);
+    for (int i = 0; i < n_gpus; ++i) {
+        if (gpus[i] < 0 || gpus[i] >= kMaxDevices) continue;
+        if (cudaSetDevice(gpus[i]) != cudaSuccess) continue;
+        cudaDeviceSynchronize();
+        FreeDevice(g_dev[gpus[i]]);
+        LegacyScratch &ls = g_legacy[gpus[i]];
+        cudaFree(ls.aux); cudaFree(ls.alpha); cudaFree(ls.ctc);
+        ls = LegacyScratch();
+    }
+    cudaSetDevice(prev);
+    return 0;
+}
+
+DenParams BaseParams(const DeviceGraph &g, const void *y, int dtype, long sn, long st, int N, int T, int V,
+                     const int *len, float *alpha, void *aux, const DenAuxLayout &L) {
+    DenParams p;
+    memset(&p, 0, sizeof(p));
+    char *a = reinterpret_cast<char *>(aux);
+    p.state_label = g.state_label; p.final_lin = g.final_lin;
+    p.S = g.S; p.start = g.start; p.n_warps = g.n_warps;
+    p.start_row_begin = g.start_row_begin; p.start_row_end = g.start_row_end; p.start_final = g.start_final;
+    p.y = y; p.y_bf16 = (dtype == CCB_DTYPE_BF16); p.sn = sn; p.st = st;
+    p.N = N; p.Npad = L.Npad; p.Tmax = T; p.V = V; p.len = len;
+    p.alpha = alpha;
+    p.bh = reinterpret_cast<float *>(a + L.bh);
+    p.colsum_a = reinterpret_cast<float *>(a + L.colsum_a);
+    p.colsum_b = reinterpret_cast<float *>(a + L.colsum_b);
+    p.absum = reinterpret_cast<float *>(a + L.absum);
+    p.zsum = reinterpret_cast<float *>(a + L.zsum);
+    p.b0 = reinterpret_cast<float *>(a + L.b0);
+    p.fmax = reinterpret_cast<float *>(a + L.fmax);
+    return p;
+}
+
+int CheckDen(const DeviceGraph &g, int dtype, int N, int T, int V) {
+    if (N <= 0 || T <= 0 || V <= 0) return Fail("den: empty batch");
+    if (dtype != CCB_DTYPE_F32 && dtype != CCB_DTYPE_BF16) return Fail("den: unsupported logits dtype");
+    if (V < g.num_labels)
+        return Fail("den graph uses label " + std::to_string(g.num_labels - 1) + " but logits have only " + std::to_string(V) + " classes");
+    if (PadLanes(N) > g.n_warps * 32) return Fail("den: batch larger than " + std::to_string(g.n_warps * 32) + " utterances per call; split the batch");
+    return 0;
+}
+
+// forward part: zero aux, frame max, alpha recursion; logz_a lands in aux
+int DenForward(const DeviceGraph &g, const void *y, int dtype, long sn, long st, int N, int T, int V, const int *len,
+               float *alpha, void *aux, cudaStream_t stream) {
+    const DenAuxLayout L = MakeDenAuxLayout(g.S, N, T);
+    char *a = reinterpret_cast<char *>(aux);
+    CCB_CUDA(cudaMemsetAsync(a, 0, L.zero_bytes, stream));
+    int rc = LaunchFrameMax(y, dtype == CCB_DTYPE_BF16, sn, st, N, T, V, len, reinterpret_cast<float *>(a + L.fmax), L.Npad, stream);
+    if (rc) return FailCuda("frame_max", (cudaError_t)rc);
+    DenParams p = BaseParams(g, y, dtype, sn, st, N, T, V, len, alpha, aux, L);
+    p.barrier = reinterpret_cast<unsigned *>(a + L.barrier);
+    p.logz = reinterpret_cast<float *>(a + L.logz_a);
+    std::string err;
+    rc = LaunchDenForward(g, p, stream, &err);
+    if (rc) return Fail(err);
+    return 0;
+}
+
+int DenBackward(const DeviceGraph &g, const void *y, int dtype, long sn, long st, int N, int T, int V, const int *len,
+                float *alpha, void *aux, float *grad, long gsn, long gst, float grad_scale, cudaStream_t stream) {
+    const DenAuxLayout L = MakeDenAuxLayout(g.S, N, T);
+    char *a = reinterpret_cast<char *>(aux);
+    DenParams p = BaseParams(g, y, dtype, sn, st, N, T, V, len, alpha, aux, L);
+    p.barrier = reinterpret_cast<unsigned *>(a + L.barrier + 128);
+    p.logz = reinterpret_cast<float *>(a + L.logz_b);
+    p.grad = grad; p.gsn = gsn; p.gst = gst;
+    std::string err;
+    int rc = LaunchDenBackward(g, p, stream, &err);
+    if (rc) return Fail(err);
+    rc = LaunchDenGradNormalize(grad, gsn, gst, p.absum, len, N, L.Npad, T, V, grad_scale, stream);
+    if (rc) return FailCuda("den_grad_normalize", (cudaError_t)rc);
+    return 0;
+}
+
+int EnsureLegacy(int dev, const DeviceGraph &g, int N, int T, float *caller_alpha, size_t caller_floats, float **alpha_out) {
+    LegacyScratch &ls = g_legacy[dev];
+    const DenAuxLayout L = MakeDenAuxLayout(g.S, N, T);
+    if (ls.aux_bytes < L.total) {
+        CCB_CUDA(cudaDeviceSynchronize());
+        cudaFree(ls.aux); ls.aux = nullptr; ls.aux_bytes = 0;
+        CCB_CUDA(cudaMalloc(&ls.aux, L.total));
+        ls.aux_bytes = L.total;
+    }
+    const size_t need = ccb_den_alpha_floats(N, T);
+    if (caller_alpha && caller_floats >= need) { *alpha_out = caller_alpha; return 0; }
+    if (ls.alpha_floats < need) {
+        CCB_CUDA(cudaDeviceSynchronize());
+        cudaFree(ls.alpha); ls.alpha = nullptr; ls.alpha_floats = 0;
+        CCB_CUDA(cudaMalloc((void **)&ls.alpha, need * sizeof(float)));
+        ls.alpha_floats = need;
+    }
+    *alpha_out = ls.alpha;
+    return 0;
+}
+
+}  // namespace
+
+namespace ccb {
+void CountLaunch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+}  // namespace ccb
+
+extern "C" {
+
+const char *ccb_last_error(void) { return g_err.c_str(); }
+long ccb_launch_count(void) { return g_launches.load(); }
+int ccb_den_loaded(int device) { return device >= 0 && device < kMaxDevices && g_dev[device].loaded ? 1 : 0; }
+
+void Init(const char *fst_name, int n_gpus, int *gpus) {
+    g_err.clear();
+    if (InitImpl(fst_name, n_gpus, gpus) != 0) fprintf(stderr, "ctc_crf_b200 Init failed: %s\n", g_err.c_str());
+}
+
+void Release(int n_gpus, int *gpus) { ReleaseImpl(n_gpus, gpus); }
+
+size_t ccb_den_alpha_floats(int N, int T) {
+    if (!g_plan_valid) return 0;
+    return (size_t)(T + 1) * (size_t)g_plan.num_states * (size_t)PadLanes(N);
+}
+
+size_t ccb_den_aux_bytes(int N, int T) {
+    if (!g_plan_valid) return 0;
+    return MakeDenAuxLayout(g_plan.num_states, N, T).total;
+}
+
+size_t ccb_ctc_workspace_bytes(int N, int T, int max_label_len) {
+    return ((size_t)N * T * (2 * (size_t)max_label_len + 1) + 64) * sizeof(float);
+}
+
+void compute_alpha(float *alpha, float *logits, const int batch_size, int T, const int alpha_size,
+                   int logits_size, int *input_lengths, float *loglikelihood, void *stream) {
+    g_err.clear();
+    DeviceGraph *g;
+    if (CurrentGraph(&g)) return;
+    if (CheckDen(*g, CCB_DTYPE_F32, batch_size, T, logits_size)) return;
+    float *al = nullptr;
+    const size_t caller = (size_t)(T + 1) * (size_t)batch_size * (size_t)(alpha_size > 0 ? alpha_size : 0);
+    if (EnsureLegacy(g->device, *g, batch_size, T, alpha, caller, &al)) return;
+    LegacyScratch &ls = g_legacy[g->device];
+    ls.N = batch_size; ls.T = T;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (DenForward(*g, logits, CCB_DTYPE_F32, (long)T * logits_size, logits_size, batch_size, T, logits_size,
+                   input_lengths, al, ls.aux, s)) return;
+    const DenAuxLayout L = MakeDenAuxLayout(g->S, batch_size, T);
+    cudaError_t e = cudaMemcpyAsync(loglikelihood, (char *)ls.aux + L.logz_a, sizeof(float) * batch_size, cudaMemcpyDeviceToDevice, s);
+    if (e != cudaSuccess) FailCuda("copy logZ", e);
+}
+
+void compute_beta_and_grad(float *beta, const float *const alpha, const float *const logits,
+                           const float *const alpha_lld, float *grad_storage, float *grad_net,
+                           const int batch_size, const int T, const int beta_size, const int logits_size,
+                           const int *const input_lengths, float *loglikelihood, void *stream) {
+    (void)beta; (void)alpha_lld; (void)grad_storage;
+    g_err.clear();
+    DeviceGraph *g;
+    if (CurrentGraph(&g)) return;
+    LegacyScratch &ls = g_legacy[g->device];
+    if (ls.N != batch_size || ls.T != T || !ls.aux) { Fail("compute_beta_and_grad: call compute_alpha on the same batch first"); return; }
+    float *al = nullptr;
+    const size_t caller = (size_t)(T + 1) * (size_t)batch_size * (size_t)(beta_size > 0 ? beta_size : 0);
+    if (EnsureLegacy(g->device, *g, batch_size, T, const_cast<float *>(alpha), caller, &al)) return;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (DenBackward(*g, logits, CCB_DTYPE_F32, (long)T * logits_size, logits_size, batch_size, T, logits_size,
+                    input_lengths, al, ls.aux, grad_net, (long)T * logits_size, logits_size, 1.f, s)) return;
+    if (loglikelihood) {
+        const DenAuxLayout L = MakeDenAuxLayout(g->S, batch_size, T);
+        cudaError_t e = cudaMemcpyAsync(loglikelihood, (char *)ls.aux + L.logz_b, sizeof(float) * batch_size, cudaMemcpyDeviceToDevice, s);
+        if (e != cudaSuccess) FailCuda("copy logZ(beta)", e);
+    }
+}
+
+int ccb_den_forward_backward(const void *logits, int dtype, long sn, long st, int N, int T, int V,
+                             const int *len_dev, float *alpha_ws, void *aux_ws, float *grad, long gsn, long gst,
+                             float grad_scale, float *logz, float *logz_beta, void *stream) {
+    g_err.clear();
+    DeviceGraph *g;
+    if (CurrentGraph(&g)) return 1;
+    if (CheckDen(*g, dtype, N, T, V)) return 1;
+    if (!alpha_ws || !aux_ws) return Fail("den: workspace missing");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (DenForward(*g, logits, dtype, sn, st, N, T, V, len_dev, alpha_ws, aux_ws, s)) return 1;
+    const DenAuxLayout L = MakeDenAuxLayout(g->S, N, T);
+    if (logz) CCB_CUDA(cudaMemcpyAsync(logz, (char *)aux_ws + L.logz_a, sizeof(float) * N, cudaMemcpyDeviceToDevice, s));
+    if (grad) {
+        if (DenBackward(*g, logits, dtype, sn, st, N, T, V, len_dev, alpha_ws, aux_ws, grad, gsn, gst, grad_scale, s)) return 1;
+        if (logz_beta) CCB_CUDA(cudaMemcpyAsync(logz_beta, (char *)aux_ws + L.logz_b, sizeof(float) * N, cudaMemcpyDeviceToDevice, s));
+    }
+    return 0;
+}
+
+int ccb_ctc_forward_backward(const void *logits, int dtype, long sn, long st, int N, int T, int V,
+                             const int *labels_dev, const int *label_off_dev, const int *label_len_dev,
+                             const int *len_dev, int max_label_len, int blank, void *workspace,
+                             float *grad, long gsn, long gst, float grad_scale, float *logp, void *stream) {
+    g_err.clear();
+    if (N <= 0 || T <= 0 || V <= 0 || !logits || !workspace || !logp) return Fail("ctc: bad arguments");
+    if (blank < 0 || blank >= V) return Fail("ctc: blank label out of range");
+    std::string err;
+    int rc = LaunchCtc(logits, dtype == CCB_DTYPE_BF16, sn, st, N, T, V, labels_dev, label_off_dev, label_len_dev,
+                       len_dev, max_label_len, blank, reinterpret_cast<float *>(workspace), grad, gsn, gst, grad_scale,
+                       logp, (cudaStream_t)stream, &err);
+    if (rc) return Fail(err);
+    return 0;
+}
+
+int ccb_ctc_crf_loss_fwd(const void *logits, int dtype, int N, int T, int V,
+                         const int *labels_dev, const int *label_off_dev, const int *label_len_dev,
+                         const int *len_dev, int max_label_len, float lamb, int size_average,
+                         float *alpha_ws, void *aux_ws, void *ctc_ws, float *grad, float *loss, float *parts,
+                         void *stream) {
+    g_err.clear();
+    DeviceGraph *g;
+    if (CurrentGraph(&g)) return 1;
+    if (CheckDen(*g, dtype, N, T, V)) return 1;
+    if (!alpha_ws || !aux_ws || !ctc_ws || !grad || !loss) return Fail("ctc_crf_loss_fwd: missing buffer");
+    cudaStream_t s = (cudaStream_t)stream;
+    const long sn = (long)T * V, st = V;
+    const float scale = size_average ? 1.f / (float)N : 1.f;
+    CCB_CUDA(cudaMemsetAsync(grad, 0, sizeof(float) * (size_t)N * T * V, s));
+    if (DenForward(*g, logits, dtype, sn, st, N, T, V, len_dev, alpha_ws, aux_ws, s)) return 1;
+    if (DenBackward(*g, logits, dtype, sn, st, N, T, V, len_dev, alpha_ws, aux_ws, grad, sn, st, scale, s)) return 1;
+    const DenAuxLayout L = MakeDenAuxLayout(g->S, N, T);
+    float *logz = reinterpret_cast<float *>((char *)aux_ws + L.logz_a);
+    float *logp = reinterpret_cast<float *>((char *)aux_ws + L.logz_b);   // logZ(beta) no longer needed: reuse
+    std::string err;
+    int rc = LaunchCtc(logits, dtype == CCB_DTYPE_BF16, sn, st, N, T, V, labels_dev, label_off_dev, label_len_dev, len_dev,
+                       max_label_len, 0, reinterpret_cast<float *>(ctc_ws), grad, sn, st, -(1.f + lamb) * scale, logp, s, &err);
+    if (rc) return Fail(err);
+    rc = LaunchAssembleLoss(logz, logp, N, lamb, scale, loss, s);
+    if (rc) return FailCuda("assemble_loss", (cudaError_t)rc);
+    if (parts) {
+        CCB_CUDA(cudaMemcpyAsync(parts, logz, sizeof(float) * N, cudaMemcpyDeviceToDevice, s));
+        CCB_CUDA(cudaMemcpyAsync(parts + N, logp, sizeof(float) * N, cudaMemcpyDeviceToDevice, s));
+    }
+    return 0;
+}
+
+/* ---- gpu_ctc/ctc.h surface ------------------------------------------------------------------- */
+const char *ctcGetStatusString(ctcStatus_t status) {
+    switch (status) {
+        case CTC_STATUS_SUCCESS: return "no error";
+        case CTC_STATUS_MEMOPS_FAILED: return "cuda memcpy or memset failed";
+        case CTC_STATUS_INVALID_VALUE: return "invalid value";
+        case CTC_STATUS_EXECUTION_FAILED: return "execution failed";
+        default: return "unknown error";
+    }
+}
+
+// workspace: [meta ints: labels | label_off | label_len | len] then the alpha spill
+ctcStatus_t get_workspace_size(const int *const label_lengths, const int *const input_lengths, int alphabet_size,
+                               int minibatch, struct ctcOptions options, size_t *size_bytes) {
+    (void)options;
+    if (!label_lengths || !input_lengths || !size_bytes || alphabet_size <= 0 || minibatch <= 0) return CTC_STATUS_INVALID_VALUE;
+    int maxL = 0, maxT = 0;
+    long sumL = 0;
+    for (int i = 0; i < minibatch; ++i) {
+        if (label_lengths[i] < 0 || input_lengths[i] < 0) return CTC_STATUS_INVALID_VALUE;
+        maxL = std::max(maxL, label_lengths[i]); maxT = std::max(maxT, input_lengths[i]); sumL += label_lengths[i];
+    }
+    size_t meta = ((size_t)(sumL + 3 * (size_t)minibatch + 1) * sizeof(int) + 255) & ~(size_t)255;
+    *size_bytes = meta + ((size_t)minibatch * sizeof(float) + 255 & ~(size_t)255) + ccb_ctc_workspace_bytes(minibatch, maxT, maxL);
+    return CTC_STATUS_SUCCESS;
+}
+
+ctcStatus_t compute_ctc_loss(const float *const activations, float *gradients, const int *const flat_labels,
+                             const int *const label_lengths, const int *const input_lengths, int alphabet_size,
+                             int minibatch, float *costs, void *workspace, struct ctcOptions options) {
+    if (!activations || !flat_labels || !label_lengths || !input_lengths || !costs || !workspace || alphabet_size <= 0 || minibatch <= 0)
+        return CTC_STATUS_INVALID_VALUE;
+    int maxL = 0, maxT = 0;
+    std::vector<int> meta;
+    long sumL = 0;
+    for (int i = 0; i < minibatch; ++i) { maxL = std::max(maxL, label_lengths[i]); maxT = std::max(maxT, input_lengths[i]); sumL += label_lengths[i]; }
+    meta.reserve((size_t)sumL + 3 * (size_t)minibatch + 1);
+    meta.insert(meta.end(), flat_labels, flat_labels + sumL);
+    int off = 0;
+    for (int i = 0; i < minibatch; ++i) { meta.push_back(off); off += label_lengths[i]; }
+    meta.push_back(off);
+    meta.insert(meta.end(), label_lengths, label_lengths + minibatch);
+    meta.insert(meta.end(), input_lengths, input_lengths + minibatch);
+    for (long i = 0; i < sumL; ++i) if (flat_labels[i] < 0 || flat_labels[i] >= alphabet_size) return CTC_STATUS_INVALID_VALUE;
+    cudaStream_t s = (cudaStream_t)options.stream;
+    char *ws = reinterpret_cast<char *>(workspace);
+    const size_t meta_bytes = (meta.size() * sizeof(int) + 255) & ~(size_t)255;
+    const size_t cost_bytes = ((size_t)minibatch * sizeof(float) + 255) & ~(size_t)255;
+    if (cudaMemcpyAsync(ws, meta.data(), meta.size() * sizeof(int), cudaMemcpyHostToDevice, s) != cudaSuccess) return CTC_STATUS_MEMOPS_FAILED;
+    // the host staging vector must outlive the (pageable => staged synchronously) copy: it does, pageable H2D
+    // returns after the source has been consumed.
+    const int *d_labels = reinterpret_cast<const int *>(ws);
+    const int *d_off = d_labels + sumL;
+    const int *d_llen = d_off + minibatch + 1;
+    const int *d_len = d_llen + minibatch;
+    float *d_costs = reinterpret_cast<float *>(ws + meta_bytes);
+    float *alpha_ws = reinterpret_cast<float *>(ws + meta_bytes + cost_bytes);
+    std::string err;
+    // (T,N,V) layout: element (n,t,k) at t*(N*V) + n*V + k
+    int rc = LaunchCtc(activations, 0, (long)alphabet_size, (long)minibatch * alphabet_size, minibatch, maxT, alphabet_size,
+                       d_labels, d_off, d_llen, d_len, maxL, options.blank_label, alpha_ws, gradients,
+                       (long)alphabet_size, (long)minibatch * alphabet_size, 1.f, d_costs, s, &err);
+    if (rc) { g_err = err; return CTC_STATUS_EXECUTION_FAILED; }
+    if (cudaMemcpyAsync(costs, d_costs, sizeof(float) * minibatch, cudaMemcpyDeviceToHost, s) != cudaSuccess) return CTC_STATUS_MEMOPS_FAILED;
+    if (cudaStreamSynchronize(s) != cudaSuccess) return CTC_STATUS_EXECUTION_FAILED;   // costs are host memory (gpu_ctc.h:365-368)
+    return CTC_STATUS_SUCCESS;
+}
+
+/* ---- host-side plan inspection ------------------------------------------------------------------ */
+void *ccb_plan_create(const char *fst_name, int n_ctas, int n_warps) {
+    g_err.clear();
+    HostFst fst;
+    std::string err;
+    if (!fst_name || !ReadFstFile(fst_name, &fst, &err)) { g_err = fst_name ? err : "null path"; return nullptr; }
+    DenPlan *p = new DenPlan();
+    if (!BuildDenPlan(fst, n_ctas, n_warps, p, &err)) { g_err = err; delete p; return nullptr; }
+    return p;
+}
+
+void ccb_plan_destroy(void *plan) { delete reinterpret_cast<DenPlan *>(plan); }
+
+int ccb_plan_info(void *plan, long *info) {
+    if (!plan || !info) return 1;
+    const DenPlan *p = reinterpret_cast<const DenPlan *>(plan);
+    info[0] = p->file_states; info[1] = p->file_arcs; info[2] = p->num_states;
+    info[3] = (long)p->fwd.arcs.size(); info[4] = (long)p->bwd.arcs.size(); info[5] = p->start;
+    info[6] = p->num_labels; info[7] = p->n_ctas; info[8] = p->n_warps;
+    info[9] = std::max(p->fwd.max_tile_arcs, p->bwd.max_tile_arcs);
+    return 0;
+}
+
+int ccb_plan_copy(void *plan, int which, void *dst, size_t dst_bytes) {
+    if (!plan || !dst) return 1;
+    const DenPlan *p = reinterpret_cast<const DenPlan *>(plan);
+    const void *src = nullptr;
+    size_t bytes = 0;
+    switch (which) {
+        case 0: src = p->state_label.data(); bytes = p->state_label.size() * 4; break;
+        case 1: src = p->final_lin.data(); bytes = p->final_lin.size() * 4; break;
+        case 2: src = p->orig_state.data(); bytes = p->orig_state.size() * 4; break;
+        case 3: src = p->fwd.arcs.data(); bytes = p->fwd.arcs.size() * sizeof(Arc); break;
+        case 4: src = p->fwd.chunk_state.data(); bytes = p->fwd.chunk_state.size() * 4; break;
+        case 5: src = p->fwd.chunk_arc.data(); bytes = p->fwd.chunk_arc.size() * 4; break;
+        case 6: src = p->bwd.arcs.data(); bytes = p->bwd.arcs.size() * sizeof(Arc); break;
+        case 7: src = p->bwd.chunk_state.data(); bytes = p->bwd.chunk_state.size() * 4; break;
+        case 8: src = p->bwd.chunk_arc.data(); bytes = p->bwd.chunk_arc.size() * 4; break;
+        default: return 1;
+    }
+    if (bytes > dst_bytes) return 2;
+    memcpy(dst, src, bytes);
+    return 0;
+}
+
+}  // extern "C"

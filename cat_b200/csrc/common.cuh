@@ -1,0 +1,139 @@
+// Shared device helpers and the internal host-side launch interface (not part of the C ABI).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+
+#include "den_graph.h"
+
+namespace ccb {
+
+// ------------------------------------------------------------------------------------------------
+// Device copy of the den plan (one per GPU listed in Init()).
+// ------------------------------------------------------------------------------------------------
+struct DevicePass {
+    Arc *arcs = nullptr;
+    int *chunk_state = nullptr;
+    int *chunk_arc = nullptr;
+    int num_arcs = 0;
+    int max_tile_arcs = 0;
+    int max_tile_labels = 0;
+};
+
+struct DeviceGraph {
+    bool loaded = false;
+    int device = -1;
+    int S = 0, start = 0, num_labels = 0;
+    int n_ctas = 0, n_warps = 0;
+    int *state_label = nullptr;
+    float *final_lin = nullptr;
+    DevicePass fwd, bwd;
+    int start_row_begin = 0, start_row_end = 0;  // backward-pass arcs of the start state
+    float start_final = 0.f;
+    int max_smem_optin = 0;
+};
+
+// Kernel parameter block shared by the two persistent den kernels.
+struct DenParams {
+    // graph
+    const Arc *arcs;
+    const int *chunk_state;
+    const int *chunk_arc;
+    const int *state_label;
+    const float *final_lin;
+    int S, start, n_warps;
+    int start_row_begin, start_row_end;
+    float start_final;
+    // problem
+    const void *y;        // (N,T,V) log-probs, fp32 or bf16
+    int y_bf16;
+    long sn, st;          // element strides of y
+    int N, Npad, Tmax, V;
+    const int *len;       // [N] device
+    // workspaces
+    float *alpha;         // [(Tmax+1)][S][Npad]   scaled-linear alpha spill
+    float *bh;            // [2][S][Npad]          backward ping-pong (emission-weighted beta)
+    float *colsum_a;      // [(Tmax+2)][Npad]
+    float *colsum_b;      // [(Tmax+2)][Npad]
+    float *absum;         // [(Tmax+2)][Npad]      sum_q alpha_t(q) beta_t(q)
+    float *zsum;          // [Npad]
+    float *b0;            // [Npad]
+    const float *fmax;    // [Tmax][Npad]          per-frame max of y (emission shift)
+    unsigned *barrier;    // grid barrier counter (zeroed before launch)
+    float *logz;          // [N] out (forward: logZ from alpha; backward: logZ from beta)
+    // gradient (backward)
+    float *grad;          // raw accumulation target, element (n,t,k) at n*gsn + t*gst + k
+    long gsn, gst;
+    int gacc_rows;        // rows of the shared-memory label accumulator (0 = direct global atomics)
+};
+
+// workspace carving (all offsets in bytes, 256-aligned)
+struct DenAuxLayout {
+    int Npad = 0;
+    size_t colsum_a = 0, colsum_b = 0, absum = 0, zsum = 0, b0 = 0, barrier = 0, zero_bytes = 0;
+    size_t fmax = 0, bh = 0, logz_a = 0, logz_b = 0, total = 0;
+};
+DenAuxLayout MakeDenAuxLayout(int S, int N, int T);
+inline int PadLanes(int N) {
+    int g = (N + 31) / 32;
+    if (g >= 3) g = (g + 3) / 4 * 4;   // lanes carry 1, 2 or 4 utterances each
+    return g * 32;
+}
+inline int LaneWidth(int Npad) { int g = Npad / 32; return g >= 4 ? 4 : g; }
+
+// host launchers; return cudaError_t-compatible int (0 = ok) and fill *err
+int LaunchFrameMax(const void *y, int y_bf16, long sn, long st, int N, int T, int V, const int *len, float *fmax,
+                   int Npad, cudaStream_t stream);
+int LaunchDenForward(const DeviceGraph &g, DenParams p, cudaStream_t stream, std::string *err);
+int LaunchDenBackward(const DeviceGraph &g, DenParams p, cudaStream_t stream, std::string *err);
+int LaunchDenGradNormalize(float *grad, long gsn, long gst, const float *absum, const int *len, int N, int Npad,
+                           int T, int V, float scale, cudaStream_t stream);
+int LaunchCtc(const void *y, int y_bf16, long sn, long st, int N, int T, int V, const int *labels,
+              const int *label_off, const int *label_len, const int *len, int max_label_len, int blank,
+              float *alpha_ws, float *grad, long gsn, long gst, float grad_scale, float *logp,
+              cudaStream_t stream, std::string *err);
+int LaunchAssembleLoss(const float *logz, const float *logp, int N, float lamb, float scale, float *loss,
+                       cudaStream_t stream);
+void CountLaunch(int n = 1);
+
+// ------------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ float load_y(const void *y, int bf16, long idx) {
+    return bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16 *>(y)[idx])
+                : __ldg(reinterpret_cast<const float *>(y) + idx);
+}
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_add_u32(unsigned *p, unsigned v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Grid-wide barrier for a co-resident (cooperatively launched) grid.  `target` is the value the
+// monotonically increasing counter reaches once every CTA has arrived at this barrier.
+__device__ __forceinline__ void grid_barrier(unsigned *counter, unsigned target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        red_release_add_u32(counter, 1u);
+        while (ld_acquire_u32(counter) < target) { }
+    }
+    __syncthreads();
+}
+
+// log-semiring add in fp32 (numerator only), same formula as den_calculate.cu:28-35 / ctc_helper.h
+__device__ __forceinline__ float log_add(float a, float b) {
+    if (a == -INFINITY) return b;
+    if (b == -INFINITY) return a;
+    float m = fmaxf(a, b);
+    return m + log1pf(expf(-fabsf(a - b)));
+}
+#endif
+
+}  // namespace ccb

@@ -1,0 +1,215 @@
+// Numerator: per-utterance CTC forward-backward over the blank-expanded label lattice (log domain).
+//
+// Replaces src/ctc_crf/gpu_ctc (compute_alpha_kernel gpu_ctc_kernels.h:87-213,
+// compute_betas_and_grad_kernel :218-458, host driver gpu_ctc.h:100-400).  Differences by design:
+//   * one kernel does forward, backward and the gradient (the reference launches two and synchronises
+//     the stream twice, gpu_ctc.h:272,368); nothing here touches the host;
+//   * thread i owns lattice cells 2i (blank) and 2i+1 (label i): the 2-/3-way log-sum of a frame needs
+//     one value from the neighbouring thread, exchanged through a shared-memory ping-pong, one
+//     __syncthreads per frame; the label row y[n][t][:] is staged coalesced one frame ahead;
+//   * occupancies are reduced per label with shared-memory float atomics in the LINEAR domain (blank cells
+//     are first summed with warp shuffles) -- no sort, no segmented reduce, no moderngpu;
+//   * any layout: element (n,t,k) at n*sn + t*st + k, so the (N,T,V) logits are read in place (the
+//     reference needs a transposed (T,N,V) copy, ctc_crf/__init__.py:70) and the gradient is ACCUMULATED
+//     with a caller scale into a buffer that may already hold the denominator part;
+//   * no 2L+1 <= 1280 limit (gpu_ctc.h:294-311): cells beyond the thread count are looped.
+// Semantics kept: inputs are log-softmax outputs (gpu_ctc/README.txt:1-2); costs = log p(l|x);
+// grad[t][k] = exp(LSE_{s: l'_s=k}(alpha_t(s)+beta_t(s)) - y_t(k) - log p) written for labels occurring in the
+// utterance and t < len only (:431-435); infeasible utterances (L+repeats > T, :108-109) get
+// log p = -inf and no gradient (the reference leaves both unwritten).
+#include "common.cuh"
+
+namespace ccb {
+
+namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+
+// shared memory carve-up (floats): lab[L1] ints | a[2][Sc] | yrow[2][V] | gk[2][V]
+__global__ void ctc_fwd_bwd_kernel(const void *y, int y_bf16, long sn, long st, int T, int V,
+                                   const int *labels, const int *label_off, const int *label_len, const int *len,
+                                   int max_label_len, int blank, float *alpha_ws,
+                                   float *grad, long gsn, long gst, float grad_scale, float *logp_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = blockIdx.x;
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const int L = label_len[n], Tn = len[n];
+    const int Sc = 2 * L + 1, L1 = L + 1;
+    const int ScMax = 2 * max_label_len + 1;
+    int *s_lab = reinterpret_cast<int *>(smem_raw);                 // [max_label_len + 1] label of cell 2i+1
+    float *s_a = reinterpret_cast<float *>(s_lab + max_label_len + 1);   // [2][ScMax]
+    float *s_y = s_a + 2 * ScMax;                                   // [2][V]
+    float *s_g = s_y + 2 * V;                                       // [2][V]
+    const int *lab = labels + label_off[n];
+
+    // feasibility (gpu_ctc_kernels.h:108-109)
+    int rep = 0;
+    for (int i = tid + 1; i < L; i += NT) rep += (lab[i] == lab[i - 1]);
+    __shared__ int s_rep;
+    if (tid == 0) s_rep = 0;
+    __syncthreads();
+    if (rep) atomicAdd(&s_rep, rep);
+    __syncthreads();
+    if (Tn <= 0 || L + s_rep > Tn) {
+        if (tid == 0) logp_out[n] = -INFINITY;
+        return;
+    }
+    for (int i = tid; i < L; i += NT) s_lab[i] = lab[i];
+    for (int k = tid; k < 2 * V; k += NT) s_g[k] = 0.f;
+    float *ws = alpha_ws + (size_t)n * T * ScMax;    // alpha spill [t][s]
+    const long ybase = n * sn;
+
+    // ---- forward ---------------------------------------------------------------------------------
+    for (int k = tid; k < V; k += NT) s_y[k] = load_y(y, y_bf16, ybase + k);
+    __syncthreads();
+    for (int s = tid; s < Sc; s += NT) {
+        float v = -INFINITY;
+        if (s == 0) v = s_y[blank];
+        else if (s == 1) v = s_y[s_lab[0]];
+        s_a[s] = v;
+        ws[s] = v;
+    }
+    for (int t = 1; t < Tn; ++t) {
+        // One barrier per frame: row t is staged into slot t&1 (last read two frames ago), the barrier
+        // publishes both the row and the previous frame's cells, then slot t&1 of the cells is rewritten
+        // (last read one barrier ago).
+        float *yc = s_y + (t & 1) * V;
+        const float *prev = s_a + ((t - 1) & 1) * ScMax;
+        float *cur = s_a + (t & 1) * ScMax;
+        for (int k = tid; k < V; k += NT) yc[k] = load_y(y, y_bf16, ybase + (long)t * st + k);
+        __syncthreads();
+        for (int i = tid; i < L1; i += NT) {
+            // blank cell 2i
+            const int sb = 2 * i;
+            float vb = prev[sb];
+            if (i > 0) vb = log_add(vb, prev[sb - 1]);
+            vb += yc[blank];
+            cur[sb] = vb;
+            ws[(size_t)t * ScMax + sb] = vb;
+            if (i < L) {   // label cell 2i+1
+                const int sl = sb + 1;
+                const int li = s_lab[i];
+                float vl = log_add(prev[sl], prev[sb]);
+                if (i > 0 && li != s_lab[i - 1]) vl = log_add(vl, prev[sl - 2]);
+                vl += yc[li];
+                cur[sl] = vl;
+                ws[(size_t)t * ScMax + sl] = vl;
+            }
+        }
+    }
+    __syncthreads();
+    float logp;
+    {
+        const float *last = s_a + ((Tn - 1) & 1) * ScMax;
+        logp = last[Sc - 1];
+        if (Sc > 1) logp = log_add(logp, last[Sc - 2]);
+    }
+    if (tid == 0) logp_out[n] = logp;
+    if (grad == nullptr || logp == -INFINITY) return;
+    __syncthreads();
+
+    // ---- backward + occupancies ------------------------------------------------------------------
+    // beta ping-pong reuses s_a; slot (t&1) holds beta_t.
+    for (int t = Tn - 1; t >= 0; --t) {
+        float *yc = s_y + (t & 1) * V;
+        float *cur = s_a + (t & 1) * ScMax;
+        const float *nxt = s_a + ((t + 1) & 1) * ScMax;
+        float *gk = s_g + (t & 1) * V;
+        for (int k = tid; k < V; k += NT) yc[k] = load_y(y, y_bf16, ybase + (long)t * st + k);
+        __syncthreads();   // the only barrier of the frame: publishes row t, beta_{t+1} and gk(t+1)
+        if (t + 1 < Tn) {  // flush the (now complete) occupancies of frame t+1 and clear their slot
+            float *gp = s_g + ((t + 1) & 1) * V;
+            float *grow = grad + n * gsn + (long)(t + 1) * gst;
+            for (int k = tid; k < V; k += NT) {
+                const float g = gp[k];
+                if (g != 0.f) { atomicAdd(grow + k, grad_scale * g); gp[k] = 0.f; }
+            }
+        }
+        const float *al = ws + (size_t)t * ScMax;
+        for (int i0 = 0; i0 < L1; i0 += NT) {
+            const int i = i0 + tid;
+            float occ_blank = 0.f;
+            if (i < L1) {
+                const int sb = 2 * i;
+                float vb;
+                if (t == Tn - 1) {
+                    vb = (sb == Sc - 1) ? yc[blank] : -INFINITY;
+                } else {
+                    vb = nxt[sb];
+                    if (sb + 1 < Sc) vb = log_add(vb, nxt[sb + 1]);
+                    vb += yc[blank];
+                }
+                cur[sb] = vb;
+                const float ob = al[sb] + vb - yc[blank] - logp;
+                occ_blank = (ob == -INFINITY || ob != ob) ? 0.f : expf(ob);
+                if (i < L) {
+                    const int sl = sb + 1;
+                    const int li = s_lab[i];
+                    float vl;
+                    if (t == Tn - 1) {
+                        vl = (sl == Sc - 2) ? yc[li] : -INFINITY;
+                    } else {
+                        vl = log_add(nxt[sl], nxt[sl + 1]);
+                        if (i + 1 < L && li != s_lab[i + 1]) vl = log_add(vl, nxt[sl + 2]);
+                        vl += yc[li];
+                    }
+                    cur[sl] = vl;
+                    const float ol = al[sl] + vl - yc[li] - logp;
+                    if (ol != -INFINITY && ol == ol) atomicAdd(&gk[li], expf(ol));
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) occ_blank += __shfl_xor_sync(kFull, occ_blank, o);
+            if ((tid & 31) == 0 && occ_blank != 0.f) atomicAdd(&gk[blank], occ_blank);
+        }
+    }
+    __syncthreads();
+    {   // flush frame 0
+        float *gp = s_g;
+        float *grow = grad + n * gsn;
+        for (int k = tid; k < V; k += NT) {
+            const float g = gp[k];
+            if (g != 0.f) atomicAdd(grow + k, grad_scale * g);
+        }
+    }
+}
+
+// loss[0] = scale * sum_n (logz[n] - (1+lamb) logp[n])      (ctc_crf/__init__.py:79-86)
+__global__ void assemble_loss_kernel(const float *logz, const float *logp, int N, float lamb, float scale, float *loss) {
+    double acc = 0.0;
+    for (int n = threadIdx.x; n < N; n += 32) acc += (double)logz[n] - (1.0 + (double)lamb) * (double)logp[n];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(kFull, acc, o);
+    if (threadIdx.x == 0) loss[0] = (float)(acc * (double)scale);
+}
+
+}  // namespace
+
+int LaunchCtc(const void *y, int y_bf16, long sn, long st, int N, int T, int V, const int *labels,
+              const int *label_off, const int *label_len, const int *len, int max_label_len, int blank,
+              float *alpha_ws, float *grad, long gsn, long gst, float grad_scale, float *logp,
+              cudaStream_t stream, std::string *err) {
+    if (N == 0) return 0;
+    const int ScMax = 2 * max_label_len + 1;
+    const size_t smem = (size_t)(max_label_len + 1) * 4 + (size_t)2 * ScMax * 4 + (size_t)4 * V * 4;
+    int threads = ((max_label_len + 1 + 31) / 32) * 32;
+    threads = threads < 64 ? 64 : (threads > 1024 ? 1024 : threads);
+    if (smem > 200 * 1024) { *err = "label sequence too long for the numerator kernel's shared memory"; return 1; }
+    cudaError_t e = cudaFuncSetAttribute(ctc_fwd_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { *err = std::string("cudaFuncSetAttribute(ctc): ") + cudaGetErrorString(e); return (int)e; }
+    ctc_fwd_bwd_kernel<<<N, threads, smem, stream>>>(y, y_bf16, sn, st, T, V, labels, label_off, label_len, len,
+                                                     max_label_len, blank, alpha_ws, grad, gsn, gst, grad_scale, logp);
+    CountLaunch();
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { *err = std::string("ctc launch: ") + cudaGetErrorString(e); return (int)e; }
+    return 0;
+}
+
+int LaunchAssembleLoss(const float *logz, const float *logp, int N, float lamb, float scale, float *loss,
+                       cudaStream_t stream) {
+    assemble_loss_kernel<<<1, 32, 0, stream>>>(logz, logp, N, lamb, scale, loss);
+    CountLaunch();
+    return (int)cudaGetLastError();
+}
+
+}  // namespace ccb

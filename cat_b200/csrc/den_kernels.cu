@@ -1,0 +1,542 @@
+// Denominator forward-backward over the shared phone-LM WFST: persistent sm_100a kernels.
+//
+// What the reference does (src/ctc_crf/gpu_den/den_calculate.cu): 3T+6 launches of <<<N,1024>>> kernels,
+// one CTA per utterance, thread per state, log-domain log1p(exp()) per arc, per-arc atomicCAS gradient.
+//
+// What this file does instead (DESIGN.md "Denominator"):
+//   * batched sparse semiring SpMM: lanes = utterances, a warp walks the arcs of its rows; every arc is
+//     one coalesced row gather alpha[t-1][peer][n0..n0+U) from L2 + U FMAs.  Arc metadata is read once
+//     per 32*U utterances and lives in shared memory for the whole kernel (loaded once per launch).
+//   * scaled-linear arithmetic: alpha/beta are kept in the linear domain with a per-(frame,utterance)
+//     power-of-two scale (exact), so the arc loop has no transcendental at all; the emission
+//     exp(y - max_k y) is applied once per (state, frame) thanks to the loader's single-in-label states.
+//   * one cooperative launch per pass; frames are separated by a hand-rolled grid barrier
+//     (red.release / ld.acquire), not by kernel launches.
+//   * gradient without arc atomics: gamma_t[k] = sum_{q: lab(q)=k} alpha_t(q) beta_t(q) / sum_q alpha_t(q) beta_t(q),
+//     accumulated per CTA in shared memory (states are sorted by label) and flushed with a few REDs.
+#include <cstdio>
+
+#include "common.cuh"
+
+namespace ccb {
+
+namespace {
+
+constexpr int kScaleExp = 32;        // per-frame column sums are renormalised to ~2^32
+constexpr unsigned kFull = 0xffffffffu;
+
+template <int U> struct Vec;
+template <> struct Vec<1> {
+    float v[1];
+    __device__ __forceinline__ static Vec ldcg(const float *p) { Vec r; r.v[0] = __ldcg(p); return r; }
+    __device__ __forceinline__ void stcg(float *p) const { __stcg(p, v[0]); }
+};
+template <> struct Vec<2> {
+    float v[2];
+    __device__ __forceinline__ static Vec ldcg(const float *p) {
+        float2 t = __ldcg(reinterpret_cast<const float2 *>(p));
+        Vec r; r.v[0] = t.x; r.v[1] = t.y; return r;
+    }
+    __device__ __forceinline__ void stcg(float *p) const { __stcg(reinterpret_cast<float2 *>(p), make_float2(v[0], v[1])); }
+};
+template <> struct Vec<4> {
+    float v[4];
+    __device__ __forceinline__ static Vec ldcg(const float *p) {
+        float4 t = __ldcg(reinterpret_cast<const float4 *>(p));
+        Vec r; r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w; return r;
+    }
+    __device__ __forceinline__ void stcg(float *p) const {
+        __stcg(reinterpret_cast<float4 *>(p), make_float4(v[0], v[1], v[2], v[3]));
+    }
+};
+template <int U> __device__ __forceinline__ Vec<U> vec_zero() {
+    Vec<U> r;
+#pragma unroll
+    for (int u = 0; u < U; ++u) r.v[u] = 0.f;
+    return r;
+}
+
+// r = 2^shift with shift = kScaleExp - floor(log2(s)); exact power of two, so rescaling never rounds.
+__device__ __forceinline__ float scale_from_sum(float s, int *shift) {
+    if (!(s > 0.f) || s > 3.0e38f) { *shift = 0; return 1.f; }
+    int field = (__float_as_int(s) >> 23) & 0xff;
+    int ex = (field == 0 ? 1 : field) - 127;
+    int sh = kScaleExp - ex;
+    sh = max(-126, min(127, sh));
+    *shift = sh;
+    return __int_as_float((sh + 127) << 23);
+}
+
+__device__ __forceinline__ void prefetch_l2(const void *p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-frame emission shift  m[t][n] = max_k y[n][t][k]
+// ------------------------------------------------------------------------------------------------
+__global__ void frame_max_kernel(const void *y, int bf16, long sn, long st, int N, int T, int V,
+                                 const int *len, float *fmax, int Npad) {
+    const int warps_per_block = blockDim.x >> 5;
+    const long row = (long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= (long)N * T) return;
+    const int n = (int)(row / T), t = (int)(row % T);
+    if (t >= len[n]) return;
+    float m = -INFINITY;
+    const long base = n * sn + t * st;
+    for (int k = lane; k < V; k += 32) m = fmaxf(m, load_y(y, bf16, base + k));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(kFull, m, o));
+    if (lane == 0) fmax[(size_t)t * Npad + n] = (m == -INFINITY) ? 0.f : m;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward: alpha recursion + logZ
+// ------------------------------------------------------------------------------------------------
+template <int NT, int U, int BATCH, bool SMEM_ARCS>
+__global__ void __launch_bounds__(NT, 1) den_forward_kernel(const DenParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *s_sum = reinterpret_cast<float *>(smem_raw);                                  // [Npad]
+    Arc *s_arcs = reinterpret_cast<Arc *>(smem_raw + (((size_t)P.Npad * 4 + 15) & ~(size_t)15));
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cta = blockIdx.x;
+    const int chunk = cta * P.n_warps + warp;
+    const int sb = __ldg(P.chunk_state + chunk), se = __ldg(P.chunk_state + chunk + 1);
+    const int ab = __ldg(P.chunk_arc + chunk), ae = __ldg(P.chunk_arc + chunk + 1);
+    const int tile_a0 = __ldg(P.chunk_arc + cta * P.n_warps);
+    const int tile_a1 = __ldg(P.chunk_arc + (cta + 1) * P.n_warps);
+    const int S = P.S, Npad = P.Npad;
+    const size_t frame_elems = (size_t)S * Npad;
+    unsigned epoch = 0;
+
+    if (SMEM_ARCS) {
+        for (int i = tid; i < tile_a1 - tile_a0; i += NT) s_arcs[i] = P.arcs[tile_a0 + i];
+    }
+    for (int i = tid; i < Npad; i += NT) s_sum[i] = 0.f;
+
+    // t = 0: alpha_0 = indicator(start); column sum 1
+    for (int q = sb; q < se; ++q)
+        for (int n = lane; n < Npad; n += 32) __stcg(P.alpha + (size_t)q * Npad + n, q == P.start ? 1.f : 0.f);
+    if (cta == 0) for (int n = tid; n < Npad; n += NT) __stcg(P.colsum_a + n, 1.f);
+    const int my_len = (cta == 0 && tid < P.N) ? __ldg(P.len + tid) : 0;   // CTA 0 keeps log-scale books
+    double runlog = 0.0;
+    grid_barrier(P.barrier, (++epoch) * gridDim.x);
+
+    for (int t = 1; t <= P.Tmax; ++t) {
+        const float *a_prev = P.alpha + (size_t)(t - 1) * frame_elems;
+        float *a_cur = P.alpha + (size_t)t * frame_elems;
+        for (int gc = 0; gc < Npad / (32 * U); ++gc) {
+            const int n0 = gc * 32 * U + lane * U;
+            bool act[U];
+            bool lane_act = false;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int ln = (n0 + u < P.N) ? __ldg(P.len + n0 + u) : 0;
+                act[u] = t <= ln;
+                lane_act |= act[u];
+            }
+            if (!__any_sync(kFull, lane_act)) continue;
+            float r[U], fm[U], e[U], acc[U], sum[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                int sh;
+                r[u] = scale_from_sum(__ldcg(P.colsum_a + (size_t)(t - 1) * Npad + n0 + u), &sh);
+                fm[u] = act[u] ? __ldg(P.fmax + (size_t)(t - 1) * Npad + n0 + u) : 0.f;
+                e[u] = 0.f; acc[u] = 0.f; sum[u] = 0.f;
+            }
+            int q = sb, curlab = -1;
+            for (int base = ab; base < ae; base += BATCH) {
+                uint32_t peer[BATCH];
+                float w[BATCH];
+                Vec<U> v[BATCH];
+#pragma unroll
+                for (int i = 0; i < BATCH; ++i) {
+                    const int a = base + i;
+                    const bool valid = a < ae;
+                    Arc k;
+                    k.peer = 0u; k.w = 0.f;
+                    if (valid) k = SMEM_ARCS ? s_arcs[a - tile_a0] : P.arcs[a];
+                    peer[i] = k.peer;
+                    w[i] = k.w;
+                    v[i] = (valid && lane_act)
+                               ? Vec<U>::ldcg(a_prev + (size_t)(k.peer & ~kLastFlag) * Npad + n0)
+                               : vec_zero<U>();
+                }
+#pragma unroll
+                for (int i = 0; i < BATCH; ++i) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) acc[u] = fmaf(w[i], v[i].v[u], acc[u]);
+                    if (peer[i] & kLastFlag) {   // warp-uniform: end of row q
+                        const int lab = __ldg(P.state_label + q);
+                        if (lab != curlab) {
+                            curlab = lab;
+#pragma unroll
+                            for (int u = 0; u < U; ++u)
+                                e[u] = act[u] ? expf(load_y(P.y, P.y_bf16, (n0 + u) * P.sn + (long)(t - 1) * P.st + lab) - fm[u])
+                                              : 0.f;
+                        }
+                        Vec<U> out;
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            out.v[u] = act[u] ? acc[u] * e[u] * r[u] : 0.f;
+                            sum[u] += out.v[u];
+                            acc[u] = 0.f;
+                        }
+                        if (lane_act) out.stcg(a_cur + (size_t)q * Npad + n0);
+                        ++q;
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (act[u] && sum[u] != 0.f) atomicAdd(&s_sum[n0 + u], sum[u]);
+        }
+        __syncthreads();
+        for (int i = tid; i < Npad; i += NT) {
+            const float v = s_sum[i];
+            if (v != 0.f) { atomicAdd(P.colsum_a + (size_t)t * Npad + i, v); s_sum[i] = 0.f; }
+        }
+        if (cta == 0 && tid < P.N && t <= my_len) {
+            int sh;
+            (void)scale_from_sum(__ldcg(P.colsum_a + (size_t)(t - 1) * Npad + tid), &sh);
+            runlog += (double)__ldg(P.fmax + (size_t)(t - 1) * Npad + tid) - (double)sh * 0.6931471805599453;
+        }
+        grid_barrier(P.barrier, (++epoch) * gridDim.x);
+    }
+
+    // logZ[n] = log sum_q alpha_len(q) final(q) + accumulated log scale      (den_calculate.cu:105-161)
+    for (int gc = 0; gc < Npad / 32; ++gc) {
+        const int n = gc * 32 + lane;
+        const int ln = (n < P.N) ? __ldg(P.len + n) : -1;
+        float zs = 0.f;
+        if (ln >= 0) {
+            for (int q = sb; q < se; ++q) {
+                const float f = __ldg(P.final_lin + q);
+                if (f != 0.f) zs = fmaf(f, __ldcg(P.alpha + ((size_t)ln * S + q) * Npad + n), zs);
+            }
+        }
+        if (zs != 0.f) atomicAdd(&s_sum[n], zs);
+    }
+    __syncthreads();
+    for (int i = tid; i < Npad; i += NT) {
+        const float v = s_sum[i];
+        if (v != 0.f) atomicAdd(P.zsum + i, v);
+    }
+    grid_barrier(P.barrier, (++epoch) * gridDim.x);
+    if (cta == 0 && tid < P.N) P.logz[tid] = (float)(log((double)__ldcg(P.zsum + tid)) + runlog);
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward: beta recursion, occupancies, logZ from beta
+// ------------------------------------------------------------------------------------------------
+template <int NT, int U, int BATCH, bool SMEM_ARCS>
+__global__ void __launch_bounds__(NT, 1) den_backward_kernel(const DenParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int Npad = P.Npad, S = P.S;
+    float *s_sum = reinterpret_cast<float *>(smem_raw);            // [2][Npad]: colsum_b, absum
+    float *s_gacc = s_sum + 2 * Npad;                              // [gacc_rows][Npad]
+    Arc *s_arcs = reinterpret_cast<Arc *>(smem_raw + ((((size_t)(2 + P.gacc_rows) * Npad) * 4 + 15) & ~(size_t)15));
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cta = blockIdx.x;
+    const int chunk = cta * P.n_warps + warp;
+    const int sb = __ldg(P.chunk_state + chunk), se = __ldg(P.chunk_state + chunk + 1);
+    const int ab = __ldg(P.chunk_arc + chunk), ae = __ldg(P.chunk_arc + chunk + 1);
+    const int tile_a0 = __ldg(P.chunk_arc + cta * P.n_warps);
+    const int tile_a1 = __ldg(P.chunk_arc + (cta + 1) * P.n_warps);
+    const int tile_s0 = __ldg(P.chunk_state + cta * P.n_warps);
+    const int tile_s1 = __ldg(P.chunk_state + (cta + 1) * P.n_warps);
+    const int tile_lab0 = tile_s1 > tile_s0 ? __ldg(P.state_label + tile_s0) : 0;
+    const int tile_labs = tile_s1 > tile_s0 ? __ldg(P.state_label + tile_s1 - 1) - tile_lab0 + 1 : 0;
+    const bool use_gacc = P.gacc_rows > 0;
+    const size_t frame_elems = (size_t)S * Npad;
+    unsigned epoch = 0;
+
+    if (SMEM_ARCS) {
+        for (int i = tid; i < tile_a1 - tile_a0; i += NT) s_arcs[i] = P.arcs[tile_a0 + i];
+    }
+    for (int i = tid; i < (2 + P.gacc_rows) * Npad; i += NT) s_sum[i] = 0.f;
+    const int my_len = (cta == 0 && tid < P.N) ? __ldg(P.len + tid) : 0;
+    double runlog = 0.0;
+    __syncthreads();
+
+    for (int tau = P.Tmax; tau >= 1; --tau) {
+        const float *bh_next = P.bh + (size_t)((tau + 1) & 1) * frame_elems;
+        float *bh_cur = P.bh + (size_t)(tau & 1) * frame_elems;
+        const float *a_row = P.alpha + (size_t)tau * frame_elems;
+        if (tau > 1 && se > sb) {   // pull next step's alpha rows of this chunk towards L2
+            const char *nb = reinterpret_cast<const char *>(a_row - frame_elems + (size_t)sb * Npad);
+            const size_t bytes = (size_t)(se - sb) * Npad * 4;
+            for (size_t off = (size_t)lane * 128; off < bytes; off += 32 * 128) prefetch_l2(nb + off);
+        }
+        for (int gc = 0; gc < Npad / (32 * U); ++gc) {
+            const int n0 = gc * 32 * U + lane * U;
+            bool act[U], gat[U];
+            bool lane_act = false, lane_gat = false;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int ln = (n0 + u < P.N) ? __ldg(P.len + n0 + u) : 0;
+                act[u] = tau <= ln;      // beta_tau exists
+                gat[u] = tau < ln;       // ... and is a sum over arcs (tau == len: final weights)
+                lane_act |= act[u];
+                lane_gat |= gat[u];
+            }
+            if (!__any_sync(kFull, lane_act)) continue;
+            float rb[U], fm[U], e[U], acc[U], sum_b[U], sum_ab[U], gsum[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                int sh;
+                rb[u] = gat[u] ? scale_from_sum(__ldcg(P.colsum_b + (size_t)(tau + 1) * Npad + n0 + u), &sh) : 1.f;
+                fm[u] = act[u] ? __ldg(P.fmax + (size_t)(tau - 1) * Npad + n0 + u) : 0.f;
+                e[u] = 0.f; acc[u] = 0.f; sum_b[u] = 0.f; sum_ab[u] = 0.f; gsum[u] = 0.f;
+            }
+            int q = sb, curlab = -1;
+            Vec<U> a_q = (se > sb && lane_act) ? Vec<U>::ldcg(a_row + (size_t)sb * Npad + n0) : vec_zero<U>();
+            for (int base = ab; base < ae; base += BATCH) {
+                uint32_t peer[BATCH];
+                float w[BATCH];
+                Vec<U> v[BATCH];
+#pragma unroll
+                for (int i = 0; i < BATCH; ++i) {
+                    const int a = base + i;
+                    const bool valid = a < ae;
+                    Arc k;
+                    k.peer = 0u; k.w = 0.f;
+                    if (valid) k = SMEM_ARCS ? s_arcs[a - tile_a0] : P.arcs[a];
+                    peer[i] = k.peer;
+                    w[i] = k.w;
+                    v[i] = (valid && lane_gat)
+                               ? Vec<U>::ldcg(bh_next + (size_t)(k.peer & ~kLastFlag) * Npad + n0)
+                               : vec_zero<U>();
+                }
+#pragma unroll
+                for (int i = 0; i < BATCH; ++i) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) acc[u] = fmaf(w[i], v[i].v[u], acc[u]);
+                    if (peer[i] & kLastFlag) {   // warp-uniform: end of row q
+                        const int lab = __ldg(P.state_label + q);
+                        if (lab != curlab) {
+                            if (curlab >= 0) {
+#pragma unroll
+                                for (int u = 0; u < U; ++u) {
+                                    if (gsum[u] != 0.f) {
+                                        if (use_gacc) atomicAdd(&s_gacc[(curlab - tile_lab0) * Npad + n0 + u], gsum[u]);
+                                        else atomicAdd(P.grad + (n0 + u) * P.gsn + (long)(tau - 1) * P.gst + curlab, gsum[u]);
+                                    }
+                                    gsum[u] = 0.f;
+                                }
+                            }
+                            curlab = lab;
+#pragma unroll
+                            for (int u = 0; u < U; ++u)
+                                e[u] = act[u] ? expf(load_y(P.y, P.y_bf16, (n0 + u) * P.sn + (long)(tau - 1) * P.st + lab) - fm[u])
+                                              : 0.f;
+                        }
+                        const float f = __ldg(P.final_lin + q);
+                        Vec<U> out;
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            const float b = act[u] ? (gat[u] ? acc[u] * rb[u] : f) : 0.f;
+                            const float abp = act[u] ? a_q.v[u] * b : 0.f;
+                            gsum[u] += abp;
+                            sum_ab[u] += abp;
+                            out.v[u] = e[u] * b;
+                            sum_b[u] += out.v[u];
+                            acc[u] = 0.f;
+                        }
+                        if (lane_act) out.stcg(bh_cur + (size_t)q * Npad + n0);
+                        ++q;
+                        a_q = (q < se && lane_act) ? Vec<U>::ldcg(a_row + (size_t)q * Npad + n0) : vec_zero<U>();
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (curlab >= 0 && gsum[u] != 0.f) {
+                    if (use_gacc) atomicAdd(&s_gacc[(curlab - tile_lab0) * Npad + n0 + u], gsum[u]);
+                    else atomicAdd(P.grad + (n0 + u) * P.gsn + (long)(tau - 1) * P.gst + curlab, gsum[u]);
+                }
+                if (act[u]) {
+                    if (sum_b[u] != 0.f) atomicAdd(&s_sum[n0 + u], sum_b[u]);
+                    if (sum_ab[u] != 0.f) atomicAdd(&s_sum[Npad + n0 + u], sum_ab[u]);
+                }
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < Npad; i += NT) {
+            const float vb = s_sum[i], vab = s_sum[Npad + i];
+            if (vb != 0.f) { atomicAdd(P.colsum_b + (size_t)tau * Npad + i, vb); s_sum[i] = 0.f; }
+            if (vab != 0.f) { atomicAdd(P.absum + (size_t)tau * Npad + i, vab); s_sum[Npad + i] = 0.f; }
+        }
+        if (use_gacc) {
+            for (int i = tid; i < tile_labs * Npad; i += NT) {
+                const float g = s_gacc[i];
+                if (g != 0.f) {
+                    const int n = i % Npad, k = tile_lab0 + i / Npad;
+                    atomicAdd(P.grad + n * P.gsn + (long)(tau - 1) * P.gst + k, g);
+                    s_gacc[i] = 0.f;
+                }
+            }
+        }
+        // log-scale of beta: LB_tau = LB_{tau+1} + m_tau - log rb_{tau+1}   (applies for tau < len)
+        if (cta == 0 && tid < P.N && tau < my_len) {
+            int sh;
+            (void)scale_from_sum(__ldcg(P.colsum_b + (size_t)(tau + 1) * Npad + tid), &sh);
+            runlog += (double)__ldg(P.fmax + (size_t)tau * Npad + tid) - (double)sh * 0.6931471805599453;
+        }
+        grid_barrier(P.barrier, (++epoch) * gridDim.x);
+    }
+
+    // tau = 0: beta_0(start) only -> logZ recomputed from the backward pass (den_calculate.cu:177-187,255-261)
+    if (P.start >= sb && P.start < se) {
+        const float *bh1 = P.bh + (size_t)(1 & 1) * frame_elems;
+        for (int n = lane; n < P.N; n += 32) {
+            const int ln = __ldg(P.len + n);
+            float b = P.start_final;
+            if (ln > 0) {
+                int sh;
+                const float rb = scale_from_sum(__ldcg(P.colsum_b + (size_t)1 * Npad + n), &sh);
+                float acc = 0.f;
+                for (int a = P.start_row_begin; a < P.start_row_end; ++a) {
+                    const Arc k = P.arcs[a];
+                    acc = fmaf(k.w, __ldcg(bh1 + (size_t)(k.peer & ~kLastFlag) * Npad + n), acc);
+                }
+                b = acc * rb;
+            }
+            __stcg(P.b0 + n, b);
+        }
+    }
+    if (cta == 0 && tid < P.N && 0 < my_len) {
+        int sh;
+        (void)scale_from_sum(__ldcg(P.colsum_b + (size_t)1 * Npad + tid), &sh);
+        runlog += (double)__ldg(P.fmax + tid) - (double)sh * 0.6931471805599453;
+    }
+    grid_barrier(P.barrier, (++epoch) * gridDim.x);
+    if (cta == 0 && tid < P.N) P.logz[tid] = (float)(log((double)__ldcg(P.b0 + tid)) + runlog);
+}
+
+// grad[n][t][:] *= scale / absum[t+1][n]   for t < len[n]
+__global__ void den_grad_normalize_kernel(float *grad, long gsn, long gst, const float *absum, const int *len,
+                                          int N, int Npad, int T, int V, float scale) {
+    const long row = blockIdx.x;   // (n, t)
+    const int n = (int)(row / T), t = (int)(row % T);
+    if (t >= len[n]) return;
+    const float s = absum[(size_t)(t + 1) * Npad + n];
+    const float f = s > 0.f ? scale / s : 0.f;
+    float *g = grad + n * gsn + t * gst;
+    for (int k = threadIdx.x; k < V; k += blockDim.x) g[k] *= f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch plumbing
+// ------------------------------------------------------------------------------------------------
+template <int NT, int U, int BATCH, bool SMEM_ARCS>
+int LaunchOne(bool backward, const DenParams &p, int n_ctas, size_t smem, cudaStream_t stream, std::string *err) {
+    const void *fn = backward ? (const void *)den_backward_kernel<NT, U, BATCH, SMEM_ARCS>
+                              : (const void *)den_forward_kernel<NT, U, BATCH, SMEM_ARCS>;
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { *err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return (int)e; }
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, NT, smem);
+    if (e != cudaSuccess || per_sm < 1) {
+        *err = "den kernel does not fit on an SM (smem=" + std::to_string(smem) + ")";
+        return e != cudaSuccess ? (int)e : 1;
+    }
+    DenParams pc = p;
+    void *args[] = {&pc};
+    e = cudaLaunchCooperativeKernel(fn, dim3(n_ctas), dim3(NT), args, smem, stream);
+    if (e != cudaSuccess) { *err = std::string("cooperative launch failed: ") + cudaGetErrorString(e); return (int)e; }
+    CountLaunch();
+    return 0;
+}
+
+template <int NT>
+int Dispatch(bool backward, const DeviceGraph &g, const DenParams &p, size_t fixed_smem, cudaStream_t stream,
+             std::string *err) {
+    const DevicePass &pass = backward ? g.bwd : g.fwd;
+    const size_t arc_bytes = (size_t)pass.max_tile_arcs * sizeof(Arc);
+    const size_t budget = (size_t)g.max_smem_optin > 2048 ? (size_t)g.max_smem_optin - 1024 : 0;
+    const bool smem_arcs = fixed_smem + arc_bytes <= budget;
+    const size_t smem = fixed_smem + (smem_arcs ? arc_bytes : 0);
+    const int U = LaneWidth(p.Npad);
+    // rows in flight per warp: 8 KB of gathers at 512 threads, 4 KB at 1024 threads (register budget)
+#define CCB_GO(UU)                                                                                      \
+    {                                                                                                   \
+        constexpr int B = (NT == 512 ? 64 : 32) / (UU == 1 ? 4 : 2 * UU);                               \
+        return smem_arcs ? LaunchOne<NT, UU, B, true>(backward, p, g.n_ctas, smem, stream, err)          \
+                         : LaunchOne<NT, UU, B, false>(backward, p, g.n_ctas, smem, stream, err);        \
+    }
+    if (U == 1) { CCB_GO(1); }
+    if (U == 2) { CCB_GO(2); }
+    CCB_GO(4);
+#undef CCB_GO
+}
+
+int DispatchThreads(bool backward, const DeviceGraph &g, const DenParams &p, size_t fixed_smem, cudaStream_t stream,
+                    std::string *err) {
+    if (p.Npad > g.n_warps * 32) { *err = "batch too large for the den kernel's bookkeeping CTA (N <= " + std::to_string(g.n_warps * 32) + ")"; return 1; }
+    if (g.n_warps == 32) return Dispatch<1024>(backward, g, p, fixed_smem, stream, err);
+    if (g.n_warps == 16) return Dispatch<512>(backward, g, p, fixed_smem, stream, err);
+    *err = "unsupported warps per CTA for den kernels (16 or 32)";
+    return 1;
+}
+
+}  // namespace
+
+DenAuxLayout MakeDenAuxLayout(int S, int N, int T) {
+    DenAuxLayout L;
+    L.Npad = PadLanes(N);
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    size_t off = 0;
+    const size_t rows = (size_t)(T + 2) * L.Npad * 4;
+    L.colsum_a = off; off = up(off + rows);
+    L.colsum_b = off; off = up(off + rows);
+    L.absum = off; off = up(off + rows);
+    L.zsum = off; off = up(off + (size_t)L.Npad * 4);
+    L.b0 = off; off = up(off + (size_t)L.Npad * 4);
+    L.barrier = off; off = up(off + 256);
+    L.zero_bytes = off;
+    L.fmax = off; off = up(off + (size_t)(T + 1) * L.Npad * 4);
+    L.logz_a = off; off = up(off + (size_t)L.Npad * 4);
+    L.logz_b = off; off = up(off + (size_t)L.Npad * 4);
+    L.bh = off; off = up(off + (size_t)2 * S * L.Npad * 4);
+    L.total = off;
+    return L;
+}
+
+int LaunchFrameMax(const void *y, int y_bf16, long sn, long st, int N, int T, int V, const int *len, float *fmax,
+                   int Npad, cudaStream_t stream) {
+    const long rows = (long)N * T;
+    if (rows == 0) return 0;
+    const int wpb = 8;
+    frame_max_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, stream>>>(y, y_bf16, sn, st, N, T, V, len, fmax, Npad);
+    CountLaunch();
+    return (int)cudaGetLastError();
+}
+
+int LaunchDenForward(const DeviceGraph &g, DenParams p, cudaStream_t stream, std::string *err) {
+    p.arcs = g.fwd.arcs; p.chunk_state = g.fwd.chunk_state; p.chunk_arc = g.fwd.chunk_arc;
+    p.gacc_rows = 0;
+    const size_t fixed = (((size_t)p.Npad * 4 + 15) & ~(size_t)15);
+    return DispatchThreads(false, g, p, fixed, stream, err);
+}
+
+int LaunchDenBackward(const DeviceGraph &g, DenParams p, cudaStream_t stream, std::string *err) {
+    p.arcs = g.bwd.arcs; p.chunk_state = g.bwd.chunk_state; p.chunk_arc = g.bwd.chunk_arc;
+    // label accumulator in shared memory when the per-CTA label range is small enough
+    size_t gacc_bytes = (size_t)g.bwd.max_tile_labels * p.Npad * 4;
+    p.gacc_rows = gacc_bytes <= 64 * 1024 ? g.bwd.max_tile_labels : 0;
+    const size_t fixed = ((((size_t)(2 + p.gacc_rows) * p.Npad) * 4 + 15) & ~(size_t)15);
+    return DispatchThreads(true, g, p, fixed, stream, err);
+}
+
+int LaunchDenGradNormalize(float *grad, long gsn, long gst, const float *absum, const int *len, int N, int Npad,
+                           int T, int V, float scale, cudaStream_t stream) {
+    if ((long)N * T == 0) return 0;
+    den_grad_normalize_kernel<<<(unsigned)((long)N * T), 128, 0, stream>>>(grad, gsn, gst, absum, len, N, Npad, T, V, scale);
+    CountLaunch();
+    return (int)cudaGetLastError();
+}
+
+}  // namespace ccb

@@ -1,0 +1,142 @@
+/*
+ * ctc_crf_b200 -- C ABI of the B200-native CTC-CRF loss hot path (drop-in for thu-spmi/CAT src/ctc_crf).
+ *
+ * Plain C, no torch types: pointers, sizes, a cudaStream_t passed as void*.  All device pointers must
+ * belong to the CUDA device that is current when the call is made (the reference has the same contract,
+ * den_calculate.cu:436-438).  Citations are relative to /root/reference/src/ctc_crf.
+ *
+ * Section 1 keeps the exact names and signatures the reference's binding.cpp binds (binding.cpp:14-49 and
+ * gpu_ctc/ctc.h:16-109), so the reference's own binding.cpp links against this library unchanged.
+ * Section 2 is the fused entry the new autograd Function uses (SURVEY.md 8b "new fused entry").
+ * Section 3 exposes the host-side den-graph plan for CPU-only tests.
+ *
+ * Error convention: section-1 den functions return void like the reference but never exit(); they record
+ * an error retrievable with ccb_last_error().  Everything else returns 0 on success, non-zero on failure.
+ */
+#ifndef CTC_CRF_B200_H_
+#define CTC_CRF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------------
+ * Section 1 -- reference-compatible entry points
+ * ---------------------------------------------------------------------------------------------- */
+
+/* replaces den_calculate.cu:263-273 globals read by binding.cpp:14-15,77-78 (scratch sizing).
+ * DEN_NUM_STATES is the state count *after* the loader's in-label state split (== the file's state
+ * count for every T-compose-LM graph). */
+extern int DEN_NUM_ARCS;
+extern int DEN_NUM_STATES;
+
+/* replaces Init / Release (binding.cpp:22-24, den_calculate.cu:288-425): load an OpenFst binary
+ * vector/standard den graph, build the kernel plan, upload it to each listed GPU. */
+void Init(const char *fst_name, int n_gpus, int *gpus);
+void Release(int n_gpus, int *gpus);
+
+/* replaces compute_alpha (binding.cpp:26-34, den_calculate.cu:427-451).
+ *   alpha      : scratch, >= ccb_den_alpha_floats(batch_size, T) floats (OPAQUE layout: [t][state][lane]);
+ *                binding.cpp's (T+1)*N*DEN_NUM_STATES suffices whenever N is a multiple of 32, otherwise the
+ *                library falls back to an internal stream-ordered allocation.
+ *   logits     : (N,T,V) fp32 log-probs, contiguous
+ *   input_lengths : (N,) int32 DEVICE
+ *   loglikelihood : (N,) fp32 DEVICE out, logZ_den per utterance */
+void compute_alpha(float *alpha, float *logits, const int batch_size, int T, const int alpha_size,
+                   int logits_size, int *input_lengths, float *loglikelihood, void *stream);
+
+/* replaces compute_beta_and_grad (binding.cpp:36-48, den_calculate.cu:453-481).
+ *   grad_net : (N,T,V) fp32, PRE-ZEROED by the caller (ctc_crf/__init__.py:66); rows t < len get the
+ *              denominator occupancies, rows t >= len stay untouched.
+ *   beta / grad_storage : scratch of the reference's sizes; unused here (kept for signature parity).
+ *   loglikelihood : (N,) out, logZ_den recomputed from the backward pass (== alpha_lld up to rounding). */
+void compute_beta_and_grad(float *beta, const float *const alpha, const float *const logits,
+                           const float *const alpha_lld, float *grad_storage, float *grad_net,
+                           const int batch_size, const int T, const int beta_size, const int logits_size,
+                           const int *const input_lengths, float *loglikelihood, void *stream);
+
+/* replaces gpu_ctc/ctc.h:16-109 */
+typedef enum {
+    CTC_STATUS_SUCCESS = 0,
+    CTC_STATUS_MEMOPS_FAILED = 1,
+    CTC_STATUS_INVALID_VALUE = 2,
+    CTC_STATUS_EXECUTION_FAILED = 3,
+    CTC_STATUS_UNKNOWN_ERROR = 4
+} ctcStatus_t;
+
+struct ctcOptions {
+    void *stream;     /* CUstream */
+    int blank_label;
+};
+
+const char *ctcGetStatusString(ctcStatus_t status);
+
+/* activations: (T,N,V) fp32 log-probs on the device; gradients: (T,N,V) pre-zeroed device buffer or NULL;
+ * flat_labels / label_lengths / input_lengths / costs: HOST pointers; costs[n] = log p(l_n | x_n). */
+ctcStatus_t compute_ctc_loss(const float *const activations, float *gradients, const int *const flat_labels,
+                             const int *const label_lengths, const int *const input_lengths, int alphabet_size,
+                             int minibatch, float *costs, void *workspace, struct ctcOptions options);
+ctcStatus_t get_workspace_size(const int *const label_lengths, const int *const input_lengths,
+                               int alphabet_size, int minibatch, struct ctcOptions options, size_t *size_bytes);
+
+/* ------------------------------------------------------------------------------------------------
+ * Section 2 -- fused entry and helpers (additions)
+ * ---------------------------------------------------------------------------------------------- */
+#define CCB_DTYPE_F32 0
+#define CCB_DTYPE_BF16 1
+
+const char *ccb_last_error(void);            /* thread-local message of the last failure ("" if none) */
+int ccb_den_loaded(int device);              /* 1 if Init() covered this device */
+
+/* scratch sizes for N utterances x T frames on the current device's den graph */
+size_t ccb_den_alpha_floats(int N, int T);   /* alpha spill, floats */
+size_t ccb_den_aux_bytes(int N, int T);      /* everything else the den passes need */
+size_t ccb_ctc_workspace_bytes(int N, int T, int max_label_len);
+
+/* Denominator only: logZ (N,) fp32 device out; grad (strided, pre-zeroed, accumulated with
+ * grad_scale); logz_beta may be NULL. */
+int ccb_den_forward_backward(const void *logits, int dtype, long sn, long st, int N, int T, int V,
+                             const int *len_dev, float *alpha_ws, void *aux_ws,
+                             float *grad, long gsn, long gst, float grad_scale,
+                             float *logz, float *logz_beta, void *stream);
+
+/* Numerator only: meta_dev = device int32 block [labels(sumL) | label_off(N+1) | label_len(N) | len(N)];
+ * grad accumulated with grad_scale (pass e.g. -(1+lamb)/N); logp (N,) fp32 device out. */
+int ccb_ctc_forward_backward(const void *logits, int dtype, long sn, long st, int N, int T, int V,
+                             const int *labels_dev, const int *label_off_dev, const int *label_len_dev,
+                             const int *len_dev, int max_label_len, int blank, void *workspace,
+                             float *grad, long gsn, long gst, float grad_scale, float *logp, void *stream);
+
+/* Fused CTC-CRF loss (ctc_crf/__init__.py:58-90 in one call, no host synchronisation):
+ *   loss[0] = sum_n (logZ_den[n] - (1+lamb) logp_ctc[n]) * (size_average ? 1/N : 1)
+ *   grad    = (gamma_den - (1+lamb) gamma_ctc) * (size_average ? 1/N : 1)      (N,T,V) fp32, zeroed here
+ * parts (optional, may be NULL): 2N floats = [logZ_den | logp_ctc]. */
+int ccb_ctc_crf_loss_fwd(const void *logits, int dtype, int N, int T, int V,
+                         const int *labels_dev, const int *label_off_dev, const int *label_len_dev,
+                         const int *len_dev, int max_label_len, float lamb, int size_average,
+                         float *alpha_ws, void *aux_ws, void *ctc_ws,
+                         float *grad, float *loss, float *parts, void *stream);
+
+/* number of kernels launched by this library since load (bench.py's gpu_launches) */
+long ccb_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Section 3 -- host-side den-graph plan (no GPU needed)
+ * ---------------------------------------------------------------------------------------------- */
+/* Parse + plan without touching CUDA.  n_ctas/n_warps describe the persistent grid the plan is cut for. */
+void *ccb_plan_create(const char *fst_name, int n_ctas, int n_warps);
+void ccb_plan_destroy(void *plan);
+/* info[0..9] = S_file, A_file, S, A_fwd, A_bwd, start, num_labels, n_ctas, n_warps, max_tile_arcs */
+int ccb_plan_info(void *plan, long *info);
+/* which: 0 state_label[S] i32, 1 final_lin[S] f32, 2 orig_state[S] i32,
+ *        3 fwd_arcs[A_fwd] {u32 src|last<<31, f32 w}, 4 fwd_chunk_state[n_ctas*n_warps+1] i32,
+ *        5 fwd_chunk_arc[n_ctas*n_warps+1] i32, 6 bwd_arcs[A_bwd], 7 bwd_chunk_state, 8 bwd_chunk_arc */
+int ccb_plan_copy(void *plan, int which, void *dst, size_t dst_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CTC_CRF_B200_H_ */

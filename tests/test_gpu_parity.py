@@ -1,0 +1,217 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the reference-facing surface
+(ctc_crf.CTC_CRF_LOSS / _C.gpu_den / _C.gpu_ctc -> C ABI), against the fp64 oracle, the committed golden
+vectors, and the reference's own CUDA code (oracle/_ref) on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): loss 1e-4 relative, gradients 1e-3 (absolute; occupancies are in [0,1]).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+LOSS_RTOL = 1e-4
+GRAD_ATOL = 1e-3
+
+
+def _ctx(path):
+    import ctc_crf
+    return ctc_crf.CRFContext(path, gpus=0)
+
+
+def _run_ours(y, labels, lx, ly, lamb, size_average=True, dtype=torch.float32):
+    import ctc_crf
+    logits = torch.tensor(y, device="cuda", dtype=dtype).requires_grad_(True)
+    crit = ctc_crf.CTC_CRF_LOSS(lamb=lamb, size_average=size_average)
+    loss = crit(logits, torch.tensor(labels, dtype=torch.int32), torch.tensor(lx, dtype=torch.int32),
+                torch.tensor(ly, dtype=torch.int32))
+    loss.backward()
+    return float(loss.item()), logits.grad.float().cpu().numpy()
+
+
+def _close_loss(a, b, rtol=LOSS_RTOL):
+    assert abs(a - b) <= rtol * max(1.0, abs(b)), (a, b)
+
+
+def test_fixture_kat(fixture_fst, fixture_inputs):
+    """The reference's own test input (test/main.py) -> survey/oracle known answers."""
+    from oracle import oracle
+    from cat_b200 import fst
+    fi = fixture_inputs
+    ctx = _ctx(fixture_fst)
+    loss, grad = _run_ours(fi["y"], fi["labels"], fi["lx"], fi["ly"], fi["lamb"])
+    _close_loss(loss, -2.47862480)
+    oloss, ograd, _ = oracle.ctc_crf(fst.read_fst(fixture_fst), fi["y"], fi["labels"], fi["lx"], fi["ly"], fi["lamb"])
+    _close_loss(loss, oloss)
+    assert np.abs(grad - ograd).max() < GRAD_ATOL
+    np.testing.assert_allclose(grad[0, 0], [0.658503, 0.311666, -0.980169, 0, 0], atol=2e-5)
+    del ctx
+
+
+@pytest.mark.parametrize("name,N,T,lens", [
+    ("tlm_small", 3, 20, [20, 13, 7]),
+    ("random_split", 3, 20, [20, 13, 7]),          # loader has to split states by in-label
+    ("tlm_small", 5, 33, [33, 33, 1, 2, 17]),
+    ("tlm_mid", 64, 40, None),                      # two utterances per lane
+    ("tlm_mid", 33, 25, None),                      # ragged lane padding
+    ("tlm_mid", 130, 12, None),                     # four utterances per lane, padded to 256
+])
+def test_den_vs_oracle(tmp_graphs, name, N, T, lens):
+    """_C.gpu_den (reference signature) vs the oracle: logZ from alpha, logZ from beta, occupancies."""
+    from oracle import oracle
+    from cat_b200 import _C
+    path, g, V = tmp_graphs[name]
+    ctx = _ctx(path)
+    if lens is None:
+        lens = np.maximum(1, T - (np.arange(N) * 7) % T).astype(np.int32)
+        lens[0] = T
+    y, _, lens, _ = oracle.synth_batch(N, T, V, seed=5, lens=lens)
+    logits = torch.tensor(y, device="cuda")
+    grad = torch.zeros_like(logits)
+    ca = torch.zeros(N, device="cuda")
+    cb = torch.zeros(N, device="cuda")
+    _C.gpu_den(logits, grad, torch.tensor(lens, dtype=torch.int32).cuda(), ca, cb)
+    la, lb, gd = oracle.den(g, y, lens)
+    np.testing.assert_allclose(ca.cpu().numpy(), la, rtol=LOSS_RTOL, atol=1e-4)
+    np.testing.assert_allclose(cb.cpu().numpy(), lb, rtol=LOSS_RTOL, atol=1e-4)
+    gn = grad.cpu().numpy()
+    assert np.abs(gn - gd).max() < GRAD_ATOL
+    for n in range(N):   # rows beyond the utterance stay untouched (den_calculate.cu:238)
+        assert not gn[n, lens[n]:].any()
+    del ctx
+
+
+@pytest.mark.parametrize("N,T,V,lens,ly", [
+    (4, 30, 12, [30, 22, 9, 5], [5, 3, 0, 5]),       # L=0 and T == L (+repeats) edge
+    (3, 50, 40, [50, 41, 17], [8, 20, 1]),
+    (2, 12, 6, [12, 3], [11, 5]),                     # one nearly-full lattice, one infeasible (L > T)
+])
+def test_ctc_vs_oracle(N, T, V, lens, ly):
+    """_C.gpu_ctc (reference signature, (T,N,V) layout, host labels/costs) vs the oracle."""
+    from oracle import oracle
+    from cat_b200 import _C
+    rng = np.random.default_rng(3)
+    y, _, lens, _ = oracle.synth_batch(N, T, V, seed=9, lens=lens)
+    ly = np.asarray(ly, np.int32)
+    labels = rng.integers(1, V, size=int(ly.sum())).astype(np.int32)
+    if ly[0] >= 3:
+        labels[1] = labels[0]                          # force a repeat
+    act = torch.tensor(y, device="cuda").transpose(0, 1).contiguous()
+    grads = torch.zeros_like(act)
+    costs = torch.zeros(N)
+    _C.gpu_ctc(act, grads, torch.tensor(labels), torch.tensor(ly), torch.tensor(lens), N, costs, 0)
+    lp, gc = oracle.ctc(y, labels, ly, lens)
+    got = costs.numpy()
+    for n in range(N):
+        if np.isinf(lp[n]):
+            assert np.isinf(got[n]) and got[n] < 0
+        else:
+            assert abs(got[n] - lp[n]) <= LOSS_RTOL * max(1.0, abs(lp[n]))
+    assert np.abs(grads.transpose(0, 1).cpu().numpy() - gc).max() < GRAD_ATOL
+
+
+def test_fused_vs_oracle_and_bf16(tmp_graphs):
+    from oracle import oracle
+    path, g, V = tmp_graphs["tlm_mid"]
+    ctx = _ctx(path)
+    N, T = 8, 60
+    lens = [60, 60, 55, 41, 33, 20, 9, 3]
+    y, labels, lens, ly = oracle.synth_batch(N, T, V, seed=21, lens=lens)
+    for sa in (True, False):
+        loss, grad = _run_ours(y, labels, lens, ly, 0.1, size_average=sa)
+        oloss, ograd, _ = oracle.ctc_crf(g, y, labels, lens, ly, 0.1, size_average=sa)
+        _close_loss(loss, oloss)
+        assert np.abs(grad - ograd).max() < GRAD_ATOL * (1 if sa else N)
+    # bf16 logits: parity is defined against the oracle fed the bf16-rounded values
+    yb = torch.tensor(y).bfloat16()
+    loss, grad = _run_ours(yb.float().numpy(), labels, lens, ly, 0.1, dtype=torch.bfloat16)
+    oloss, ograd, _ = oracle.ctc_crf(g, yb.float().numpy(), labels, lens, ly, 0.1)
+    _close_loss(loss, oloss)
+    assert np.abs(grad - ograd).max() < GRAD_ATOL
+    del ctx
+
+
+def test_vs_reference_cuda(tmp_path):
+    """Side by side with the reference's own CUDA code (oracle/_ref) on the AISHELL-shaped config scaled to
+    what the fp64 oracle also finishes in seconds: V=218, 100k-arc T-compose-LM graph, N=8, T=120."""
+    from oracle import oracle, ref_cuda
+    from cat_b200 import fst
+    if not ref_cuda.available():
+        pytest.skip("oracle/_ref not built")
+    V = 218
+    g = fst.make_synthetic_den(2000, 24, V, seed=7)
+    path = str(tmp_path / "den.fst")
+    fst.write_fst(path, g)
+    N, T = 8, 120
+    lens = [120, 120, 111, 97, 80, 64, 30, 12]
+    y, labels, lens, ly = oracle.synth_batch(N, T, V, seed=1234, lens=lens)
+    ctx = _ctx(path)
+    loss, grad = _run_ours(y, labels, lens, ly, 0.01)
+    rctx = ref_cuda.RefContext(path, 0)
+    rl, rg, parts = ref_cuda.ctc_crf_forward(rctx, torch.tensor(y, device="cuda"), torch.tensor(labels),
+                                             torch.tensor(lens), torch.tensor(ly), 0.01, True)
+    torch.cuda.synchronize()
+    rctx.close()
+    _close_loss(loss, float(rl.item()))
+    assert np.abs(grad - rg.cpu().numpy()).max() < GRAD_ATOL
+    oloss, ograd, _ = oracle.ctc_crf(g, y, labels, lens, ly, 0.01)
+    _close_loss(float(rl.item()), oloss)          # pins the oracle to the reference's actual output
+    assert np.abs(rg.cpu().numpy() - ograd).max() < GRAD_ATOL
+    del ctx
+
+
+def test_full_size_properties(tmp_path):
+    """BASELINE config 2 (N=32, T=800, V=218, ~1M-arc graph) against the reference CUDA build, plus the
+    size-independent invariants: occupancy rows sum to 1 (den) / gradient rows sum to -lamb/N, logZ(alpha)
+    == logZ(beta), idempotence (same result twice)."""
+    from oracle import oracle, ref_cuda
+    from cat_b200 import fst, _C
+    V = 218
+    g = fst.make_synthetic_den(20000, 24, V, seed=7)
+    path = str(tmp_path / "den1m.fst")
+    fst.write_fst(path, g)
+    N, T = 32, 800
+    y, labels, lens, ly = oracle.synth_batch(N, T, V, seed=1234)
+    ctx = _ctx(path)
+    logits = torch.tensor(y, device="cuda")
+    gden = torch.zeros_like(logits)
+    ca = torch.zeros(N, device="cuda"); cb = torch.zeros(N, device="cuda")
+    _C.gpu_den(logits, gden, torch.tensor(lens).cuda(), ca, cb)
+    rows = gden.sum(-1).cpu().numpy()
+    assert np.abs(rows - 1.0).max() < 1e-4
+    np.testing.assert_allclose(ca.cpu().numpy(), cb.cpu().numpy(), rtol=1e-5)
+    lamb = 0.01
+    loss, grad = _run_ours(y, labels, lens, ly, lamb)
+    loss2, grad2 = _run_ours(y, labels, lens, ly, lamb)
+    _close_loss(loss, loss2, 1e-6)
+    assert np.abs(grad - grad2).max() < 1e-5
+    assert np.abs(grad.sum(-1) * N + lamb).max() < 2e-4      # sum_k (gamma_den - (1+lamb) gamma_ctc) = -lamb
+    if ref_cuda.available():
+        rctx = ref_cuda.RefContext(path, 0)
+        rl, rg, parts = ref_cuda.ctc_crf_forward(rctx, logits, torch.tensor(labels), torch.tensor(lens),
+                                                 torch.tensor(ly), lamb, True)
+        torch.cuda.synchronize()
+        rctx.close()
+        _close_loss(loss, float(rl.item()))
+        assert np.abs(grad - rg.cpu().numpy()).max() < GRAD_ATOL / N * 4   # grads are scaled by 1/N
+    del ctx
+
+
+def test_error_paths(fixture_fst, tmp_path):
+    import ctc_crf
+    with pytest.raises(RuntimeError):
+        ctc_crf.CRFContext(str(tmp_path / "missing.fst"), gpus=0)
+    bad = tmp_path / "bad.fst"
+    bad.write_bytes(b"not an fst at all")
+    with pytest.raises(RuntimeError):
+        ctc_crf.CRFContext(str(bad), gpus=0)
+    with pytest.raises(RuntimeError):
+        ctc_crf.CRFContext(fixture_fst, gpus=99)
+    ctx = ctc_crf.CRFContext(fixture_fst, gpus=0)
+    crit = ctc_crf.CTC_CRF_LOSS()
+    with pytest.raises(RuntimeError):   # V smaller than the den graph's label set
+        crit(torch.zeros(1, 4, 3, device="cuda").log_softmax(-1), torch.tensor([1], dtype=torch.int32),
+             torch.tensor([4], dtype=torch.int32), torch.tensor([1], dtype=torch.int32))
+    del ctx
