@@ -2,6 +2,7 @@
 // Mirrors the roles of the reference's binding.cpp:51-117 + den_calculate.cu:288-481 host code +
 // gpu_ctc/ctc_entrypoint.cu:29-109, without torch and without ever calling exit().
 #include <atomic>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -121,12 +122,15 @@ int InitImpl(const char *fst_name, int n_gpus, const int *gpus) {
         // backward-pass row of the start state (for logZ recomputed from beta)
         {
             // rows are contiguous: find the start row by walking chunk boundaries on the host plan
-            int a = 0, q = 0;
+            // rows end at quads whose 4th weight carries the sign flag; unflagged padding quads in front of a
+            // row are zero-weight and harmless to include
             const auto &arcs = g_plan.bwd.arcs;
-            for (; q < g_plan.start; ++a) if (arcs[(size_t)a].peer & kLastFlag) ++q;
-            d.start_row_begin = a;
-            while (!(arcs[(size_t)a].peer & kLastFlag)) ++a;
-            d.start_row_end = a + 1;
+            auto flagged = [&](size_t quad) { return std::signbit(arcs[quad * kQuad + kQuad - 1].w); };
+            size_t quad = 0;
+            for (int q = 0; q < g_plan.start; ++quad) if (flagged(quad)) ++q;
+            d.start_row_begin = (int)(quad * kQuad);
+            while (!flagged(quad)) ++quad;
+            d.start_row_end = (int)((quad + 1) * kQuad);
             d.start_final = g_plan.final_lin[(size_t)g_plan.start];
         }
         d.loaded = (rc == 0);
@@ -178,6 +182,7 @@ int CheckDen(const DeviceGraph &g, int dtype, int N, int T, int V) {
     if (dtype != CCB_DTYPE_F32 && dtype != CCB_DTYPE_BF16) return Fail("den: unsupported logits dtype");
     if (V < g.num_labels)
         return Fail("den graph uses label " + std::to_string(g.num_labels - 1) + " but logits have only " + std::to_string(V) + " classes");
+    if ((size_t)g.S * (size_t)PadLanes(N) * 4 >= ((size_t)1 << 32)) return Fail("den: states x batch too large for 32-bit row offsets; split the batch");
     if (PadLanes(N) > g.n_warps * 32) return Fail("den: batch larger than " + std::to_string(g.n_warps * 32) + " utterances per call; split the batch");
     return 0;
 }
@@ -266,7 +271,9 @@ size_t ccb_den_aux_bytes(int N, int T) {
 }
 
 size_t ccb_ctc_workspace_bytes(int N, int T, int max_label_len) {
-    return ((size_t)N * T * (2 * (size_t)max_label_len + 1) + 64) * sizeof(float);
+    // per utterance: alpha_rel [T][2L+1] floats (rounded up to an even count) + per-frame fp64 offsets [T]
+    const size_t per_utt = ((size_t)T * (2 * (size_t)max_label_len + 1) + 1) / 2 * 2 + 2 * (size_t)T;
+    return ((size_t)N * per_utt + 64) * sizeof(float);
 }
 
 void compute_alpha(float *alpha, float *logits, const int batch_size, int T, const int alpha_size,

@@ -25,14 +25,27 @@ namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
 
-// shared memory carve-up (floats): lab[L1] ints | a[2][Sc] | yrow[2][V] | gk[2][V]
+// Block-wide max of the values the warps published for the previous frame (one LDS + 5 shuffles).
+__device__ __forceinline__ float block_max_from(const float *s_wmax, int nwarps) {
+    const int lane = threadIdx.x & 31;
+    float m = lane < nwarps ? s_wmax[lane] : -INFINITY;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(kFull, m, o));
+    return m == -INFINITY ? 0.f : m;
+}
+
+// Precision: cells are kept RELATIVE to a per-frame offset (the block max of the previous frame, accumulated in
+// fp64), so fp32 log-add rounding stays ~1e-6 absolute instead of growing with |alpha| (the reference's plain fp32
+// log domain loses ~1e-2 relative on the occupancies at T ~ 1000).  alpha_true_t(s) = a_rel_t(s) + C_t,
+// beta_true_t(s) = b_rel_t(s) + D_t, occupancy = exp(a_rel + b_rel - y + (C_t + D_t - log p)).
+// shared memory carve-up: lab[Lmax+1] ints | a[2][ScMax] | yrow[2][V] | gk[2][V] | wmax[2][32]
 __global__ void ctc_fwd_bwd_kernel(const void *y, int y_bf16, long sn, long st, int T, int V,
                                    const int *labels, const int *label_off, const int *label_len, const int *len,
                                    int max_label_len, int blank, float *alpha_ws,
                                    float *grad, long gsn, long gst, float grad_scale, float *logp_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = blockIdx.x;
-    const int tid = threadIdx.x, NT = blockDim.x;
+    const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = NT >> 5;
     const int L = label_len[n], Tn = len[n];
     const int Sc = 2 * L + 1, L1 = L + 1;
     const int ScMax = 2 * max_label_len + 1;
@@ -40,6 +53,7 @@ __global__ void ctc_fwd_bwd_kernel(const void *y, int y_bf16, long sn, long st, 
     float *s_a = reinterpret_cast<float *>(s_lab + max_label_len + 1);   // [2][ScMax]
     float *s_y = s_a + 2 * ScMax;                                   // [2][V]
     float *s_g = s_y + 2 * V;                                       // [2][V]
+    float *s_wmax = s_g + 2 * V;                                    // [2][32]
     const int *lab = labels + label_off[n];
 
     // feasibility (gpu_ctc_kernels.h:108-109)
@@ -56,67 +70,90 @@ __global__ void ctc_fwd_bwd_kernel(const void *y, int y_bf16, long sn, long st, 
     }
     for (int i = tid; i < L; i += NT) s_lab[i] = lab[i];
     for (int k = tid; k < 2 * V; k += NT) s_g[k] = 0.f;
-    float *ws = alpha_ws + (size_t)n * T * ScMax;    // alpha spill [t][s]
+    // per-utterance workspace: alpha_rel [T][ScMax] floats, then C_t [T] doubles
+    const size_t per_utt = ((size_t)T * ScMax + 1) / 2 * 2 + 2 * (size_t)T;
+    float *ws = alpha_ws + (size_t)n * per_utt;
+    double *coff = reinterpret_cast<double *>(ws + ((size_t)T * ScMax + 1) / 2 * 2);
     const long ybase = n * sn;
 
     // ---- forward ---------------------------------------------------------------------------------
     for (int k = tid; k < V; k += NT) s_y[k] = load_y(y, y_bf16, ybase + k);
     __syncthreads();
-    for (int s = tid; s < Sc; s += NT) {
-        float v = -INFINITY;
-        if (s == 0) v = s_y[blank];
-        else if (s == 1) v = s_y[s_lab[0]];
-        s_a[s] = v;
-        ws[s] = v;
+    {
+        float mx = -INFINITY;
+        for (int s = tid; s < Sc; s += NT) {
+            float v = -INFINITY;
+            if (s == 0) v = s_y[blank];
+            else if (s == 1) v = s_y[s_lab[0]];
+            s_a[s] = v;
+            ws[s] = v;
+            mx = fmaxf(mx, v);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, o));
+        if (lane == 0) s_wmax[warp] = mx;
+        if (tid == 0) coff[0] = 0.0;
     }
+    double C = 0.0;
     for (int t = 1; t < Tn; ++t) {
         // One barrier per frame: row t is staged into slot t&1 (last read two frames ago), the barrier
-        // publishes both the row and the previous frame's cells, then slot t&1 of the cells is rewritten
-        // (last read one barrier ago).
+        // publishes the row, the previous frame's cells and their per-warp maxima.
         float *yc = s_y + (t & 1) * V;
         const float *prev = s_a + ((t - 1) & 1) * ScMax;
         float *cur = s_a + (t & 1) * ScMax;
         for (int k = tid; k < V; k += NT) yc[k] = load_y(y, y_bf16, ybase + (long)t * st + k);
         __syncthreads();
+        const float m = block_max_from(s_wmax + ((t - 1) & 1) * 32, nwarps);
+        C += (double)m;
+        if (tid == 0) coff[t] = C;
+        float mx = -INFINITY;
         for (int i = tid; i < L1; i += NT) {
             // blank cell 2i
             const int sb = 2 * i;
             float vb = prev[sb];
             if (i > 0) vb = log_add(vb, prev[sb - 1]);
-            vb += yc[blank];
+            vb += yc[blank] - m;
             cur[sb] = vb;
             ws[(size_t)t * ScMax + sb] = vb;
+            mx = fmaxf(mx, vb);
             if (i < L) {   // label cell 2i+1
                 const int sl = sb + 1;
                 const int li = s_lab[i];
                 float vl = log_add(prev[sl], prev[sb]);
                 if (i > 0 && li != s_lab[i - 1]) vl = log_add(vl, prev[sl - 2]);
-                vl += yc[li];
+                vl += yc[li] - m;
                 cur[sl] = vl;
                 ws[(size_t)t * ScMax + sl] = vl;
+                mx = fmaxf(mx, vl);
             }
         }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, o));
+        if (lane == 0) s_wmax[(t & 1) * 32 + warp] = mx;
     }
     __syncthreads();
-    float logp;
+    double logp_d;
     {
         const float *last = s_a + ((Tn - 1) & 1) * ScMax;
-        logp = last[Sc - 1];
-        if (Sc > 1) logp = log_add(logp, last[Sc - 2]);
+        float lp = last[Sc - 1];
+        if (Sc > 1) lp = log_add(lp, last[Sc - 2]);
+        logp_d = (double)lp + C;
     }
-    if (tid == 0) logp_out[n] = logp;
-    if (grad == nullptr || logp == -INFINITY) return;
+    if (tid == 0) logp_out[n] = (float)logp_d;
+    if (grad == nullptr || !(logp_d > -INFINITY)) return;
     __syncthreads();
 
     // ---- backward + occupancies ------------------------------------------------------------------
-    // beta ping-pong reuses s_a; slot (t&1) holds beta_t.
+    // beta ping-pong reuses s_a (slot t&1 holds beta_rel_t) and s_wmax.
+    double D = 0.0;
     for (int t = Tn - 1; t >= 0; --t) {
         float *yc = s_y + (t & 1) * V;
         float *cur = s_a + (t & 1) * ScMax;
         const float *nxt = s_a + ((t + 1) & 1) * ScMax;
         float *gk = s_g + (t & 1) * V;
         for (int k = tid; k < V; k += NT) yc[k] = load_y(y, y_bf16, ybase + (long)t * st + k);
-        __syncthreads();   // the only barrier of the frame: publishes row t, beta_{t+1} and gk(t+1)
+        const double Ct = coff[t];
+        __syncthreads();   // the only barrier of the frame: publishes row t, beta_{t+1}, its maxima and gk(t+1)
         if (t + 1 < Tn) {  // flush the (now complete) occupancies of frame t+1 and clear their slot
             float *gp = s_g + ((t + 1) & 1) * V;
             float *grow = grad + n * gsn + (long)(t + 1) * gst;
@@ -125,7 +162,14 @@ __global__ void ctc_fwd_bwd_kernel(const void *y, int y_bf16, long sn, long st, 
                 if (g != 0.f) { atomicAdd(grow + k, grad_scale * g); gp[k] = 0.f; }
             }
         }
+        float m = 0.f;
+        if (t < Tn - 1) {
+            m = block_max_from(s_wmax + ((t + 1) & 1) * 32, nwarps);
+            D += (double)m;
+        }
+        const float K = (float)(Ct + D - logp_d);
         const float *al = ws + (size_t)t * ScMax;
+        float mx = -INFINITY;
         for (int i0 = 0; i0 < L1; i0 += NT) {
             const int i = i0 + tid;
             float occ_blank = 0.f;
@@ -137,10 +181,11 @@ __global__ void ctc_fwd_bwd_kernel(const void *y, int y_bf16, long sn, long st, 
                 } else {
                     vb = nxt[sb];
                     if (sb + 1 < Sc) vb = log_add(vb, nxt[sb + 1]);
-                    vb += yc[blank];
+                    vb += yc[blank] - m;
                 }
                 cur[sb] = vb;
-                const float ob = al[sb] + vb - yc[blank] - logp;
+                mx = fmaxf(mx, vb);
+                const float ob = al[sb] + vb - yc[blank] + K;
                 occ_blank = (ob == -INFINITY || ob != ob) ? 0.f : expf(ob);
                 if (i < L) {
                     const int sl = sb + 1;
@@ -151,17 +196,21 @@ __global__ void ctc_fwd_bwd_kernel(const void *y, int y_bf16, long sn, long st, 
                     } else {
                         vl = log_add(nxt[sl], nxt[sl + 1]);
                         if (i + 1 < L && li != s_lab[i + 1]) vl = log_add(vl, nxt[sl + 2]);
-                        vl += yc[li];
+                        vl += yc[li] - m;
                     }
                     cur[sl] = vl;
-                    const float ol = al[sl] + vl - yc[li] - logp;
+                    mx = fmaxf(mx, vl);
+                    const float ol = al[sl] + vl - yc[li] + K;
                     if (ol != -INFINITY && ol == ol) atomicAdd(&gk[li], expf(ol));
                 }
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) occ_blank += __shfl_xor_sync(kFull, occ_blank, o);
-            if ((tid & 31) == 0 && occ_blank != 0.f) atomicAdd(&gk[blank], occ_blank);
+            if (lane == 0 && occ_blank != 0.f) atomicAdd(&gk[blank], occ_blank);
         }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, o));
+        if (lane == 0) s_wmax[(t & 1) * 32 + warp] = mx;
     }
     __syncthreads();
     {   // flush frame 0
@@ -191,7 +240,7 @@ int LaunchCtc(const void *y, int y_bf16, long sn, long st, int N, int T, int V, 
               cudaStream_t stream, std::string *err) {
     if (N == 0) return 0;
     const int ScMax = 2 * max_label_len + 1;
-    const size_t smem = (size_t)(max_label_len + 1) * 4 + (size_t)2 * ScMax * 4 + (size_t)4 * V * 4;
+    const size_t smem = (size_t)(max_label_len + 1) * 4 + (size_t)2 * ScMax * 4 + (size_t)4 * V * 4 + 64 * 4;
     int threads = ((max_label_len + 1 + 31) / 32) * 32;
     threads = threads < 64 ? 64 : (threads > 1024 ? 1024 : threads);
     if (smem > 200 * 1024) { *err = "label sequence too long for the numerator kernel's shared memory"; return 1; }

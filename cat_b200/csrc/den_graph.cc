@@ -93,39 +93,30 @@ bool ReadFstFile(const char *path, HostFst *out, std::string *err) {
 
 namespace {
 
-// rows[q] lists (peer, w); emits flat arcs with the last-of-row flag and a dummy zero arc for empty rows.
-void Flatten(const std::vector<std::vector<Arc>> &rows, std::vector<Arc> *arcs, std::vector<int> *row_ptr) {
-    size_t total = 0;
-    for (auto &r : rows) total += std::max<size_t>(r.size(), 1);
-    arcs->clear();
-    arcs->reserve(total);
-    row_ptr->assign(rows.size() + 1, 0);
-    for (size_t q = 0; q < rows.size(); ++q) {
-        (*row_ptr)[q] = (int)arcs->size();
-        if (rows[q].empty()) {
-            arcs->push_back(Arc{(uint32_t)q | kLastFlag, 0.f});
-        } else {
-            for (size_t i = 0; i < rows[q].size(); ++i) {
-                Arc a = rows[q][i];
-                if (i + 1 == rows[q].size()) a.peer |= kLastFlag;
-                arcs->push_back(a);
-            }
-        }
-    }
-    (*row_ptr)[rows.size()] = (int)arcs->size();
+inline float NegateBits(float w) {
+    uint32_t b;
+    memcpy(&b, &w, 4);
+    b |= 0x80000000u;
+    memcpy(&w, &b, 4);
+    return w;
 }
 
-// Cut rows into n_chunks contiguous chunks of near-equal cost (cost = arcs + kRowCost per row).
-void Partition(const std::vector<int> &row_ptr, const std::vector<int> &state_label, int n_ctas, int n_warps,
-               PassPlan *pp) {
+// Cut rows into n_chunks contiguous chunks of near-equal cost and emit the chunk-major padded arc stream.
+// cost(row) = quads(row) * 4 + kRowCost.
+void Layout(const std::vector<std::vector<Arc>> &rows, const std::vector<int> &state_label, int n_ctas, int n_warps,
+            PassPlan *pp) {
     constexpr int64_t kRowCost = 4;
-    const int S = (int)row_ptr.size() - 1;
+    const int S = (int)rows.size();
     const int n_chunks = n_ctas * n_warps;
+    auto quads = [&](int q) { return std::max<int64_t>(1, ((int64_t)rows[(size_t)q].size() + kQuad - 1) / kQuad); };
     std::vector<int64_t> prefix((size_t)S + 1, 0);
-    for (int q = 0; q < S; ++q) prefix[q + 1] = prefix[q] + (row_ptr[q + 1] - row_ptr[q]) + kRowCost;
+    pp->real_arcs = 0;
+    for (int q = 0; q < S; ++q) {
+        prefix[q + 1] = prefix[q] + quads(q) * kQuad + kRowCost;
+        pp->real_arcs += (int)rows[(size_t)q].size();
+    }
     const int64_t total = prefix[S];
     pp->chunk_state.assign((size_t)n_chunks + 1, 0);
-    pp->chunk_arc.assign((size_t)n_chunks + 1, 0);
     for (int c = 1; c < n_chunks; ++c) {
         int64_t target = (total * c + n_chunks / 2) / n_chunks;
         int q = (int)(std::lower_bound(prefix.begin(), prefix.end(), target) - prefix.begin());
@@ -133,7 +124,23 @@ void Partition(const std::vector<int> &row_ptr, const std::vector<int> &state_la
         pp->chunk_state[c] = q;
     }
     pp->chunk_state[n_chunks] = S;
-    for (int c = 0; c <= n_chunks; ++c) pp->chunk_arc[c] = row_ptr[pp->chunk_state[c]];
+
+    pp->arcs.clear();
+    pp->chunk_arc.assign((size_t)n_chunks + 1, 0);
+    for (int c = 0; c < n_chunks; ++c) {
+        pp->chunk_arc[c] = (int)pp->arcs.size();
+        for (int q = pp->chunk_state[c]; q < pp->chunk_state[c + 1]; ++q) {
+            const auto &r = rows[(size_t)q];
+            const size_t padded = (size_t)quads(q) * kQuad;
+            for (size_t i = 0; i < padded; ++i) {
+                Arc a = i < r.size() ? r[i] : Arc{0u, 0.f};
+                if (i + 1 == padded) a.w = NegateBits(a.w);   // last quad of the row
+                pp->arcs.push_back(a);
+            }
+        }
+        while (pp->arcs.size() % kChunkArcPad) pp->arcs.push_back(Arc{0u, 0.f});
+    }
+    pp->chunk_arc[n_chunks] = (int)pp->arcs.size();
     pp->max_tile_arcs = 0;
     pp->max_tile_labels = 1;
     for (int c = 0; c < n_ctas; ++c) {
@@ -219,11 +226,9 @@ bool BuildDenPlan(const HostFst &fst, int n_ctas, int n_warps, DenPlan *plan, st
     for (auto &r : in_rows) std::sort(r.begin(), r.end(), [](const Arc &a, const Arc &b) { return a.peer < b.peer; });
     for (auto &r : out_rows) std::sort(r.begin(), r.end(), [](const Arc &a, const Arc &b) { return a.peer < b.peer; });
 
-    std::vector<int> row_ptr;
-    Flatten(in_rows, &plan->fwd.arcs, &row_ptr);
-    Partition(row_ptr, plan->state_label, n_ctas, n_warps, &plan->fwd);
-    Flatten(out_rows, &plan->bwd.arcs, &row_ptr);
-    Partition(row_ptr, plan->state_label, n_ctas, n_warps, &plan->bwd);
+    for (auto &r : in_rows) for (auto &a : r) if (!(a.w >= 0.f) || std::isinf(a.w)) { *err = "den graph arc weight is not a finite probability-like value"; return false; }
+    Layout(in_rows, plan->state_label, n_ctas, n_warps, &plan->fwd);
+    Layout(out_rows, plan->state_label, n_ctas, n_warps, &plan->bwd);
     return true;
 }
 

@@ -10,15 +10,18 @@
 
 namespace ccb {
 
-// One arc as the kernels read it: 8 bytes, broadcast-loaded from shared memory.
+// One arc as the kernels read it: 8 bytes, broadcast-loaded from shared memory two at a time (LDS.128).
 //   peer : state id the kernel gathers from (source state for the forward pass, destination state for the
-//          backward pass); bit 31 set on the last arc of a row.
-//   w    : arc weight in the LINEAR domain, exp(-tropical weight).
+//          backward pass).
+//   w    : arc weight in the LINEAR domain, exp(-tropical weight), always >= 0.  Rows are padded with
+//          zero-weight arcs (peer 0) to whole QUADS of 4 arcs; the SIGN BIT of the 4th weight of a quad is set
+//          when the quad is the last one of its row (tested once per quad, applied as |w| in the FMA).
 struct alignas(8) Arc {
     uint32_t peer;
     float w;
 };
-static constexpr uint32_t kLastFlag = 0x80000000u;
+static constexpr int kQuad = 4;          // arcs per quad (row padding granule)
+static constexpr int kChunkArcPad = 16;  // every warp chunk's arc count is padded to a multiple of this
 
 // Den graph as stored in the file, in the view fst_read.cc:40-59 gives the kernels.
 struct HostFst {
@@ -36,9 +39,10 @@ bool ReadFstFile(const char *path, HostFst *out, std::string *err);
 // pass sums over (in-arcs for forward, out-arcs for backward).  chunk_* cut the rows into
 // n_ctas*n_warps contiguous chunks of near-equal cost; CTA c owns chunks [c*n_warps, (c+1)*n_warps).
 struct PassPlan {
-    std::vector<Arc> arcs;              // row-major, every row has >= 1 arc (zero-weight self arc if empty)
+    std::vector<Arc> arcs;              // chunk-major: rows as whole quads, chunk tails padded with unflagged zero quads
     std::vector<int> chunk_state;       // [n_chunks+1] first state of each chunk
-    std::vector<int> chunk_arc;         // [n_chunks+1] first arc of each chunk
+    std::vector<int> chunk_arc;         // [n_chunks+1] first arc of each chunk (multiples of kChunkArcPad)
+    int real_arcs = 0;                  // arcs of the graph in this pass (before padding)
     int max_tile_arcs = 0;              // max arcs owned by one CTA
     int max_tile_labels = 0;            // max (label range + 1) over CTAs
 };

@@ -67,6 +67,16 @@ __device__ __forceinline__ float scale_from_sum(float s, int *shift) {
     return __int_as_float((sh + 127) << 23);
 }
 
+// Two consecutive arcs as one 16-byte word {off0, w0, off1, w1}; off = byte offset of the gathered row.
+template <bool SMEM_ARCS>
+__device__ __forceinline__ uint4 load_arc_pair(const Arc *s_arcs, const Arc *g_arcs, int a, int tile_a0, uint32_t row_bytes) {
+    if (SMEM_ARCS) return reinterpret_cast<const uint4 *>(s_arcs)[(a - tile_a0) >> 1];   // a, tile_a0 even: LDS.128
+    uint4 m = __ldg(reinterpret_cast<const uint4 *>(g_arcs + a));
+    m.x *= row_bytes;
+    m.z *= row_bytes;
+    return m;
+}
+
 __device__ __forceinline__ void prefetch_l2(const void *p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
@@ -110,8 +120,13 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const DenParams P) {
     const size_t frame_elems = (size_t)S * Npad;
     unsigned epoch = 0;
 
-    if (SMEM_ARCS) {
-        for (int i = tid; i < tile_a1 - tile_a0; i += NT) s_arcs[i] = P.arcs[tile_a0 + i];
+    const uint32_t row_bytes = (uint32_t)Npad * 4u;
+    if (SMEM_ARCS) {   // stage the tile once; peers become byte offsets of the gathered rows
+        for (int i = tid; i < tile_a1 - tile_a0; i += NT) {
+            Arc k = P.arcs[tile_a0 + i];
+            k.peer *= row_bytes;
+            s_arcs[i] = k;
+        }
     }
     for (int i = tid; i < Npad; i += NT) s_sum[i] = 0.f;
 
@@ -146,28 +161,28 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const DenParams P) {
                 e[u] = 0.f; acc[u] = 0.f; sum[u] = 0.f;
             }
             int q = sb, curlab = -1;
-            for (int base = ab; base < ae; base += BATCH) {
-                uint32_t peer[BATCH];
-                float w[BATCH];
-                Vec<U> v[BATCH];
+            const char *lane_base = reinterpret_cast<const char *>(a_prev + n0);
+            Vec<U> v[BATCH];
 #pragma unroll
-                for (int i = 0; i < BATCH; ++i) {
-                    const int a = base + i;
-                    const bool valid = a < ae;
-                    Arc k;
-                    k.peer = 0u; k.w = 0.f;
-                    if (valid) k = SMEM_ARCS ? s_arcs[a - tile_a0] : P.arcs[a];
-                    peer[i] = k.peer;
-                    w[i] = k.w;
-                    v[i] = (valid && lane_act)
-                               ? Vec<U>::ldcg(a_prev + (size_t)(k.peer & ~kLastFlag) * Npad + n0)
-                               : vec_zero<U>();
+            for (int i = 0; i < BATCH; ++i) v[i] = vec_zero<U>();
+            for (int base = ab; base < ae; base += BATCH) {
+                uint4 m[BATCH / 2];   // two arcs per 16-byte word: {off0, w0, off1, w1}
+#pragma unroll
+                for (int j = 0; j < BATCH / 2; ++j) m[j] = load_arc_pair<SMEM_ARCS>(s_arcs, P.arcs, base + 2 * j, tile_a0, row_bytes);
+                if (lane_act) {
+#pragma unroll
+                    for (int i = 0; i < BATCH; ++i)
+                        v[i] = Vec<U>::ldcg(reinterpret_cast<const float *>(lane_base + ((i & 1) ? m[i / 2].z : m[i / 2].x)));
                 }
 #pragma unroll
-                for (int i = 0; i < BATCH; ++i) {
+                for (int g4 = 0; g4 < BATCH / kQuad; ++g4) {
 #pragma unroll
-                    for (int u = 0; u < U; ++u) acc[u] = fmaf(w[i], v[i].v[u], acc[u]);
-                    if (peer[i] & kLastFlag) {   // warp-uniform: end of row q
+                    for (int i = g4 * kQuad; i < (g4 + 1) * kQuad; ++i) {
+                        const float w = fabsf(__uint_as_float((i & 1) ? m[i / 2].w : m[i / 2].y));
+#pragma unroll
+                        for (int u = 0; u < U; ++u) acc[u] = fmaf(w, v[i].v[u], acc[u]);
+                    }
+                    if ((int)m[(g4 * kQuad + 3) / 2].w < 0) {   // warp-uniform: this quad ends row q
                         const int lab = __ldg(P.state_label + q);
                         if (lab != curlab) {
                             curlab = lab;
@@ -253,8 +268,13 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const DenParams P) 
     const size_t frame_elems = (size_t)S * Npad;
     unsigned epoch = 0;
 
+    const uint32_t row_bytes = (uint32_t)Npad * 4u;
     if (SMEM_ARCS) {
-        for (int i = tid; i < tile_a1 - tile_a0; i += NT) s_arcs[i] = P.arcs[tile_a0 + i];
+        for (int i = tid; i < tile_a1 - tile_a0; i += NT) {
+            Arc k = P.arcs[tile_a0 + i];
+            k.peer *= row_bytes;
+            s_arcs[i] = k;
+        }
     }
     for (int i = tid; i < (2 + P.gacc_rows) * Npad; i += NT) s_sum[i] = 0.f;
     const int my_len = (cta == 0 && tid < P.N) ? __ldg(P.len + tid) : 0;
@@ -293,28 +313,28 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const DenParams P) 
             }
             int q = sb, curlab = -1;
             Vec<U> a_q = (se > sb && lane_act) ? Vec<U>::ldcg(a_row + (size_t)sb * Npad + n0) : vec_zero<U>();
-            for (int base = ab; base < ae; base += BATCH) {
-                uint32_t peer[BATCH];
-                float w[BATCH];
-                Vec<U> v[BATCH];
+            const char *lane_base = reinterpret_cast<const char *>(bh_next + n0);
+            Vec<U> v[BATCH];
 #pragma unroll
-                for (int i = 0; i < BATCH; ++i) {
-                    const int a = base + i;
-                    const bool valid = a < ae;
-                    Arc k;
-                    k.peer = 0u; k.w = 0.f;
-                    if (valid) k = SMEM_ARCS ? s_arcs[a - tile_a0] : P.arcs[a];
-                    peer[i] = k.peer;
-                    w[i] = k.w;
-                    v[i] = (valid && lane_gat)
-                               ? Vec<U>::ldcg(bh_next + (size_t)(k.peer & ~kLastFlag) * Npad + n0)
-                               : vec_zero<U>();
+            for (int i = 0; i < BATCH; ++i) v[i] = vec_zero<U>();
+            for (int base = ab; base < ae; base += BATCH) {
+                uint4 m[BATCH / 2];
+#pragma unroll
+                for (int j = 0; j < BATCH / 2; ++j) m[j] = load_arc_pair<SMEM_ARCS>(s_arcs, P.arcs, base + 2 * j, tile_a0, row_bytes);
+                if (lane_gat) {
+#pragma unroll
+                    for (int i = 0; i < BATCH; ++i)
+                        v[i] = Vec<U>::ldcg(reinterpret_cast<const float *>(lane_base + ((i & 1) ? m[i / 2].z : m[i / 2].x)));
                 }
 #pragma unroll
-                for (int i = 0; i < BATCH; ++i) {
+                for (int g4 = 0; g4 < BATCH / kQuad; ++g4) {
 #pragma unroll
-                    for (int u = 0; u < U; ++u) acc[u] = fmaf(w[i], v[i].v[u], acc[u]);
-                    if (peer[i] & kLastFlag) {   // warp-uniform: end of row q
+                    for (int i = g4 * kQuad; i < (g4 + 1) * kQuad; ++i) {
+                        const float w = fabsf(__uint_as_float((i & 1) ? m[i / 2].w : m[i / 2].y));
+#pragma unroll
+                        for (int u = 0; u < U; ++u) acc[u] = fmaf(w, v[i].v[u], acc[u]);
+                    }
+                    if ((int)m[(g4 * kQuad + 3) / 2].w < 0) {   // warp-uniform: this quad ends row q
                         const int lab = __ldg(P.state_label + q);
                         if (lab != curlab) {
                             if (curlab >= 0) {
@@ -400,7 +420,7 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const DenParams P) 
                 float acc = 0.f;
                 for (int a = P.start_row_begin; a < P.start_row_end; ++a) {
                     const Arc k = P.arcs[a];
-                    acc = fmaf(k.w, __ldcg(bh1 + (size_t)(k.peer & ~kLastFlag) * Npad + n), acc);
+                    acc = fmaf(fabsf(k.w), __ldcg(bh1 + (size_t)k.peer * Npad + n), acc);
                 }
                 b = acc * rb;
             }

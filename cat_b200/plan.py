@@ -12,7 +12,8 @@ import numpy as np
 
 from . import _lib
 
-LAST_FLAG = np.uint32(0x80000000)
+QUAD = 4            # rows are padded to whole quads of arcs (den_graph.h kQuad)
+CHUNK_ARC_PAD = 16  # chunk arc counts are padded to a multiple of this (kChunkArcPad)
 ARC_DTYPE = np.dtype([("peer", "<u4"), ("w", "<f4")])
 
 
@@ -22,10 +23,18 @@ class PassView:
     chunk_state: np.ndarray   # int32 [n_chunks+1]
     chunk_arc: np.ndarray     # int32 [n_chunks+1]
 
-    def row_ptr(self) -> np.ndarray:
-        last = (self.arcs["peer"] & LAST_FLAG) != 0
-        ends = np.nonzero(last)[0] + 1
-        return np.concatenate([[0], ends]).astype(np.int64)
+    def row_ends(self) -> np.ndarray:
+        """Arc index one past each row: rows end at quads whose 4th weight has its sign bit set."""
+        w4 = self.arcs["w"][QUAD - 1::QUAD]
+        return (np.nonzero(np.signbit(w4))[0] + 1) * QUAD
+
+    def row_of_arc(self) -> np.ndarray:
+        """Row id of every arc slot (chunk-tail padding quads attach to the following row, weight 0)."""
+        ends = self.row_ends()
+        return np.searchsorted(ends, np.arange(len(self.arcs)), side="right")
+
+    def weights(self) -> np.ndarray:
+        return np.abs(self.arcs["w"])
 
 
 @dataclass

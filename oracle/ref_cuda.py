@@ -14,7 +14,12 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "_ref", "libctc_crf_ref.so")
+# "sm100fix": the reference sources with the two sm_70+ defects patched at build time (oracle/Makefile): the
+#             shfl.sync membermask in moderngpu's intrinsics and the non-volatile warp-synchronous reduction in
+#             alpha_lld_kernal.  "unmodified": the sources exactly as they are -- on B200 its CTC kernel traps
+#             (Illegal instruction) and its logZ/gradients are wrong (profiles/ref_unmodified_on_b200.txt).
+VARIANT = os.environ.get("CCB_REF_VARIANT", "sm100fix")
+_SO = os.path.join(_HERE, "_ref", "libctc_crf_ref.so" if VARIANT == "unmodified" else "libctc_crf_ref_sm100fix.so")
 _lib = None
 ATOMIC_CONST = 32   # binding.cpp:17-18
 

@@ -6,7 +6,6 @@ disagreement with the oracle is a plan/algorithm error, not rounding.
 """
 import numpy as np
 
-from cat_b200.plan import LAST_FLAG
 
 SCALE_EXP = 32
 
@@ -19,11 +18,11 @@ def _scale(s):
 
 
 def _rows(passview):
-    rp = passview.row_ptr()
-    peer = (passview.arcs["peer"] & ~LAST_FLAG).astype(np.int64)
-    w = passview.arcs["w"].astype(np.float64)
-    row = np.repeat(np.arange(len(rp) - 1), np.diff(rp))
-    return row, peer, w
+    row = passview.row_of_arc()
+    peer = passview.arcs["peer"].astype(np.int64)
+    w = passview.weights().astype(np.float64)
+    keep = row < len(passview.row_ends())     # padding after the very last row belongs to no row
+    return row[keep], peer[keep], w[keep]
 
 
 def den_emulate(plan, y, lens):

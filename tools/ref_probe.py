@@ -1,10 +1,11 @@
-"""Probe the reference CUDA build on the GPU box: which part works on sm_100a?"""
+"""Probe the reference CUDA builds on the GPU box: CCB_REF_VARIANT=unmodified|sm100fix python tools/ref_probe.py den|ctc"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from oracle import oracle, ref_cuda
 from cat_b200 import fst
 which = sys.argv[1]
+print("variant", ref_cuda.VARIANT, which)
 g = fst.read_fst("tests/golden/golden_tlm_a.fst")
 y, labels, lens, ly = oracle.synth_batch(4, 40, 12, seed=11, lens=[40, 31, 18, 6])
 if which == "den":
