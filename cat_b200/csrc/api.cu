@@ -37,6 +37,10 @@ struct LegacyScratch {
 };
 LegacyScratch g_legacy[kMaxDevices];
 
+// profiling aid (ccb_debug_timeline)
+unsigned long long *g_timeline = nullptr;
+int g_tl_step0 = 0, g_tl_steps = 0;
+
 int Fail(const std::string &m) { g_err = m; return 1; }
 int FailCuda(const char *what, cudaError_t e) { g_err = std::string(what) + ": " + cudaGetErrorString(e); return (int)e ? (int)e : 1; }
 
@@ -174,6 +178,7 @@ DenParams BaseParams(const DeviceGraph &g, const void *y, int dtype, long sn, lo
     p.zsum = reinterpret_cast<float *>(a + L.zsum);
     p.b0 = reinterpret_cast<float *>(a + L.b0);
     p.fmax = reinterpret_cast<float *>(a + L.fmax);
+    p.timeline = g_timeline; p.tl_step0 = g_tl_step0; p.tl_steps = g_tl_steps;
     return p;
 }
 
@@ -251,6 +256,9 @@ extern "C" {
 
 const char *ccb_last_error(void) { return g_err.c_str(); }
 long ccb_launch_count(void) { return g_launches.load(); }
+void ccb_debug_timeline(void *dev_buffer, int step0, int nsteps) {
+    g_timeline = reinterpret_cast<unsigned long long *>(dev_buffer); g_tl_step0 = step0; g_tl_steps = nsteps;
+}
 int ccb_den_loaded(int device) { return device >= 0 && device < kMaxDevices && g_dev[device].loaded ? 1 : 0; }
 
 void Init(const char *fst_name, int n_gpus, int *gpus) {

@@ -67,6 +67,9 @@ struct DenParams {
     float *grad;          // raw accumulation target, element (n,t,k) at n*gsn + t*gst + k
     long gsn, gst;
     int gacc_rows;        // rows of the shared-memory label accumulator (0 = direct global atomics)
+    // optional per-warp timeline (profiling aid, normally null)
+    unsigned long long *timeline;
+    int tl_step0, tl_steps;
 };
 
 // workspace carving (all offsets in bytes, 256-aligned)

@@ -101,6 +101,85 @@ __global__ void frame_max_kernel(const void *y, int bf16, long sn, long st, int 
 }
 
 // ------------------------------------------------------------------------------------------------
+// The arc walk shared by both passes: a software-pipelined stream over the warp's chunk of arcs.
+//   * arcs come two per LDS.128 (SMEM_ARCS) as {byte offset of the gathered row, weight};
+//   * BATCH row gathers (ld.global.cg, 32*U*4 bytes each, one per arc) are issued for batch k+1 BEFORE batch k
+//     is consumed, so a warp keeps BATCH..2*BATCH loads in flight (the recursion is latency-bound on L2);
+//   * weights are applied as |w|; the sign bit of a quad's 4th weight marks the end of a row, at which point
+//     `row_end(acc)` runs (warp-uniform branch) and the accumulators restart.
+// ------------------------------------------------------------------------------------------------
+template <int U, int BATCH, bool SMEM_ARCS, typename RowEnd>
+__device__ __forceinline__ void walk_arcs(const Arc *s_arcs, const Arc *g_arcs, int ab, int ae, int tile_a0,
+                                          uint32_t row_bytes, const char *lane_base, bool do_load, RowEnd &&row_end) {
+    Vec<U> vA[BATCH], vB[BATCH];
+    float acc[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) acc[u] = 0.f;
+
+    // issue: arc words are transient here (only the offsets are needed); consume re-reads them from shared memory
+    // for the weights, which keeps 2*BATCH gathers in flight without holding 2*BATCH arc words in registers.
+    auto issue = [&](int base, Vec<U> *v) {
+#pragma unroll
+        for (int j = 0; j < BATCH / 2; ++j) {
+            const uint4 m = load_arc_pair<SMEM_ARCS>(s_arcs, g_arcs, base + 2 * j, tile_a0, row_bytes);
+            v[2 * j] = do_load ? Vec<U>::ldcg(reinterpret_cast<const float *>(lane_base + m.x)) : vec_zero<U>();
+            v[2 * j + 1] = do_load ? Vec<U>::ldcg(reinterpret_cast<const float *>(lane_base + m.z)) : vec_zero<U>();
+        }
+    };
+    auto consume = [&](int base, const Vec<U> *v) {
+#pragma unroll
+        for (int g4 = 0; g4 < BATCH / kQuad; ++g4) {
+            const uint4 m0 = load_arc_pair<SMEM_ARCS>(s_arcs, g_arcs, base + g4 * kQuad, tile_a0, row_bytes);
+            const uint4 m1 = load_arc_pair<SMEM_ARCS>(s_arcs, g_arcs, base + g4 * kQuad + 2, tile_a0, row_bytes);
+            const float w0 = fabsf(__uint_as_float(m0.y)), w1 = fabsf(__uint_as_float(m0.w));
+            const float w2 = fabsf(__uint_as_float(m1.y)), w3 = fabsf(__uint_as_float(m1.w));
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                acc[u] = fmaf(w0, v[g4 * kQuad + 0].v[u], acc[u]);
+                acc[u] = fmaf(w1, v[g4 * kQuad + 1].v[u], acc[u]);
+                acc[u] = fmaf(w2, v[g4 * kQuad + 2].v[u], acc[u]);
+                acc[u] = fmaf(w3, v[g4 * kQuad + 3].v[u], acc[u]);
+            }
+            if ((int)m1.w < 0) {   // warp-uniform: this quad ends a row
+                row_end(acc);
+#pragma unroll
+                for (int u = 0; u < U; ++u) acc[u] = 0.f;
+            }
+        }
+    };
+
+    int base = ab;
+    if (base < ae) issue(base, vA);
+    while (base < ae) {
+        int nb = base + BATCH;
+        if (nb < ae) issue(nb, vB);
+        consume(base, vA);
+        base = nb;
+        if (base >= ae) break;
+        nb = base + BATCH;
+        if (nb < ae) issue(nb, vA);
+        consume(base, vB);
+        base = nb;
+    }
+}
+
+__device__ __forceinline__ unsigned long long global_timer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// optional per-warp timeline (debug/profiling only): [step][chunk][4] = {globaltimer at step start,
+// clock64 at step start, clock64 when the chunk is done, clock64 after the grid barrier}
+__device__ __forceinline__ void tl_mark(const DenParams &P, int step_index, int chunk, int n_chunks, int slot, int lane) {
+    if (P.timeline == nullptr || lane != 0) return;
+    const int s = step_index - P.tl_step0;
+    if (s < 0 || s >= P.tl_steps) return;
+    unsigned long long *rec = P.timeline + ((size_t)s * n_chunks + chunk) * 4;
+    if (slot == 0) { rec[0] = global_timer(); rec[1] = clock64(); }
+    else rec[slot + 1] = clock64();
+}
+
+// ------------------------------------------------------------------------------------------------
 // forward: alpha recursion + logZ
 // ------------------------------------------------------------------------------------------------
 template <int NT, int U, int BATCH, bool SMEM_ARCS>
@@ -112,12 +191,14 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const DenParams P) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int cta = blockIdx.x;
     const int chunk = cta * P.n_warps + warp;
+    const int n_chunks = gridDim.x * P.n_warps;
     const int sb = __ldg(P.chunk_state + chunk), se = __ldg(P.chunk_state + chunk + 1);
     const int ab = __ldg(P.chunk_arc + chunk), ae = __ldg(P.chunk_arc + chunk + 1);
     const int tile_a0 = __ldg(P.chunk_arc + cta * P.n_warps);
     const int tile_a1 = __ldg(P.chunk_arc + (cta + 1) * P.n_warps);
     const int S = P.S, Npad = P.Npad;
     const size_t frame_elems = (size_t)S * Npad;
+    const int lab0 = se > sb ? __ldg(P.state_label + sb) : 0;
     unsigned epoch = 0;
 
     const uint32_t row_bytes = (uint32_t)Npad * 4u;
@@ -139,6 +220,7 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const DenParams P) {
     grid_barrier(P.barrier, (++epoch) * gridDim.x);
 
     for (int t = 1; t <= P.Tmax; ++t) {
+        tl_mark(P, t, chunk, n_chunks, 0, lane);
         const float *a_prev = P.alpha + (size_t)(t - 1) * frame_elems;
         float *a_cur = P.alpha + (size_t)t * frame_elems;
         for (int gc = 0; gc < Npad / (32 * U); ++gc) {
@@ -152,61 +234,43 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const DenParams P) {
                 lane_act |= act[u];
             }
             if (!__any_sync(kFull, lane_act)) continue;
-            float r[U], fm[U], e[U], acc[U], sum[U];
+            float r[U], fm[U], e[U], sum[U], ypre[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 int sh;
                 r[u] = scale_from_sum(__ldcg(P.colsum_a + (size_t)(t - 1) * Npad + n0 + u), &sh);
                 fm[u] = act[u] ? __ldg(P.fmax + (size_t)(t - 1) * Npad + n0 + u) : 0.f;
-                e[u] = 0.f; acc[u] = 0.f; sum[u] = 0.f;
+                // emission of the chunk's first label: issued now, consumed at the first row end
+                ypre[u] = act[u] ? load_y(P.y, P.y_bf16, (n0 + u) * P.sn + (long)(t - 1) * P.st + lab0) : 0.f;
+                e[u] = 0.f; sum[u] = 0.f;
             }
             int q = sb, curlab = -1;
-            const char *lane_base = reinterpret_cast<const char *>(a_prev + n0);
-            Vec<U> v[BATCH];
+            walk_arcs<U, BATCH, SMEM_ARCS>(s_arcs, P.arcs, ab, ae, tile_a0, row_bytes,
+                                           reinterpret_cast<const char *>(a_prev + n0), lane_act, [&](const float *acc) {
+                const int lab = __ldg(P.state_label + q);
+                if (lab != curlab) {
+                    curlab = lab;
 #pragma unroll
-            for (int i = 0; i < BATCH; ++i) v[i] = vec_zero<U>();
-            for (int base = ab; base < ae; base += BATCH) {
-                uint4 m[BATCH / 2];   // two arcs per 16-byte word: {off0, w0, off1, w1}
-#pragma unroll
-                for (int j = 0; j < BATCH / 2; ++j) m[j] = load_arc_pair<SMEM_ARCS>(s_arcs, P.arcs, base + 2 * j, tile_a0, row_bytes);
-                if (lane_act) {
-#pragma unroll
-                    for (int i = 0; i < BATCH; ++i)
-                        v[i] = Vec<U>::ldcg(reinterpret_cast<const float *>(lane_base + ((i & 1) ? m[i / 2].z : m[i / 2].x)));
-                }
-#pragma unroll
-                for (int g4 = 0; g4 < BATCH / kQuad; ++g4) {
-#pragma unroll
-                    for (int i = g4 * kQuad; i < (g4 + 1) * kQuad; ++i) {
-                        const float w = fabsf(__uint_as_float((i & 1) ? m[i / 2].w : m[i / 2].y));
-#pragma unroll
-                        for (int u = 0; u < U; ++u) acc[u] = fmaf(w, v[i].v[u], acc[u]);
-                    }
-                    if ((int)m[(g4 * kQuad + 3) / 2].w < 0) {   // warp-uniform: this quad ends row q
-                        const int lab = __ldg(P.state_label + q);
-                        if (lab != curlab) {
-                            curlab = lab;
-#pragma unroll
-                            for (int u = 0; u < U; ++u)
-                                e[u] = act[u] ? expf(load_y(P.y, P.y_bf16, (n0 + u) * P.sn + (long)(t - 1) * P.st + lab) - fm[u])
-                                              : 0.f;
-                        }
-                        Vec<U> out;
-#pragma unroll
-                        for (int u = 0; u < U; ++u) {
-                            out.v[u] = act[u] ? acc[u] * e[u] * r[u] : 0.f;
-                            sum[u] += out.v[u];
-                            acc[u] = 0.f;
-                        }
-                        if (lane_act) out.stcg(a_cur + (size_t)q * Npad + n0);
-                        ++q;
+                    for (int u = 0; u < U; ++u) {
+                        const float yv = (lab == lab0) ? ypre[u]
+                                         : (act[u] ? load_y(P.y, P.y_bf16, (n0 + u) * P.sn + (long)(t - 1) * P.st + lab) : 0.f);
+                        e[u] = act[u] ? expf(yv - fm[u]) : 0.f;
                     }
                 }
-            }
+                Vec<U> out;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    out.v[u] = act[u] ? acc[u] * e[u] * r[u] : 0.f;
+                    sum[u] += out.v[u];
+                }
+                if (lane_act) out.stcg(a_cur + (size_t)q * Npad + n0);
+                ++q;
+            });
 #pragma unroll
             for (int u = 0; u < U; ++u)
                 if (act[u] && sum[u] != 0.f) atomicAdd(&s_sum[n0 + u], sum[u]);
         }
+        tl_mark(P, t, chunk, n_chunks, 1, lane);
         __syncthreads();
         for (int i = tid; i < Npad; i += NT) {
             const float v = s_sum[i];
@@ -218,6 +282,7 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const DenParams P) {
             runlog += (double)__ldg(P.fmax + (size_t)(t - 1) * Npad + tid) - (double)sh * 0.6931471805599453;
         }
         grid_barrier(P.barrier, (++epoch) * gridDim.x);
+        tl_mark(P, t, chunk, n_chunks, 2, lane);
     }
 
     // logZ[n] = log sum_q alpha_len(q) final(q) + accumulated log scale      (den_calculate.cu:105-161)
@@ -256,6 +321,7 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const DenParams P) 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int cta = blockIdx.x;
     const int chunk = cta * P.n_warps + warp;
+    const int n_chunks = gridDim.x * P.n_warps;
     const int sb = __ldg(P.chunk_state + chunk), se = __ldg(P.chunk_state + chunk + 1);
     const int ab = __ldg(P.chunk_arc + chunk), ae = __ldg(P.chunk_arc + chunk + 1);
     const int tile_a0 = __ldg(P.chunk_arc + cta * P.n_warps);
@@ -264,6 +330,7 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const DenParams P) 
     const int tile_s1 = __ldg(P.chunk_state + (cta + 1) * P.n_warps);
     const int tile_lab0 = tile_s1 > tile_s0 ? __ldg(P.state_label + tile_s0) : 0;
     const int tile_labs = tile_s1 > tile_s0 ? __ldg(P.state_label + tile_s1 - 1) - tile_lab0 + 1 : 0;
+    const int lab0 = se > sb ? __ldg(P.state_label + sb) : 0;
     const bool use_gacc = P.gacc_rows > 0;
     const size_t frame_elems = (size_t)S * Npad;
     unsigned epoch = 0;
@@ -282,6 +349,7 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const DenParams P) 
     __syncthreads();
 
     for (int tau = P.Tmax; tau >= 1; --tau) {
+        tl_mark(P, P.Tmax - tau, chunk, n_chunks, 0, lane);
         const float *bh_next = P.bh + (size_t)((tau + 1) & 1) * frame_elems;
         float *bh_cur = P.bh + (size_t)(tau & 1) * frame_elems;
         const float *a_row = P.alpha + (size_t)tau * frame_elems;
@@ -303,86 +371,65 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const DenParams P) 
                 lane_gat |= gat[u];
             }
             if (!__any_sync(kFull, lane_act)) continue;
-            float rb[U], fm[U], e[U], acc[U], sum_b[U], sum_ab[U], gsum[U];
+            float rb[U], fm[U], e[U], sum_b[U], sum_ab[U], gsum[U], ypre[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 int sh;
                 rb[u] = gat[u] ? scale_from_sum(__ldcg(P.colsum_b + (size_t)(tau + 1) * Npad + n0 + u), &sh) : 1.f;
                 fm[u] = act[u] ? __ldg(P.fmax + (size_t)(tau - 1) * Npad + n0 + u) : 0.f;
-                e[u] = 0.f; acc[u] = 0.f; sum_b[u] = 0.f; sum_ab[u] = 0.f; gsum[u] = 0.f;
+                ypre[u] = act[u] ? load_y(P.y, P.y_bf16, (n0 + u) * P.sn + (long)(tau - 1) * P.st + lab0) : 0.f;
+                e[u] = 0.f; sum_b[u] = 0.f; sum_ab[u] = 0.f; gsum[u] = 0.f;
             }
             int q = sb, curlab = -1;
             Vec<U> a_q = (se > sb && lane_act) ? Vec<U>::ldcg(a_row + (size_t)sb * Npad + n0) : vec_zero<U>();
-            const char *lane_base = reinterpret_cast<const char *>(bh_next + n0);
-            Vec<U> v[BATCH];
+            auto flush_gsum = [&]() {
 #pragma unroll
-            for (int i = 0; i < BATCH; ++i) v[i] = vec_zero<U>();
-            for (int base = ab; base < ae; base += BATCH) {
-                uint4 m[BATCH / 2];
-#pragma unroll
-                for (int j = 0; j < BATCH / 2; ++j) m[j] = load_arc_pair<SMEM_ARCS>(s_arcs, P.arcs, base + 2 * j, tile_a0, row_bytes);
-                if (lane_gat) {
-#pragma unroll
-                    for (int i = 0; i < BATCH; ++i)
-                        v[i] = Vec<U>::ldcg(reinterpret_cast<const float *>(lane_base + ((i & 1) ? m[i / 2].z : m[i / 2].x)));
-                }
-#pragma unroll
-                for (int g4 = 0; g4 < BATCH / kQuad; ++g4) {
-#pragma unroll
-                    for (int i = g4 * kQuad; i < (g4 + 1) * kQuad; ++i) {
-                        const float w = fabsf(__uint_as_float((i & 1) ? m[i / 2].w : m[i / 2].y));
-#pragma unroll
-                        for (int u = 0; u < U; ++u) acc[u] = fmaf(w, v[i].v[u], acc[u]);
+                for (int u = 0; u < U; ++u) {
+                    if (gsum[u] != 0.f) {
+                        if (use_gacc) atomicAdd(&s_gacc[(curlab - tile_lab0) * Npad + n0 + u], gsum[u]);
+                        else atomicAdd(P.grad + (n0 + u) * P.gsn + (long)(tau - 1) * P.gst + curlab, gsum[u]);
                     }
-                    if ((int)m[(g4 * kQuad + 3) / 2].w < 0) {   // warp-uniform: this quad ends row q
-                        const int lab = __ldg(P.state_label + q);
-                        if (lab != curlab) {
-                            if (curlab >= 0) {
+                    gsum[u] = 0.f;
+                }
+            };
+            walk_arcs<U, BATCH, SMEM_ARCS>(s_arcs, P.arcs, ab, ae, tile_a0, row_bytes,
+                                           reinterpret_cast<const char *>(bh_next + n0), lane_gat, [&](const float *acc) {
+                const int lab = __ldg(P.state_label + q);
+                if (lab != curlab) {
+                    if (curlab >= 0) flush_gsum();
+                    curlab = lab;
 #pragma unroll
-                                for (int u = 0; u < U; ++u) {
-                                    if (gsum[u] != 0.f) {
-                                        if (use_gacc) atomicAdd(&s_gacc[(curlab - tile_lab0) * Npad + n0 + u], gsum[u]);
-                                        else atomicAdd(P.grad + (n0 + u) * P.gsn + (long)(tau - 1) * P.gst + curlab, gsum[u]);
-                                    }
-                                    gsum[u] = 0.f;
-                                }
-                            }
-                            curlab = lab;
-#pragma unroll
-                            for (int u = 0; u < U; ++u)
-                                e[u] = act[u] ? expf(load_y(P.y, P.y_bf16, (n0 + u) * P.sn + (long)(tau - 1) * P.st + lab) - fm[u])
-                                              : 0.f;
-                        }
-                        const float f = __ldg(P.final_lin + q);
-                        Vec<U> out;
-#pragma unroll
-                        for (int u = 0; u < U; ++u) {
-                            const float b = act[u] ? (gat[u] ? acc[u] * rb[u] : f) : 0.f;
-                            const float abp = act[u] ? a_q.v[u] * b : 0.f;
-                            gsum[u] += abp;
-                            sum_ab[u] += abp;
-                            out.v[u] = e[u] * b;
-                            sum_b[u] += out.v[u];
-                            acc[u] = 0.f;
-                        }
-                        if (lane_act) out.stcg(bh_cur + (size_t)q * Npad + n0);
-                        ++q;
-                        a_q = (q < se && lane_act) ? Vec<U>::ldcg(a_row + (size_t)q * Npad + n0) : vec_zero<U>();
+                    for (int u = 0; u < U; ++u) {
+                        const float yv = (lab == lab0) ? ypre[u]
+                                         : (act[u] ? load_y(P.y, P.y_bf16, (n0 + u) * P.sn + (long)(tau - 1) * P.st + lab) : 0.f);
+                        e[u] = act[u] ? expf(yv - fm[u]) : 0.f;
                     }
                 }
-            }
+                const float f = __ldg(P.final_lin + q);
+                Vec<U> out;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const float b = act[u] ? (gat[u] ? acc[u] * rb[u] : f) : 0.f;
+                    const float abp = act[u] ? a_q.v[u] * b : 0.f;
+                    gsum[u] += abp;
+                    sum_ab[u] += abp;
+                    out.v[u] = e[u] * b;
+                    sum_b[u] += out.v[u];
+                }
+                if (lane_act) out.stcg(bh_cur + (size_t)q * Npad + n0);
+                ++q;
+                a_q = (q < se && lane_act) ? Vec<U>::ldcg(a_row + (size_t)q * Npad + n0) : vec_zero<U>();
+            });
+            if (curlab >= 0) flush_gsum();
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                if (curlab >= 0 && gsum[u] != 0.f) {
-                    if (use_gacc) atomicAdd(&s_gacc[(curlab - tile_lab0) * Npad + n0 + u], gsum[u]);
-                    else atomicAdd(P.grad + (n0 + u) * P.gsn + (long)(tau - 1) * P.gst + curlab, gsum[u]);
-                }
                 if (act[u]) {
                     if (sum_b[u] != 0.f) atomicAdd(&s_sum[n0 + u], sum_b[u]);
                     if (sum_ab[u] != 0.f) atomicAdd(&s_sum[Npad + n0 + u], sum_ab[u]);
                 }
             }
         }
+        tl_mark(P, P.Tmax - tau, chunk, n_chunks, 1, lane);
         __syncthreads();
         for (int i = tid; i < Npad; i += NT) {
             const float vb = s_sum[i], vab = s_sum[Npad + i];
@@ -406,6 +453,7 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const DenParams P) 
             runlog += (double)__ldg(P.fmax + (size_t)tau * Npad + tid) - (double)sh * 0.6931471805599453;
         }
         grid_barrier(P.barrier, (++epoch) * gridDim.x);
+        tl_mark(P, P.Tmax - tau, chunk, n_chunks, 2, lane);
     }
 
     // tau = 0: beta_0(start) only -> logZ recomputed from the backward pass (den_calculate.cu:177-187,255-261)
@@ -480,10 +528,10 @@ int Dispatch(bool backward, const DeviceGraph &g, const DenParams &p, size_t fix
     const bool smem_arcs = fixed_smem + arc_bytes <= budget;
     const size_t smem = fixed_smem + (smem_arcs ? arc_bytes : 0);
     const int U = LaneWidth(p.Npad);
-    // rows in flight per warp: 8 KB of gathers at 512 threads, 4 KB at 1024 threads (register budget)
+    // gathers per batch (two batches are in flight per warp); bounded by the register budget of the variant
 #define CCB_GO(UU)                                                                                      \
     {                                                                                                   \
-        constexpr int B = (NT == 512 ? 64 : 32) / (UU == 1 ? 4 : 2 * UU);                               \
+        constexpr int B = NT == 512 ? (UU == 4 ? 8 : 16) : (UU == 1 ? 8 : 4);                           \
         return smem_arcs ? LaunchOne<NT, UU, B, true>(backward, p, g.n_ctas, smem, stream, err)          \
                          : LaunchOne<NT, UU, B, false>(backward, p, g.n_ctas, smem, stream, err);        \
     }

@@ -123,6 +123,11 @@ int ccb_ctc_crf_loss_fwd(const void *logits, int dtype, int N, int T, int V,
 /* number of kernels launched by this library since load (bench.py's gpu_launches) */
 long ccb_launch_count(void);
 
+/* Profiling aid: when dev_buffer != NULL the den kernels record, for frames [step0, step0+nsteps) of each pass,
+ * per warp chunk 4 x u64 {globaltimer at frame start, clock64 at frame start, clock64 at chunk done, clock64 after
+ * the grid barrier} into dev_buffer[(frame-step0) * n_chunks + chunk][4].  Pass NULL to switch it off. */
+void ccb_debug_timeline(void *dev_buffer, int step0, int nsteps);
+
 /* ------------------------------------------------------------------------------------------------
  * Section 3 -- host-side den-graph plan (no GPU needed)
  * ---------------------------------------------------------------------------------------------- */
