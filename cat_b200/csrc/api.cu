@@ -72,6 +72,7 @@ int UploadPass(const PassPlan &h, DevicePass *d) {
     d->num_arcs = (int)h.arcs.size();
     d->max_tile_arcs = h.max_tile_arcs;
     d->max_tile_labels = h.max_tile_labels;
+    d->max_tile_rows = h.max_tile_rows;
     return 0;
 }
 

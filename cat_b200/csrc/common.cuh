@@ -20,6 +20,7 @@ struct DevicePass {
     int num_arcs = 0;
     int max_tile_arcs = 0;
     int max_tile_labels = 0;
+    int max_tile_rows = 0;
 };
 
 struct DeviceGraph {
@@ -67,6 +68,7 @@ struct DenParams {
     float *grad;          // raw accumulation target, element (n,t,k) at n*gsn + t*gst + k
     long gsn, gst;
     int gacc_rows;        // rows of the shared-memory label accumulator (0 = direct global atomics)
+    int tile_rows;        // max rows (states) owned by one CTA: size of the shared-memory row metadata
     // optional per-warp timeline (profiling aid, normally null)
     unsigned long long *timeline;
     int tl_step0, tl_steps;
@@ -121,11 +123,17 @@ __device__ __forceinline__ void red_release_add_u32(unsigned *p, unsigned v) {
 
 // Grid-wide barrier for a co-resident (cooperatively launched) grid.  `target` is the value the
 // monotonically increasing counter reaches once every CTA has arrived at this barrier.
+// Arrive with a release reduction, poll with relaxed loads (an acquire load would invalidate L1 on every poll),
+// then one acquire fence before the CTA is released.
 __device__ __forceinline__ void grid_barrier(unsigned *counter, unsigned target) {
     __syncthreads();
     if (threadIdx.x == 0) {
         red_release_add_u32(counter, 1u);
-        while (ld_acquire_u32(counter) < target) { }
+        unsigned v;
+        do {
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+        } while (v < target);
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
     }
     __syncthreads();
 }

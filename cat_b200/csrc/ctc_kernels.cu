@@ -95,13 +95,28 @@ __global__ void ctc_fwd_bwd_kernel(const void *y, int y_bf16, long sn, long st, 
         if (tid == 0) coff[0] = 0.0;
     }
     double C = 0.0;
+    // Row prefetch: the emission row of frame t+1 is loaded into registers while frame t is computed and parked in
+    // shared memory afterwards, so no frame waits on a global-memory round trip (V <= kRowRegs * blockDim).
+    constexpr int kRowRegs = 4;
+    const bool row_in_regs = V <= kRowRegs * NT;
+    float yreg[kRowRegs];
+    if (row_in_regs && Tn > 1) {
+#pragma unroll
+        for (int j = 0; j < kRowRegs; ++j) { const int k = tid + j * NT; yreg[j] = k < V ? load_y(y, y_bf16, ybase + st + k) : 0.f; }
+#pragma unroll
+        for (int j = 0; j < kRowRegs; ++j) { const int k = tid + j * NT; if (k < V) s_y[V + k] = yreg[j]; }
+    }
     for (int t = 1; t < Tn; ++t) {
-        // One barrier per frame: row t is staged into slot t&1 (last read two frames ago), the barrier
-        // publishes the row, the previous frame's cells and their per-warp maxima.
+        // One barrier per frame: it publishes row t (parked in slot t&1 during the previous frame), the previous
+        // frame's cells and their per-warp maxima.
         float *yc = s_y + (t & 1) * V;
         const float *prev = s_a + ((t - 1) & 1) * ScMax;
         float *cur = s_a + (t & 1) * ScMax;
-        for (int k = tid; k < V; k += NT) yc[k] = load_y(y, y_bf16, ybase + (long)t * st + k);
+        if (!row_in_regs) for (int k = tid; k < V; k += NT) yc[k] = load_y(y, y_bf16, ybase + (long)t * st + k);
+        else if (t + 1 < Tn) {
+#pragma unroll
+            for (int j = 0; j < kRowRegs; ++j) { const int k = tid + j * NT; yreg[j] = k < V ? load_y(y, y_bf16, ybase + (long)(t + 1) * st + k) : 0.f; }
+        }
         __syncthreads();
         const float m = block_max_from(s_wmax + ((t - 1) & 1) * 32, nwarps);
         C += (double)m;
@@ -130,6 +145,11 @@ __global__ void ctc_fwd_bwd_kernel(const void *y, int y_bf16, long sn, long st, 
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, o));
         if (lane == 0) s_wmax[(t & 1) * 32 + warp] = mx;
+        if (row_in_regs && t + 1 < Tn) {   // park row t+1 in the slot last read during frame t-1
+            float *yn = s_y + ((t + 1) & 1) * V;
+#pragma unroll
+            for (int j = 0; j < kRowRegs; ++j) { const int k = tid + j * NT; if (k < V) yn[k] = yreg[j]; }
+        }
     }
     __syncthreads();
     double logp_d;
@@ -146,12 +166,35 @@ __global__ void ctc_fwd_bwd_kernel(const void *y, int y_bf16, long sn, long st, 
     // ---- backward + occupancies ------------------------------------------------------------------
     // beta ping-pong reuses s_a (slot t&1 holds beta_rel_t) and s_wmax.
     double D = 0.0;
+    // prefetch state: emission row and this thread's two alpha cells of the NEXT frame to be processed (t-1)
+    const bool cells_in_regs = L1 <= NT;
+    float a_sb = -INFINITY, a_sl = -INFINITY;   // alpha_rel of cells 2*tid, 2*tid+1 for the current frame
+    {
+        const int t = Tn - 1;
+        float *yc = s_y + (t & 1) * V;
+        for (int k = tid; k < V; k += NT) yc[k] = load_y(y, y_bf16, ybase + (long)t * st + k);
+        if (cells_in_regs && tid < L1) {
+            a_sb = ws[(size_t)t * ScMax + 2 * tid];
+            if (tid < L) a_sl = ws[(size_t)t * ScMax + 2 * tid + 1];
+        }
+    }
     for (int t = Tn - 1; t >= 0; --t) {
         float *yc = s_y + (t & 1) * V;
         float *cur = s_a + (t & 1) * ScMax;
         const float *nxt = s_a + ((t + 1) & 1) * ScMax;
         float *gk = s_g + (t & 1) * V;
-        for (int k = tid; k < V; k += NT) yc[k] = load_y(y, y_bf16, ybase + (long)t * st + k);
+        // issue the loads for frame t-1 now; they are consumed after this frame's work
+        float an_sb = -INFINITY, an_sl = -INFINITY;
+        if (t > 0) {
+            if (row_in_regs) {
+#pragma unroll
+                for (int j = 0; j < kRowRegs; ++j) { const int k = tid + j * NT; yreg[j] = k < V ? load_y(y, y_bf16, ybase + (long)(t - 1) * st + k) : 0.f; }
+            }
+            if (cells_in_regs && tid < L1) {
+                an_sb = ws[(size_t)(t - 1) * ScMax + 2 * tid];
+                if (tid < L) an_sl = ws[(size_t)(t - 1) * ScMax + 2 * tid + 1];
+            }
+        }
         const double Ct = coff[t];
         __syncthreads();   // the only barrier of the frame: publishes row t, beta_{t+1}, its maxima and gk(t+1)
         if (t + 1 < Tn) {  // flush the (now complete) occupancies of frame t+1 and clear their slot
@@ -185,7 +228,7 @@ __global__ void ctc_fwd_bwd_kernel(const void *y, int y_bf16, long sn, long st, 
                 }
                 cur[sb] = vb;
                 mx = fmaxf(mx, vb);
-                const float ob = al[sb] + vb - yc[blank] + K;
+                const float ob = (cells_in_regs ? a_sb : al[sb]) + vb - yc[blank] + K;
                 occ_blank = (ob == -INFINITY || ob != ob) ? 0.f : expf(ob);
                 if (i < L) {
                     const int sl = sb + 1;
@@ -200,7 +243,7 @@ __global__ void ctc_fwd_bwd_kernel(const void *y, int y_bf16, long sn, long st, 
                     }
                     cur[sl] = vl;
                     mx = fmaxf(mx, vl);
-                    const float ol = al[sl] + vl - yc[li] + K;
+                    const float ol = (cells_in_regs ? a_sl : al[sl]) + vl - yc[li] + K;
                     if (ol != -INFINITY && ol == ol) atomicAdd(&gk[li], expf(ol));
                 }
             }
@@ -211,6 +254,16 @@ __global__ void ctc_fwd_bwd_kernel(const void *y, int y_bf16, long sn, long st, 
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, o));
         if (lane == 0) s_wmax[(t & 1) * 32 + warp] = mx;
+        if (t > 0) {   // park row t-1 (slot last read during frame t+1) and rotate the alpha cells
+            float *yn = s_y + ((t - 1) & 1) * V;
+            if (row_in_regs) {
+#pragma unroll
+                for (int j = 0; j < kRowRegs; ++j) { const int k = tid + j * NT; if (k < V) yn[k] = yreg[j]; }
+            } else {
+                for (int k = tid; k < V; k += NT) yn[k] = load_y(y, y_bf16, ybase + (long)(t - 1) * st + k);
+            }
+            a_sb = an_sb; a_sl = an_sl;
+        }
     }
     __syncthreads();
     {   // flush frame 0

@@ -105,7 +105,7 @@ inline float NegateBits(float w) {
 // cost(row) = quads(row) * 4 + kRowCost.
 void Layout(const std::vector<std::vector<Arc>> &rows, const std::vector<int> &state_label, int n_ctas, int n_warps,
             PassPlan *pp) {
-    constexpr int64_t kRowCost = 4;
+    constexpr int64_t kRowCost = 2;   // a row end costs about two arcs' worth of a (latency-bound) warp's time
     const int S = (int)rows.size();
     const int n_chunks = n_ctas * n_warps;
     auto quads = [&](int q) { return std::max<int64_t>(1, ((int64_t)rows[(size_t)q].size() + kQuad - 1) / kQuad); };
@@ -143,11 +143,13 @@ void Layout(const std::vector<std::vector<Arc>> &rows, const std::vector<int> &s
     pp->chunk_arc[n_chunks] = (int)pp->arcs.size();
     pp->max_tile_arcs = 0;
     pp->max_tile_labels = 1;
+    pp->max_tile_rows = 1;
     for (int c = 0; c < n_ctas; ++c) {
         int a0 = pp->chunk_arc[(size_t)c * n_warps], a1 = pp->chunk_arc[(size_t)(c + 1) * n_warps];
         pp->max_tile_arcs = std::max(pp->max_tile_arcs, a1 - a0);
         int s0 = pp->chunk_state[(size_t)c * n_warps], s1 = pp->chunk_state[(size_t)(c + 1) * n_warps];
         if (s1 > s0) pp->max_tile_labels = std::max(pp->max_tile_labels, state_label[s1 - 1] - state_label[s0] + 1);
+        pp->max_tile_rows = std::max(pp->max_tile_rows, s1 - s0);
     }
 }
 

@@ -45,6 +45,7 @@ struct PassPlan {
     int real_arcs = 0;                  // arcs of the graph in this pass (before padding)
     int max_tile_arcs = 0;              // max arcs owned by one CTA
     int max_tile_labels = 0;            // max (label range + 1) over CTAs
+    int max_tile_rows = 0;              // max rows owned by one CTA
 };
 
 struct DenPlan {

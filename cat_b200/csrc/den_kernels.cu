@@ -186,7 +186,8 @@ template <int NT, int U, int BATCH, bool SMEM_ARCS>
 __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const DenParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *s_sum = reinterpret_cast<float *>(smem_raw);                                  // [Npad]
-    Arc *s_arcs = reinterpret_cast<Arc *>(smem_raw + (((size_t)P.Npad * 4 + 15) & ~(size_t)15));
+    int *s_label = reinterpret_cast<int *>(s_sum + P.Npad);                              // [tile_rows] label per row
+    Arc *s_arcs = reinterpret_cast<Arc *>(smem_raw + (((size_t)(P.Npad + P.tile_rows) * 4 + 15) & ~(size_t)15));
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int cta = blockIdx.x;
@@ -196,11 +197,16 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const DenParams P) {
     const int ab = __ldg(P.chunk_arc + chunk), ae = __ldg(P.chunk_arc + chunk + 1);
     const int tile_a0 = __ldg(P.chunk_arc + cta * P.n_warps);
     const int tile_a1 = __ldg(P.chunk_arc + (cta + 1) * P.n_warps);
+    const int tile_s0 = __ldg(P.chunk_state + cta * P.n_warps);
+    const int tile_s1 = __ldg(P.chunk_state + (cta + 1) * P.n_warps);
     const int S = P.S, Npad = P.Npad;
     const size_t frame_elems = (size_t)S * Npad;
     const int lab0 = se > sb ? __ldg(P.state_label + sb) : 0;
     unsigned epoch = 0;
 
+    // per-row metadata lives in shared memory: L1 is invalidated at every grid barrier, and a global load on the
+    // row-end path would cost an L2 round trip per row
+    for (int i = tid; i < tile_s1 - tile_s0; i += NT) s_label[i] = __ldg(P.state_label + tile_s0 + i);
     const uint32_t row_bytes = (uint32_t)Npad * 4u;
     if (SMEM_ARCS) {   // stage the tile once; peers become byte offsets of the gathered rows
         for (int i = tid; i < tile_a1 - tile_a0; i += NT) {
@@ -216,6 +222,9 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const DenParams P) {
         for (int n = lane; n < Npad; n += 32) __stcg(P.alpha + (size_t)q * Npad + n, q == P.start ? 1.f : 0.f);
     if (cta == 0) for (int n = tid; n < Npad; n += NT) __stcg(P.colsum_a + n, 1.f);
     const int my_len = (cta == 0 && tid < P.N) ? __ldg(P.len + tid) : 0;   // CTA 0 keeps log-scale books
+    int len0[U];   // lengths of this lane's utterances in lane group 0 (the only group for N <= 32*U)
+#pragma unroll
+    for (int u = 0; u < U; ++u) len0[u] = (lane * U + u < P.N) ? __ldg(P.len + lane * U + u) : 0;
     double runlog = 0.0;
     grid_barrier(P.barrier, (++epoch) * gridDim.x);
 
@@ -229,7 +238,7 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const DenParams P) {
             bool lane_act = false;
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const int ln = (n0 + u < P.N) ? __ldg(P.len + n0 + u) : 0;
+                const int ln = gc == 0 ? len0[u] : ((n0 + u < P.N) ? __ldg(P.len + n0 + u) : 0);
                 act[u] = t <= ln;
                 lane_act |= act[u];
             }
@@ -247,7 +256,7 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const DenParams P) {
             int q = sb, curlab = -1;
             walk_arcs<U, BATCH, SMEM_ARCS>(s_arcs, P.arcs, ab, ae, tile_a0, row_bytes,
                                            reinterpret_cast<const char *>(a_prev + n0), lane_act, [&](const float *acc) {
-                const int lab = __ldg(P.state_label + q);
+                const int lab = s_label[q - tile_s0];
                 if (lab != curlab) {
                     curlab = lab;
 #pragma unroll
@@ -316,7 +325,9 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const DenParams P) 
     const int Npad = P.Npad, S = P.S;
     float *s_sum = reinterpret_cast<float *>(smem_raw);            // [2][Npad]: colsum_b, absum
     float *s_gacc = s_sum + 2 * Npad;                              // [gacc_rows][Npad]
-    Arc *s_arcs = reinterpret_cast<Arc *>(smem_raw + ((((size_t)(2 + P.gacc_rows) * Npad) * 4 + 15) & ~(size_t)15));
+    int *s_label = reinterpret_cast<int *>(s_gacc + (size_t)P.gacc_rows * Npad);   // [tile_rows]
+    float *s_final = reinterpret_cast<float *>(s_label + P.tile_rows);             // [tile_rows]
+    Arc *s_arcs = reinterpret_cast<Arc *>(smem_raw + ((((size_t)(2 + P.gacc_rows) * Npad + 2 * (size_t)P.tile_rows) * 4 + 15) & ~(size_t)15));
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int cta = blockIdx.x;
@@ -335,6 +346,10 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const DenParams P) 
     const size_t frame_elems = (size_t)S * Npad;
     unsigned epoch = 0;
 
+    for (int i = tid; i < tile_s1 - tile_s0; i += NT) {
+        s_label[i] = __ldg(P.state_label + tile_s0 + i);
+        s_final[i] = __ldg(P.final_lin + tile_s0 + i);
+    }
     const uint32_t row_bytes = (uint32_t)Npad * 4u;
     if (SMEM_ARCS) {
         for (int i = tid; i < tile_a1 - tile_a0; i += NT) {
@@ -345,6 +360,9 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const DenParams P) 
     }
     for (int i = tid; i < (2 + P.gacc_rows) * Npad; i += NT) s_sum[i] = 0.f;
     const int my_len = (cta == 0 && tid < P.N) ? __ldg(P.len + tid) : 0;
+    int len0[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) len0[u] = (lane * U + u < P.N) ? __ldg(P.len + lane * U + u) : 0;
     double runlog = 0.0;
     __syncthreads();
 
@@ -364,7 +382,7 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const DenParams P) 
             bool lane_act = false, lane_gat = false;
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const int ln = (n0 + u < P.N) ? __ldg(P.len + n0 + u) : 0;
+                const int ln = gc == 0 ? len0[u] : ((n0 + u < P.N) ? __ldg(P.len + n0 + u) : 0);
                 act[u] = tau <= ln;      // beta_tau exists
                 gat[u] = tau < ln;       // ... and is a sum over arcs (tau == len: final weights)
                 lane_act |= act[u];
@@ -394,7 +412,7 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const DenParams P) 
             };
             walk_arcs<U, BATCH, SMEM_ARCS>(s_arcs, P.arcs, ab, ae, tile_a0, row_bytes,
                                            reinterpret_cast<const char *>(bh_next + n0), lane_gat, [&](const float *acc) {
-                const int lab = __ldg(P.state_label + q);
+                const int lab = s_label[q - tile_s0];
                 if (lab != curlab) {
                     if (curlab >= 0) flush_gsum();
                     curlab = lab;
@@ -405,7 +423,7 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const DenParams P) 
                         e[u] = act[u] ? expf(yv - fm[u]) : 0.f;
                     }
                 }
-                const float f = __ldg(P.final_lin + q);
+                const float f = s_final[q - tile_s0];
                 Vec<U> out;
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
@@ -586,7 +604,8 @@ int LaunchFrameMax(const void *y, int y_bf16, long sn, long st, int N, int T, in
 int LaunchDenForward(const DeviceGraph &g, DenParams p, cudaStream_t stream, std::string *err) {
     p.arcs = g.fwd.arcs; p.chunk_state = g.fwd.chunk_state; p.chunk_arc = g.fwd.chunk_arc;
     p.gacc_rows = 0;
-    const size_t fixed = (((size_t)p.Npad * 4 + 15) & ~(size_t)15);
+    p.tile_rows = g.fwd.max_tile_rows;
+    const size_t fixed = (((size_t)(p.Npad + p.tile_rows) * 4 + 15) & ~(size_t)15);
     return DispatchThreads(false, g, p, fixed, stream, err);
 }
 
@@ -595,7 +614,8 @@ int LaunchDenBackward(const DeviceGraph &g, DenParams p, cudaStream_t stream, st
     // label accumulator in shared memory when the per-CTA label range is small enough
     size_t gacc_bytes = (size_t)g.bwd.max_tile_labels * p.Npad * 4;
     p.gacc_rows = gacc_bytes <= 64 * 1024 ? g.bwd.max_tile_labels : 0;
-    const size_t fixed = ((((size_t)(2 + p.gacc_rows) * p.Npad) * 4 + 15) & ~(size_t)15);
+    p.tile_rows = g.bwd.max_tile_rows;
+    const size_t fixed = ((((size_t)(2 + p.gacc_rows) * p.Npad + 2 * (size_t)p.tile_rows) * 4 + 15) & ~(size_t)15);
     return DispatchThreads(true, g, p, fixed, stream, err);
 }
 

@@ -189,6 +189,15 @@ def test_full_size_properties(tmp_path):
     assert np.abs(grad - grad2).max() < 1e-5
     # sum_k (gamma_den - (1+lamb) gamma_ctc) = -lamb; the numerator is fp32 log-domain over 800 frames (measured 8e-4)
     assert np.abs(grad.sum(-1) * N + lamb).max() < 2e-3
+    # the fp64 oracle on two of the utterances (it needs ~1 min per utterance at this size)
+    sub = [0, N - 1]
+    off = np.concatenate([[0], np.cumsum(ly)])
+    sub_labels = np.concatenate([labels[off[i]:off[i + 1]] for i in sub])
+    oloss, ograd, oparts = oracle.ctc_crf(g, y[sub], sub_labels, lens[sub], ly[sub], lamb, size_average=False, nthreads=2)
+    d_or = np.abs(grad[sub] * N - ograd).max()
+    print("max |grad - oracle| (unscaled occupancies, N=32 T=800 A=1M):", d_or)
+    assert d_or < GRAD_ATOL
+    np.testing.assert_allclose(ca.cpu().numpy()[sub], oparts["logz_alpha"], rtol=LOSS_RTOL)
     if ref_cuda.available():
         rctx = ref_cuda.RefContext(path, 0)
         rl, rg, parts = ref_cuda.ctc_crf_forward(rctx, logits, torch.tensor(labels), torch.tensor(lens),
@@ -196,9 +205,16 @@ def test_full_size_properties(tmp_path):
         torch.cuda.synchronize()
         rctx.close()
         _close_loss(loss, float(rl.item()))
-        d = np.abs(grad - rg.cpu().numpy()).max() * N
-        print('max |grad - reference CUDA| (unscaled occupancies):', d)
-        assert d < 3 * GRAD_ATOL   # the reference is fp32 log-domain (|alpha| ~ 2500): ~1e-3 of its own rounding
+        rgn = rg.cpu().numpy()
+        d = np.abs(grad - rgn).max() * N
+        ref_self = np.abs(rgn.sum(-1) * N + lamb).max()          # the reference's own row-sum inconsistency
+        d_ref_or = np.abs(rgn[sub] * N - ograd).max()
+        print("max |grad - reference CUDA| (unscaled):", d, "| reference row-sum error:", ref_self,
+              "| max |reference - oracle|:", d_ref_or)
+        # at T=800 the reference's fp32 log domain (|alpha| ~ 2500) is itself several 1e-2 off the fp64 oracle; the
+        # tight comparison against the reference is test_vs_reference_cuda (T=120).  Here: no worse than the reference.
+        assert d_or <= d_ref_or + GRAD_ATOL
+        assert d < 0.1
     del ctx
 
 
