@@ -180,6 +180,7 @@ DenParams BaseParams(const DeviceGraph &g, const void *y, int dtype, long sn, lo
     p.b0 = reinterpret_cast<float *>(a + L.b0);
     p.fmax = reinterpret_cast<float *>(a + L.fmax);
     p.timeline = g_timeline; p.tl_step0 = g_tl_step0; p.tl_steps = g_tl_steps;
+    { const char *e = getenv("CCB_DEBUG"); p.debug = e ? atoi(e) : 0; }
     return p;
 }
 

@@ -72,6 +72,7 @@ struct DenParams {
     // optional per-warp timeline (profiling aid, normally null)
     unsigned long long *timeline;
     int tl_step0, tl_steps;
+    int debug;            // CCB_DEBUG bit 0: skip row-end work, bit 1: skip the grid barrier (TIMING EXPERIMENTS ONLY)
 };
 
 // workspace carving (all offsets in bytes, 256-aligned)

@@ -127,18 +127,24 @@ void Layout(const std::vector<std::vector<Arc>> &rows, const std::vector<int> &s
 
     pp->arcs.clear();
     pp->chunk_arc.assign((size_t)n_chunks + 1, 0);
+    uint32_t last_peer = 0;
     for (int c = 0; c < n_chunks; ++c) {
         pp->chunk_arc[c] = (int)pp->arcs.size();
         for (int q = pp->chunk_state[c]; q < pp->chunk_state[c + 1]; ++q) {
             const auto &r = rows[(size_t)q];
             const size_t padded = (size_t)quads(q) * kQuad;
+            // Padding arcs carry weight 0 but are still gathered: point them at a row this warp reads anyway (the
+            // previous arc's peer, or the row itself).  Pointing them all at one fixed row would make every warp of
+            // the grid hammer a single L2 line (measured: 2x frame time from that hot spot alone).
+            uint32_t pad_peer = r.empty() ? (uint32_t)q : r.back().peer;
             for (size_t i = 0; i < padded; ++i) {
-                Arc a = i < r.size() ? r[i] : Arc{0u, 0.f};
+                Arc a = i < r.size() ? r[i] : Arc{pad_peer, 0.f};
                 if (i + 1 == padded) a.w = NegateBits(a.w);   // last quad of the row
                 pp->arcs.push_back(a);
             }
+            last_peer = pad_peer;
         }
-        while (pp->arcs.size() % kChunkArcPad) pp->arcs.push_back(Arc{0u, 0.f});
+        while (pp->arcs.size() % kChunkArcPad) pp->arcs.push_back(Arc{last_peer, 0.f});
     }
     pp->chunk_arc[n_chunks] = (int)pp->arcs.size();
     pp->max_tile_arcs = 0;

@@ -256,6 +256,7 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const DenParams P) {
             int q = sb, curlab = -1;
             walk_arcs<U, BATCH, SMEM_ARCS>(s_arcs, P.arcs, ab, ae, tile_a0, row_bytes,
                                            reinterpret_cast<const char *>(a_prev + n0), lane_act, [&](const float *acc) {
+                if (P.debug & 1) { sum[0] += acc[0]; ++q; return; }
                 const int lab = s_label[q - tile_s0];
                 if (lab != curlab) {
                     curlab = lab;
@@ -290,7 +291,7 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const DenParams P) {
             (void)scale_from_sum(__ldcg(P.colsum_a + (size_t)(t - 1) * Npad + tid), &sh);
             runlog += (double)__ldg(P.fmax + (size_t)(t - 1) * Npad + tid) - (double)sh * 0.6931471805599453;
         }
-        grid_barrier(P.barrier, (++epoch) * gridDim.x);
+        if (!(P.debug & 2)) grid_barrier(P.barrier, (++epoch) * gridDim.x); else __syncthreads();
         tl_mark(P, t, chunk, n_chunks, 2, lane);
     }
 
@@ -412,6 +413,7 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const DenParams P) 
             };
             walk_arcs<U, BATCH, SMEM_ARCS>(s_arcs, P.arcs, ab, ae, tile_a0, row_bytes,
                                            reinterpret_cast<const char *>(bh_next + n0), lane_gat, [&](const float *acc) {
+                if (P.debug & 1) { sum_b[0] += acc[0]; ++q; return; }
                 const int lab = s_label[q - tile_s0];
                 if (lab != curlab) {
                     if (curlab >= 0) flush_gsum();
@@ -470,7 +472,7 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const DenParams P) 
             (void)scale_from_sum(__ldcg(P.colsum_b + (size_t)(tau + 1) * Npad + tid), &sh);
             runlog += (double)__ldg(P.fmax + (size_t)tau * Npad + tid) - (double)sh * 0.6931471805599453;
         }
-        grid_barrier(P.barrier, (++epoch) * gridDim.x);
+        if (!(P.debug & 2)) grid_barrier(P.barrier, (++epoch) * gridDim.x); else __syncthreads();
         tl_mark(P, P.Tmax - tau, chunk, n_chunks, 2, lane);
     }
 
