@@ -59,9 +59,8 @@ int Upload(T **dst, const std::vector<T> &src) {
 
 void FreeDevice(DeviceGraph &d) {
     if (!d.loaded) return;
-    cudaFree(d.state_label); cudaFree(d.final_lin);
-    cudaFree(d.fwd.arcs); cudaFree(d.fwd.chunk_state); cudaFree(d.fwd.chunk_arc);
-    cudaFree(d.bwd.arcs); cudaFree(d.bwd.chunk_state); cudaFree(d.bwd.chunk_arc);
+    cudaFree(d.state_label); cudaFree(d.state_pos); cudaFree(d.final_lin); cudaFree(d.start_arcs);
+    for (DevicePass *p : {&d.fwd, &d.bwd}) { cudaFree(p->arcs); cudaFree(p->chunk_state); cudaFree(p->chunk_arc); cudaFree(p->chunk_pair); cudaFree(p->cta_labels); }
     d = DeviceGraph();
 }
 
@@ -69,6 +68,8 @@ int UploadPass(const PassPlan &h, DevicePass *d) {
     if (Upload(&d->arcs, h.arcs)) return 1;
     if (Upload(&d->chunk_state, h.chunk_state)) return 1;
     if (Upload(&d->chunk_arc, h.chunk_arc)) return 1;
+    if (Upload(&d->chunk_pair, h.chunk_pair)) return 1;
+    if (Upload(&d->cta_labels, h.cta_labels)) return 1;
     d->num_arcs = (int)h.arcs.size();
     d->max_tile_arcs = h.max_tile_arcs;
     d->max_tile_labels = h.max_tile_labels;
@@ -108,7 +109,7 @@ int InitImpl(const char *fst_name, int n_gpus, const int *gpus) {
     if (!prop.cooperativeLaunch) return Fail("device does not support cooperative launch");
     if (!BuildDenPlan(fst, prop.multiProcessorCount, DenWarps(), &g_plan, &err)) return Fail(err);
     g_plan_valid = true;
-    DEN_NUM_STATES = g_plan.num_states;
+    DEN_NUM_STATES = g_plan.num_states + g_plan.num_pairs;   // rows per alpha frame (what binding.cpp sizes scratch with)
     DEN_NUM_ARCS = (int)g_plan.fwd.arcs.size();
     int rc = 0;
     for (int i = 0; i < n_gpus && rc == 0; ++i) {
@@ -119,25 +120,14 @@ int InitImpl(const char *fst_name, int n_gpus, const int *gpus) {
         CCB_CUDA(cudaGetDeviceProperties(&p2, gpus[i]));
         if (p2.multiProcessorCount != prop.multiProcessorCount) { rc = Fail("Init: heterogeneous GPUs are not supported"); break; }
         d.device = gpus[i];
-        d.S = g_plan.num_states; d.start = g_plan.start; d.num_labels = g_plan.num_labels;
+        d.S = g_plan.num_states; d.P = g_plan.num_pairs; d.start = g_plan.start; d.num_labels = g_plan.num_labels;
         d.n_ctas = g_plan.n_ctas; d.n_warps = g_plan.n_warps;
         d.max_smem_optin = (int)p2.sharedMemPerBlockOptin;
-        rc = Upload(&d.state_label, g_plan.state_label) || Upload(&d.final_lin, g_plan.final_lin) ||
+        rc = Upload(&d.state_label, g_plan.state_label) || Upload(&d.state_pos, g_plan.state_pos) ||
+             Upload(&d.final_lin, g_plan.final_lin) || Upload(&d.start_arcs, g_plan.start_arcs) ||
              UploadPass(g_plan.fwd, &d.fwd) || UploadPass(g_plan.bwd, &d.bwd);
-        // backward-pass row of the start state (for logZ recomputed from beta)
-        {
-            // rows are contiguous: find the start row by walking chunk boundaries on the host plan
-            // rows end at quads whose 4th weight carries the sign flag; unflagged padding quads in front of a
-            // row are zero-weight and harmless to include
-            const auto &arcs = g_plan.bwd.arcs;
-            auto flagged = [&](size_t quad) { return std::signbit(arcs[quad * kQuad + kQuad - 1].w); };
-            size_t quad = 0;
-            for (int q = 0; q < g_plan.start; ++quad) if (flagged(quad)) ++q;
-            d.start_row_begin = (int)(quad * kQuad);
-            while (!flagged(quad)) ++quad;
-            d.start_row_end = (int)((quad + 1) * kQuad);
-            d.start_final = g_plan.final_lin[(size_t)g_plan.start];
-        }
+        d.n_start_arcs = (int)g_plan.start_arcs.size();
+        d.start_final = g_plan.final_lin[(size_t)g_plan.start];
         d.loaded = (rc == 0);
     }
     cudaSetDevice(prev);
@@ -166,9 +156,10 @@ DenParams BaseParams(const DeviceGraph &g, const void *y, int dtype, long sn, lo
     DenParams p;
     memset(&p, 0, sizeof(p));
     char *a = reinterpret_cast<char *>(aux);
-    p.state_label = g.state_label; p.final_lin = g.final_lin;
-    p.S = g.S; p.start = g.start; p.n_warps = g.n_warps;
-    p.start_row_begin = g.start_row_begin; p.start_row_end = g.start_row_end; p.start_final = g.start_final;
+    p.state_label = g.state_label; p.state_pos = g.state_pos; p.final_lin = g.final_lin;
+    p.start_arcs = g.start_arcs; p.n_start_arcs = g.n_start_arcs;
+    p.S = g.S; p.num_pairs = g.P; p.start = g.start; p.n_warps = g.n_warps;
+    p.start_final = g.start_final;
     p.y = y; p.y_bf16 = (dtype == CCB_DTYPE_BF16); p.sn = sn; p.st = st;
     p.N = N; p.Npad = L.Npad; p.Tmax = T; p.V = V; p.len = len;
     p.alpha = alpha;
@@ -189,7 +180,7 @@ int CheckDen(const DeviceGraph &g, int dtype, int N, int T, int V) {
     if (dtype != CCB_DTYPE_F32 && dtype != CCB_DTYPE_BF16) return Fail("den: unsupported logits dtype");
     if (V < g.num_labels)
         return Fail("den graph uses label " + std::to_string(g.num_labels - 1) + " but logits have only " + std::to_string(V) + " classes");
-    if ((size_t)g.S * (size_t)PadLanes(N) * 4 >= ((size_t)1 << 32)) return Fail("den: states x batch too large for 32-bit row offsets; split the batch");
+    if ((size_t)(g.S + g.P) * (size_t)PadLanes(N) * 4 >= ((size_t)1 << 32)) return Fail("den: states x batch too large for 32-bit row offsets; split the batch");
     if (PadLanes(N) > g.n_warps * 32) return Fail("den: batch larger than " + std::to_string(g.n_warps * 32) + " utterances per call; split the batch");
     return 0;
 }
@@ -272,7 +263,7 @@ void Release(int n_gpus, int *gpus) { ReleaseImpl(n_gpus, gpus); }
 
 size_t ccb_den_alpha_floats(int N, int T) {
     if (!g_plan_valid) return 0;
-    return (size_t)(T + 1) * (size_t)g_plan.num_states * (size_t)PadLanes(N);
+    return (size_t)(T + 1) * (size_t)(g_plan.num_states + g_plan.num_pairs) * (size_t)PadLanes(N);
 }
 
 size_t ccb_den_aux_bytes(int N, int T) {
@@ -482,6 +473,7 @@ int ccb_plan_info(void *plan, long *info) {
     info[3] = (long)p->fwd.arcs.size(); info[4] = (long)p->bwd.arcs.size(); info[5] = p->start;
     info[6] = p->num_labels; info[7] = p->n_ctas; info[8] = p->n_warps;
     info[9] = std::max(p->fwd.max_tile_arcs, p->bwd.max_tile_arcs);
+    info[10] = p->num_pairs; info[11] = (long)p->start_arcs.size();
     return 0;
 }
 
@@ -500,6 +492,12 @@ int ccb_plan_copy(void *plan, int which, void *dst, size_t dst_bytes) {
         case 6: src = p->bwd.arcs.data(); bytes = p->bwd.arcs.size() * sizeof(Arc); break;
         case 7: src = p->bwd.chunk_state.data(); bytes = p->bwd.chunk_state.size() * 4; break;
         case 8: src = p->bwd.chunk_arc.data(); bytes = p->bwd.chunk_arc.size() * 4; break;
+        case 9: src = p->state_pos.data(); bytes = p->state_pos.size() * 4; break;
+        case 10: src = p->fwd.chunk_pair.data(); bytes = p->fwd.chunk_pair.size() * 4; break;
+        case 11: src = p->bwd.chunk_pair.data(); bytes = p->bwd.chunk_pair.size() * 4; break;
+        case 12: src = p->start_arcs.data(); bytes = p->start_arcs.size() * sizeof(Arc); break;
+        case 13: src = p->fwd.cta_labels.data(); bytes = p->fwd.cta_labels.size() * 4; break;
+        case 14: src = p->bwd.cta_labels.data(); bytes = p->bwd.cta_labels.size() * 4; break;
         default: return 1;
     }
     if (bytes > dst_bytes) return 2;

@@ -17,6 +17,8 @@ struct DevicePass {
     Arc *arcs = nullptr;
     int *chunk_state = nullptr;
     int *chunk_arc = nullptr;
+    int *chunk_pair = nullptr;
+    int *cta_labels = nullptr;
     int num_arcs = 0;
     int max_tile_arcs = 0;
     int max_tile_labels = 0;
@@ -26,12 +28,14 @@ struct DevicePass {
 struct DeviceGraph {
     bool loaded = false;
     int device = -1;
-    int S = 0, start = 0, num_labels = 0;
+    int S = 0, P = 0, start = 0, num_labels = 0;   // S states, P pairs (virtual rows S..S+P-1 of the alpha frames)
     int n_ctas = 0, n_warps = 0;
     int *state_label = nullptr;
+    int *state_pos = nullptr;
     float *final_lin = nullptr;
     DevicePass fwd, bwd;
-    int start_row_begin = 0, start_row_end = 0;  // backward-pass arcs of the start state
+    Arc *start_arcs = nullptr;   // out-arcs of the start state
+    int n_start_arcs = 0;
     float start_final = 0.f;
     int max_smem_optin = 0;
 };
@@ -42,10 +46,14 @@ struct DenParams {
     const Arc *arcs;
     const int *chunk_state;
     const int *chunk_arc;
+    const int *chunk_pair;
+    const int *cta_labels;
     const int *state_label;
+    const int *state_pos;
     const float *final_lin;
-    int S, start, n_warps;
-    int start_row_begin, start_row_end;
+    const Arc *start_arcs;
+    int n_start_arcs;
+    int S, num_pairs, start, n_warps;
     float start_final;
     // problem
     const void *y;        // (N,T,V) log-probs, fp32 or bf16
@@ -54,7 +62,7 @@ struct DenParams {
     int N, Npad, Tmax, V;
     const int *len;       // [N] device
     // workspaces
-    float *alpha;         // [(Tmax+1)][S][Npad]   scaled-linear alpha spill
+    float *alpha;         // [(Tmax+1)][S+P][Npad] scaled-linear alpha spill (+ pair-sum rows)
     float *bh;            // [2][S][Npad]          backward ping-pong (emission-weighted beta)
     float *colsum_a;      // [(Tmax+2)][Npad]
     float *colsum_b;      // [(Tmax+2)][Npad]

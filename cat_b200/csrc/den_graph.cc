@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <numeric>
@@ -93,69 +94,96 @@ bool ReadFstFile(const char *path, HostFst *out, std::string *err) {
 
 namespace {
 
-inline float NegateBits(float w) {
-    uint32_t b;
-    memcpy(&b, &w, 4);
-    b |= 0x80000000u;
-    memcpy(&w, &b, 4);
-    return w;
-}
+inline uint32_t Bits(float w) { uint32_t b; memcpy(&b, &w, 4); return b; }
+inline float WithSign(float w) { uint32_t b = Bits(w) | 0x80000000u; float r; memcpy(&r, &b, 4); return r; }
 
-// Cut rows into n_chunks contiguous chunks of near-equal cost and emit the chunk-major padded arc stream.
-// cost(row) = quads(row) * 4 + kRowCost.
-void Layout(const std::vector<std::vector<Arc>> &rows, const std::vector<int> &state_label, int n_ctas, int n_warps,
-            PassPlan *pp) {
-    constexpr int64_t kRowCost = 2;   // a row end costs about two arcs' worth of a (latency-bound) warp's time
-    const int S = (int)rows.size();
+struct Segment {
+    std::vector<Arc> arcs;
+    int event = kEvRow;
+};
+struct Group {
+    std::vector<Segment> segs;
+    int first_state = 0, rows = 0, pairs = 0;
+};
+
+// Cut groups into n_chunks contiguous chunks of near-equal cost and emit the chunk-major padded arc stream.
+void Layout(const std::vector<Group> &groups, int S, const std::vector<int> &state_label, const std::vector<int> &state_pos,
+            int n_ctas, int n_warps, int64_t row_cost, PassPlan *pp) {
+    const int G = (int)groups.size();
     const int n_chunks = n_ctas * n_warps;
-    auto quads = [&](int q) { return std::max<int64_t>(1, ((int64_t)rows[(size_t)q].size() + kQuad - 1) / kQuad); };
-    std::vector<int64_t> prefix((size_t)S + 1, 0);
+    auto quads = [](const Segment &sg) { return std::max<int64_t>(1, ((int64_t)sg.arcs.size() + kQuad - 1) / kQuad); };
+    std::vector<int64_t> prefix((size_t)G + 1, 0);
     pp->real_arcs = 0;
-    for (int q = 0; q < S; ++q) {
-        prefix[q + 1] = prefix[q] + quads(q) * kQuad + kRowCost;
-        pp->real_arcs += (int)rows[(size_t)q].size();
+    for (int g = 0; g < G; ++g) {
+        int64_t c = 0;
+        for (auto &sg : groups[(size_t)g].segs) { c += quads(sg) * kQuad; pp->real_arcs += (int)sg.arcs.size(); }
+        prefix[g + 1] = prefix[g] + c + row_cost * groups[(size_t)g].rows;
     }
-    const int64_t total = prefix[S];
-    pp->chunk_state.assign((size_t)n_chunks + 1, 0);
+    const int64_t total = prefix[G];
+    std::vector<int> chunk_group((size_t)n_chunks + 1, 0);
     for (int c = 1; c < n_chunks; ++c) {
         int64_t target = (total * c + n_chunks / 2) / n_chunks;
-        int q = (int)(std::lower_bound(prefix.begin(), prefix.end(), target) - prefix.begin());
-        q = std::min(std::max(q, pp->chunk_state[c - 1]), S);
-        pp->chunk_state[c] = q;
+        int g = (int)(std::lower_bound(prefix.begin(), prefix.end(), target) - prefix.begin());
+        chunk_group[c] = std::min(std::max(g, chunk_group[c - 1]), G);
     }
-    pp->chunk_state[n_chunks] = S;
+    chunk_group[n_chunks] = G;
 
     pp->arcs.clear();
+    pp->chunk_state.assign((size_t)n_chunks + 1, S);
     pp->chunk_arc.assign((size_t)n_chunks + 1, 0);
+    pp->chunk_pair.assign((size_t)n_chunks + 1, 0);
+    int pairs_seen = 0;
     uint32_t last_peer = 0;
     for (int c = 0; c < n_chunks; ++c) {
         pp->chunk_arc[c] = (int)pp->arcs.size();
-        for (int q = pp->chunk_state[c]; q < pp->chunk_state[c + 1]; ++q) {
-            const auto &r = rows[(size_t)q];
-            const size_t padded = (size_t)quads(q) * kQuad;
-            // Padding arcs carry weight 0 but are still gathered: point them at a row this warp reads anyway (the
-            // previous arc's peer, or the row itself).  Pointing them all at one fixed row would make every warp of
-            // the grid hammer a single L2 line (measured: 2x frame time from that hot spot alone).
-            uint32_t pad_peer = r.empty() ? (uint32_t)q : r.back().peer;
-            for (size_t i = 0; i < padded; ++i) {
-                Arc a = i < r.size() ? r[i] : Arc{pad_peer, 0.f};
-                if (i + 1 == padded) a.w = NegateBits(a.w);   // last quad of the row
-                pp->arcs.push_back(a);
+        pp->chunk_pair[c] = pairs_seen;
+        pp->chunk_state[c] = chunk_group[c] < G ? groups[(size_t)chunk_group[c]].first_state : S;
+        for (int g = chunk_group[c]; g < chunk_group[c + 1]; ++g) {
+            const Group &gr = groups[(size_t)g];
+            pairs_seen += gr.pairs;
+            for (auto &sg : gr.segs) {
+                const size_t padded = (size_t)quads(sg) * kQuad;
+                // Padding arcs carry weight 0 but are still gathered: point them at a row this warp reads anyway.
+                // Pointing them all at one fixed row makes every warp of the grid hammer a single L2 line
+                // (measured: 2x frame time from that hot spot alone).
+                const uint32_t pad_peer = sg.arcs.empty() ? (uint32_t)gr.first_state : sg.arcs.back().peer;
+                for (size_t i = 0; i < padded; ++i) {
+                    Arc a = i < sg.arcs.size() ? sg.arcs[i] : Arc{pad_peer, 0.f};
+                    if (i + 1 == padded) a.w = WithSign(a.w);
+                    if (i + 2 == padded && (sg.event & 2)) a.w = WithSign(a.w);
+                    if (i + 3 == padded && (sg.event & 1)) a.w = WithSign(a.w);
+                    pp->arcs.push_back(a);
+                }
+                last_peer = pad_peer;
             }
-            last_peer = pad_peer;
         }
         while (pp->arcs.size() % kChunkArcPad) pp->arcs.push_back(Arc{last_peer, 0.f});
     }
     pp->chunk_arc[n_chunks] = (int)pp->arcs.size();
+    pp->chunk_pair[n_chunks] = pairs_seen;
+    pp->chunk_state[n_chunks] = S;
+    for (int c = n_chunks - 1; c >= 0; --c)   // empty trailing chunks start where the next one does
+        if (chunk_group[c] == chunk_group[c + 1]) pp->chunk_state[c] = pp->chunk_state[c + 1];
+
     pp->max_tile_arcs = 0;
     pp->max_tile_labels = 1;
     pp->max_tile_rows = 1;
+    pp->cta_labels.assign((size_t)n_ctas * 4, 0);
     for (int c = 0; c < n_ctas; ++c) {
         int a0 = pp->chunk_arc[(size_t)c * n_warps], a1 = pp->chunk_arc[(size_t)(c + 1) * n_warps];
         pp->max_tile_arcs = std::max(pp->max_tile_arcs, a1 - a0);
         int s0 = pp->chunk_state[(size_t)c * n_warps], s1 = pp->chunk_state[(size_t)(c + 1) * n_warps];
-        if (s1 > s0) pp->max_tile_labels = std::max(pp->max_tile_labels, state_label[s1 - 1] - state_label[s0] + 1);
         pp->max_tile_rows = std::max(pp->max_tile_rows, s1 - s0);
+        int lo[2] = {1 << 30, 1 << 30}, hi[2] = {-1, -1};
+        for (int q = s0; q < s1; ++q) {
+            const int k = state_pos[(size_t)q] ? 1 : 0;
+            lo[k] = std::min(lo[k], state_label[(size_t)q]);
+            hi[k] = std::max(hi[k], state_label[(size_t)q]);
+        }
+        int *cl = &pp->cta_labels[(size_t)c * 4];
+        cl[0] = hi[0] >= 0 ? lo[0] : 0; cl[1] = hi[0] >= 0 ? hi[0] - lo[0] + 1 : 0;
+        cl[2] = hi[1] >= 0 ? lo[1] : 0; cl[3] = hi[1] >= 0 ? hi[1] - lo[1] + 1 : 0;
+        pp->max_tile_labels = std::max(pp->max_tile_labels, cl[1] + cl[3]);
     }
 }
 
@@ -166,7 +194,7 @@ bool BuildDenPlan(const HostFst &fst, int n_ctas, int n_warps, DenPlan *plan, st
     const size_t A0 = fst.src.size();
     if (n_ctas < 1 || n_warps < 1) { *err = "bad grid for den plan"; return false; }
 
-    // 1. distinct in-labels per file state
+    // 1. distinct in-labels per file state; split states ("sid" = id after the split, sorted by label)
     std::vector<std::vector<int>> in_labels((size_t)S0);
     for (size_t a = 0; a < A0; ++a) in_labels[(size_t)fst.dst[a]].push_back(fst.label[a]);
     size_t S = 0;
@@ -179,64 +207,205 @@ bool BuildDenPlan(const HostFst &fst, int n_ctas, int n_warps, DenPlan *plan, st
         S += v.size();
         max_label = std::max(max_label, v.back());
     }
-    // split-arc count and a sanity bound on the blow-up
     size_t A = 0;
     for (size_t a = 0; a < A0; ++a) A += in_labels[(size_t)fst.src[a]].size();
     if (S > (size_t)0x3fffffff || A > (size_t)0x3fffffff) {
         *err = "den graph too large after in-label state split (S=" + std::to_string(S) + ", A=" + std::to_string(A) + ")";
         return false;
     }
-
-    // 2. renumber (label, file state) sorted by label
     struct Copy { int label, orig; };
     std::vector<Copy> copies;
     copies.reserve(S);
     for (int q = 0; q < S0; ++q) for (int k : in_labels[(size_t)q]) copies.push_back(Copy{k, q});
     std::stable_sort(copies.begin(), copies.end(), [](const Copy &a, const Copy &b) { return a.label < b.label; });
-    // first_copy[q] + index of label within in_labels[q] -> new id
-    std::vector<std::vector<int>> new_id((size_t)S0);
-    for (int q = 0; q < S0; ++q) new_id[(size_t)q].assign(in_labels[(size_t)q].size(), -1);
-    plan->state_label.resize(S);
-    plan->orig_state.resize(S);
-    plan->final_lin.resize(S);
+    std::vector<std::vector<int>> sid_of((size_t)S0);
+    for (int q = 0; q < S0; ++q) sid_of[(size_t)q].assign(in_labels[(size_t)q].size(), -1);
+    std::vector<int> sid_label(S), sid_orig(S);
     for (size_t i = 0; i < S; ++i) {
         const Copy &c = copies[i];
         auto &labs = in_labels[(size_t)c.orig];
         size_t j = (size_t)(std::lower_bound(labs.begin(), labs.end(), c.label) - labs.begin());
-        new_id[(size_t)c.orig][j] = (int)i;
-        plan->state_label[i] = c.label;
-        plan->orig_state[i] = c.orig;
-        float fw = fst.final_logw[(size_t)c.orig];
-        plan->final_lin[i] = std::isinf(fw) ? 0.f : std::exp(fw);
+        sid_of[(size_t)c.orig][j] = (int)i;
+        sid_label[i] = c.label;
+        sid_orig[i] = c.orig;
     }
-    plan->file_states = S0;
-    plan->file_arcs = (int)A0;
-    plan->num_states = (int)S;
-    plan->num_labels = max_label + 1;
-    plan->start = new_id[(size_t)fst.start][0];  // all start mass on one copy (copies share out-arcs)
-    plan->n_ctas = n_ctas;
-    plan->n_warps = n_warps;
-
-    // 3. rows
-    std::vector<std::vector<Arc>> in_rows(S), out_rows(S);
+    struct SArc { int peer; float w; };
+    std::vector<std::vector<SArc>> in_s(S), out_s(S);   // by sid
     for (size_t a = 0; a < A0; ++a) {
         const int p = fst.src[a], q = fst.dst[a];
         auto &labs = in_labels[(size_t)q];
         size_t j = (size_t)(std::lower_bound(labs.begin(), labs.end(), fst.label[a]) - labs.begin());
-        const int qn = new_id[(size_t)q][j];
+        const int qs = sid_of[(size_t)q][j];
         const float w = std::exp(fst.logw[a]);
-        for (int pn : new_id[(size_t)p]) {
-            in_rows[(size_t)qn].push_back(Arc{(uint32_t)pn, w});
-            out_rows[(size_t)pn].push_back(Arc{(uint32_t)qn, w});
+        if (!(w >= 0.f) || std::isinf(w)) { *err = "den graph arc weight is not a finite probability-like value"; return false; }
+        for (int ps : sid_of[(size_t)p]) {
+            in_s[(size_t)qs].push_back(SArc{ps, w});
+            out_s[(size_t)ps].push_back(SArc{qs, w});
         }
     }
-    // gather locality: visit peers in ascending order
-    for (auto &r : in_rows) std::sort(r.begin(), r.end(), [](const Arc &a, const Arc &b) { return a.peer < b.peer; });
-    for (auto &r : out_rows) std::sort(r.begin(), r.end(), [](const Arc &a, const Arc &b) { return a.peer < b.peer; });
 
-    for (auto &r : in_rows) for (auto &a : r) if (!(a.w >= 0.f) || std::isinf(a.w)) { *err = "den graph arc weight is not a finite probability-like value"; return false; }
-    Layout(in_rows, plan->state_label, n_ctas, n_warps, &plan->fwd);
-    Layout(out_rows, plan->state_label, n_ctas, n_warps, &plan->bwd);
+    // 2. pair detection: two sources that enter a destination with bit-equal weights, counted over destinations
+    std::vector<int> partner(S, -1);
+    {
+        std::vector<std::pair<uint64_t, int>> keys;   // (p1<<32|p2) occurrences
+        std::vector<uint64_t> occ;
+        std::vector<std::pair<uint32_t, int>> tmp;
+        for (size_t q = 0; q < S; ++q) {
+            tmp.clear();
+            for (auto &a : in_s[q]) tmp.emplace_back(Bits(a.w), a.peer);
+            std::sort(tmp.begin(), tmp.end());
+            for (size_t i = 0; i < tmp.size();) {
+                size_t j = i;
+                while (j < tmp.size() && tmp[j].first == tmp[i].first) ++j;
+                if (j - i == 2 && tmp[i].second != tmp[i + 1].second)
+                    occ.push_back(((uint64_t)(uint32_t)tmp[i].second << 32) | (uint32_t)tmp[i + 1].second);
+                i = j;
+            }
+        }
+        std::sort(occ.begin(), occ.end());
+        struct Cand { int count, p1, p2; };
+        std::vector<Cand> cands;
+        for (size_t i = 0; i < occ.size();) {
+            size_t j = i;
+            while (j < occ.size() && occ[j] == occ[i]) ++j;
+            if (j - i >= 2) cands.push_back(Cand{(int)(j - i), (int)(occ[i] >> 32), (int)(occ[i] & 0xffffffffu)});
+            i = j;
+        }
+        std::sort(cands.begin(), cands.end(), [](const Cand &a, const Cand &b) {
+            return a.count != b.count ? a.count > b.count : (a.p1 != b.p1 ? a.p1 < b.p1 : a.p2 < b.p2);
+        });
+        const char *nopair = getenv("CCB_NO_PAIRS");
+        if (!(nopair && nopair[0] == '1'))
+            for (auto &c : cands)
+                if (partner[(size_t)c.p1] < 0 && partner[(size_t)c.p2] < 0) { partner[(size_t)c.p1] = c.p2; partner[(size_t)c.p2] = c.p1; }
+    }
+
+    // 3. groups and final state order ("fid")
+    struct GroupKey { int lab1, lab0, s0, s1; };   // s0 = pos0 sid or -1, s1 = pos1 sid
+    std::vector<GroupKey> gk;
+    for (size_t s = 0; s < S; ++s) {
+        const int o = partner[s];
+        if (o < 0) { gk.push_back(GroupKey{sid_label[s], -1, -1, (int)s}); continue; }
+        if ((int)s > o) continue;   // handle each pair once
+        int a = (int)s, b = o;      // pos0 = smaller label (ties: smaller sid)
+        if (sid_label[(size_t)b] < sid_label[(size_t)a]) std::swap(a, b);
+        gk.push_back(GroupKey{sid_label[(size_t)b], sid_label[(size_t)a], a, b});
+    }
+    std::sort(gk.begin(), gk.end(), [](const GroupKey &x, const GroupKey &y) {
+        if (x.lab1 != y.lab1) return x.lab1 < y.lab1;
+        if (x.lab0 != y.lab0) return x.lab0 < y.lab0;
+        return x.s1 < y.s1;
+    });
+    std::vector<int> fid(S, -1), pair_of(S, -1);
+    plan->state_label.assign(S, 0); plan->state_pos.assign(S, 1); plan->orig_state.assign(S, 0); plan->final_lin.assign(S, 0.f);
+    int next = 0, n_pairs = 0;
+    for (auto &g : gk) {
+        if (g.s0 >= 0) { fid[(size_t)g.s0] = next++; pair_of[(size_t)g.s0] = n_pairs; pair_of[(size_t)g.s1] = n_pairs; }
+        fid[(size_t)g.s1] = next++;
+        if (g.s0 >= 0) ++n_pairs;
+    }
+    for (size_t s = 0; s < S; ++s) {
+        const int f = fid[s];
+        plan->state_label[(size_t)f] = sid_label[s];
+        plan->orig_state[(size_t)f] = sid_orig[s];
+        const float fw = fst.final_logw[(size_t)sid_orig[s]];
+        plan->final_lin[(size_t)f] = std::isinf(fw) ? 0.f : std::exp(fw);
+    }
+    for (auto &g : gk) if (g.s0 >= 0) plan->state_pos[(size_t)fid[(size_t)g.s0]] = 0;
+    plan->file_states = S0;
+    plan->file_arcs = (int)A0;
+    plan->num_states = (int)S;
+    plan->num_pairs = n_pairs;
+    plan->num_labels = max_label + 1;
+    plan->start = fid[(size_t)sid_of[(size_t)fst.start][0]];   // all start mass on one copy (copies share out-arcs)
+    plan->n_ctas = n_ctas;
+    plan->n_warps = n_warps;
+    plan->start_arcs.clear();
+    for (auto &a : out_s[(size_t)sid_of[(size_t)fst.start][0]]) plan->start_arcs.push_back(Arc{(uint32_t)fid[(size_t)a.peer], a.w});
+
+    auto by_peer = [](const Arc &a, const Arc &b) { return a.peer < b.peer; };
+
+    // 4a. forward rows: a pair's two arcs with equal weight become one arc to the pair's virtual row S + j
+    std::vector<Group> fgroups, bgroups;
+    fgroups.reserve(gk.size()); bgroups.reserve(gk.size());
+    struct Ent { int pair; uint32_t wb; int member; int peer_fid; float w; };
+    std::vector<Ent> ents;
+    auto forward_row = [&](int s, std::vector<Arc> *row) {
+        ents.clear();
+        for (auto &a : in_s[(size_t)s]) {
+            const int pj = pair_of[(size_t)a.peer];
+            const int member = pj >= 0 ? plan->state_pos[(size_t)fid[(size_t)a.peer]] : 0;
+            ents.push_back(Ent{pj, Bits(a.w), member, fid[(size_t)a.peer], a.w});
+        }
+        std::sort(ents.begin(), ents.end(), [](const Ent &x, const Ent &y) {
+            if (x.pair != y.pair) return x.pair < y.pair;
+            if (x.wb != y.wb) return x.wb < y.wb;
+            return x.member < y.member;
+        });
+        row->clear();
+        for (size_t i = 0; i < ents.size();) {
+            if (ents[i].pair < 0) { row->push_back(Arc{(uint32_t)ents[i].peer_fid, ents[i].w}); ++i; continue; }
+            size_t j = i;
+            int n0 = 0, n1 = 0;
+            while (j < ents.size() && ents[j].pair == ents[i].pair && ents[j].wb == ents[i].wb) { (ents[j].member ? n1 : n0)++; ++j; }
+            const int merged = std::min(n0, n1);
+            for (int k = 0; k < merged; ++k) row->push_back(Arc{(uint32_t)(S + (size_t)ents[i].pair), ents[i].w});
+            // leftovers keep their own rows: member-0 entries come first in [i, j)
+            for (int k = merged; k < n0; ++k) row->push_back(Arc{(uint32_t)ents[i + (size_t)k].peer_fid, ents[i].w});
+            for (int k = merged; k < n1; ++k) row->push_back(Arc{(uint32_t)ents[i + (size_t)n0 + (size_t)k].peer_fid, ents[i].w});
+            i = j;
+        }
+        std::sort(row->begin(), row->end(), by_peer);
+    };
+    // 4b. backward: out-arcs of a pair split into common (same destination, bit-equal weight) and private parts
+    struct OEnt { int q; uint32_t wb; float w; };
+    auto out_list = [&](int s, std::vector<OEnt> *l) {
+        l->clear();
+        for (auto &a : out_s[(size_t)s]) l->push_back(OEnt{fid[(size_t)a.peer], Bits(a.w), a.w});
+        std::sort(l->begin(), l->end(), [](const OEnt &x, const OEnt &y) { return x.q != y.q ? x.q < y.q : x.wb < y.wb; });
+    };
+    std::vector<OEnt> l0, l1;
+    for (auto &g : gk) {
+        Group fg, bg;
+        fg.first_state = bg.first_state = g.s0 >= 0 ? fid[(size_t)g.s0] : fid[(size_t)g.s1];
+        fg.rows = bg.rows = g.s0 >= 0 ? 2 : 1;
+        fg.pairs = bg.pairs = g.s0 >= 0 ? 1 : 0;
+        if (g.s0 < 0) {
+            Segment f, b;
+            forward_row(g.s1, &f.arcs);
+            f.event = kEvRow;
+            out_list(g.s1, &l1);
+            for (auto &e : l1) b.arcs.push_back(Arc{(uint32_t)e.q, e.w});
+            b.event = kEvRow;
+            fg.segs.push_back(std::move(f));
+            bg.segs.push_back(std::move(b));
+        } else {
+            Segment f0, f1, bc, b0, b1;
+            forward_row(g.s0, &f0.arcs); f0.event = kEvRowPos0;
+            forward_row(g.s1, &f1.arcs); f1.event = kEvRowPos1;
+            out_list(g.s0, &l0);
+            out_list(g.s1, &l1);
+            size_t i = 0, j = 0;
+            while (i < l0.size() || j < l1.size()) {
+                if (i < l0.size() && j < l1.size() && l0[i].q == l1[j].q && l0[i].wb == l1[j].wb) {
+                    bc.arcs.push_back(Arc{(uint32_t)l0[i].q, l0[i].w}); ++i; ++j;
+                } else if (j >= l1.size() || (i < l0.size() && (l0[i].q < l1[j].q || (l0[i].q == l1[j].q && l0[i].wb < l1[j].wb)))) {
+                    b0.arcs.push_back(Arc{(uint32_t)l0[i].q, l0[i].w}); ++i;
+                } else {
+                    b1.arcs.push_back(Arc{(uint32_t)l1[j].q, l1[j].w}); ++j;
+                }
+            }
+            bc.event = kEvCommon; b0.event = kEvRowPos0; b1.event = kEvRowPos1;
+            fg.segs.push_back(std::move(f0)); fg.segs.push_back(std::move(f1));
+            if (!bc.arcs.empty()) bg.segs.push_back(std::move(bc));
+            bg.segs.push_back(std::move(b0)); bg.segs.push_back(std::move(b1));
+        }
+        fgroups.push_back(std::move(fg));
+        bgroups.push_back(std::move(bg));
+    }
+    // row costs in arc units, fitted to per-warp timelines on B200 (tools/timeline.py)
+    Layout(fgroups, (int)S, plan->state_label, plan->state_pos, n_ctas, n_warps, 4, &plan->fwd);
+    Layout(bgroups, (int)S, plan->state_label, plan->state_pos, n_ctas, n_warps, 10, &plan->bwd);
     return true;
 }
 

@@ -11,17 +11,22 @@
 namespace ccb {
 
 // One arc as the kernels read it: 8 bytes, broadcast-loaded from shared memory two at a time (LDS.128).
-//   peer : state id the kernel gathers from (source state for the forward pass, destination state for the
-//          backward pass).
-//   w    : arc weight in the LINEAR domain, exp(-tropical weight), always >= 0.  Rows are padded with
-//          zero-weight arcs (peer 0) to whole QUADS of 4 arcs; the SIGN BIT of the 4th weight of a quad is set
-//          when the quad is the last one of its row (tested once per quad, applied as |w| in the FMA).
+//   peer : row of the gather table the arc reads: a state id (< S) or, in the forward pass, S + j for the
+//          virtual row of pair j (the sum of the pair's two alphas, see DenPlan).
+//   w    : arc weight in the LINEAR domain, exp(-tropical weight), always >= 0.  Arc segments are padded with
+//          zero-weight arcs to whole QUADS of 4 arcs.  SIGN BITS of the last quad of a segment carry the event
+//          (applied as |w| in the FMA): sign(w[3]) = "a segment ends here", sign(w[2]):sign(w[1]) = event code.
 struct alignas(8) Arc {
     uint32_t peer;
     float w;
 };
-static constexpr int kQuad = 4;          // arcs per quad (row padding granule)
+static constexpr int kQuad = 4;          // arcs per quad (segment padding granule)
 static constexpr int kChunkArcPad = 16;  // every warp chunk's arc count is padded to a multiple of this
+// event codes
+static constexpr int kEvRow = 0;         // end of the row of an unpaired state
+static constexpr int kEvRowPos0 = 1;     // end of the row of the first member of a pair
+static constexpr int kEvRowPos1 = 2;     // end of the row of the second member of a pair
+static constexpr int kEvCommon = 3;      // backward only: end of the arcs the two members of a pair share
 
 // Den graph as stored in the file, in the view fst_read.cc:40-59 gives the kernels.
 struct HostFst {
@@ -35,28 +40,32 @@ struct HostFst {
 // Returns false and fills err on failure (never exits, unlike den_calculate.cu:16-25,331-334).
 bool ReadFstFile(const char *path, HostFst *out, std::string *err);
 
-// Pass-specific half of the plan: rows are states (in the renumbered order), a row's arcs are the arcs the
-// pass sums over (in-arcs for forward, out-arcs for backward).  chunk_* cut the rows into
-// n_ctas*n_warps contiguous chunks of near-equal cost; CTA c owns chunks [c*n_warps, (c+1)*n_warps).
+// Pass-specific half of the plan: a chunk-major stream of arc segments.  chunk_* cut the states (whole groups)
+// into n_ctas*n_warps contiguous chunks of near-equal cost; CTA c owns chunks [c*n_warps, (c+1)*n_warps).
 struct PassPlan {
-    std::vector<Arc> arcs;              // chunk-major: rows as whole quads, chunk tails padded with unflagged zero quads
+    std::vector<Arc> arcs;              // chunk-major: segments as whole quads, chunk tails padded with unflagged zero quads
     std::vector<int> chunk_state;       // [n_chunks+1] first state of each chunk
     std::vector<int> chunk_arc;         // [n_chunks+1] first arc of each chunk (multiples of kChunkArcPad)
-    int real_arcs = 0;                  // arcs of the graph in this pass (before padding)
+    std::vector<int> chunk_pair;        // [n_chunks+1] first pair (virtual row) of each chunk
+    std::vector<int> cta_labels;        // [n_ctas][4] = {min label of pos0 rows, #labels, min label of other rows, #labels}
+    int real_arcs = 0;                  // arcs in this pass's stream (before padding)
     int max_tile_arcs = 0;              // max arcs owned by one CTA
-    int max_tile_labels = 0;            // max (label range + 1) over CTAs
-    int max_tile_rows = 0;              // max rows owned by one CTA
+    int max_tile_labels = 0;            // max rows of the per-CTA label accumulator (both ranges)
+    int max_tile_rows = 0;              // max states owned by one CTA
 };
 
 struct DenPlan {
     int file_states = 0, file_arcs = 0;
-    int num_states = 0;                 // after in-label split
+    int num_states = 0;                 // S: states after the in-label split
+    int num_pairs = 0;                  // P: paired states = 2P; virtual rows S..S+P-1 in the forward gather table
     int start = 0;                      // renumbered start state
     int num_labels = 0;                 // max label + 1
     int n_ctas = 0, n_warps = 0;
     std::vector<int> state_label;       // [S] the single label carried by every arc INTO the state
+    std::vector<int> state_pos;         // [S] 0 = first member of a pair, 1 = second member or unpaired
     std::vector<float> final_lin;       // [S] exp(final_logw) (0 for non-final)
     std::vector<int> orig_state;        // [S] state id in the file
+    std::vector<Arc> start_arcs;        // out-arcs of the start state (plain), for logZ recomputed from beta
     PassPlan fwd, bwd;
 };
 
@@ -67,9 +76,16 @@ struct DenPlan {
 //         alpha_t(q) = y_{t-1}[lab(q)] * sum_p w_pq alpha_{t-1}(p)
 //     and turns the per-arc atomic gradient of den_calculate.cu:219-223 into a per-state product
 //         gamma_t[k] = sum_{q: lab(q)=k} alpha_{t+1}(q) beta_{t+1}(q) / Z.
-//  2. renumber states sorted by label (so a CTA tile spans very few labels);
-//  3. build in-arc and out-arc rows with linear-domain weights;
-//  4. cut rows into cost-balanced chunks for an n_ctas x n_warps persistent grid.
+//  2. PAIR states that feed the same destinations with bit-equal weights (in a T-compose-LM graph the blank and
+//     label twins (h,B),(h,L) of an LM history h: ~all their out-arcs).  For a pair (p0,p1) with common
+//     destinations C: the forward pass gathers ONE virtual row alpha(p0)+alpha(p1) per destination in C instead of
+//     two rows; the backward pass sums the arcs into C once and reuses the partial sum for both members.  Exact
+//     (sums are regrouped, nothing is approximated) and generic (pairs are found from the arc lists; an unpaired
+//     state is a group of one).  Halves the gathers of a T-compose-LM graph.
+//  3. order states group by group (pairs adjacent: p0 then p1), groups sorted by the label of their last member,
+//     so a CTA tile spans few labels;
+//  4. emit the forward (in-arc) and backward (out-arc) segment streams with linear-domain weights and cut them
+//     into cost-balanced chunks for an n_ctas x n_warps persistent grid.
 bool BuildDenPlan(const HostFst &fst, int n_ctas, int n_warps, DenPlan *plan, std::string *err);
 
 }  // namespace ccb

@@ -105,12 +105,12 @@ __global__ void frame_max_kernel(const void *y, int bf16, long sn, long st, int 
 //   * arcs come two per LDS.128 (SMEM_ARCS) as {byte offset of the gathered row, weight};
 //   * BATCH row gathers (ld.global.cg, 32*U*4 bytes each, one per arc) are issued for batch k+1 BEFORE batch k
 //     is consumed, so a warp keeps BATCH..2*BATCH loads in flight (the recursion is latency-bound on L2);
-//   * weights are applied as |w|; the sign bit of a quad's 4th weight marks the end of a row, at which point
-//     `row_end(acc)` runs (warp-uniform branch) and the accumulators restart.
+//   * weights are applied as |w|; the sign bit of a quad's 4th weight marks the end of a segment and the sign bits
+//     of its 3rd/2nd weights the event code (den_graph.h kEv*): `seg_end(acc, event)` runs (warp-uniform branch).
 // ------------------------------------------------------------------------------------------------
-template <int U, int BATCH, bool SMEM_ARCS, typename RowEnd>
+template <int U, int BATCH, bool SMEM_ARCS, typename SegEnd>
 __device__ __forceinline__ void walk_arcs(const Arc *s_arcs, const Arc *g_arcs, int ab, int ae, int tile_a0,
-                                          uint32_t row_bytes, const char *lane_base, bool do_load, RowEnd &&row_end) {
+                                          uint32_t row_bytes, const char *lane_base, bool do_load, SegEnd &&seg_end) {
     Vec<U> vA[BATCH], vB[BATCH];
     float acc[U];
 #pragma unroll
@@ -140,11 +140,8 @@ __device__ __forceinline__ void walk_arcs(const Arc *s_arcs, const Arc *g_arcs, 
                 acc[u] = fmaf(w2, v[g4 * kQuad + 2].v[u], acc[u]);
                 acc[u] = fmaf(w3, v[g4 * kQuad + 3].v[u], acc[u]);
             }
-            if ((int)m1.w < 0) {   // warp-uniform: this quad ends a row
-                row_end(acc);
-#pragma unroll
-                for (int u = 0; u < U; ++u) acc[u] = 0.f;
-            }
+            if ((int)m1.w < 0)   // warp-uniform: a segment ends at this quad; the callback owns the accumulators
+                seg_end(acc, (int)(((m1.y >> 31) << 1) | (m0.w >> 31)));
         }
     };
 
@@ -199,9 +196,12 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const DenParams P) {
     const int tile_a1 = __ldg(P.chunk_arc + (cta + 1) * P.n_warps);
     const int tile_s0 = __ldg(P.chunk_state + cta * P.n_warps);
     const int tile_s1 = __ldg(P.chunk_state + (cta + 1) * P.n_warps);
+    const int vj0 = __ldg(P.chunk_pair + chunk);   // first virtual (pair-sum) row written by this warp
     const int S = P.S, Npad = P.Npad;
-    const size_t frame_elems = (size_t)S * Npad;
-    const int lab0 = se > sb ? __ldg(P.state_label + sb) : 0;
+    const size_t frame_elems = (size_t)(S + P.num_pairs) * Npad;   // real rows, then one virtual row per pair
+    // first label of each row position in this chunk (pair first members / everything else): emission prefetch
+    int labp[2] = {-1, -1};
+    for (int q = se - 1; q >= sb; --q) labp[__ldg(P.state_pos + q) ? 1 : 0] = __ldg(P.state_label + q);
     unsigned epoch = 0;
 
     // per-row metadata lives in shared memory: L1 is invalidated at every grid barrier, and a global load on the
@@ -217,9 +217,19 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const DenParams P) {
     }
     for (int i = tid; i < Npad; i += NT) s_sum[i] = 0.f;
 
-    // t = 0: alpha_0 = indicator(start); column sum 1
+    // t = 0: alpha_0 = indicator(start) (virtual rows: the pair sum); column sum 1
     for (int q = sb; q < se; ++q)
         for (int n = lane; n < Npad; n += 32) __stcg(P.alpha + (size_t)q * Npad + n, q == P.start ? 1.f : 0.f);
+    {
+        int vj = vj0;
+        for (int q = sb; q < se; ++q) {
+            if (__ldg(P.state_pos + q) == 0) {   // q, q+1 are a pair
+                const float v = (q == P.start || q + 1 == P.start) ? 1.f : 0.f;
+                for (int n = lane; n < Npad; n += 32) __stcg(P.alpha + (size_t)(S + vj) * Npad + n, v);
+                ++vj;
+            }
+        }
+    }
     if (cta == 0) for (int n = tid; n < Npad; n += NT) __stcg(P.colsum_a + n, 1.f);
     const int my_len = (cta == 0 && tid < P.N) ? __ldg(P.len + tid) : 0;   // CTA 0 keeps log-scale books
     int len0[U];   // lengths of this lane's utterances in lane group 0 (the only group for N <= 32*U)
@@ -243,37 +253,52 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const DenParams P) {
                 lane_act |= act[u];
             }
             if (!__any_sync(kFull, lane_act)) continue;
-            float r[U], fm[U], e[U], sum[U], ypre[U];
+            float r[U], fm[U], sum[U], ypre[2][U], ec[2][U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 int sh;
                 r[u] = scale_from_sum(__ldcg(P.colsum_a + (size_t)(t - 1) * Npad + n0 + u), &sh);
                 fm[u] = act[u] ? __ldg(P.fmax + (size_t)(t - 1) * Npad + n0 + u) : 0.f;
-                // emission of the chunk's first label: issued now, consumed at the first row end
-                ypre[u] = act[u] ? load_y(P.y, P.y_bf16, (n0 + u) * P.sn + (long)(t - 1) * P.st + lab0) : 0.f;
-                e[u] = 0.f; sum[u] = 0.f;
+                // emissions of the chunk's first labels: issued now, consumed at the first row ends
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    ypre[k][u] = (act[u] && labp[k] >= 0) ? load_y(P.y, P.y_bf16, (n0 + u) * P.sn + (long)(t - 1) * P.st + labp[k]) : 0.f;
+                    ec[k][u] = 0.f;
+                }
+                sum[u] = 0.f;
             }
-            int q = sb, curlab = -1;
+            int q = sb, vj = vj0;
+            int curlab[2] = {-1, -1};
+            Vec<U> cacc = vec_zero<U>();
             walk_arcs<U, BATCH, SMEM_ARCS>(s_arcs, P.arcs, ab, ae, tile_a0, row_bytes,
-                                           reinterpret_cast<const char *>(a_prev + n0), lane_act, [&](const float *acc) {
-                if (P.debug & 1) { sum[0] += acc[0]; ++q; return; }
+                                           reinterpret_cast<const char *>(a_prev + n0), lane_act, [&](float *acc, int ev) {
+                const int k = ev == kEvRowPos0 ? 0 : 1;
+                if (P.debug & 1) { sum[0] += acc[0]; ++q; acc[0] = 0.f; return; }
                 const int lab = s_label[q - tile_s0];
-                if (lab != curlab) {
-                    curlab = lab;
+                if (lab != curlab[k]) {
+                    curlab[k] = lab;
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
-                        const float yv = (lab == lab0) ? ypre[u]
+                        const float yv = (lab == labp[k]) ? ypre[k][u]
                                          : (act[u] ? load_y(P.y, P.y_bf16, (n0 + u) * P.sn + (long)(t - 1) * P.st + lab) : 0.f);
-                        e[u] = act[u] ? expf(yv - fm[u]) : 0.f;
+                        ec[k][u] = act[u] ? expf(yv - fm[u]) : 0.f;
                     }
                 }
                 Vec<U> out;
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    out.v[u] = act[u] ? acc[u] * e[u] * r[u] : 0.f;
+                    out.v[u] = act[u] ? acc[u] * ec[k][u] * r[u] : 0.f;
                     sum[u] += out.v[u];
+                    acc[u] = 0.f;
                 }
                 if (lane_act) out.stcg(a_cur + (size_t)q * Npad + n0);
+                if (ev == kEvRowPos0) cacc = out;
+                else if (ev == kEvRowPos1) {   // the pair's virtual row: what the next frame gathers instead of both
+#pragma unroll
+                    for (int u = 0; u < U; ++u) cacc.v[u] += out.v[u];
+                    if (lane_act) cacc.stcg(a_cur + (size_t)(S + vj) * Npad + n0);
+                    ++vj;
+                }
                 ++q;
             });
 #pragma unroll
@@ -303,7 +328,7 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const DenParams P) {
         if (ln >= 0) {
             for (int q = sb; q < se; ++q) {
                 const float f = __ldg(P.final_lin + q);
-                if (f != 0.f) zs = fmaf(f, __ldcg(P.alpha + ((size_t)ln * S + q) * Npad + n), zs);
+                if (f != 0.f) zs = fmaf(f, __ldcg(P.alpha + (size_t)ln * frame_elems + (size_t)q * Npad + n), zs);
             }
         }
         if (zs != 0.f) atomicAdd(&s_sum[n], zs);
@@ -340,11 +365,14 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const DenParams P) 
     const int tile_a1 = __ldg(P.chunk_arc + (cta + 1) * P.n_warps);
     const int tile_s0 = __ldg(P.chunk_state + cta * P.n_warps);
     const int tile_s1 = __ldg(P.chunk_state + (cta + 1) * P.n_warps);
-    const int tile_lab0 = tile_s1 > tile_s0 ? __ldg(P.state_label + tile_s0) : 0;
-    const int tile_labs = tile_s1 > tile_s0 ? __ldg(P.state_label + tile_s1 - 1) - tile_lab0 + 1 : 0;
-    const int lab0 = se > sb ? __ldg(P.state_label + sb) : 0;
+    // label accumulator rows of this CTA: [cl_n0 labels from cl_lab0 (pair first members)] [cl_n1 from cl_lab1 (others)]
+    const int cl_lab0 = __ldg(P.cta_labels + cta * 4), cl_n0 = __ldg(P.cta_labels + cta * 4 + 1);
+    const int cl_lab1 = __ldg(P.cta_labels + cta * 4 + 2), cl_n1 = __ldg(P.cta_labels + cta * 4 + 3);
+    int labp[2] = {-1, -1};
+    for (int q = se - 1; q >= sb; --q) labp[__ldg(P.state_pos + q) ? 1 : 0] = __ldg(P.state_label + q);
     const bool use_gacc = P.gacc_rows > 0;
-    const size_t frame_elems = (size_t)S * Npad;
+    const size_t frame_elems = (size_t)S * Npad;                         // beta ping-pong: real rows only
+    const size_t alpha_frame = (size_t)(S + P.num_pairs) * Npad;          // alpha spill: real + virtual rows
     unsigned epoch = 0;
 
     for (int i = tid; i < tile_s1 - tile_s0; i += NT) {
@@ -371,9 +399,9 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const DenParams P) 
         tl_mark(P, P.Tmax - tau, chunk, n_chunks, 0, lane);
         const float *bh_next = P.bh + (size_t)((tau + 1) & 1) * frame_elems;
         float *bh_cur = P.bh + (size_t)(tau & 1) * frame_elems;
-        const float *a_row = P.alpha + (size_t)tau * frame_elems;
+        const float *a_row = P.alpha + (size_t)tau * alpha_frame;
         if (tau > 1 && se > sb) {   // pull next step's alpha rows of this chunk towards L2
-            const char *nb = reinterpret_cast<const char *>(a_row - frame_elems + (size_t)sb * Npad);
+            const char *nb = reinterpret_cast<const char *>(a_row - alpha_frame + (size_t)sb * Npad);
             const size_t bytes = (size_t)(se - sb) * Npad * 4;
             for (size_t off = (size_t)lane * 128; off < bytes; off += 32 * 128) prefetch_l2(nb + off);
         }
@@ -390,39 +418,51 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const DenParams P) 
                 lane_gat |= gat[u];
             }
             if (!__any_sync(kFull, lane_act)) continue;
-            float rb[U], fm[U], e[U], sum_b[U], sum_ab[U], gsum[U], ypre[U];
+            float rb[U], fm[U], sum_b[U], sum_ab[U], gsum[2][U], ypre[2][U], ec[2][U], acc_c[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 int sh;
                 rb[u] = gat[u] ? scale_from_sum(__ldcg(P.colsum_b + (size_t)(tau + 1) * Npad + n0 + u), &sh) : 1.f;
                 fm[u] = act[u] ? __ldg(P.fmax + (size_t)(tau - 1) * Npad + n0 + u) : 0.f;
-                ypre[u] = act[u] ? load_y(P.y, P.y_bf16, (n0 + u) * P.sn + (long)(tau - 1) * P.st + lab0) : 0.f;
-                e[u] = 0.f; sum_b[u] = 0.f; sum_ab[u] = 0.f; gsum[u] = 0.f;
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    ypre[k][u] = (act[u] && labp[k] >= 0) ? load_y(P.y, P.y_bf16, (n0 + u) * P.sn + (long)(tau - 1) * P.st + labp[k]) : 0.f;
+                    ec[k][u] = 0.f; gsum[k][u] = 0.f;
+                }
+                sum_b[u] = 0.f; sum_ab[u] = 0.f; acc_c[u] = 0.f;
             }
-            int q = sb, curlab = -1;
+            int q = sb;
+            int curlab[2] = {-1, -1};
             Vec<U> a_q = (se > sb && lane_act) ? Vec<U>::ldcg(a_row + (size_t)sb * Npad + n0) : vec_zero<U>();
-            auto flush_gsum = [&]() {
+            auto flush_gsum = [&](int k) {
+                const int row = k == 0 ? curlab[0] - cl_lab0 : cl_n0 + curlab[1] - cl_lab1;
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    if (gsum[u] != 0.f) {
-                        if (use_gacc) atomicAdd(&s_gacc[(curlab - tile_lab0) * Npad + n0 + u], gsum[u]);
-                        else atomicAdd(P.grad + (n0 + u) * P.gsn + (long)(tau - 1) * P.gst + curlab, gsum[u]);
+                    if (gsum[k][u] != 0.f) {
+                        if (use_gacc) atomicAdd(&s_gacc[row * Npad + n0 + u], gsum[k][u]);
+                        else atomicAdd(P.grad + (n0 + u) * P.gsn + (long)(tau - 1) * P.gst + curlab[k], gsum[k][u]);
                     }
-                    gsum[u] = 0.f;
+                    gsum[k][u] = 0.f;
                 }
             };
             walk_arcs<U, BATCH, SMEM_ARCS>(s_arcs, P.arcs, ab, ae, tile_a0, row_bytes,
-                                           reinterpret_cast<const char *>(bh_next + n0), lane_gat, [&](const float *acc) {
-                if (P.debug & 1) { sum_b[0] += acc[0]; ++q; return; }
+                                           reinterpret_cast<const char *>(bh_next + n0), lane_gat, [&](float *acc, int ev) {
+                if (ev == kEvCommon) {   // arcs shared by both members of a pair: keep the partial sum, keep accumulating
+#pragma unroll
+                    for (int u = 0; u < U; ++u) acc_c[u] = acc[u];
+                    return;
+                }
+                const int k = ev == kEvRowPos0 ? 0 : 1;
+                if (P.debug & 1) { sum_b[0] += acc[0]; ++q; acc[0] = 0.f; return; }
                 const int lab = s_label[q - tile_s0];
-                if (lab != curlab) {
-                    if (curlab >= 0) flush_gsum();
-                    curlab = lab;
+                if (lab != curlab[k]) {
+                    if (curlab[k] >= 0) flush_gsum(k);
+                    curlab[k] = lab;
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
-                        const float yv = (lab == lab0) ? ypre[u]
+                        const float yv = (lab == labp[k]) ? ypre[k][u]
                                          : (act[u] ? load_y(P.y, P.y_bf16, (n0 + u) * P.sn + (long)(tau - 1) * P.st + lab) : 0.f);
-                        e[u] = act[u] ? expf(yv - fm[u]) : 0.f;
+                        ec[k][u] = act[u] ? expf(yv - fm[u]) : 0.f;
                     }
                 }
                 const float f = s_final[q - tile_s0];
@@ -431,16 +471,20 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const DenParams P) 
                 for (int u = 0; u < U; ++u) {
                     const float b = act[u] ? (gat[u] ? acc[u] * rb[u] : f) : 0.f;
                     const float abp = act[u] ? a_q.v[u] * b : 0.f;
-                    gsum[u] += abp;
+                    gsum[k][u] += abp;
                     sum_ab[u] += abp;
-                    out.v[u] = e[u] * b;
+                    out.v[u] = ec[k][u] * b;
                     sum_b[u] += out.v[u];
+                    // first member of a pair: the second member restarts from the shared partial sum
+                    acc[u] = ev == kEvRowPos0 ? acc_c[u] : 0.f;
+                    if (ev != kEvRowPos0) acc_c[u] = 0.f;
                 }
                 if (lane_act) out.stcg(bh_cur + (size_t)q * Npad + n0);
                 ++q;
                 a_q = (q < se && lane_act) ? Vec<U>::ldcg(a_row + (size_t)q * Npad + n0) : vec_zero<U>();
             });
-            if (curlab >= 0) flush_gsum();
+            if (curlab[0] >= 0) flush_gsum(0);
+            if (curlab[1] >= 0) flush_gsum(1);
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 if (act[u]) {
@@ -457,10 +501,11 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const DenParams P) 
             if (vab != 0.f) { atomicAdd(P.absum + (size_t)tau * Npad + i, vab); s_sum[Npad + i] = 0.f; }
         }
         if (use_gacc) {
-            for (int i = tid; i < tile_labs * Npad; i += NT) {
+            for (int i = tid; i < (cl_n0 + cl_n1) * Npad; i += NT) {
                 const float g = s_gacc[i];
                 if (g != 0.f) {
-                    const int n = i % Npad, k = tile_lab0 + i / Npad;
+                    const int n = i % Npad, row = i / Npad;
+                    const int k = row < cl_n0 ? cl_lab0 + row : cl_lab1 + row - cl_n0;
                     atomicAdd(P.grad + n * P.gsn + (long)(tau - 1) * P.gst + k, g);
                     s_gacc[i] = 0.f;
                 }
@@ -477,7 +522,7 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const DenParams P) 
     }
 
     // tau = 0: beta_0(start) only -> logZ recomputed from the backward pass (den_calculate.cu:177-187,255-261)
-    if (P.start >= sb && P.start < se) {
+    if (cta == 0 && warp == 0) {
         const float *bh1 = P.bh + (size_t)(1 & 1) * frame_elems;
         for (int n = lane; n < P.N; n += 32) {
             const int ln = __ldg(P.len + n);
@@ -486,9 +531,9 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const DenParams P) 
                 int sh;
                 const float rb = scale_from_sum(__ldcg(P.colsum_b + (size_t)1 * Npad + n), &sh);
                 float acc = 0.f;
-                for (int a = P.start_row_begin; a < P.start_row_end; ++a) {
-                    const Arc k = P.arcs[a];
-                    acc = fmaf(fabsf(k.w), __ldcg(bh1 + (size_t)k.peer * Npad + n), acc);
+                for (int a = 0; a < P.n_start_arcs; ++a) {
+                    const Arc k = P.start_arcs[a];
+                    acc = fmaf(k.w, __ldcg(bh1 + (size_t)k.peer * Npad + n), acc);
                 }
                 b = acc * rb;
             }
@@ -605,6 +650,7 @@ int LaunchFrameMax(const void *y, int y_bf16, long sn, long st, int N, int T, in
 
 int LaunchDenForward(const DeviceGraph &g, DenParams p, cudaStream_t stream, std::string *err) {
     p.arcs = g.fwd.arcs; p.chunk_state = g.fwd.chunk_state; p.chunk_arc = g.fwd.chunk_arc;
+    p.chunk_pair = g.fwd.chunk_pair; p.cta_labels = g.fwd.cta_labels;
     p.gacc_rows = 0;
     p.tile_rows = g.fwd.max_tile_rows;
     const size_t fixed = (((size_t)(p.Npad + p.tile_rows) * 4 + 15) & ~(size_t)15);
@@ -613,6 +659,7 @@ int LaunchDenForward(const DeviceGraph &g, DenParams p, cudaStream_t stream, std
 
 int LaunchDenBackward(const DeviceGraph &g, DenParams p, cudaStream_t stream, std::string *err) {
     p.arcs = g.bwd.arcs; p.chunk_state = g.bwd.chunk_state; p.chunk_arc = g.bwd.chunk_arc;
+    p.chunk_pair = g.bwd.chunk_pair; p.cta_labels = g.bwd.cta_labels;
     // label accumulator in shared memory when the per-CTA label range is small enough
     size_t gacc_bytes = (size_t)g.bwd.max_tile_labels * p.Npad * 4;
     p.gacc_rows = gacc_bytes <= 64 * 1024 ? g.bwd.max_tile_labels : 0;

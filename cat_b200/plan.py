@@ -12,8 +12,9 @@ import numpy as np
 
 from . import _lib
 
-QUAD = 4            # rows are padded to whole quads of arcs (den_graph.h kQuad)
+QUAD = 4            # arc segments are padded to whole quads (den_graph.h kQuad)
 CHUNK_ARC_PAD = 16  # chunk arc counts are padded to a multiple of this (kChunkArcPad)
+EV_ROW, EV_ROW_POS0, EV_ROW_POS1, EV_COMMON = 0, 1, 2, 3   # den_graph.h kEv*
 ARC_DTYPE = np.dtype([("peer", "<u4"), ("w", "<f4")])
 
 
@@ -22,19 +23,23 @@ class PassView:
     arcs: np.ndarray          # ARC_DTYPE [A]
     chunk_state: np.ndarray   # int32 [n_chunks+1]
     chunk_arc: np.ndarray     # int32 [n_chunks+1]
-
-    def row_ends(self) -> np.ndarray:
-        """Arc index one past each row: rows end at quads whose 4th weight has its sign bit set."""
-        w4 = self.arcs["w"][QUAD - 1::QUAD]
-        return (np.nonzero(np.signbit(w4))[0] + 1) * QUAD
-
-    def row_of_arc(self) -> np.ndarray:
-        """Row id of every arc slot (chunk-tail padding quads attach to the following row, weight 0)."""
-        ends = self.row_ends()
-        return np.searchsorted(ends, np.arange(len(self.arcs)), side="right")
+    chunk_pair: np.ndarray    # int32 [n_chunks+1]
+    cta_labels: np.ndarray    # int32 [n_ctas, 4]
 
     def weights(self) -> np.ndarray:
         return np.abs(self.arcs["w"])
+
+    def segments(self):
+        """Decode the stream the way the kernels walk it: yields (arc_begin, arc_end, event) per segment.
+        Chunk-tail padding quads (unflagged, weight 0) attach to the following segment."""
+        w = self.arcs["w"].reshape(-1, QUAD)
+        sign = np.signbit(w)
+        ends = np.nonzero(sign[:, 3])[0]
+        ev = (sign[ends, 2].astype(int) << 1) | sign[ends, 1].astype(int)
+        begin = 0
+        for e, v in zip(ends, ev):
+            yield begin * QUAD, (e + 1) * QUAD, int(v)
+            begin = e + 1
 
 
 @dataclass
@@ -42,14 +47,17 @@ class PlanView:
     file_states: int
     file_arcs: int
     num_states: int
+    num_pairs: int
     start: int
     num_labels: int
     n_ctas: int
     n_warps: int
     max_tile_arcs: int
     state_label: np.ndarray
+    state_pos: np.ndarray
     final_lin: np.ndarray
     orig_state: np.ndarray
+    start_arcs: np.ndarray
     fwd: PassView
     bwd: PassView
 
@@ -60,9 +68,9 @@ def load_plan(path: str, n_ctas: int = 148, n_warps: int = 16) -> PlanView:
     if not h:
         raise RuntimeError(_lib.last_error())
     try:
-        info = (C.c_long * 10)()
+        info = (C.c_long * 12)()
         assert L.ccb_plan_info(h, info) == 0
-        S0, A0, S, Af, Ab, start, nl, nc, nw, mta = [int(x) for x in info]
+        S0, A0, S, Af, Ab, start, nl, nc, nw, mta, P, nsa = [int(x) for x in info]
         n_chunks = nc * nw
 
         def get(which, dtype, count):
@@ -71,9 +79,12 @@ def load_plan(path: str, n_ctas: int = 148, n_warps: int = 16) -> PlanView:
             assert rc == 0, f"ccb_plan_copy({which}) -> {rc}"
             return a
 
-        return PlanView(S0, A0, S, start, nl, nc, nw, mta,
-                        get(0, np.int32, S), get(1, np.float32, S), get(2, np.int32, S),
-                        PassView(get(3, ARC_DTYPE, Af), get(4, np.int32, n_chunks + 1), get(5, np.int32, n_chunks + 1)),
-                        PassView(get(6, ARC_DTYPE, Ab), get(7, np.int32, n_chunks + 1), get(8, np.int32, n_chunks + 1)))
+        return PlanView(S0, A0, S, P, start, nl, nc, nw, mta,
+                        get(0, np.int32, S), get(9, np.int32, S), get(1, np.float32, S), get(2, np.int32, S),
+                        get(12, ARC_DTYPE, nsa),
+                        PassView(get(3, ARC_DTYPE, Af), get(4, np.int32, n_chunks + 1), get(5, np.int32, n_chunks + 1),
+                                 get(10, np.int32, n_chunks + 1), get(13, np.int32, nc * 4).reshape(nc, 4)),
+                        PassView(get(6, ARC_DTYPE, Ab), get(7, np.int32, n_chunks + 1), get(8, np.int32, n_chunks + 1),
+                                 get(11, np.int32, n_chunks + 1), get(14, np.int32, nc * 4).reshape(nc, 4)))
     finally:
         L.ccb_plan_destroy(h)

@@ -17,12 +17,56 @@ def _scale(s):
     return 2.0 ** (SCALE_EXP - ex), SCALE_EXP - ex
 
 
-def _rows(passview):
-    row = passview.row_of_arc()
-    peer = passview.arcs["peer"].astype(np.int64)
-    w = passview.weights().astype(np.float64)
-    keep = row < len(passview.row_ends())     # padding after the very last row belongs to no row
-    return row[keep], peer[keep], w[keep]
+def _decode_forward(plan):
+    """Walk the forward stream like den_forward_kernel: returns (row, peer, w) triples over the gather table of
+    S real rows + P virtual (pair-sum) rows, and for every pair its two member rows."""
+    S = plan.num_states
+    row, peer, w = [], [], []
+    pairs = []
+    q = 0
+    arcs = plan.fwd.arcs
+    for a0, a1, ev in plan.fwd.segments():
+        assert ev != 3, "kEvCommon must not appear in the forward stream"
+        n = a1 - a0
+        row.append(np.full(n, q)); peer.append(arcs["peer"][a0:a1].astype(np.int64)); w.append(np.abs(arcs["w"][a0:a1]).astype(np.float64))
+        if ev == 1:
+            assert plan.state_pos[q] == 0
+            pos0 = q
+        else:
+            assert plan.state_pos[q] == 1
+            if ev == 2:
+                assert pos0 == q - 1
+                pairs.append((pos0, q))
+        q += 1
+    assert q == S and len(pairs) == plan.num_pairs
+    return np.concatenate(row), np.concatenate(peer), np.concatenate(w), np.array(pairs, dtype=np.int64).reshape(-1, 2)
+
+
+def _decode_backward(plan):
+    """Walk the backward stream like den_backward_kernel: common segments count for both members of the pair."""
+    S = plan.num_states
+    row, peer, w = [], [], []
+    q = 0
+    arcs = plan.bwd.arcs
+    pend = None
+    for a0, a1, ev in plan.bwd.segments():
+        pr = arcs["peer"][a0:a1].astype(np.int64); ww = np.abs(arcs["w"][a0:a1]).astype(np.float64)
+        assert (pr < S).all()
+        if ev == 3:
+            assert pend is None
+            pend = (pr, ww)
+            continue
+        n = a1 - a0
+        row.append(np.full(n, q)); peer.append(pr); w.append(ww)
+        if pend is not None:
+            row.append(np.full(len(pend[0]), q)); peer.append(pend[0]); w.append(pend[1])
+        if ev != 1:
+            pend = None
+        else:
+            assert plan.state_pos[q] == 0
+        q += 1
+    assert q == S
+    return np.concatenate(row), np.concatenate(peer), np.concatenate(w)
 
 
 def den_emulate(plan, y, lens):
@@ -31,8 +75,10 @@ def den_emulate(plan, y, lens):
     S = plan.num_states
     lab = plan.state_label.astype(np.int64)
     fin = plan.final_lin.astype(np.float64)
-    frow, fpeer, fw = _rows(plan.fwd)
-    brow, bpeer, bw = _rows(plan.bwd)
+    frow, fpeer, fw, pairs = _decode_forward(plan)
+    brow, bpeer, bw = _decode_backward(plan)
+    P = plan.num_pairs
+    sa = plan.start_arcs
     logz_a = np.zeros(N)
     logz_b = np.zeros(N)
     gamma = np.zeros((N, T, V))
@@ -40,19 +86,23 @@ def den_emulate(plan, y, lens):
         Tn = int(lens[n])
         yn = y[n].astype(np.float64)
         fmax = yn.max(-1)
-        alpha = np.zeros((Tn + 1, S))
+        alpha = np.zeros((Tn + 1, S + P))       # real rows, then the pair-sum rows the next frame gathers
         alpha[0, plan.start] = 1.0
+        if P:
+            alpha[0, S:] = alpha[0, pairs[:, 0]] + alpha[0, pairs[:, 1]]
         colsum = 1.0
         runlog = 0.0
         for t in range(1, Tn + 1):
             r, sh = _scale(colsum)
             acc = np.bincount(frow, weights=fw * alpha[t - 1, fpeer], minlength=S)
             e = np.exp(yn[t - 1, lab] - fmax[t - 1])
-            alpha[t] = acc * e * r
+            alpha[t, :S] = acc * e * r
+            if P:
+                alpha[t, S:] = alpha[t, pairs[:, 0]] + alpha[t, pairs[:, 1]]
             runlog += fmax[t - 1] - sh * np.log(2.0)
-            colsum = alpha[t].sum()
+            colsum = alpha[t, :S].sum()
         with np.errstate(divide="ignore"):
-            logz_a[n] = np.log((alpha[Tn] * fin).sum()) + runlog
+            logz_a[n] = np.log((alpha[Tn, :S] * fin).sum()) + runlog
         # backward
         bh_next = None
         colsum_b = 0.0
@@ -64,7 +114,7 @@ def den_emulate(plan, y, lens):
                 rb, sh = _scale(colsum_b)
                 b = rb * np.bincount(brow, weights=bw * bh_next[bpeer], minlength=S)
                 runlog += fmax[tau] - sh * np.log(2.0)
-            ab = alpha[tau] * b
+            ab = alpha[tau, :S] * b
             tot = ab.sum()
             if tot > 0:
                 gamma[n, tau - 1] = np.bincount(lab, weights=ab, minlength=V)[:V] / tot
@@ -74,8 +124,7 @@ def den_emulate(plan, y, lens):
         if Tn > 0:
             rb, sh = _scale(colsum_b)
             runlog += fmax[0] - sh * np.log(2.0)
-            m = brow == plan.start
-            b0 = rb * (bw[m] * bh_next[bpeer[m]]).sum()
+            b0 = rb * (sa["w"].astype(np.float64) * bh_next[sa["peer"].astype(np.int64)]).sum()
         else:
             b0 = fin[plan.start]
         with np.errstate(divide="ignore"):

@@ -1,0 +1,49 @@
+"""Turns gpurun_out/ artefacts into the tracked summaries under profiles/ (round-tagged).
+   python tools/summarize_profiles.py <tag> <launches.csv> <prof.ncu-rep> <bench.json> [<bench_ref.json>]"""
+import collections, csv, json, os, subprocess, sys
+tag, launches, rep, bench = sys.argv[1:5]
+ref = sys.argv[5] if len(sys.argv) > 5 else None
+out = [f"# {tag}: ncu + bench summary (B200, sm_100a)\n"]
+j = json.load(open(bench))
+out.append("## bench.py line (N=1)\n```json\n" + json.dumps(j, indent=1)[:6000] + "\n```\n")
+if ref and os.path.exists(ref):
+    out.append("## bench.py --impl reference line\n```json\n" + open(ref).read().strip()[:3000] + "\n```\n")
+rows = list(csv.reader(open(launches)))
+hi = [i for i, r in enumerate(rows) if "Kernel Name" in r][0]
+hdr = rows[hi]; kn, mv, mu = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+agg = collections.OrderedDict()
+for r in rows[hi + 1:]:
+    if len(r) <= mv: continue
+    v = float(r[mv].replace(",", "")); u = r[mu]
+    v = v / 1e3 if u == "us" else v / 1e6 if u == "ns" else v * 1e3 if u in ("s", "second") else v
+    name = r[kn].split("(")[0]
+    a = agg.setdefault(name, [0, 0.0]); a[0] += 1; a[1] += v
+tot = sum(v[1] for v in agg.values())
+out.append("## launch list (ncu --metrics gpu__time_duration.sum, same bench command; cold-cache, serialised: compare shares)\n")
+out.append("| kernel | launches | total ms | share |\n|---|---|---|---|")
+for k, (c, v) in agg.items():
+    out.append(f"| `{k[-70:]}` | {c} | {v:.3f} | {100 * v / tot:.1f}% |")
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rr = list(csv.reader(raw.splitlines())); hdr, units = rr[0], rr[1]
+want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "l1tex__m_xbar2l1tex_read_bytes.sum",
+        "lts__t_sectors_srcunit_tex_op_read.sum", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum", "launch__registers_per_thread",
+        "launch__shared_mem_per_block_dynamic", "lts__t_sector_hit_rate.pct",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_membar_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+        "smsp__average_warp_latency_per_inst_issued.ratio"]
+out.append("\n## ncu --set full, den kernels (bench.py --T 100: one launch = 100 frames of N=64; traffic scales with T)\n")
+for r in rr[2:]:
+    out.append(f"### `{r[hdr.index('Kernel Name')][:90]}`\n| metric | value | unit |\n|---|---|---|")
+    for w in want:
+        if w in hdr:
+            i = hdr.index(w); out.append(f"| {w} | {r[i]} | {units[i]} |")
+    out.append("")
+os.makedirs("profiles", exist_ok=True)
+open(f"profiles/{tag}_summary.md", "w").write("\n".join(out) + "\n")
+print("wrote", f"profiles/{tag}_summary.md")
