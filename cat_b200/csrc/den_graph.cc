@@ -405,7 +405,7 @@ bool BuildDenPlan(const HostFst &fst, int n_ctas, int n_warps, DenPlan *plan, st
     }
     // row costs in arc units, fitted to per-warp timelines on B200 (tools/timeline.py)
     Layout(fgroups, (int)S, plan->state_label, plan->state_pos, n_ctas, n_warps, 4, &plan->fwd);
-    Layout(bgroups, (int)S, plan->state_label, plan->state_pos, n_ctas, n_warps, 10, &plan->bwd);
+    Layout(bgroups, (int)S, plan->state_label, plan->state_pos, n_ctas, n_warps, 6, &plan->bwd);
     return true;
 }
 

@@ -69,12 +69,26 @@ __device__ __forceinline__ float scale_from_sum(float s, int *shift) {
 
 // Two consecutive arcs as one 16-byte word {off0, w0, off1, w1}; off = byte offset of the gathered row.
 template <bool SMEM_ARCS>
-__device__ __forceinline__ uint4 load_arc_pair(const Arc *s_arcs, const Arc *g_arcs, int a, int tile_a0, uint32_t row_bytes) {
-    if (SMEM_ARCS) return reinterpret_cast<const uint4 *>(s_arcs)[(a - tile_a0) >> 1];   // a, tile_a0 even: LDS.128
-    uint4 m = __ldg(reinterpret_cast<const uint4 *>(g_arcs + a));
+__device__ __forceinline__ uint4 load_arc_pair(const uint4 *p, uint32_t row_bytes) {
+    if (SMEM_ARCS) return *p;     // LDS.128, offsets were converted when the tile was staged
+    uint4 m = __ldg(p);
     m.x *= row_bytes;
     m.z *= row_bytes;
     return m;
+}
+
+// base + zero-extended 32-bit byte offset in ONE instruction (IMAD.WIDE.U32), then the row gather
+template <int U>
+__device__ __forceinline__ Vec<U> gather_row(const char *lane_base, uint32_t off) {
+    unsigned long long addr;
+    asm("mad.wide.u32 %0, %1, 1, %2;" : "=l"(addr) : "r"(off), "l"(lane_base));
+    return Vec<U>::ldcg(reinterpret_cast<const float *>(addr));
+}
+template <int U>
+__device__ __forceinline__ float *row_ptr(float *lane_base, uint32_t off) {
+    unsigned long long addr;
+    asm("mad.wide.u32 %0, %1, 1, %2;" : "=l"(addr) : "r"(off), "l"(lane_base));
+    return reinterpret_cast<float *>(addr);
 }
 
 __device__ __forceinline__ void prefetch_l2(const void *p) {
@@ -102,35 +116,40 @@ __global__ void frame_max_kernel(const void *y, int bf16, long sn, long st, int 
 
 // ------------------------------------------------------------------------------------------------
 // The arc walk shared by both passes: a software-pipelined stream over the warp's chunk of arcs.
-//   * arcs come two per LDS.128 (SMEM_ARCS) as {byte offset of the gathered row, weight};
+//   * arcs come two per 16-byte word (LDS.128 when the tile is shared-memory resident);
 //   * BATCH row gathers (ld.global.cg, 32*U*4 bytes each, one per arc) are issued for batch k+1 BEFORE batch k
 //     is consumed, so a warp keeps BATCH..2*BATCH loads in flight (the recursion is latency-bound on L2);
 //   * weights are applied as |w|; the sign bit of a quad's 4th weight marks the end of a segment and the sign bits
 //     of its 3rd/2nd weights the event code (den_graph.h kEv*): `seg_end(acc, event)` runs (warp-uniform branch).
+// `arcs` points at the chunk's first arc pair, n_batches = chunk arcs / BATCH.
 // ------------------------------------------------------------------------------------------------
 template <int U, int BATCH, bool SMEM_ARCS, typename SegEnd>
-__device__ __forceinline__ void walk_arcs(const Arc *s_arcs, const Arc *g_arcs, int ab, int ae, int tile_a0,
-                                          uint32_t row_bytes, const char *lane_base, bool do_load, SegEnd &&seg_end) {
+__device__ __forceinline__ void walk_arcs(const uint4 *arcs, int n_batches, uint32_t row_bytes, const char *lane_base,
+                                          bool do_load, SegEnd &&seg_end) {
     Vec<U> vA[BATCH], vB[BATCH];
+#pragma unroll
+    for (int i = 0; i < BATCH; ++i) { vA[i] = vec_zero<U>(); vB[i] = vec_zero<U>(); }   // lanes that never load stay 0
     float acc[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) acc[u] = 0.f;
 
     // issue: arc words are transient here (only the offsets are needed); consume re-reads them from shared memory
     // for the weights, which keeps 2*BATCH gathers in flight without holding 2*BATCH arc words in registers.
-    auto issue = [&](int base, Vec<U> *v) {
+    auto issue = [&](const uint4 *p, Vec<U> *v) {
+        if (do_load) {
 #pragma unroll
-        for (int j = 0; j < BATCH / 2; ++j) {
-            const uint4 m = load_arc_pair<SMEM_ARCS>(s_arcs, g_arcs, base + 2 * j, tile_a0, row_bytes);
-            v[2 * j] = do_load ? Vec<U>::ldcg(reinterpret_cast<const float *>(lane_base + m.x)) : vec_zero<U>();
-            v[2 * j + 1] = do_load ? Vec<U>::ldcg(reinterpret_cast<const float *>(lane_base + m.z)) : vec_zero<U>();
+            for (int j = 0; j < BATCH / 2; ++j) {
+                const uint4 m = load_arc_pair<SMEM_ARCS>(p + j, row_bytes);
+                v[2 * j] = gather_row<U>(lane_base, m.x);
+                v[2 * j + 1] = gather_row<U>(lane_base, m.z);
+            }
         }
     };
-    auto consume = [&](int base, const Vec<U> *v) {
+    auto consume = [&](const uint4 *p, const Vec<U> *v) {
 #pragma unroll
         for (int g4 = 0; g4 < BATCH / kQuad; ++g4) {
-            const uint4 m0 = load_arc_pair<SMEM_ARCS>(s_arcs, g_arcs, base + g4 * kQuad, tile_a0, row_bytes);
-            const uint4 m1 = load_arc_pair<SMEM_ARCS>(s_arcs, g_arcs, base + g4 * kQuad + 2, tile_a0, row_bytes);
+            const uint4 m0 = load_arc_pair<SMEM_ARCS>(p + 2 * g4, row_bytes);
+            const uint4 m1 = load_arc_pair<SMEM_ARCS>(p + 2 * g4 + 1, row_bytes);
             const float w0 = fabsf(__uint_as_float(m0.y)), w1 = fabsf(__uint_as_float(m0.w));
             const float w2 = fabsf(__uint_as_float(m1.y)), w3 = fabsf(__uint_as_float(m1.w));
 #pragma unroll
@@ -145,18 +164,17 @@ __device__ __forceinline__ void walk_arcs(const Arc *s_arcs, const Arc *g_arcs, 
         }
     };
 
-    int base = ab;
-    if (base < ae) issue(base, vA);
-    while (base < ae) {
-        int nb = base + BATCH;
-        if (nb < ae) issue(nb, vB);
-        consume(base, vA);
-        base = nb;
-        if (base >= ae) break;
-        nb = base + BATCH;
-        if (nb < ae) issue(nb, vA);
-        consume(base, vB);
-        base = nb;
+    const uint4 *pi = arcs, *pc = arcs;
+    int nb = n_batches;
+    if (nb <= 0) return;
+    issue(pi, vA); pi += BATCH / 2;
+    while (true) {
+        if (nb > 1) { issue(pi, vB); pi += BATCH / 2; }
+        consume(pc, vA); pc += BATCH / 2;
+        if (--nb == 0) break;
+        if (nb > 1) { issue(pi, vA); pi += BATCH / 2; }
+        consume(pc, vB); pc += BATCH / 2;
+        if (--nb == 0) break;
     }
 }
 
@@ -200,9 +218,12 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const DenParams P) {
     const int S = P.S, Npad = P.Npad;
     const size_t frame_elems = (size_t)(S + P.num_pairs) * Npad;   // real rows, then one virtual row per pair
     // first label of each row position in this chunk (pair first members / everything else): emission prefetch
-    int labp[2] = {-1, -1};
-    for (int q = se - 1; q >= sb; --q) labp[__ldg(P.state_pos + q) ? 1 : 0] = __ldg(P.state_label + q);
+    int labp0 = -1, labp1 = -1;
+    for (int q = se - 1; q >= sb; --q) { if (__ldg(P.state_pos + q)) labp1 = __ldg(P.state_label + q); else labp0 = __ldg(P.state_label + q); }
     unsigned epoch = 0;
+    const int n_batches = (ae - ab) / BATCH;
+    const uint4 *const arc4 = SMEM_ARCS ? reinterpret_cast<const uint4 *>(s_arcs + (ab - tile_a0))
+                                        : reinterpret_cast<const uint4 *>(P.arcs + ab);
 
     // per-row metadata lives in shared memory: L1 is invalidated at every grid barrier, and a global load on the
     // row-end path would cost an L2 round trip per row
@@ -253,53 +274,57 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const DenParams P) {
                 lane_act |= act[u];
             }
             if (!__any_sync(kFull, lane_act)) continue;
-            float r[U], fm[U], sum[U], ypre[2][U], ec[2][U];
+            float r[U], fm[U], sum[U], ypre0[U], ypre1[U], ec0[U], ec1[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 int sh;
                 r[u] = scale_from_sum(__ldcg(P.colsum_a + (size_t)(t - 1) * Npad + n0 + u), &sh);
                 fm[u] = act[u] ? __ldg(P.fmax + (size_t)(t - 1) * Npad + n0 + u) : 0.f;
                 // emissions of the chunk's first labels: issued now, consumed at the first row ends
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    ypre[k][u] = (act[u] && labp[k] >= 0) ? load_y(P.y, P.y_bf16, (n0 + u) * P.sn + (long)(t - 1) * P.st + labp[k]) : 0.f;
-                    ec[k][u] = 0.f;
-                }
-                sum[u] = 0.f;
+                const long yb = (n0 + u) * P.sn + (long)(t - 1) * P.st;
+                ypre0[u] = (act[u] && labp0 >= 0) ? load_y(P.y, P.y_bf16, yb + labp0) : 0.f;
+                ypre1[u] = (act[u] && labp1 >= 0) ? load_y(P.y, P.y_bf16, yb + labp1) : 0.f;
+                ec0[u] = 0.f; ec1[u] = 0.f; sum[u] = 0.f;
             }
-            int q = sb, vj = vj0;
-            int curlab[2] = {-1, -1};
+            int curlab0 = -1, curlab1 = -1;
+            int ql = sb - tile_s0;                               // row index inside the CTA tile
+            uint32_t out_off = (uint32_t)sb * row_bytes;         // byte offset of row q in the frame
+            uint32_t virt_off = (uint32_t)(S + vj0) * row_bytes; // ... of the next virtual row
+            float *const out_base = a_cur + n0;
             Vec<U> cacc = vec_zero<U>();
-            walk_arcs<U, BATCH, SMEM_ARCS>(s_arcs, P.arcs, ab, ae, tile_a0, row_bytes,
-                                           reinterpret_cast<const char *>(a_prev + n0), lane_act, [&](float *acc, int ev) {
-                const int k = ev == kEvRowPos0 ? 0 : 1;
-                if (P.debug & 1) { sum[0] += acc[0]; ++q; acc[0] = 0.f; return; }
-                const int lab = s_label[q - tile_s0];
-                if (lab != curlab[k]) {
-                    curlab[k] = lab;
+            walk_arcs<U, BATCH, SMEM_ARCS>(arc4, n_batches, row_bytes, reinterpret_cast<const char *>(a_prev + n0), lane_act,
+                                           [&](float *acc, int ev) {
+                const bool k1 = ev != kEvRowPos0;
+                if (P.debug & 1) { sum[0] += acc[0]; acc[0] = 0.f; return; }
+                const int lab = s_label[ql];
+                if (lab != (k1 ? curlab1 : curlab0)) {   // rare: a new label for this row position
+                    const int lp = k1 ? labp1 : labp0;
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
-                        const float yv = (lab == labp[k]) ? ypre[k][u]
+                        const float yv = (lab == lp) ? (k1 ? ypre1[u] : ypre0[u])
                                          : (act[u] ? load_y(P.y, P.y_bf16, (n0 + u) * P.sn + (long)(t - 1) * P.st + lab) : 0.f);
-                        ec[k][u] = act[u] ? expf(yv - fm[u]) : 0.f;
+                        const float en = act[u] ? expf(yv - fm[u]) : 0.f;
+                        if (k1) ec1[u] = en; else ec0[u] = en;
                     }
+                    if (k1) curlab1 = lab; else curlab0 = lab;
                 }
                 Vec<U> out;
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    out.v[u] = act[u] ? acc[u] * ec[k][u] * r[u] : 0.f;
+                    out.v[u] = acc[u] * (k1 ? ec1[u] : ec0[u]) * r[u];   // ec is 0 for inactive utterances
                     sum[u] += out.v[u];
                     acc[u] = 0.f;
                 }
-                if (lane_act) out.stcg(a_cur + (size_t)q * Npad + n0);
+                if (lane_act) out.stcg(row_ptr<U>(out_base, out_off));
                 if (ev == kEvRowPos0) cacc = out;
                 else if (ev == kEvRowPos1) {   // the pair's virtual row: what the next frame gathers instead of both
 #pragma unroll
                     for (int u = 0; u < U; ++u) cacc.v[u] += out.v[u];
-                    if (lane_act) cacc.stcg(a_cur + (size_t)(S + vj) * Npad + n0);
-                    ++vj;
+                    if (lane_act) cacc.stcg(row_ptr<U>(out_base, virt_off));
+                    virt_off += row_bytes;
                 }
-                ++q;
+                out_off += row_bytes;
+                ++ql;
             });
 #pragma unroll
             for (int u = 0; u < U; ++u)
@@ -368,8 +393,11 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const DenParams P) 
     // label accumulator rows of this CTA: [cl_n0 labels from cl_lab0 (pair first members)] [cl_n1 from cl_lab1 (others)]
     const int cl_lab0 = __ldg(P.cta_labels + cta * 4), cl_n0 = __ldg(P.cta_labels + cta * 4 + 1);
     const int cl_lab1 = __ldg(P.cta_labels + cta * 4 + 2), cl_n1 = __ldg(P.cta_labels + cta * 4 + 3);
-    int labp[2] = {-1, -1};
-    for (int q = se - 1; q >= sb; --q) labp[__ldg(P.state_pos + q) ? 1 : 0] = __ldg(P.state_label + q);
+    int labp0 = -1, labp1 = -1;
+    for (int q = se - 1; q >= sb; --q) { if (__ldg(P.state_pos + q)) labp1 = __ldg(P.state_label + q); else labp0 = __ldg(P.state_label + q); }
+    const int n_batches = (ae - ab) / BATCH;
+    const uint4 *const arc4 = SMEM_ARCS ? reinterpret_cast<const uint4 *>(s_arcs + (ab - tile_a0))
+                                        : reinterpret_cast<const uint4 *>(P.arcs + ab);
     const bool use_gacc = P.gacc_rows > 0;
     const size_t frame_elems = (size_t)S * Npad;                         // beta ping-pong: real rows only
     const size_t alpha_frame = (size_t)(S + P.num_pairs) * Npad;          // alpha spill: real + virtual rows
@@ -418,73 +446,85 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const DenParams P) 
                 lane_gat |= gat[u];
             }
             if (!__any_sync(kFull, lane_act)) continue;
-            float rb[U], fm[U], sum_b[U], sum_ab[U], gsum[2][U], ypre[2][U], ec[2][U], acc_c[U];
+            float rb[U], fm[U], sum_b[U], sum_ab[U], gsum0[U], gsum1[U], ypre0[U], ypre1[U], ec0[U], ec1[U], acc_c[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 int sh;
                 rb[u] = gat[u] ? scale_from_sum(__ldcg(P.colsum_b + (size_t)(tau + 1) * Npad + n0 + u), &sh) : 1.f;
                 fm[u] = act[u] ? __ldg(P.fmax + (size_t)(tau - 1) * Npad + n0 + u) : 0.f;
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    ypre[k][u] = (act[u] && labp[k] >= 0) ? load_y(P.y, P.y_bf16, (n0 + u) * P.sn + (long)(tau - 1) * P.st + labp[k]) : 0.f;
-                    ec[k][u] = 0.f; gsum[k][u] = 0.f;
-                }
+                const long yb = (n0 + u) * P.sn + (long)(tau - 1) * P.st;
+                ypre0[u] = (act[u] && labp0 >= 0) ? load_y(P.y, P.y_bf16, yb + labp0) : 0.f;
+                ypre1[u] = (act[u] && labp1 >= 0) ? load_y(P.y, P.y_bf16, yb + labp1) : 0.f;
+                ec0[u] = 0.f; ec1[u] = 0.f; gsum0[u] = 0.f; gsum1[u] = 0.f;
                 sum_b[u] = 0.f; sum_ab[u] = 0.f; acc_c[u] = 0.f;
             }
-            int q = sb;
-            int curlab[2] = {-1, -1};
-            Vec<U> a_q = (se > sb && lane_act) ? Vec<U>::ldcg(a_row + (size_t)sb * Npad + n0) : vec_zero<U>();
-            auto flush_gsum = [&](int k) {
-                const int row = k == 0 ? curlab[0] - cl_lab0 : cl_n0 + curlab[1] - cl_lab1;
+            int curlab0 = -1, curlab1 = -1;
+            int ql = sb - tile_s0;
+            uint32_t out_off = (uint32_t)sb * row_bytes;
+            float *const out_base = bh_cur + n0;
+            const char *const a_base = reinterpret_cast<const char *>(a_row + n0);
+            const uint32_t end_off = (uint32_t)se * row_bytes;
+            // alpha rows of the next two states are kept in flight: a pair's private segments are one quad long, so a
+            // one-row lookahead would expose a full L2 round trip at every second row end
+            Vec<U> a_q = (se > sb && lane_act) ? gather_row<U>(a_base, out_off) : vec_zero<U>();
+            Vec<U> a_q1 = (se > sb + 1 && lane_act) ? gather_row<U>(a_base, out_off + row_bytes) : vec_zero<U>();
+            auto flush_gsum = [&](bool k1) {
+                const int lab = k1 ? curlab1 : curlab0;
+                const int row = k1 ? cl_n0 + lab - cl_lab1 : lab - cl_lab0;
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    if (gsum[k][u] != 0.f) {
-                        if (use_gacc) atomicAdd(&s_gacc[row * Npad + n0 + u], gsum[k][u]);
-                        else atomicAdd(P.grad + (n0 + u) * P.gsn + (long)(tau - 1) * P.gst + curlab[k], gsum[k][u]);
+                    const float g = k1 ? gsum1[u] : gsum0[u];
+                    if (g != 0.f) {
+                        if (use_gacc) atomicAdd(&s_gacc[row * Npad + n0 + u], g);
+                        else atomicAdd(P.grad + (n0 + u) * P.gsn + (long)(tau - 1) * P.gst + lab, g);
                     }
-                    gsum[k][u] = 0.f;
+                    if (k1) gsum1[u] = 0.f; else gsum0[u] = 0.f;
                 }
             };
-            walk_arcs<U, BATCH, SMEM_ARCS>(s_arcs, P.arcs, ab, ae, tile_a0, row_bytes,
-                                           reinterpret_cast<const char *>(bh_next + n0), lane_gat, [&](float *acc, int ev) {
+            walk_arcs<U, BATCH, SMEM_ARCS>(arc4, n_batches, row_bytes, reinterpret_cast<const char *>(bh_next + n0), lane_gat,
+                                           [&](float *acc, int ev) {
                 if (ev == kEvCommon) {   // arcs shared by both members of a pair: keep the partial sum, keep accumulating
 #pragma unroll
                     for (int u = 0; u < U; ++u) acc_c[u] = acc[u];
                     return;
                 }
-                const int k = ev == kEvRowPos0 ? 0 : 1;
-                if (P.debug & 1) { sum_b[0] += acc[0]; ++q; acc[0] = 0.f; return; }
-                const int lab = s_label[q - tile_s0];
-                if (lab != curlab[k]) {
-                    if (curlab[k] >= 0) flush_gsum(k);
-                    curlab[k] = lab;
+                const bool k1 = ev != kEvRowPos0;
+                if (P.debug & 1) { sum_b[0] += acc[0]; acc[0] = 0.f; return; }
+                const int lab = s_label[ql];
+                if (lab != (k1 ? curlab1 : curlab0)) {
+                    if ((k1 ? curlab1 : curlab0) >= 0) flush_gsum(k1);
+                    const int lp = k1 ? labp1 : labp0;
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
-                        const float yv = (lab == labp[k]) ? ypre[k][u]
+                        const float yv = (lab == lp) ? (k1 ? ypre1[u] : ypre0[u])
                                          : (act[u] ? load_y(P.y, P.y_bf16, (n0 + u) * P.sn + (long)(tau - 1) * P.st + lab) : 0.f);
-                        ec[k][u] = act[u] ? expf(yv - fm[u]) : 0.f;
+                        const float en = act[u] ? expf(yv - fm[u]) : 0.f;
+                        if (k1) ec1[u] = en; else ec0[u] = en;
                     }
+                    if (k1) curlab1 = lab; else curlab0 = lab;
                 }
-                const float f = s_final[q - tile_s0];
+                const float f = s_final[ql];
                 Vec<U> out;
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const float b = act[u] ? (gat[u] ? acc[u] * rb[u] : f) : 0.f;
-                    const float abp = act[u] ? a_q.v[u] * b : 0.f;
-                    gsum[k][u] += abp;
+                    const float abp = a_q.v[u] * b;          // a_q is 0 for inactive lanes
+                    if (k1) gsum1[u] += abp; else gsum0[u] += abp;
                     sum_ab[u] += abp;
-                    out.v[u] = ec[k][u] * b;
+                    out.v[u] = (k1 ? ec1[u] : ec0[u]) * b;
                     sum_b[u] += out.v[u];
                     // first member of a pair: the second member restarts from the shared partial sum
-                    acc[u] = ev == kEvRowPos0 ? acc_c[u] : 0.f;
-                    if (ev != kEvRowPos0) acc_c[u] = 0.f;
+                    acc[u] = k1 ? 0.f : acc_c[u];
+                    if (k1) acc_c[u] = 0.f;
                 }
-                if (lane_act) out.stcg(bh_cur + (size_t)q * Npad + n0);
-                ++q;
-                a_q = (q < se && lane_act) ? Vec<U>::ldcg(a_row + (size_t)q * Npad + n0) : vec_zero<U>();
+                if (lane_act) out.stcg(row_ptr<U>(out_base, out_off));
+                out_off += row_bytes;
+                ++ql;
+                a_q = a_q1;
+                a_q1 = (out_off + row_bytes < end_off && lane_act) ? gather_row<U>(a_base, out_off + row_bytes) : vec_zero<U>();
             });
-            if (curlab[0] >= 0) flush_gsum(0);
-            if (curlab[1] >= 0) flush_gsum(1);
+            if (curlab0 >= 0) flush_gsum(false);
+            if (curlab1 >= 0) flush_gsum(true);
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 if (act[u]) {
