@@ -138,10 +138,21 @@ void Layout(const std::vector<Group> &groups, int S, const std::vector<int> &sta
         pp->chunk_arc[c] = (int)pp->arcs.size();
         pp->chunk_pair[c] = pairs_seen;
         pp->chunk_state[c] = chunk_group[c] < G ? groups[(size_t)chunk_group[c]].first_state : S;
+        int prev_label[2] = {-1, -1};   // last label seen in this chunk per row position (-1: none yet)
         for (int g = chunk_group[c]; g < chunk_group[c + 1]; ++g) {
             const Group &gr = groups[(size_t)g];
             pairs_seen += gr.pairs;
+            int row = gr.first_state;
             for (auto &sg : gr.segs) {
+                // sign(w[0]) of a row's last quad: "the label differs from the previous row of this position in the
+                // chunk" -- the kernels then skip the label lookup / emission refresh on the common path
+                bool label_changed = false;
+                if (sg.event != kEvCommon) {
+                    const int k = sg.event == kEvRowPos0 ? 0 : 1;
+                    label_changed = state_label[(size_t)row] != prev_label[k];
+                    prev_label[k] = state_label[(size_t)row];
+                    ++row;
+                }
                 const size_t padded = (size_t)quads(sg) * kQuad;
                 // Padding arcs carry weight 0 but are still gathered: point them at a row this warp reads anyway.
                 // Pointing them all at one fixed row makes every warp of the grid hammer a single L2 line
@@ -152,6 +163,7 @@ void Layout(const std::vector<Group> &groups, int S, const std::vector<int> &sta
                     if (i + 1 == padded) a.w = WithSign(a.w);
                     if (i + 2 == padded && (sg.event & 2)) a.w = WithSign(a.w);
                     if (i + 3 == padded && (sg.event & 1)) a.w = WithSign(a.w);
+                    if (i + 4 == padded && label_changed) a.w = WithSign(a.w);
                     pp->arcs.push_back(a);
                 }
                 last_peer = pad_peer;

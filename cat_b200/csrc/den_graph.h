@@ -15,7 +15,8 @@ namespace ccb {
 //          virtual row of pair j (the sum of the pair's two alphas, see DenPlan).
 //   w    : arc weight in the LINEAR domain, exp(-tropical weight), always >= 0.  Arc segments are padded with
 //          zero-weight arcs to whole QUADS of 4 arcs.  SIGN BITS of the last quad of a segment carry the event
-//          (applied as |w| in the FMA): sign(w[3]) = "a segment ends here", sign(w[2]):sign(w[1]) = event code.
+//          (applied as |w| in the FMA): sign(w[3]) = "a segment ends here", sign(w[2]):sign(w[1]) = event code,
+//          sign(w[0]) = "this row's label differs from the previous row of the same position in the chunk".
 struct alignas(8) Arc {
     uint32_t peer;
     float w;

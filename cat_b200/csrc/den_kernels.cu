@@ -15,6 +15,7 @@
 //   * gradient without arc atomics: gamma_t[k] = sum_{q: lab(q)=k} alpha_t(q) beta_t(q) / sum_q alpha_t(q) beta_t(q),
 //     accumulated per CTA in shared memory (states are sorted by label) and flushed with a few REDs.
 #include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -67,28 +68,31 @@ __device__ __forceinline__ float scale_from_sum(float s, int *shift) {
     return __int_as_float((sh + 127) << 23);
 }
 
-// Two consecutive arcs as one 16-byte word {off0, w0, off1, w1}; off = byte offset of the gathered row.
+// One quad of arcs as two 16-byte words: {peer0..3} and {w0..3}.  In shared memory the tile is staged quad-wise in
+// exactly this (SoA) form, so each word is one LDS.128 whose four lanes are all used; the global-memory fallback
+// (tiles too large for shared memory) reads the plan's AoS arcs.
 template <bool SMEM_ARCS>
-__device__ __forceinline__ uint4 load_arc_pair(const uint4 *p, uint32_t row_bytes) {
-    if (SMEM_ARCS) return *p;     // LDS.128, offsets were converted when the tile was staged
-    uint4 m = __ldg(p);
-    m.x *= row_bytes;
-    m.z *= row_bytes;
-    return m;
+__device__ __forceinline__ uint4 load_quad_peers(const uint4 *quad, uint32_t row_bytes) {
+    if (SMEM_ARCS) return quad[0];   // already byte offsets
+    const uint4 m0 = __ldg(quad), m1 = __ldg(quad + 1);
+    return make_uint4(m0.x * row_bytes, m0.z * row_bytes, m1.x * row_bytes, m1.z * row_bytes);
+}
+template <bool SMEM_ARCS>
+__device__ __forceinline__ uint4 load_quad_weights(const uint4 *quad) {
+    if (SMEM_ARCS) return quad[1];
+    const uint4 m0 = __ldg(quad), m1 = __ldg(quad + 1);
+    return make_uint4(m0.y, m0.w, m1.y, m1.w);
 }
 
-// base + zero-extended 32-bit byte offset in ONE instruction (IMAD.WIDE.U32), then the row gather
+// Row address = 64-bit lane base + 32-bit BYTE offset (two integer adds; ptxas splits every mad.wide form into three
+// instructions, so the multiplication by the row pitch is done once, when the tile is staged / in the fallback loader).
 template <int U>
-__device__ __forceinline__ Vec<U> gather_row(const char *lane_base, uint32_t off) {
-    unsigned long long addr;
-    asm("mad.wide.u32 %0, %1, 1, %2;" : "=l"(addr) : "r"(off), "l"(lane_base));
-    return Vec<U>::ldcg(reinterpret_cast<const float *>(addr));
+__device__ __forceinline__ Vec<U> gather_row(const char *lane_base, uint32_t byte_off) {
+    return Vec<U>::ldcg(reinterpret_cast<const float *>(lane_base + byte_off));
 }
 template <int U>
-__device__ __forceinline__ float *row_ptr(float *lane_base, uint32_t off) {
-    unsigned long long addr;
-    asm("mad.wide.u32 %0, %1, 1, %2;" : "=l"(addr) : "r"(off), "l"(lane_base));
-    return reinterpret_cast<float *>(addr);
+__device__ __forceinline__ float *row_ptr(float *lane_base, uint32_t row, uint32_t row_bytes) {
+    return reinterpret_cast<float *>(reinterpret_cast<char *>(lane_base) + (size_t)row * row_bytes);
 }
 
 __device__ __forceinline__ void prefetch_l2(const void *p) {
@@ -116,12 +120,12 @@ __global__ void frame_max_kernel(const void *y, int bf16, long sn, long st, int 
 
 // ------------------------------------------------------------------------------------------------
 // The arc walk shared by both passes: a software-pipelined stream over the warp's chunk of arcs.
-//   * arcs come two per 16-byte word (LDS.128 when the tile is shared-memory resident);
+//   * arcs come a quad at a time: one LDS.128 of four peers for the gathers, one LDS.128 of four weights for the FMAs;
 //   * BATCH row gathers (ld.global.cg, 32*U*4 bytes each, one per arc) are issued for batch k+1 BEFORE batch k
 //     is consumed, so a warp keeps BATCH..2*BATCH loads in flight (the recursion is latency-bound on L2);
 //   * weights are applied as |w|; the sign bit of a quad's 4th weight marks the end of a segment and the sign bits
 //     of its 3rd/2nd weights the event code (den_graph.h kEv*): `seg_end(acc, event)` runs (warp-uniform branch).
-// `arcs` points at the chunk's first arc pair, n_batches = chunk arcs / BATCH.
+// `arcs` points at the chunk's first quad (two 16-byte words per quad), n_batches = chunk arcs / BATCH.
 // ------------------------------------------------------------------------------------------------
 template <int U, int BATCH, bool SMEM_ARCS, typename SegEnd>
 __device__ __forceinline__ void walk_arcs(const uint4 *arcs, int n_batches, uint32_t row_bytes, const char *lane_base,
@@ -135,23 +139,26 @@ __device__ __forceinline__ void walk_arcs(const uint4 *arcs, int n_batches, uint
 
     // issue: arc words are transient here (only the offsets are needed); consume re-reads them from shared memory
     // for the weights, which keeps 2*BATCH gathers in flight without holding 2*BATCH arc words in registers.
+    // a quad is two 16-byte words (peers, weights); `issue` needs only the first, `consume` only the second, so
+    // 2*BATCH gathers stay in flight without holding 2*BATCH arc words in registers.
     auto issue = [&](const uint4 *p, Vec<U> *v) {
         if (do_load) {
 #pragma unroll
-            for (int j = 0; j < BATCH / 2; ++j) {
-                const uint4 m = load_arc_pair<SMEM_ARCS>(p + j, row_bytes);
-                v[2 * j] = gather_row<U>(lane_base, m.x);
-                v[2 * j + 1] = gather_row<U>(lane_base, m.z);
+            for (int g4 = 0; g4 < BATCH / kQuad; ++g4) {
+                const uint4 pr = load_quad_peers<SMEM_ARCS>(p + 2 * g4, row_bytes);
+                v[g4 * kQuad + 0] = gather_row<U>(lane_base, pr.x);
+                v[g4 * kQuad + 1] = gather_row<U>(lane_base, pr.y);
+                v[g4 * kQuad + 2] = gather_row<U>(lane_base, pr.z);
+                v[g4 * kQuad + 3] = gather_row<U>(lane_base, pr.w);
             }
         }
     };
     auto consume = [&](const uint4 *p, const Vec<U> *v) {
 #pragma unroll
         for (int g4 = 0; g4 < BATCH / kQuad; ++g4) {
-            const uint4 m0 = load_arc_pair<SMEM_ARCS>(p + 2 * g4, row_bytes);
-            const uint4 m1 = load_arc_pair<SMEM_ARCS>(p + 2 * g4 + 1, row_bytes);
-            const float w0 = fabsf(__uint_as_float(m0.y)), w1 = fabsf(__uint_as_float(m0.w));
-            const float w2 = fabsf(__uint_as_float(m1.y)), w3 = fabsf(__uint_as_float(m1.w));
+            const uint4 wq = load_quad_weights<SMEM_ARCS>(p + 2 * g4);
+            const float w0 = fabsf(__uint_as_float(wq.x)), w1 = fabsf(__uint_as_float(wq.y));
+            const float w2 = fabsf(__uint_as_float(wq.z)), w3 = fabsf(__uint_as_float(wq.w));
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 acc[u] = fmaf(w0, v[g4 * kQuad + 0].v[u], acc[u]);
@@ -159,8 +166,8 @@ __device__ __forceinline__ void walk_arcs(const uint4 *arcs, int n_batches, uint
                 acc[u] = fmaf(w2, v[g4 * kQuad + 2].v[u], acc[u]);
                 acc[u] = fmaf(w3, v[g4 * kQuad + 3].v[u], acc[u]);
             }
-            if ((int)m1.w < 0)   // warp-uniform: a segment ends at this quad; the callback owns the accumulators
-                seg_end(acc, (int)(((m1.y >> 31) << 1) | (m0.w >> 31)));
+            if ((int)wq.w < 0)   // warp-uniform: a segment ends at this quad; the callback owns the accumulators
+                seg_end(acc, (int)(((wq.z >> 31) << 1) | (wq.y >> 31)), (int)wq.x < 0);
         }
     };
 
@@ -229,11 +236,12 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const DenParams P) {
     // row-end path would cost an L2 round trip per row
     for (int i = tid; i < tile_s1 - tile_s0; i += NT) s_label[i] = __ldg(P.state_label + tile_s0 + i);
     const uint32_t row_bytes = (uint32_t)Npad * 4u;
-    if (SMEM_ARCS) {   // stage the tile once; peers become byte offsets of the gathered rows
+    if (SMEM_ARCS) {   // stage the tile once, quad-wise transposed: {byte offset 0..3}{w0..3}
+        uint32_t *sq = reinterpret_cast<uint32_t *>(s_arcs);
         for (int i = tid; i < tile_a1 - tile_a0; i += NT) {
-            Arc k = P.arcs[tile_a0 + i];
-            k.peer *= row_bytes;
-            s_arcs[i] = k;
+            const Arc k = P.arcs[tile_a0 + i];
+            sq[(i >> 2) * 8 + (i & 3)] = k.peer * row_bytes;   // byte offset of the gathered row
+            sq[(i >> 2) * 8 + 4 + (i & 3)] = __float_as_uint(k.w);
         }
     }
     for (int i = tid; i < Npad; i += NT) s_sum[i] = 0.f;
@@ -286,18 +294,17 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const DenParams P) {
                 ypre1[u] = (act[u] && labp1 >= 0) ? load_y(P.y, P.y_bf16, yb + labp1) : 0.f;
                 ec0[u] = 0.f; ec1[u] = 0.f; sum[u] = 0.f;
             }
-            int curlab0 = -1, curlab1 = -1;
             int ql = sb - tile_s0;                               // row index inside the CTA tile
-            uint32_t out_off = (uint32_t)sb * row_bytes;         // byte offset of row q in the frame
-            uint32_t virt_off = (uint32_t)(S + vj0) * row_bytes; // ... of the next virtual row
+            uint32_t out_row = (uint32_t)sb;                     // row q of the frame
+            uint32_t virt_row = (uint32_t)(S + vj0);             // the next virtual row
             float *const out_base = a_cur + n0;
             Vec<U> cacc = vec_zero<U>();
             walk_arcs<U, BATCH, SMEM_ARCS>(arc4, n_batches, row_bytes, reinterpret_cast<const char *>(a_prev + n0), lane_act,
-                                           [&](float *acc, int ev) {
+                                           [&](float *acc, int ev, bool new_label) {
                 const bool k1 = ev != kEvRowPos0;
                 if (P.debug & 1) { sum[0] += acc[0]; acc[0] = 0.f; return; }
-                const int lab = s_label[ql];
-                if (lab != (k1 ? curlab1 : curlab0)) {   // rare: a new label for this row position
+                if (new_label) {   // rare: a new label for this row position -> refresh its emission
+                    const int lab = s_label[ql];
                     const int lp = k1 ? labp1 : labp0;
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
@@ -306,7 +313,6 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const DenParams P) {
                         const float en = act[u] ? expf(yv - fm[u]) : 0.f;
                         if (k1) ec1[u] = en; else ec0[u] = en;
                     }
-                    if (k1) curlab1 = lab; else curlab0 = lab;
                 }
                 Vec<U> out;
 #pragma unroll
@@ -315,15 +321,15 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const DenParams P) {
                     sum[u] += out.v[u];
                     acc[u] = 0.f;
                 }
-                if (lane_act) out.stcg(row_ptr<U>(out_base, out_off));
+                if (lane_act) out.stcg(row_ptr<U>(out_base, out_row, row_bytes));
                 if (ev == kEvRowPos0) cacc = out;
                 else if (ev == kEvRowPos1) {   // the pair's virtual row: what the next frame gathers instead of both
 #pragma unroll
                     for (int u = 0; u < U; ++u) cacc.v[u] += out.v[u];
-                    if (lane_act) cacc.stcg(row_ptr<U>(out_base, virt_off));
-                    virt_off += row_bytes;
+                    if (lane_act) cacc.stcg(row_ptr<U>(out_base, virt_row, row_bytes));
+                    ++virt_row;
                 }
-                out_off += row_bytes;
+                ++out_row;
                 ++ql;
             });
 #pragma unroll
@@ -409,10 +415,11 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const DenParams P) 
     }
     const uint32_t row_bytes = (uint32_t)Npad * 4u;
     if (SMEM_ARCS) {
+        uint32_t *sq = reinterpret_cast<uint32_t *>(s_arcs);
         for (int i = tid; i < tile_a1 - tile_a0; i += NT) {
-            Arc k = P.arcs[tile_a0 + i];
-            k.peer *= row_bytes;
-            s_arcs[i] = k;
+            const Arc k = P.arcs[tile_a0 + i];
+            sq[(i >> 2) * 8 + (i & 3)] = k.peer * row_bytes;   // byte offset of the gathered row
+            sq[(i >> 2) * 8 + 4 + (i & 3)] = __float_as_uint(k.w);
         }
     }
     for (int i = tid; i < (2 + P.gacc_rows) * Npad; i += NT) s_sum[i] = 0.f;
@@ -460,14 +467,13 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const DenParams P) 
             }
             int curlab0 = -1, curlab1 = -1;
             int ql = sb - tile_s0;
-            uint32_t out_off = (uint32_t)sb * row_bytes;
+            uint32_t out_row = (uint32_t)sb;
             float *const out_base = bh_cur + n0;
             const char *const a_base = reinterpret_cast<const char *>(a_row + n0);
-            const uint32_t end_off = (uint32_t)se * row_bytes;
             // alpha rows of the next two states are kept in flight: a pair's private segments are one quad long, so a
             // one-row lookahead would expose a full L2 round trip at every second row end
-            Vec<U> a_q = (se > sb && lane_act) ? gather_row<U>(a_base, out_off) : vec_zero<U>();
-            Vec<U> a_q1 = (se > sb + 1 && lane_act) ? gather_row<U>(a_base, out_off + row_bytes) : vec_zero<U>();
+            Vec<U> a_q = (se > sb && lane_act) ? gather_row<U>(a_base, out_row * row_bytes) : vec_zero<U>();
+            Vec<U> a_q1 = (se > sb + 1 && lane_act) ? gather_row<U>(a_base, (out_row + 1) * row_bytes) : vec_zero<U>();
             auto flush_gsum = [&](bool k1) {
                 const int lab = k1 ? curlab1 : curlab0;
                 const int row = k1 ? cl_n0 + lab - cl_lab1 : lab - cl_lab0;
@@ -482,7 +488,7 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const DenParams P) 
                 }
             };
             walk_arcs<U, BATCH, SMEM_ARCS>(arc4, n_batches, row_bytes, reinterpret_cast<const char *>(bh_next + n0), lane_gat,
-                                           [&](float *acc, int ev) {
+                                           [&](float *acc, int ev, bool new_label) {
                 if (ev == kEvCommon) {   // arcs shared by both members of a pair: keep the partial sum, keep accumulating
 #pragma unroll
                     for (int u = 0; u < U; ++u) acc_c[u] = acc[u];
@@ -490,8 +496,8 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const DenParams P) 
                 }
                 const bool k1 = ev != kEvRowPos0;
                 if (P.debug & 1) { sum_b[0] += acc[0]; acc[0] = 0.f; return; }
-                const int lab = s_label[ql];
-                if (lab != (k1 ? curlab1 : curlab0)) {
+                if (new_label) {
+                    const int lab = s_label[ql];
                     if ((k1 ? curlab1 : curlab0) >= 0) flush_gsum(k1);
                     const int lp = k1 ? labp1 : labp0;
 #pragma unroll
@@ -517,11 +523,11 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const DenParams P) 
                     acc[u] = k1 ? 0.f : acc_c[u];
                     if (k1) acc_c[u] = 0.f;
                 }
-                if (lane_act) out.stcg(row_ptr<U>(out_base, out_off));
-                out_off += row_bytes;
+                if (lane_act) out.stcg(row_ptr<U>(out_base, out_row, row_bytes));
+                ++out_row;
                 ++ql;
                 a_q = a_q1;
-                a_q1 = (out_off + row_bytes < end_off && lane_act) ? gather_row<U>(a_base, out_off + row_bytes) : vec_zero<U>();
+                a_q1 = ((int)out_row + 1 < se && lane_act) ? gather_row<U>(a_base, (out_row + 1) * row_bytes) : vec_zero<U>();
             });
             if (curlab0 >= 0) flush_gsum(false);
             if (curlab1 >= 0) flush_gsum(true);
@@ -633,16 +639,26 @@ int Dispatch(bool backward, const DeviceGraph &g, const DenParams &p, size_t fix
     const bool smem_arcs = fixed_smem + arc_bytes <= budget;
     const size_t smem = fixed_smem + (smem_arcs ? arc_bytes : 0);
     const int U = LaneWidth(p.Npad);
-    // gathers per batch (two batches are in flight per warp); bounded by the register budget of the variant
+    // gathers per batch (two batches are in flight per warp); bounded by the register budget of the variant.
+    // CCB_BATCH_FWD / CCB_BATCH_BWD (8 or 16) override the 512-thread defaults for tuning.
+    int want = NT == 512 ? (U == 4 ? 8 : (backward ? 8 : 16)) : (U == 1 ? 8 : 4);
+    if (NT == 512 && U != 4) {
+        const char *e = getenv(backward ? "CCB_BATCH_BWD" : "CCB_BATCH_FWD");
+        if (e && (atoi(e) == 8 || atoi(e) == 16)) want = atoi(e);
+    }
+#define CCB_LAUNCH(UU, BB)                                                                               \
+    return smem_arcs ? LaunchOne<NT, UU, BB, true>(backward, p, g.n_ctas, smem, stream, err)            \
+                     : LaunchOne<NT, UU, BB, false>(backward, p, g.n_ctas, smem, stream, err)
 #define CCB_GO(UU)                                                                                      \
     {                                                                                                   \
-        constexpr int B = NT == 512 ? (UU == 4 ? 8 : 16) : (UU == 1 ? 8 : 4);                           \
-        return smem_arcs ? LaunchOne<NT, UU, B, true>(backward, p, g.n_ctas, smem, stream, err)          \
-                         : LaunchOne<NT, UU, B, false>(backward, p, g.n_ctas, smem, stream, err);        \
+        if (NT == 512 && UU != 4 && want == 16) { CCB_LAUNCH(UU, 16); }                                 \
+        if (NT == 512 || UU == 1) { CCB_LAUNCH(UU, 8); }                                                \
+        CCB_LAUNCH(UU, 4);                                                                              \
     }
     if (U == 1) { CCB_GO(1); }
     if (U == 2) { CCB_GO(2); }
     CCB_GO(4);
+#undef CCB_LAUNCH
 #undef CCB_GO
 }
 

@@ -30,15 +30,15 @@ class PassView:
         return np.abs(self.arcs["w"])
 
     def segments(self):
-        """Decode the stream the way the kernels walk it: yields (arc_begin, arc_end, event) per segment.
-        Chunk-tail padding quads (unflagged, weight 0) attach to the following segment."""
+        """Decode the stream the way the kernels walk it: yields (arc_begin, arc_end, event, label_changed) per
+        segment.  Chunk-tail padding quads (unflagged, weight 0) attach to the following segment."""
         w = self.arcs["w"].reshape(-1, QUAD)
         sign = np.signbit(w)
         ends = np.nonzero(sign[:, 3])[0]
         ev = (sign[ends, 2].astype(int) << 1) | sign[ends, 1].astype(int)
         begin = 0
         for e, v in zip(ends, ev):
-            yield begin * QUAD, (e + 1) * QUAD, int(v)
+            yield begin * QUAD, (e + 1) * QUAD, int(v), bool(sign[e, 0])
             begin = e + 1
 
 

@@ -25,7 +25,7 @@ def _decode_forward(plan):
     pairs = []
     q = 0
     arcs = plan.fwd.arcs
-    for a0, a1, ev in plan.fwd.segments():
+    for a0, a1, ev, _chg in plan.fwd.segments():
         assert ev != 3, "kEvCommon must not appear in the forward stream"
         n = a1 - a0
         row.append(np.full(n, q)); peer.append(arcs["peer"][a0:a1].astype(np.int64)); w.append(np.abs(arcs["w"][a0:a1]).astype(np.float64))
@@ -49,7 +49,7 @@ def _decode_backward(plan):
     q = 0
     arcs = plan.bwd.arcs
     pend = None
-    for a0, a1, ev in plan.bwd.segments():
+    for a0, a1, ev, _chg in plan.bwd.segments():
         pr = arcs["peer"][a0:a1].astype(np.int64); ww = np.abs(arcs["w"][a0:a1]).astype(np.float64)
         assert (pr < S).all()
         if ev == 3:

@@ -66,11 +66,11 @@ def test_plan_invariants(tmp_graphs, n_ctas, n_warps):
         assert (P.state_pos[p0 + 1] == 1).all()
         for pv, is_fwd in ((P.fwd, True), (P.bwd, False)):
             segs = list(pv.segments())
-            rows = [sg for sg in segs if sg[2] != plan.EV_COMMON]
+            rows = [x for x in segs if x[2] != plan.EV_COMMON]
             assert len(rows) == S                                        # one row-end event per state
-            assert sum(1 for sg in segs if sg[2] == plan.EV_ROW_POS1) == NP == sum(1 for sg in segs if sg[2] == plan.EV_ROW_POS0)
+            assert sum(1 for x in segs if x[2] == plan.EV_ROW_POS1) == NP == sum(1 for x in segs if x[2] == plan.EV_ROW_POS0)
             if is_fwd:
-                assert not any(sg[2] == plan.EV_COMMON for sg in segs)
+                assert not any(x[2] == plan.EV_COMMON for x in segs)
                 assert (pv.arcs["peer"] < S + NP).all()
             else:
                 assert (pv.arcs["peer"] < S).all()
@@ -83,8 +83,21 @@ def test_plan_invariants(tmp_graphs, n_ctas, n_warps):
             assert (P.state_pos[cs - 1] == 1).all() if (cs > 0).any() else True
             np.testing.assert_array_equal(pv.chunk_pair, np.concatenate([[0], np.cumsum(P.state_pos == 0)])[pv.chunk_state])
             assert (pv.weights() >= 0).all()
-            # event sign bits live only in the last three slots of a quad
-            assert not np.signbit(pv.arcs["w"].reshape(-1, plan.QUAD)[:, 0]).any()
+            # sign bits appear only on a segment's last quad; slot 0 = "label changed" and only on row ends
+            sg = np.signbit(pv.arcs["w"].reshape(-1, plan.QUAD))
+            assert not sg[~sg[:, 3]].any()
+            # label-changed flag == the label differs from the previous row of that position within the chunk
+            q = 0
+            prev = {}
+            chunk_of = np.searchsorted(pv.chunk_arc, np.arange(0, len(pv.arcs), plan.QUAD), side="right") - 1
+            for a0, a1, ev, chg in segs:
+                if ev == plan.EV_COMMON:
+                    assert not chg
+                    continue
+                key = (int(chunk_of[(a1 - 1) // plan.QUAD]), 0 if ev == plan.EV_ROW_POS0 else 1)
+                assert chg == (prev.get(key) != int(P.state_label[q]))
+                prev[key] = int(P.state_label[q])
+                q += 1
             # label accumulator ranges cover every state of the CTA
             for c in range(n_ctas):
                 s0, s1 = pv.chunk_state[c * n_warps], pv.chunk_state[(c + 1) * n_warps]
