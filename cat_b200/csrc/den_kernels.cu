@@ -127,9 +127,9 @@ __global__ void frame_max_kernel(const void *y, int bf16, long sn, long st, int 
 //     of its 3rd/2nd weights the event code (den_graph.h kEv*): `seg_end(acc, event)` runs (warp-uniform branch).
 // `arcs` points at the chunk's first quad (two 16-byte words per quad), n_batches = chunk arcs / BATCH.
 // ------------------------------------------------------------------------------------------------
-template <int U, int BATCH, bool SMEM_ARCS, typename SegEnd>
+template <int U, int BATCH, bool SMEM_ARCS, typename Prologue, typename SegEnd>
 __device__ __forceinline__ void walk_arcs(const uint4 *arcs, int n_batches, uint32_t row_bytes, const char *lane_base,
-                                          bool do_load, SegEnd &&seg_end) {
+                                          bool do_load, Prologue &&prologue, SegEnd &&seg_end) {
     Vec<U> vA[BATCH], vB[BATCH];
 #pragma unroll
     for (int i = 0; i < BATCH; ++i) { vA[i] = vec_zero<U>(); vB[i] = vec_zero<U>(); }   // lanes that never load stay 0
@@ -172,16 +172,18 @@ __device__ __forceinline__ void walk_arcs(const uint4 *arcs, int n_batches, uint
     };
 
     const uint4 *pi = arcs, *pc = arcs;
-    int nb = n_batches;
-    if (nb <= 0) return;
+    int nb = n_batches;   // batches not yet consumed
+    if (nb <= 0) { prologue(); return; }
     issue(pi, vA); pi += BATCH / 2;
+    if (nb > 1) { issue(pi, vB); pi += BATCH / 2; }
+    prologue();   // per-frame scalars (scales, emissions) are fetched while the first gathers are in flight
     while (true) {
-        if (nb > 1) { issue(pi, vB); pi += BATCH / 2; }
         consume(pc, vA); pc += BATCH / 2;
         if (--nb == 0) break;
         if (nb > 1) { issue(pi, vA); pi += BATCH / 2; }
         consume(pc, vB); pc += BATCH / 2;
         if (--nb == 0) break;
+        if (nb > 1) { issue(pi, vB); pi += BATCH / 2; }
     }
 }
 
@@ -284,23 +286,26 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const DenParams P) {
             if (!__any_sync(kFull, lane_act)) continue;
             float r[U], fm[U], sum[U], ypre0[U], ypre1[U], ec0[U], ec1[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                int sh;
-                r[u] = scale_from_sum(__ldcg(P.colsum_a + (size_t)(t - 1) * Npad + n0 + u), &sh);
-                fm[u] = act[u] ? __ldg(P.fmax + (size_t)(t - 1) * Npad + n0 + u) : 0.f;
-                // emissions of the chunk's first labels: issued now, consumed at the first row ends
-                const long yb = (n0 + u) * P.sn + (long)(t - 1) * P.st;
-                ypre0[u] = (act[u] && labp0 >= 0) ? load_y(P.y, P.y_bf16, yb + labp0) : 0.f;
-                ypre1[u] = (act[u] && labp1 >= 0) ? load_y(P.y, P.y_bf16, yb + labp1) : 0.f;
-                ec0[u] = 0.f; ec1[u] = 0.f; sum[u] = 0.f;
-            }
+            for (int u = 0; u < U; ++u) { r[u] = 1.f; fm[u] = 0.f; ypre0[u] = 0.f; ypre1[u] = 0.f; ec0[u] = 0.f; ec1[u] = 0.f; sum[u] = 0.f; }
+            auto frame_scalars = [&]() {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    int sh;
+                    r[u] = scale_from_sum(__ldcg(P.colsum_a + (size_t)(t - 1) * Npad + n0 + u), &sh);
+                    fm[u] = act[u] ? __ldg(P.fmax + (size_t)(t - 1) * Npad + n0 + u) : 0.f;
+                    // emissions of the chunk's first labels: issued now, consumed at the first row ends
+                    const long yb = (n0 + u) * P.sn + (long)(t - 1) * P.st;
+                    ypre0[u] = (act[u] && labp0 >= 0) ? load_y(P.y, P.y_bf16, yb + labp0) : 0.f;
+                    ypre1[u] = (act[u] && labp1 >= 0) ? load_y(P.y, P.y_bf16, yb + labp1) : 0.f;
+                }
+            };
             int ql = sb - tile_s0;                               // row index inside the CTA tile
             uint32_t out_row = (uint32_t)sb;                     // row q of the frame
             uint32_t virt_row = (uint32_t)(S + vj0);             // the next virtual row
             float *const out_base = a_cur + n0;
             Vec<U> cacc = vec_zero<U>();
             walk_arcs<U, BATCH, SMEM_ARCS>(arc4, n_batches, row_bytes, reinterpret_cast<const char *>(a_prev + n0), lane_act,
-                                           [&](float *acc, int ev, bool new_label) {
+                                           frame_scalars, [&](float *acc, int ev, bool new_label) {
                 const bool k1 = ev != kEvRowPos0;
                 if (P.debug & 1) { sum[0] += acc[0]; acc[0] = 0.f; return; }
                 if (new_label) {   // rare: a new label for this row position -> refresh its emission
@@ -456,15 +461,20 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const DenParams P) 
             float rb[U], fm[U], sum_b[U], sum_ab[U], gsum0[U], gsum1[U], ypre0[U], ypre1[U], ec0[U], ec1[U], acc_c[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                int sh;
-                rb[u] = gat[u] ? scale_from_sum(__ldcg(P.colsum_b + (size_t)(tau + 1) * Npad + n0 + u), &sh) : 1.f;
-                fm[u] = act[u] ? __ldg(P.fmax + (size_t)(tau - 1) * Npad + n0 + u) : 0.f;
-                const long yb = (n0 + u) * P.sn + (long)(tau - 1) * P.st;
-                ypre0[u] = (act[u] && labp0 >= 0) ? load_y(P.y, P.y_bf16, yb + labp0) : 0.f;
-                ypre1[u] = (act[u] && labp1 >= 0) ? load_y(P.y, P.y_bf16, yb + labp1) : 0.f;
-                ec0[u] = 0.f; ec1[u] = 0.f; gsum0[u] = 0.f; gsum1[u] = 0.f;
-                sum_b[u] = 0.f; sum_ab[u] = 0.f; acc_c[u] = 0.f;
+                rb[u] = 1.f; fm[u] = 0.f; ypre0[u] = 0.f; ypre1[u] = 0.f; ec0[u] = 0.f; ec1[u] = 0.f;
+                gsum0[u] = 0.f; gsum1[u] = 0.f; sum_b[u] = 0.f; sum_ab[u] = 0.f; acc_c[u] = 0.f;
             }
+            auto frame_scalars = [&]() {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    int sh;
+                    rb[u] = gat[u] ? scale_from_sum(__ldcg(P.colsum_b + (size_t)(tau + 1) * Npad + n0 + u), &sh) : 1.f;
+                    fm[u] = act[u] ? __ldg(P.fmax + (size_t)(tau - 1) * Npad + n0 + u) : 0.f;
+                    const long yb = (n0 + u) * P.sn + (long)(tau - 1) * P.st;
+                    ypre0[u] = (act[u] && labp0 >= 0) ? load_y(P.y, P.y_bf16, yb + labp0) : 0.f;
+                    ypre1[u] = (act[u] && labp1 >= 0) ? load_y(P.y, P.y_bf16, yb + labp1) : 0.f;
+                }
+            };
             int curlab0 = -1, curlab1 = -1;
             int ql = sb - tile_s0;
             uint32_t out_row = (uint32_t)sb;
@@ -488,7 +498,7 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const DenParams P) 
                 }
             };
             walk_arcs<U, BATCH, SMEM_ARCS>(arc4, n_batches, row_bytes, reinterpret_cast<const char *>(bh_next + n0), lane_gat,
-                                           [&](float *acc, int ev, bool new_label) {
+                                           frame_scalars, [&](float *acc, int ev, bool new_label) {
                 if (ev == kEvCommon) {   // arcs shared by both members of a pair: keep the partial sum, keep accumulating
 #pragma unroll
                     for (int u = 0; u < U; ++u) acc_c[u] = acc[u];
@@ -636,7 +646,8 @@ int Dispatch(bool backward, const DeviceGraph &g, const DenParams &p, size_t fix
     const DevicePass &pass = backward ? g.bwd : g.fwd;
     const size_t arc_bytes = (size_t)pass.max_tile_arcs * sizeof(Arc);
     const size_t budget = (size_t)g.max_smem_optin > 2048 ? (size_t)g.max_smem_optin - 1024 : 0;
-    const bool smem_arcs = fixed_smem + arc_bytes <= budget;
+    const char *force_global = getenv("CCB_ARCS_IN_GLOBAL");   // test hook: exercise the large-graph fallback
+    const bool smem_arcs = fixed_smem + arc_bytes <= budget && !(force_global && force_global[0] == '1');
     const size_t smem = fixed_smem + (smem_arcs ? arc_bytes : 0);
     const int U = LaneWidth(p.Npad);
     // gathers per batch (two batches are in flight per warp); bounded by the register budget of the variant.

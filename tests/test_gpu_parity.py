@@ -57,6 +57,7 @@ def test_fixture_kat(fixture_fst, fixture_inputs):
     ("tlm_mid", 64, 40, None),                      # two utterances per lane
     ("tlm_mid", 33, 25, None),                      # ragged lane padding
     ("tlm_mid", 130, 12, None),                     # four utterances per lane, padded to 256
+    ("tlm_mid", 200, 9, None),                      # ... and two lane groups per warp (Npad = 256)
 ])
 def test_den_vs_oracle(tmp_graphs, name, N, T, lens):
     """_C.gpu_den (reference signature) vs the oracle: logZ from alpha, logZ from beta, occupancies."""
@@ -110,6 +111,29 @@ def test_ctc_vs_oracle(N, T, V, lens, ly):
         else:
             assert abs(got[n] - lp[n]) <= LOSS_RTOL * max(1.0, abs(lp[n]))
     assert np.abs(grads.transpose(0, 1).cpu().numpy() - gc).max() < GRAD_ATOL
+
+
+@pytest.mark.parametrize("env", ["CCB_ARCS_IN_GLOBAL", "CCB_NO_PAIRS"])
+def test_fallback_paths(tmp_graphs, monkeypatch, env):
+    """Arc tiles streamed from global memory (graphs too large for shared memory) and the un-paired plan give the
+    same answers as the default path."""
+    from oracle import oracle
+    from cat_b200 import _C
+    monkeypatch.setenv(env, "1")
+    path, g, V = tmp_graphs["tlm_mid"]
+    ctx = _ctx(path)
+    N, T = 40, 30
+    lens = np.maximum(1, T - (np.arange(N) * 5) % T).astype(np.int32)
+    y, _, lens, _ = oracle.synth_batch(N, T, V, seed=8, lens=lens)
+    logits = torch.tensor(y, device="cuda")
+    grad = torch.zeros_like(logits)
+    ca = torch.zeros(N, device="cuda"); cb = torch.zeros(N, device="cuda")
+    _C.gpu_den(logits, grad, torch.tensor(lens, dtype=torch.int32).cuda(), ca, cb)
+    la, lb, gd = oracle.den(g, y, lens)
+    np.testing.assert_allclose(ca.cpu().numpy(), la, rtol=LOSS_RTOL, atol=1e-4)
+    np.testing.assert_allclose(cb.cpu().numpy(), lb, rtol=LOSS_RTOL, atol=1e-4)
+    assert np.abs(grad.cpu().numpy() - gd).max() < GRAD_ATOL
+    del ctx
 
 
 def test_fused_vs_oracle_and_bf16(tmp_graphs):
