@@ -195,7 +195,8 @@ def main():
     N, T, V = args.N, args.T, args.V
     path, graph = den_graph_file(args.H, args.d, V)
     ctx = ctc_crf.CRFContext(path, gpus=local_rank)
-    S_plan, A_plan = _C.den_num_states(), _C.den_num_arcs()
+    info = _C.den_info()
+    S_plan, A_file = info["states"], info["file_arcs"]     # algorithmic bytes use the den graph's own S and A
     dtype = torch.float32 if args.dtype == "f32" else torch.bfloat16
     b_in = 4 if args.dtype == "f32" else 2
 
@@ -284,10 +285,10 @@ def main():
     ms_fb = timed(lambda: den(True), reps, 1) / reps
     ms_bwd = max(ms_fb - ms_fwd, 1e-6)
     peak, peak_src = peaks()
-    graph_bytes = A_plan * 8 + S_plan * 8
-    bytes_fwd = frames_per_step * (V * b_in + 4 * S_plan) + graph_bytes
-    bytes_bwd = frames_per_step * (V * b_in + 4 * V + 4 * S_plan) + graph_bytes
-    bytes_den = frames_per_step * (2 * V * b_in + 4 * V + 8 * S_plan) + 2 * graph_bytes
+    graph_bytes = A_file * 12 + S_plan * 16
+    bytes_fwd = frames_per_step * (V * b_in + 4 * S_plan) + graph_bytes // 2
+    bytes_bwd = frames_per_step * (V * b_in + 4 * V + 4 * S_plan) + graph_bytes // 2
+    bytes_den = frames_per_step * (2 * V * b_in + 4 * V + 8 * S_plan) + graph_bytes
     ach = bytes_den / (ms_fb * 1e-3) / 1e9
     roofline = {
         "bound": "hbm", "kernel": "den_forward_kernel + den_backward_kernel (denominator forward-backward)",
@@ -298,7 +299,9 @@ def main():
             "den_forward_kernel": {"ms": ms_fwd, "GB/s": bytes_fwd / (ms_fwd * 1e-3) / 1e9, "frac": bytes_fwd / (ms_fwd * 1e-3) / 1e9 / peak},
             "den_backward_kernel": {"ms": ms_bwd, "GB/s": bytes_bwd / (ms_bwd * 1e-3) / 1e9, "frac": bytes_bwd / (ms_bwd * 1e-3) / 1e9 / peak},
         },
-        "arc_evals_per_s": 2.0 * A_plan * frames_per_step / (ms_fb * 1e-3),
+        "arc_evals_per_s": 2.0 * A_file * frames_per_step / (ms_fb * 1e-3),
+        "row_gathers_per_frame": info["fwd_slots"] + info["bwd_slots"],
+        "l2_gather_TBps": (info["fwd_slots"] + info["bwd_slots"]) * frames_per_step * (128 if N <= 32 else 256 if N <= 64 else 512) / (ms_fb * 1e-3) / 1e12,
     }
     del alpha_ws, aux_ws, gden
 
@@ -344,7 +347,7 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": f"CTC-CRF loss+grad N={N}/GPU,T={T},V={V} (BASELINE configs headline)",
-                       "den_graph": f"synthetic T-compose-LM H={args.H},d={args.d}: file S={graph.num_states} A={graph.num_arcs}; plan S={S_plan} A={A_plan}",
+                       "den_graph": f"synthetic T-compose-LM H={args.H},d={args.d}: file S={graph.num_states} A={graph.num_arcs}; plan S={info['states']} pairs={info['pairs']} gathered arcs fwd/bwd={info['fwd_arcs']}/{info['bwd_arcs']}",
                        "global_batch": N * world, "parallelism": f"minibatch sharded x{world}, den graph replicated, 1 all-reduce of [cost,count]",
                        "lamb": args.lamb,
                        "l2": "no explicit flush: each step streams a 15.4 GB alpha spill (>> 126 MB L2)" if N * T >= 20000 else "small dev workload"},

@@ -59,6 +59,15 @@ def den_num_states() -> int:
     return C.c_int.in_dll(_lib.lib(), "DEN_NUM_STATES").value
 
 
+def den_info() -> dict:
+    """Sizes of the loaded den graph and of its kernel plan."""
+    info = (C.c_long * 8)()
+    if _lib.lib().ccb_den_info(info) != 0:
+        raise RuntimeError("den graph not loaded")
+    keys = ("file_states", "file_arcs", "states", "pairs", "fwd_slots", "bwd_slots", "fwd_arcs", "bwd_arcs")
+    return dict(zip(keys, [int(x) for x in info]))
+
+
 def den_num_arcs() -> int:
     return C.c_int.in_dll(_lib.lib(), "DEN_NUM_ARCS").value
 
@@ -162,11 +171,40 @@ def upload_meta(labels: torch.Tensor, lx: torch.Tensor, ly: torch.Tensor, device
     return meta, sum_l, int(ly.max()) if N else 0
 
 
+MAX_UTTS_PER_CALL = 512          # bookkeeping CTA of the den kernels handles one utterance per thread
+_WS_FRACTION = 0.85              # of the currently free device memory a call may use for scratch
+
+
+def _plan_slices(L, lx, ly, N, V, dev):
+    """Split the batch into contiguous slices whose scratch (alpha spill etc.) fits the free device memory.
+    Each slice walks only max(lx[slice]) frames."""
+    free, _ = torch.cuda.mem_get_info(dev)
+    budget = int(free * _WS_FRACTION)
+    slices, n0 = [], 0
+    while n0 < N:
+        n1 = min(N, n0 + MAX_UTTS_PER_CALL)
+        while True:
+            tmax = max(1, int(lx[n0:n1].max()))
+            maxl = int(ly[n0:n1].max())
+            need = (int(L.ccb_den_alpha_floats(n1 - n0, tmax)) * 4 + int(L.ccb_den_aux_bytes(n1 - n0, tmax))
+                    + int(L.ccb_ctc_workspace_bytes(n1 - n0, tmax, maxl)))
+            if need <= budget or n1 - n0 == 1:
+                break
+            n1 = n0 + max(1, (n1 - n0) // 2)
+        if need > budget:
+            raise RuntimeError(f"CTC-CRF scratch for a single utterance of {tmax} frames needs {need >> 20} MiB, "
+                               f"only {budget >> 20} MiB free")
+        slices.append((n0, n1, tmax, maxl))
+        n0 = n1
+    return slices
+
+
 def ctc_crf_loss_fwd(logits: torch.Tensor, labels: torch.Tensor, lx: torch.Tensor, ly: torch.Tensor,
                      lamb: float, size_average: bool, want_parts: bool = False
                      ) -> Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]:
     """Fused CTC-CRF loss.  logits (N,T,V) fp32 or bf16 CUDA contiguous log-probs; labels/lx/ly int32 CPU.
-    Returns (loss[1] fp32 CUDA, grad (N,T,V) fp32 CUDA, parts[2N] or None).  Never synchronises the host."""
+    Returns (loss[1] fp32 CUDA, grad (N,T,V) fp32 CUDA, parts[2N] or None).  Never synchronises the host.
+    Batches whose scratch does not fit the free memory (or > 512 utterances) are processed in slices."""
     L = _lib.lib()
     assert logits.is_cuda and logits.dim() == 3 and logits.is_contiguous()
     if logits.dtype not in _DTYPES:
@@ -179,23 +217,35 @@ def ctc_crf_loss_fwd(logits: torch.Tensor, labels: torch.Tensor, lx: torch.Tenso
         raise RuntimeError("input lengths must lie in [0, T]")
     if labels.numel() and (int(labels.min()) < 0 or int(labels.max()) >= V):
         raise RuntimeError("label out of range")
+    esz = logits.element_size()
+    scale = 1.0 / N if size_average else 1.0
     with torch.cuda.device(dev):
-        meta, sum_l, max_l = upload_meta(labels, lx, ly, dev)
+        meta, sum_l, _ = upload_meta(labels, lx, ly, dev)
         base = meta.data_ptr()
         p_labels, p_off = base, base + 4 * sum_l
         p_ly, p_lx = p_off + 4 * (N + 1), p_off + 4 * (2 * N + 1)
-        alpha_ws = torch.empty(int(L.ccb_den_alpha_floats(N, T)), dtype=torch.float32, device=dev)
-        aux_ws = torch.empty(int(L.ccb_den_aux_bytes(N, T)), dtype=torch.uint8, device=dev)
-        ctc_ws = torch.empty(int(L.ccb_ctc_workspace_bytes(N, T, max_l)), dtype=torch.uint8, device=dev)
         grad = torch.empty((N, T, V), dtype=torch.float32, device=dev)
-        loss = torch.empty(1, dtype=torch.float32, device=dev)
         parts = torch.empty(2 * N, dtype=torch.float32, device=dev) if want_parts else None
-        rc = L.ccb_ctc_crf_loss_fwd(logits.data_ptr(), _DTYPES[logits.dtype], N, T, V, p_labels, p_off, p_ly, p_lx,
-                                    max_l, float(lamb), 1 if size_average else 0, alpha_ws.data_ptr(),
-                                    aux_ws.data_ptr(), ctc_ws.data_ptr(), grad.data_ptr(), loss.data_ptr(),
-                                    parts.data_ptr() if parts is not None else None, _stream(dev))
-        _check(rc, "ctc_crf_loss_fwd")
-        # scratch is released to the caching allocator here; it is stream-ordered, so reuse is safe
+        slices = _plan_slices(L, lx, ly, N, V, dev)
+        losses = torch.empty(len(slices), dtype=torch.float32, device=dev)
+        stream = _stream(dev)
+        for i, (n0, n1, tmax, maxl) in enumerate(slices):
+            n = n1 - n0
+            alpha_ws = torch.empty(int(L.ccb_den_alpha_floats(n, tmax)), dtype=torch.float32, device=dev)
+            aux_ws = torch.empty(int(L.ccb_den_aux_bytes(n, tmax)), dtype=torch.uint8, device=dev)
+            ctc_ws = torch.empty(int(L.ccb_ctc_workspace_bytes(n, tmax, maxl)), dtype=torch.uint8, device=dev)
+            sub_parts = torch.empty(2 * n, dtype=torch.float32, device=dev) if want_parts else None
+            rc = L.ccb_ctc_crf_loss_fwd(logits.data_ptr() + n0 * T * V * esz, _DTYPES[logits.dtype], n, T, V, tmax,
+                                        p_labels, p_off + 4 * n0, p_ly + 4 * n0, p_lx + 4 * n0, maxl, float(lamb),
+                                        float(scale), alpha_ws.data_ptr(), aux_ws.data_ptr(), ctc_ws.data_ptr(),
+                                        grad.data_ptr() + n0 * T * V * 4, losses.data_ptr() + 4 * i,
+                                        sub_parts.data_ptr() if want_parts else None, stream)
+            _check(rc, "ctc_crf_loss_fwd")
+            if want_parts:
+                parts[n0:n1] = sub_parts[:n]
+                parts[N + n0:N + n1] = sub_parts[n:]
+            del alpha_ws, aux_ws, ctc_ws      # stream-ordered reuse by the caching allocator for the next slice
+        loss = losses.sum().reshape(1) if len(slices) > 1 else losses
         meta.record_stream(torch.cuda.current_stream(dev))
     return loss, grad, parts
 

@@ -20,7 +20,7 @@ class ctcOptions(C.Structure):
 # every symbol include/ctc_crf_b200.h declares (tests check the export list against the header)
 SYMBOLS = [
     "Init", "Release", "compute_alpha", "compute_beta_and_grad", "compute_ctc_loss", "get_workspace_size",
-    "ctcGetStatusString", "ccb_last_error", "ccb_den_loaded", "ccb_den_alpha_floats", "ccb_den_aux_bytes",
+    "ctcGetStatusString", "ccb_last_error", "ccb_den_loaded", "ccb_den_info", "ccb_den_alpha_floats", "ccb_den_aux_bytes",
     "ccb_ctc_workspace_bytes", "ccb_den_forward_backward", "ccb_ctc_forward_backward", "ccb_ctc_crf_loss_fwd",
     "ccb_launch_count", "ccb_debug_timeline", "ccb_plan_create", "ccb_plan_destroy", "ccb_plan_info", "ccb_plan_copy",
 ]
@@ -50,6 +50,7 @@ def lib() -> C.CDLL:
     L.ctcGetStatusString.argtypes = [C.c_int]; L.ctcGetStatusString.restype = C.c_char_p
     L.ccb_last_error.argtypes = []; L.ccb_last_error.restype = C.c_char_p
     L.ccb_den_loaded.argtypes = [C.c_int]; L.ccb_den_loaded.restype = C.c_int
+    L.ccb_den_info.argtypes = [C.POINTER(C.c_long)]; L.ccb_den_info.restype = C.c_int
     L.ccb_den_alpha_floats.argtypes = [C.c_int, C.c_int]; L.ccb_den_alpha_floats.restype = C.c_size_t
     L.ccb_den_aux_bytes.argtypes = [C.c_int, C.c_int]; L.ccb_den_aux_bytes.restype = C.c_size_t
     L.ccb_ctc_workspace_bytes.argtypes = [C.c_int, C.c_int, C.c_int]; L.ccb_ctc_workspace_bytes.restype = C.c_size_t
@@ -59,8 +60,8 @@ def lib() -> C.CDLL:
     L.ccb_ctc_forward_backward.argtypes = [vp, C.c_int, C.c_long, C.c_long, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp,
                                            C.c_int, C.c_int, vp, vp, C.c_long, C.c_long, C.c_float, vp, vp]
     L.ccb_ctc_forward_backward.restype = C.c_int
-    L.ccb_ctc_crf_loss_fwd.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, C.c_int, C.c_float,
-                                       C.c_int, vp, vp, vp, vp, vp, vp, vp]
+    L.ccb_ctc_crf_loss_fwd.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, C.c_int,
+                                       C.c_float, C.c_float, vp, vp, vp, vp, vp, vp, vp]
     L.ccb_ctc_crf_loss_fwd.restype = C.c_int
     L.ccb_launch_count.argtypes = []; L.ccb_launch_count.restype = C.c_long
     L.ccb_debug_timeline.argtypes = [vp, C.c_int, C.c_int]; L.ccb_debug_timeline.restype = None

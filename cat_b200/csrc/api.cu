@@ -252,6 +252,13 @@ long ccb_launch_count(void) { return g_launches.load(); }
 void ccb_debug_timeline(void *dev_buffer, int step0, int nsteps) {
     g_timeline = reinterpret_cast<unsigned long long *>(dev_buffer); g_tl_step0 = step0; g_tl_steps = nsteps;
 }
+int ccb_den_info(long *info) {
+    if (!g_plan_valid || !info) return 1;
+    info[0] = g_plan.file_states; info[1] = g_plan.file_arcs; info[2] = g_plan.num_states; info[3] = g_plan.num_pairs;
+    info[4] = (long)g_plan.fwd.arcs.size(); info[5] = (long)g_plan.bwd.arcs.size();
+    info[6] = g_plan.fwd.real_arcs; info[7] = g_plan.bwd.real_arcs;
+    return 0;
+}
 int ccb_den_loaded(int device) { return device >= 0 && device < kMaxDevices && g_dev[device].loaded ? 1 : 0; }
 
 void Init(const char *fst_name, int n_gpus, int *gpus) {
@@ -353,27 +360,27 @@ int ccb_ctc_forward_backward(const void *logits, int dtype, long sn, long st, in
     return 0;
 }
 
-int ccb_ctc_crf_loss_fwd(const void *logits, int dtype, int N, int T, int V,
+int ccb_ctc_crf_loss_fwd(const void *logits, int dtype, int N, int T, int V, int Tmax,
                          const int *labels_dev, const int *label_off_dev, const int *label_len_dev,
-                         const int *len_dev, int max_label_len, float lamb, int size_average,
+                         const int *len_dev, int max_label_len, float lamb, float scale,
                          float *alpha_ws, void *aux_ws, void *ctc_ws, float *grad, float *loss, float *parts,
                          void *stream) {
     g_err.clear();
     DeviceGraph *g;
     if (CurrentGraph(&g)) return 1;
-    if (CheckDen(*g, dtype, N, T, V)) return 1;
+    if (Tmax <= 0 || Tmax > T) return Fail("ctc_crf_loss_fwd: Tmax must lie in [1, T]");
+    if (CheckDen(*g, dtype, N, Tmax, V)) return 1;
     if (!alpha_ws || !aux_ws || !ctc_ws || !grad || !loss) return Fail("ctc_crf_loss_fwd: missing buffer");
     cudaStream_t s = (cudaStream_t)stream;
-    const long sn = (long)T * V, st = V;
-    const float scale = size_average ? 1.f / (float)N : 1.f;
+    const long sn = (long)T * V, st = V;     // the (N,T,V) block is addressed in place; only Tmax frames are walked
     CCB_CUDA(cudaMemsetAsync(grad, 0, sizeof(float) * (size_t)N * T * V, s));
-    if (DenForward(*g, logits, dtype, sn, st, N, T, V, len_dev, alpha_ws, aux_ws, s)) return 1;
-    if (DenBackward(*g, logits, dtype, sn, st, N, T, V, len_dev, alpha_ws, aux_ws, grad, sn, st, scale, s)) return 1;
-    const DenAuxLayout L = MakeDenAuxLayout(g->S, N, T);
+    if (DenForward(*g, logits, dtype, sn, st, N, Tmax, V, len_dev, alpha_ws, aux_ws, s)) return 1;
+    if (DenBackward(*g, logits, dtype, sn, st, N, Tmax, V, len_dev, alpha_ws, aux_ws, grad, sn, st, scale, s)) return 1;
+    const DenAuxLayout L = MakeDenAuxLayout(g->S, N, Tmax);
     float *logz = reinterpret_cast<float *>((char *)aux_ws + L.logz_a);
     float *logp = reinterpret_cast<float *>((char *)aux_ws + L.logz_b);   // logZ(beta) no longer needed: reuse
     std::string err;
-    int rc = LaunchCtc(logits, dtype == CCB_DTYPE_BF16, sn, st, N, T, V, labels_dev, label_off_dev, label_len_dev, len_dev,
+    int rc = LaunchCtc(logits, dtype == CCB_DTYPE_BF16, sn, st, N, Tmax, V, labels_dev, label_off_dev, label_len_dev, len_dev,
                        max_label_len, 0, reinterpret_cast<float *>(ctc_ws), grad, sn, st, -(1.f + lamb) * scale, logp, s, &err);
     if (rc) return Fail(err);
     rc = LaunchAssembleLoss(logz, logp, N, lamb, scale, loss, s);

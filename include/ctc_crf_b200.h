@@ -90,6 +90,9 @@ ctcStatus_t get_workspace_size(const int *const label_lengths, const int *const 
 
 const char *ccb_last_error(void);            /* thread-local message of the last failure ("" if none) */
 int ccb_den_loaded(int device);              /* 1 if Init() covered this device */
+/* info[0..7] = file states, file arcs, states after the in-label split, pairs, forward / backward stream slots
+ * (with padding), forward / backward arcs actually gathered per frame and utterance */
+int ccb_den_info(long *info);
 
 /* scratch sizes for N utterances x T frames on the current device's den graph */
 size_t ccb_den_alpha_floats(int N, int T);   /* alpha spill, floats */
@@ -110,13 +113,15 @@ int ccb_ctc_forward_backward(const void *logits, int dtype, long sn, long st, in
                              const int *len_dev, int max_label_len, int blank, void *workspace,
                              float *grad, long gsn, long gst, float grad_scale, float *logp, void *stream);
 
-/* Fused CTC-CRF loss (ctc_crf/__init__.py:58-90 in one call, no host synchronisation):
- *   loss[0] = sum_n (logZ_den[n] - (1+lamb) logp_ctc[n]) * (size_average ? 1/N : 1)
- *   grad    = (gamma_den - (1+lamb) gamma_ctc) * (size_average ? 1/N : 1)      (N,T,V) fp32, zeroed here
- * parts (optional, may be NULL): 2N floats = [logZ_den | logp_ctc]. */
-int ccb_ctc_crf_loss_fwd(const void *logits, int dtype, int N, int T, int V,
+/* Fused CTC-CRF loss (ctc_crf/__init__.py:58-90 in one call, no host synchronisation) of an (N,T,V) block:
+ *   loss[0] = scale * sum_n (logZ_den[n] - (1+lamb) logp_ctc[n])
+ *   grad    = scale * (gamma_den - (1+lamb) gamma_ctc)                     (N,T,V) fp32, zeroed here
+ * scale = 1/batch for size_average (the caller may split a batch into several calls and sum the losses).
+ * Tmax <= T is the number of frames actually walked (max input length of the block); workspaces are sized with
+ * ccb_*_floats/bytes(N, Tmax).  parts (optional, may be NULL): 2N floats = [logZ_den | logp_ctc]. */
+int ccb_ctc_crf_loss_fwd(const void *logits, int dtype, int N, int T, int V, int Tmax,
                          const int *labels_dev, const int *label_off_dev, const int *label_len_dev,
-                         const int *len_dev, int max_label_len, float lamb, int size_average,
+                         const int *len_dev, int max_label_len, float lamb, float scale,
                          float *alpha_ws, void *aux_ws, void *ctc_ws,
                          float *grad, float *loss, float *parts, void *stream);
 

@@ -157,6 +157,29 @@ def test_fused_vs_oracle_and_bf16(tmp_graphs):
     del ctx
 
 
+def test_sliced_batches_and_padded_frames(tmp_graphs, monkeypatch):
+    """Batches are processed in memory-bounded slices that walk only max(len) frames: same loss/grad as one call,
+    and frames beyond every length (T padded past max len) cost nothing and stay zero."""
+    from oracle import oracle
+    from cat_b200 import _C
+    path, g, V = tmp_graphs["tlm_mid"]
+    ctx = _ctx(path)
+    N, T = 11, 50
+    lens = np.array([37, 37, 30, 28, 25, 19, 12, 9, 7, 3, 1], np.int32)      # T=50 > max len
+    y, labels, lens, ly = oracle.synth_batch(N, T, V, seed=31, lens=lens)
+    ref_loss, ref_grad = _run_ours(y, labels, lens, ly, 0.05)
+    monkeypatch.setattr(_C, "MAX_UTTS_PER_CALL", 4)                            # 3 slices
+    loss, grad = _run_ours(y, labels, lens, ly, 0.05)
+    _close_loss(loss, ref_loss, 1e-6)
+    assert np.abs(grad - ref_grad).max() < 1e-6
+    oloss, ograd, _ = oracle.ctc_crf(g, y, labels, lens, ly, 0.05)
+    _close_loss(loss, oloss)
+    assert np.abs(grad - ograd).max() < GRAD_ATOL
+    for n in range(N):
+        assert not grad[n, lens[n]:].any()
+    del ctx
+
+
 def test_vs_reference_cuda(tmp_path):
     """Side by side with the reference's own CUDA code (oracle/_ref) on the AISHELL-shaped config scaled to
     what the fp64 oracle also finishes in seconds: V=218, 100k-arc T-compose-LM graph, N=8, T=120."""
