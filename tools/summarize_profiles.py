@@ -44,6 +44,18 @@ for r in rr[2:]:
         if w in hdr:
             i = hdr.index(w); out.append(f"| {w} | {r[i]} | {units[i]} |")
     out.append("")
+# per-launch DRAM traffic of the den kernels, per frame (the capture ran bench.py --T 100 => 100 frames per launch)
+traffic = {}
+for r in rr[2:]:
+    name = r[hdr.index("Kernel Name")]
+    key = "den_forward_kernel" if "den_forward" in name else "den_backward_kernel" if "den_backward" in name else None
+    if not key: continue
+    def val(m):
+        i = hdr.index(m); v = float(r[i].replace(",", "")); u = units[i].lower()
+        return v * (1e9 if u.startswith("gbyte") else 1e6 if u.startswith("mbyte") else 1e3 if u.startswith("kbyte") else 1)
+    traffic[key] = {"dram_bytes_per_frame": (val("dram__bytes_read.sum") + val("dram__bytes_write.sum")) / 100.0,
+                    "capture": f"{tag}: ncu --set full, bench.py --T 100 (N=64, V=218, 1M-arc graph)"}
+json.dump(traffic, open("profiles/traffic.json", "w"), indent=1)
 os.makedirs("profiles", exist_ok=True)
 open(f"profiles/{tag}_summary.md", "w").write("\n".join(out) + "\n")
 print("wrote", f"profiles/{tag}_summary.md")
