@@ -60,7 +60,7 @@ int Upload(T **dst, const std::vector<T> &src) {
 void FreeDevice(DeviceGraph &d) {
     if (!d.loaded) return;
     cudaFree(d.state_label); cudaFree(d.state_pos); cudaFree(d.final_lin); cudaFree(d.start_arcs);
-    for (DevicePass *p : {&d.fwd, &d.bwd}) { cudaFree(p->arcs); cudaFree(p->chunk_state); cudaFree(p->chunk_arc); cudaFree(p->chunk_pair); cudaFree(p->cta_labels); }
+    for (DevicePass *p : {&d.fwd, &d.bwd}) { cudaFree(p->arcs); cudaFree(p->chunk_state); cudaFree(p->chunk_arc); cudaFree(p->chunk_pair); cudaFree(p->cta_labels); cudaFree(p->w1); }
     d = DeviceGraph();
 }
 
@@ -70,6 +70,7 @@ int UploadPass(const PassPlan &h, DevicePass *d) {
     if (Upload(&d->chunk_arc, h.chunk_arc)) return 1;
     if (Upload(&d->chunk_pair, h.chunk_pair)) return 1;
     if (Upload(&d->cta_labels, h.cta_labels)) return 1;
+    if (Upload(&d->w1, h.w1)) return 1;
     d->num_arcs = (int)h.arcs.size();
     d->max_tile_arcs = h.max_tile_arcs;
     d->max_tile_labels = h.max_tile_labels;
@@ -505,6 +506,7 @@ int ccb_plan_copy(void *plan, int which, void *dst, size_t dst_bytes) {
         case 12: src = p->start_arcs.data(); bytes = p->start_arcs.size() * sizeof(Arc); break;
         case 13: src = p->fwd.cta_labels.data(); bytes = p->fwd.cta_labels.size() * 4; break;
         case 14: src = p->bwd.cta_labels.data(); bytes = p->bwd.cta_labels.size() * 4; break;
+        case 15: src = p->bwd.w1.data(); bytes = p->bwd.w1.size() * 4; break;
         default: return 1;
     }
     if (bytes > dst_bytes) return 2;

@@ -19,6 +19,7 @@ struct DevicePass {
     int *chunk_arc = nullptr;
     int *chunk_pair = nullptr;
     int *cta_labels = nullptr;
+    float *w1 = nullptr;      // backward pass: second weight per slot
     int num_arcs = 0;
     int max_tile_arcs = 0;
     int max_tile_labels = 0;
@@ -44,6 +45,7 @@ struct DeviceGraph {
 struct DenParams {
     // graph
     const Arc *arcs;
+    const float *w1;      // backward pass only
     const int *chunk_state;
     const int *chunk_arc;
     const int *chunk_pair;

@@ -99,7 +99,9 @@ inline float WithSign(float w) { uint32_t b = Bits(w) | 0x80000000u; float r; me
 
 struct Segment {
     std::vector<Arc> arcs;
+    std::vector<float> w1;   // backward group segments only (same length as arcs)
     int event = kEvRow;
+    int rows = 1;            // rows that end with this segment (0 for kEvCommon, 2 for a backward pair group)
 };
 struct Group {
     std::vector<Segment> segs;
@@ -108,7 +110,7 @@ struct Group {
 
 // Cut groups into n_chunks contiguous chunks of near-equal cost and emit the chunk-major padded arc stream.
 void Layout(const std::vector<Group> &groups, int S, const std::vector<int> &state_label, const std::vector<int> &state_pos,
-            int n_ctas, int n_warps, int64_t row_cost, PassPlan *pp) {
+            int n_ctas, int n_warps, int64_t row_cost, bool emit_w1, PassPlan *pp) {
     const int G = (int)groups.size();
     const int n_chunks = n_ctas * n_warps;
     auto quads = [](const Segment &sg) { return std::max<int64_t>(1, ((int64_t)sg.arcs.size() + kQuad - 1) / kQuad); };
@@ -129,6 +131,7 @@ void Layout(const std::vector<Group> &groups, int S, const std::vector<int> &sta
     chunk_group[n_chunks] = G;
 
     pp->arcs.clear();
+    pp->w1.clear();
     pp->chunk_state.assign((size_t)n_chunks + 1, S);
     pp->chunk_arc.assign((size_t)n_chunks + 1, 0);
     pp->chunk_pair.assign((size_t)n_chunks + 1, 0);
@@ -144,32 +147,44 @@ void Layout(const std::vector<Group> &groups, int S, const std::vector<int> &sta
             pairs_seen += gr.pairs;
             int row = gr.first_state;
             for (auto &sg : gr.segs) {
-                // sign(w[0]) of a row's last quad: "the label differs from the previous row of this position in the
-                // chunk" -- the kernels then skip the label lookup / emission refresh on the common path
-                bool label_changed = false;
-                if (sg.event != kEvCommon) {
+                // "label changed" flags: the row's label differs from the previous row of its position in this chunk;
+                // the kernels then skip the label lookup / emission refresh on the common path.
+                // one-row segments: sign(w[0]); two-row (backward pair) segments: sign(w[0]) for p0, sign(w[1]) for p1.
+                bool chg0 = false, chg1 = false;
+                if (sg.rows == 1) {
                     const int k = sg.event == kEvRowPos0 ? 0 : 1;
-                    label_changed = state_label[(size_t)row] != prev_label[k];
+                    chg0 = state_label[(size_t)row] != prev_label[k];
                     prev_label[k] = state_label[(size_t)row];
-                    ++row;
+                } else if (sg.rows == 2) {
+                    chg0 = state_label[(size_t)row] != prev_label[0];
+                    prev_label[0] = state_label[(size_t)row];
+                    chg1 = state_label[(size_t)row + 1] != prev_label[1];
+                    prev_label[1] = state_label[(size_t)row + 1];
                 }
+                row += sg.rows;
                 const size_t padded = (size_t)quads(sg) * kQuad;
                 // Padding arcs carry weight 0 but are still gathered: point them at a row this warp reads anyway.
                 // Pointing them all at one fixed row makes every warp of the grid hammer a single L2 line
                 // (measured: 2x frame time from that hot spot alone).
                 const uint32_t pad_peer = sg.arcs.empty() ? (uint32_t)gr.first_state : sg.arcs.back().peer;
+                const bool dual = !sg.w1.empty() || sg.rows == 2;
                 for (size_t i = 0; i < padded; ++i) {
                     Arc a = i < sg.arcs.size() ? sg.arcs[i] : Arc{pad_peer, 0.f};
                     if (i + 1 == padded) a.w = WithSign(a.w);
                     if (i + 2 == padded && (sg.event & 2)) a.w = WithSign(a.w);
-                    if (i + 3 == padded && (sg.event & 1)) a.w = WithSign(a.w);
-                    if (i + 4 == padded && label_changed) a.w = WithSign(a.w);
+                    if (dual) {
+                        if (i + 3 == padded && chg1) a.w = WithSign(a.w);
+                    } else {
+                        if (i + 3 == padded && (sg.event & 1)) a.w = WithSign(a.w);
+                    }
+                    if (i + 4 == padded && chg0) a.w = WithSign(a.w);
                     pp->arcs.push_back(a);
+                    if (emit_w1) pp->w1.push_back(i < sg.w1.size() ? sg.w1[i] : 0.f);
                 }
                 last_peer = pad_peer;
             }
         }
-        while (pp->arcs.size() % kChunkArcPad) pp->arcs.push_back(Arc{last_peer, 0.f});
+        while (pp->arcs.size() % kChunkArcPad) { pp->arcs.push_back(Arc{last_peer, 0.f}); if (emit_w1) pp->w1.push_back(0.f); }
     }
     pp->chunk_arc[n_chunks] = (int)pp->arcs.size();
     pp->chunk_pair[n_chunks] = pairs_seen;
@@ -387,37 +402,39 @@ bool BuildDenPlan(const HostFst &fst, int n_ctas, int n_warps, DenPlan *plan, st
             forward_row(g.s1, &f.arcs);
             f.event = kEvRow;
             out_list(g.s1, &l1);
-            for (auto &e : l1) b.arcs.push_back(Arc{(uint32_t)e.q, e.w});
+            for (auto &e : l1) { b.arcs.push_back(Arc{(uint32_t)e.q, e.w}); b.w1.push_back(0.f); }
             b.event = kEvRow;
+            b.rows = 1;
             fg.segs.push_back(std::move(f));
             bg.segs.push_back(std::move(b));
         } else {
-            Segment f0, f1, bc, b0, b1;
+            Segment f0, f1, b;
             forward_row(g.s0, &f0.arcs); f0.event = kEvRowPos0;
             forward_row(g.s1, &f1.arcs); f1.event = kEvRowPos1;
+            // backward: ONE segment for the pair; slot weights (w for p0, w1 for p1): shared arcs carry both
             out_list(g.s0, &l0);
             out_list(g.s1, &l1);
             size_t i = 0, j = 0;
             while (i < l0.size() || j < l1.size()) {
                 if (i < l0.size() && j < l1.size() && l0[i].q == l1[j].q && l0[i].wb == l1[j].wb) {
-                    bc.arcs.push_back(Arc{(uint32_t)l0[i].q, l0[i].w}); ++i; ++j;
+                    b.arcs.push_back(Arc{(uint32_t)l0[i].q, l0[i].w}); b.w1.push_back(l1[j].w); ++i; ++j;
                 } else if (j >= l1.size() || (i < l0.size() && (l0[i].q < l1[j].q || (l0[i].q == l1[j].q && l0[i].wb < l1[j].wb)))) {
-                    b0.arcs.push_back(Arc{(uint32_t)l0[i].q, l0[i].w}); ++i;
+                    b.arcs.push_back(Arc{(uint32_t)l0[i].q, l0[i].w}); b.w1.push_back(0.f); ++i;
                 } else {
-                    b1.arcs.push_back(Arc{(uint32_t)l1[j].q, l1[j].w}); ++j;
+                    b.arcs.push_back(Arc{(uint32_t)l1[j].q, 0.f}); b.w1.push_back(l1[j].w); ++j;
                 }
             }
-            bc.event = kEvCommon; b0.event = kEvRowPos0; b1.event = kEvRowPos1;
+            b.event = kEvRowPos1;
+            b.rows = 2;
             fg.segs.push_back(std::move(f0)); fg.segs.push_back(std::move(f1));
-            if (!bc.arcs.empty()) bg.segs.push_back(std::move(bc));
-            bg.segs.push_back(std::move(b0)); bg.segs.push_back(std::move(b1));
+            bg.segs.push_back(std::move(b));
         }
         fgroups.push_back(std::move(fg));
         bgroups.push_back(std::move(bg));
     }
     // row costs in arc units, fitted to per-warp timelines on B200 (tools/timeline.py)
-    Layout(fgroups, (int)S, plan->state_label, plan->state_pos, n_ctas, n_warps, 4, &plan->fwd);
-    Layout(bgroups, (int)S, plan->state_label, plan->state_pos, n_ctas, n_warps, 6, &plan->bwd);
+    Layout(fgroups, (int)S, plan->state_label, plan->state_pos, n_ctas, n_warps, 4, false, &plan->fwd);
+    Layout(bgroups, (int)S, plan->state_label, plan->state_pos, n_ctas, n_warps, 8, true, &plan->bwd);
     return true;
 }
 

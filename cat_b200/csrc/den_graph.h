@@ -45,6 +45,7 @@ bool ReadFstFile(const char *path, HostFst *out, std::string *err);
 // into n_ctas*n_warps contiguous chunks of near-equal cost; CTA c owns chunks [c*n_warps, (c+1)*n_warps).
 struct PassPlan {
     std::vector<Arc> arcs;              // chunk-major: segments as whole quads, chunk tails padded with unflagged zero quads
+    std::vector<float> w1;              // backward only: second weight of every slot (see DenPlan::bwd)
     std::vector<int> chunk_state;       // [n_chunks+1] first state of each chunk
     std::vector<int> chunk_arc;         // [n_chunks+1] first arc of each chunk (multiples of kChunkArcPad)
     std::vector<int> chunk_pair;        // [n_chunks+1] first pair (virtual row) of each chunk
@@ -67,6 +68,11 @@ struct DenPlan {
     std::vector<float> final_lin;       // [S] exp(final_logw) (0 for non-final)
     std::vector<int> orig_state;        // [S] state id in the file
     std::vector<Arc> start_arcs;        // out-arcs of the start state (plain), for logZ recomputed from beta
+    // fwd: one segment per state (its in-arcs; peers may be virtual pair rows), events kEvRow / kEvRowPos0 / kEvRowPos1.
+    // bwd: one segment per GROUP (an unpaired state, or a pair p0,p1): every slot carries two weights, arcs[i].w for the
+    //      group's first row and w1[i] for its second row (0 when the arc does not belong to that row), so the arcs the
+    //      two members share are gathered once.  Event kEvRow = one-row group, kEvRowPos1 = two-row group; the
+    //      label-changed flags of the two rows are sign(w[0]) and sign(w[1]) of the last quad.
     PassPlan fwd, bwd;
 };
 

@@ -187,6 +187,76 @@ __device__ __forceinline__ void walk_arcs(const uint4 *arcs, int n_batches, uint
     }
 }
 
+// Backward variant: every slot carries two weights (den_graph.h DenPlan::bwd) -- w0 for the group's first row, w1 for
+// its second row -- so the arcs shared by the two members of a pair are gathered once and feed two accumulators.
+// Shared-memory quads are three 16-byte words {byte offsets}{w0}{w1}; the global fallback reads the plan's AoS arcs
+// plus the separate w1 array.  `group_end(acc0, acc1, pair, new_label0, new_label1)` runs at the last quad of a group.
+template <int U, int BATCH, bool SMEM_ARCS, typename Prologue, typename GroupEnd>
+__device__ __forceinline__ void walk_arcs_dual(const uint4 *arcs, const float4 *w1g, int n_batches, uint32_t row_bytes,
+                                               const char *lane_base, bool do_load, Prologue &&prologue, GroupEnd &&group_end) {
+    constexpr int kWordsPerQuad = SMEM_ARCS ? 3 : 2;
+    Vec<U> vA[BATCH], vB[BATCH];
+#pragma unroll
+    for (int i = 0; i < BATCH; ++i) { vA[i] = vec_zero<U>(); vB[i] = vec_zero<U>(); }
+    float acc0[U], acc1[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) { acc0[u] = 0.f; acc1[u] = 0.f; }
+
+    auto issue = [&](const uint4 *p, Vec<U> *v) {
+        if (do_load) {
+#pragma unroll
+            for (int g4 = 0; g4 < BATCH / kQuad; ++g4) {
+                const uint4 pr = SMEM_ARCS ? p[kWordsPerQuad * g4] : load_quad_peers<false>(p + 2 * g4, row_bytes);
+                v[g4 * kQuad + 0] = gather_row<U>(lane_base, pr.x);
+                v[g4 * kQuad + 1] = gather_row<U>(lane_base, pr.y);
+                v[g4 * kQuad + 2] = gather_row<U>(lane_base, pr.z);
+                v[g4 * kQuad + 3] = gather_row<U>(lane_base, pr.w);
+            }
+        }
+    };
+    auto consume = [&](const uint4 *p, const float4 *pw1, const Vec<U> *v) {
+#pragma unroll
+        for (int g4 = 0; g4 < BATCH / kQuad; ++g4) {
+            const uint4 wq = SMEM_ARCS ? p[kWordsPerQuad * g4 + 1] : load_quad_weights<false>(p + 2 * g4);
+            float4 w1;
+            if (SMEM_ARCS) { const uint4 t = p[kWordsPerQuad * g4 + 2]; w1 = make_float4(__uint_as_float(t.x), __uint_as_float(t.y), __uint_as_float(t.z), __uint_as_float(t.w)); }
+            else w1 = __ldg(pw1 + g4);
+            const float a0 = fabsf(__uint_as_float(wq.x)), a1 = fabsf(__uint_as_float(wq.y));
+            const float a2 = fabsf(__uint_as_float(wq.z)), a3 = fabsf(__uint_as_float(wq.w));
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                acc0[u] = fmaf(a0, v[g4 * kQuad + 0].v[u], acc0[u]);
+                acc1[u] = fmaf(w1.x, v[g4 * kQuad + 0].v[u], acc1[u]);
+                acc0[u] = fmaf(a1, v[g4 * kQuad + 1].v[u], acc0[u]);
+                acc1[u] = fmaf(w1.y, v[g4 * kQuad + 1].v[u], acc1[u]);
+                acc0[u] = fmaf(a2, v[g4 * kQuad + 2].v[u], acc0[u]);
+                acc1[u] = fmaf(w1.z, v[g4 * kQuad + 2].v[u], acc1[u]);
+                acc0[u] = fmaf(a3, v[g4 * kQuad + 3].v[u], acc0[u]);
+                acc1[u] = fmaf(w1.w, v[g4 * kQuad + 3].v[u], acc1[u]);
+            }
+            if ((int)wq.w < 0)   // warp-uniform: the group ends at this quad
+                group_end(acc0, acc1, (int)wq.z < 0, (int)wq.x < 0, (int)wq.y < 0);
+        }
+    };
+
+    constexpr int kStep = kWordsPerQuad * (BATCH / kQuad);   // 16-byte words per batch
+    const uint4 *pi = arcs, *pc = arcs;
+    const float4 *pw = w1g;
+    int nb = n_batches;
+    if (nb <= 0) { prologue(); return; }
+    issue(pi, vA); pi += kStep;
+    if (nb > 1) { issue(pi, vB); pi += kStep; }
+    prologue();
+    while (true) {
+        consume(pc, pw, vA); pc += kStep; pw += BATCH / kQuad;
+        if (--nb == 0) break;
+        if (nb > 1) { issue(pi, vA); pi += kStep; }
+        consume(pc, pw, vB); pc += kStep; pw += BATCH / kQuad;
+        if (--nb == 0) break;
+        if (nb > 1) { issue(pi, vB); pi += kStep; }
+    }
+}
+
 __device__ __forceinline__ unsigned long long global_timer() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -407,8 +477,10 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const DenParams P) 
     int labp0 = -1, labp1 = -1;
     for (int q = se - 1; q >= sb; --q) { if (__ldg(P.state_pos + q)) labp1 = __ldg(P.state_label + q); else labp0 = __ldg(P.state_label + q); }
     const int n_batches = (ae - ab) / BATCH;
-    const uint4 *const arc4 = SMEM_ARCS ? reinterpret_cast<const uint4 *>(s_arcs + (ab - tile_a0))
+    // shared memory: 3 words of 16 bytes per quad {byte offsets}{w0}{w1}; global fallback: AoS arcs + w1 array
+    const uint4 *const arc4 = SMEM_ARCS ? reinterpret_cast<const uint4 *>(s_arcs) + 3 * ((ab - tile_a0) / kQuad)
                                         : reinterpret_cast<const uint4 *>(P.arcs + ab);
+    const float4 *const w1g = reinterpret_cast<const float4 *>(P.w1 + ab);
     const bool use_gacc = P.gacc_rows > 0;
     const size_t frame_elems = (size_t)S * Npad;                         // beta ping-pong: real rows only
     const size_t alpha_frame = (size_t)(S + P.num_pairs) * Npad;          // alpha spill: real + virtual rows
@@ -419,12 +491,13 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const DenParams P) 
         s_final[i] = __ldg(P.final_lin + tile_s0 + i);
     }
     const uint32_t row_bytes = (uint32_t)Npad * 4u;
-    if (SMEM_ARCS) {
+    if (SMEM_ARCS) {   // stage the tile once, quad-wise transposed: {byte offset 0..3}{w0 0..3}{w1 0..3}
         uint32_t *sq = reinterpret_cast<uint32_t *>(s_arcs);
         for (int i = tid; i < tile_a1 - tile_a0; i += NT) {
             const Arc k = P.arcs[tile_a0 + i];
-            sq[(i >> 2) * 8 + (i & 3)] = k.peer * row_bytes;   // byte offset of the gathered row
-            sq[(i >> 2) * 8 + 4 + (i & 3)] = __float_as_uint(k.w);
+            sq[(i >> 2) * 12 + (i & 3)] = k.peer * row_bytes;
+            sq[(i >> 2) * 12 + 4 + (i & 3)] = __float_as_uint(k.w);
+            sq[(i >> 2) * 12 + 8 + (i & 3)] = __float_as_uint(__ldg(P.w1 + tile_a0 + i));
         }
     }
     for (int i = tid; i < (2 + P.gacc_rows) * Npad; i += NT) s_sum[i] = 0.f;
@@ -458,11 +531,11 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const DenParams P) 
                 lane_gat |= gat[u];
             }
             if (!__any_sync(kFull, lane_act)) continue;
-            float rb[U], fm[U], sum_b[U], sum_ab[U], gsum0[U], gsum1[U], ypre0[U], ypre1[U], ec0[U], ec1[U], acc_c[U];
+            float rb[U], fm[U], sum_b[U], sum_ab[U], gsum0[U], gsum1[U], ypre0[U], ypre1[U], ec0[U], ec1[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 rb[u] = 1.f; fm[u] = 0.f; ypre0[u] = 0.f; ypre1[u] = 0.f; ec0[u] = 0.f; ec1[u] = 0.f;
-                gsum0[u] = 0.f; gsum1[u] = 0.f; sum_b[u] = 0.f; sum_ab[u] = 0.f; acc_c[u] = 0.f;
+                gsum0[u] = 0.f; gsum1[u] = 0.f; sum_b[u] = 0.f; sum_ab[u] = 0.f;
             }
             auto frame_scalars = [&]() {
 #pragma unroll
@@ -480,8 +553,7 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const DenParams P) 
             uint32_t out_row = (uint32_t)sb;
             float *const out_base = bh_cur + n0;
             const char *const a_base = reinterpret_cast<const char *>(a_row + n0);
-            // alpha rows of the next two states are kept in flight: a pair's private segments are one quad long, so a
-            // one-row lookahead would expose a full L2 round trip at every second row end
+            // alpha rows of the next group (one or two states) are fetched one group ahead
             Vec<U> a_q = (se > sb && lane_act) ? gather_row<U>(a_base, out_row * row_bytes) : vec_zero<U>();
             Vec<U> a_q1 = (se > sb + 1 && lane_act) ? gather_row<U>(a_base, (out_row + 1) * row_bytes) : vec_zero<U>();
             auto flush_gsum = [&](bool k1) {
@@ -497,15 +569,8 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const DenParams P) 
                     if (k1) gsum1[u] = 0.f; else gsum0[u] = 0.f;
                 }
             };
-            walk_arcs<U, BATCH, SMEM_ARCS>(arc4, n_batches, row_bytes, reinterpret_cast<const char *>(bh_next + n0), lane_gat,
-                                           frame_scalars, [&](float *acc, int ev, bool new_label) {
-                if (ev == kEvCommon) {   // arcs shared by both members of a pair: keep the partial sum, keep accumulating
-#pragma unroll
-                    for (int u = 0; u < U; ++u) acc_c[u] = acc[u];
-                    return;
-                }
-                const bool k1 = ev != kEvRowPos0;
-                if (P.debug & 1) { sum_b[0] += acc[0]; acc[0] = 0.f; return; }
+            // one state's row end: beta_tau(q), its occupancy, the emission-weighted value the next frame gathers
+            auto do_row = [&](bool k1, bool new_label, float *acc, const Vec<U> &a_val) {
                 if (new_label) {
                     const int lab = s_label[ql];
                     if ((k1 ? curlab1 : curlab0) >= 0) flush_gsum(k1);
@@ -524,19 +589,30 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const DenParams P) 
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const float b = act[u] ? (gat[u] ? acc[u] * rb[u] : f) : 0.f;
-                    const float abp = a_q.v[u] * b;          // a_q is 0 for inactive lanes
+                    const float abp = a_val.v[u] * b;          // a_val is 0 for inactive lanes
                     if (k1) gsum1[u] += abp; else gsum0[u] += abp;
                     sum_ab[u] += abp;
                     out.v[u] = (k1 ? ec1[u] : ec0[u]) * b;
                     sum_b[u] += out.v[u];
-                    // first member of a pair: the second member restarts from the shared partial sum
-                    acc[u] = k1 ? 0.f : acc_c[u];
-                    if (k1) acc_c[u] = 0.f;
+                    acc[u] = 0.f;
                 }
                 if (lane_act) out.stcg(row_ptr<U>(out_base, out_row, row_bytes));
                 ++out_row;
                 ++ql;
-                a_q = a_q1;
+            };
+            walk_arcs_dual<U, BATCH, SMEM_ARCS>(arc4, w1g, n_batches, row_bytes, reinterpret_cast<const char *>(bh_next + n0),
+                                                lane_gat, frame_scalars,
+                                                [&](float *acc0, float *acc1, bool pair, bool new0, bool new1) {
+                if (P.debug & 1) { sum_b[0] += acc0[0] + acc1[0]; acc0[0] = 0.f; acc1[0] = 0.f; return; }
+                if (pair) {
+                    do_row(false, new0, acc0, a_q);
+                    do_row(true, new1, acc1, a_q1);
+                } else {
+                    do_row(true, new0, acc0, a_q);
+#pragma unroll
+                    for (int u = 0; u < U; ++u) acc1[u] = 0.f;
+                }
+                a_q = ((int)out_row < se && lane_act) ? gather_row<U>(a_base, out_row * row_bytes) : vec_zero<U>();
                 a_q1 = ((int)out_row + 1 < se && lane_act) ? gather_row<U>(a_base, (out_row + 1) * row_bytes) : vec_zero<U>();
             });
             if (curlab0 >= 0) flush_gsum(false);
@@ -644,7 +720,7 @@ template <int NT>
 int Dispatch(bool backward, const DeviceGraph &g, const DenParams &p, size_t fixed_smem, cudaStream_t stream,
              std::string *err) {
     const DevicePass &pass = backward ? g.bwd : g.fwd;
-    const size_t arc_bytes = (size_t)pass.max_tile_arcs * sizeof(Arc);
+    const size_t arc_bytes = (size_t)pass.max_tile_arcs * (backward ? 12 : sizeof(Arc));
     const size_t budget = (size_t)g.max_smem_optin > 2048 ? (size_t)g.max_smem_optin - 1024 : 0;
     const char *force_global = getenv("CCB_ARCS_IN_GLOBAL");   // test hook: exercise the large-graph fallback
     const bool smem_arcs = fixed_smem + arc_bytes <= budget && !(force_global && force_global[0] == '1');
@@ -726,7 +802,7 @@ int LaunchDenForward(const DeviceGraph &g, DenParams p, cudaStream_t stream, std
 
 int LaunchDenBackward(const DeviceGraph &g, DenParams p, cudaStream_t stream, std::string *err) {
     p.arcs = g.bwd.arcs; p.chunk_state = g.bwd.chunk_state; p.chunk_arc = g.bwd.chunk_arc;
-    p.chunk_pair = g.bwd.chunk_pair; p.cta_labels = g.bwd.cta_labels;
+    p.chunk_pair = g.bwd.chunk_pair; p.cta_labels = g.bwd.cta_labels; p.w1 = g.bwd.w1;
     // label accumulator in shared memory when the per-CTA label range is small enough
     size_t gacc_bytes = (size_t)g.bwd.max_tile_labels * p.Npad * 4;
     p.gacc_rows = gacc_bytes <= 64 * 1024 ? g.bwd.max_tile_labels : 0;

@@ -25,20 +25,27 @@ class PassView:
     chunk_arc: np.ndarray     # int32 [n_chunks+1]
     chunk_pair: np.ndarray    # int32 [n_chunks+1]
     cta_labels: np.ndarray    # int32 [n_ctas, 4]
+    w1: np.ndarray = None     # float32 [A] backward pass only: second weight per slot
 
     def weights(self) -> np.ndarray:
         return np.abs(self.arcs["w"])
 
     def segments(self):
         """Decode the stream the way the kernels walk it: yields (arc_begin, arc_end, event, label_changed) per
-        segment.  Chunk-tail padding quads (unflagged, weight 0) attach to the following segment."""
+        segment.  Chunk-tail padding quads (unflagged, weight 0) attach to the following segment.
+        Forward: event = kEv* code, label_changed = bool.  Backward (dual-weight groups): event = EV_ROW (one row) or
+        EV_ROW_POS1 (a pair: two rows), label_changed = (flag of the first row, flag of the second row)."""
         w = self.arcs["w"].reshape(-1, QUAD)
         sign = np.signbit(w)
         ends = np.nonzero(sign[:, 3])[0]
-        ev = (sign[ends, 2].astype(int) << 1) | sign[ends, 1].astype(int)
         begin = 0
-        for e, v in zip(ends, ev):
-            yield begin * QUAD, (e + 1) * QUAD, int(v), bool(sign[e, 0])
+        for e in ends:
+            if self.w1 is None:
+                ev = (int(sign[e, 2]) << 1) | int(sign[e, 1])
+                yield begin * QUAD, (e + 1) * QUAD, ev, bool(sign[e, 0])
+            else:
+                ev = EV_ROW_POS1 if sign[e, 2] else EV_ROW
+                yield begin * QUAD, (e + 1) * QUAD, ev, (bool(sign[e, 0]), bool(sign[e, 1]))
             begin = e + 1
 
 
@@ -85,6 +92,7 @@ def load_plan(path: str, n_ctas: int = 148, n_warps: int = 16) -> PlanView:
                         PassView(get(3, ARC_DTYPE, Af), get(4, np.int32, n_chunks + 1), get(5, np.int32, n_chunks + 1),
                                  get(10, np.int32, n_chunks + 1), get(13, np.int32, nc * 4).reshape(nc, 4)),
                         PassView(get(6, ARC_DTYPE, Ab), get(7, np.int32, n_chunks + 1), get(8, np.int32, n_chunks + 1),
-                                 get(11, np.int32, n_chunks + 1), get(14, np.int32, nc * 4).reshape(nc, 4)))
+                                 get(11, np.int32, n_chunks + 1), get(14, np.int32, nc * 4).reshape(nc, 4),
+                                 get(15, np.float32, Ab)))
     finally:
         L.ccb_plan_destroy(h)

@@ -43,29 +43,27 @@ def _decode_forward(plan):
 
 
 def _decode_backward(plan):
-    """Walk the backward stream like den_backward_kernel: common segments count for both members of the pair."""
+    """Walk the backward stream like den_backward_kernel: one segment per group, two weights per slot (w for the
+    group's first row, w1 for its second row)."""
     S = plan.num_states
     row, peer, w = [], [], []
     q = 0
-    arcs = plan.bwd.arcs
-    pend = None
+    arcs, w1 = plan.bwd.arcs, plan.bwd.w1
     for a0, a1, ev, _chg in plan.bwd.segments():
-        pr = arcs["peer"][a0:a1].astype(np.int64); ww = np.abs(arcs["w"][a0:a1]).astype(np.float64)
+        pr = arcs["peer"][a0:a1].astype(np.int64)
         assert (pr < S).all()
-        if ev == 3:
-            assert pend is None
-            pend = (pr, ww)
-            continue
         n = a1 - a0
-        row.append(np.full(n, q)); peer.append(pr); w.append(ww)
-        if pend is not None:
-            row.append(np.full(len(pend[0]), q)); peer.append(pend[0]); w.append(pend[1])
-        if ev != 1:
-            pend = None
+        if ev == 2:     # pair: rows q (pos0) and q+1 (pos1)
+            assert plan.state_pos[q] == 0 and plan.state_pos[q + 1] == 1
+            row.append(np.full(n, q)); peer.append(pr); w.append(np.abs(arcs["w"][a0:a1]).astype(np.float64))
+            row.append(np.full(n, q + 1)); peer.append(pr); w.append(w1[a0:a1].astype(np.float64))
+            q += 2
         else:
-            assert plan.state_pos[q] == 0
-        q += 1
+            assert ev == 0 and plan.state_pos[q] == 1 and not w1[a0:a1].any()
+            row.append(np.full(n, q)); peer.append(pr); w.append(np.abs(arcs["w"][a0:a1]).astype(np.float64))
+            q += 1
     assert q == S
+    assert (w1 >= 0).all()
     return np.concatenate(row), np.concatenate(peer), np.concatenate(w)
 
 

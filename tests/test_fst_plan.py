@@ -15,7 +15,7 @@ def test_fixture_parses(fixture_fst):
     np.testing.assert_allclose(g.final[[4, 6]], 0.6931472, rtol=1e-6)
     P = plan.load_plan(fixture_fst, 4, 2)
     assert (P.file_states, P.file_arcs, P.num_states) == (9, 24, 9)      # T-compose-LM: no state split
-    assert int((P.fwd.weights() > 0).sum()) == int((P.bwd.weights() > 0).sum()) <= 24
+    assert int((P.fwd.weights() > 0).sum()) == int(((P.bwd.weights() > 0) | (P.bwd.w1 > 0)).sum()) <= 24
 
 
 def test_roundtrip_and_cxx_reader_agree(tmp_path):
@@ -66,14 +66,15 @@ def test_plan_invariants(tmp_graphs, n_ctas, n_warps):
         assert (P.state_pos[p0 + 1] == 1).all()
         for pv, is_fwd in ((P.fwd, True), (P.bwd, False)):
             segs = list(pv.segments())
-            rows = [x for x in segs if x[2] != plan.EV_COMMON]
-            assert len(rows) == S                                        # one row-end event per state
-            assert sum(1 for x in segs if x[2] == plan.EV_ROW_POS1) == NP == sum(1 for x in segs if x[2] == plan.EV_ROW_POS0)
             if is_fwd:
+                assert len(segs) == S                                    # one row-end event per state
+                assert sum(1 for x in segs if x[2] == plan.EV_ROW_POS1) == NP == sum(1 for x in segs if x[2] == plan.EV_ROW_POS0)
                 assert not any(x[2] == plan.EV_COMMON for x in segs)
-                assert (pv.arcs["peer"] < S + NP).all()
+                assert (pv.arcs["peer"] < S + NP).all() and pv.w1 is None
             else:
-                assert (pv.arcs["peer"] < S).all()
+                assert len(segs) == S - NP                               # one group-end event per group
+                assert sum(1 for x in segs if x[2] == plan.EV_ROW_POS1) == NP
+                assert (pv.arcs["peer"] < S).all() and len(pv.w1) == len(pv.arcs) and (pv.w1 >= 0).all()
             assert len(pv.arcs) % plan.QUAD == 0
             assert pv.chunk_state[0] == 0 and pv.chunk_state[-1] == S
             assert (np.diff(pv.chunk_state) >= 0).all() and (np.diff(pv.chunk_pair) >= 0).all() and pv.chunk_pair[-1] == NP
@@ -83,21 +84,26 @@ def test_plan_invariants(tmp_graphs, n_ctas, n_warps):
             assert (P.state_pos[cs - 1] == 1).all() if (cs > 0).any() else True
             np.testing.assert_array_equal(pv.chunk_pair, np.concatenate([[0], np.cumsum(P.state_pos == 0)])[pv.chunk_state])
             assert (pv.weights() >= 0).all()
-            # sign bits appear only on a segment's last quad; slot 0 = "label changed" and only on row ends
+            # sign bits appear only on a segment's last quad
             sg = np.signbit(pv.arcs["w"].reshape(-1, plan.QUAD))
             assert not sg[~sg[:, 3]].any()
-            # label-changed flag == the label differs from the previous row of that position within the chunk
+            # label-changed flags == the label differs from the previous row of that position within the chunk
             q = 0
             prev = {}
             chunk_of = np.searchsorted(pv.chunk_arc, np.arange(0, len(pv.arcs), plan.QUAD), side="right") - 1
             for a0, a1, ev, chg in segs:
-                if ev == plan.EV_COMMON:
-                    assert not chg
-                    continue
-                key = (int(chunk_of[(a1 - 1) // plan.QUAD]), 0 if ev == plan.EV_ROW_POS0 else 1)
-                assert chg == (prev.get(key) != int(P.state_label[q]))
-                prev[key] = int(P.state_label[q])
-                q += 1
+                c = int(chunk_of[(a1 - 1) // plan.QUAD])
+                if is_fwd:
+                    rows = [(0 if ev == plan.EV_ROW_POS0 else 1, chg)]
+                else:
+                    rows = [(0, chg[0]), (1, chg[1])] if ev == plan.EV_ROW_POS1 else [(1, chg[0])]
+                    if ev != plan.EV_ROW_POS1:
+                        assert not chg[1]
+                for k, flag in rows:
+                    assert flag == (prev.get((c, k)) != int(P.state_label[q]))
+                    prev[(c, k)] = int(P.state_label[q])
+                    q += 1
+            assert q == S
             # label accumulator ranges cover every state of the CTA
             for c in range(n_ctas):
                 s0, s1 = pv.chunk_state[c * n_warps], pv.chunk_state[(c + 1) * n_warps]
@@ -105,7 +111,8 @@ def test_plan_invariants(tmp_graphs, n_ctas, n_warps):
                     labs = P.state_label[s0:s1][P.state_pos[s0:s1] == pos]
                     if len(labs):
                         assert lo <= labs.min() and labs.max() < lo + n
-        nz_f, nz_b = int((P.fwd.weights() > 0).sum()), int((P.bwd.weights() > 0).sum())
+        nz_f = int((P.fwd.weights() > 0).sum())
+        nz_b = int(((P.bwd.weights() > 0) | (P.bwd.w1 > 0)).sum())
         if name == "random_split":
             assert S > g.num_states
         else:
