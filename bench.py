@@ -310,7 +310,7 @@ def main():
         },
         "arc_evals_per_s": 2.0 * A_file * frames_per_step / (ms_fb * 1e-3),
         "row_gathers_per_frame": info["fwd_slots"] + info["bwd_slots"],
-        "l2_gather_TBps": (info["fwd_slots"] + info["bwd_slots"]) * frames_per_step * (128 if N <= 32 else 256 if N <= 64 else 512) / (ms_fb * 1e-3) / 1e12,
+        "l2_gather_TBps": (info["fwd_slots"] + info["bwd_slots"]) * T * (-(-N // (32 * (1 if N <= 32 else 2 if N <= 64 else 4)))) * (128 if N <= 32 else 256 if N <= 64 else 512) / (ms_fb * 1e-3) / 1e12,
     }
     del alpha_ws, aux_ws, gden
 

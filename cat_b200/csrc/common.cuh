@@ -149,12 +149,13 @@ __device__ __forceinline__ void grid_barrier(unsigned *counter, unsigned target)
     __syncthreads();
 }
 
-// log-semiring add in fp32 (numerator only), same formula as den_calculate.cu:28-35 / ctc_helper.h
+// log-semiring add in fp32 (numerator only), same formula as den_calculate.cu:28-35 / ctc_helper.h.  The operands
+// are kept relative to a per-frame offset (|values| stay small), so the hardware ex2/lg2 approximations
+// (abs. error ~1e-7 here) are as accurate as the libm versions were on the reference's un-normalised values.
 __device__ __forceinline__ float log_add(float a, float b) {
-    if (a == -INFINITY) return b;
-    if (b == -INFINITY) return a;
-    float m = fmaxf(a, b);
-    return m + log1pf(expf(-fabsf(a - b)));
+    const float m = fmaxf(a, b);
+    if (m == -INFINITY) return m;
+    return m + __logf(1.f + __expf(-fabsf(a - b)));   // exp(-inf) = 0 covers a one-sided -inf
 }
 #endif
 
