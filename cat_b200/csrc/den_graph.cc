@@ -109,26 +109,16 @@ struct Group {
 };
 
 // Cut groups into n_chunks contiguous chunks of near-equal cost and emit the chunk-major padded arc stream.
+// Emit the chunk-major padded arc stream of one pass for the given chunk boundaries (chunk c = groups
+// [chunk_group[c], chunk_group[c+1])).
 void Layout(const std::vector<Group> &groups, int S, const std::vector<int> &state_label, const std::vector<int> &state_pos,
-            int n_ctas, int n_warps, int64_t row_cost, bool emit_w1, PassPlan *pp) {
+            int n_ctas, int n_warps, const std::vector<int> &chunk_group, bool emit_w1, PassPlan *pp) {
     const int G = (int)groups.size();
     const int n_chunks = n_ctas * n_warps;
     auto quads = [](const Segment &sg) { return std::max<int64_t>(1, ((int64_t)sg.arcs.size() + kQuad - 1) / kQuad); };
-    std::vector<int64_t> prefix((size_t)G + 1, 0);
     pp->real_arcs = 0;
-    for (int g = 0; g < G; ++g) {
-        int64_t c = 0;
-        for (auto &sg : groups[(size_t)g].segs) { c += quads(sg) * kQuad; pp->real_arcs += (int)sg.arcs.size(); }
-        prefix[g + 1] = prefix[g] + c + row_cost * groups[(size_t)g].rows;
-    }
-    const int64_t total = prefix[G];
-    std::vector<int> chunk_group((size_t)n_chunks + 1, 0);
-    for (int c = 1; c < n_chunks; ++c) {
-        int64_t target = (total * c + n_chunks / 2) / n_chunks;
-        int g = (int)(std::lower_bound(prefix.begin(), prefix.end(), target) - prefix.begin());
-        chunk_group[c] = std::min(std::max(g, chunk_group[c - 1]), G);
-    }
-    chunk_group[n_chunks] = G;
+    for (int g = 0; g < G; ++g)
+        for (auto &sg : groups[(size_t)g].segs) pp->real_arcs += (int)sg.arcs.size();
 
     pp->arcs.clear();
     pp->w1.clear();
@@ -324,117 +314,172 @@ bool BuildDenPlan(const HostFst &fst, int n_ctas, int n_warps, DenPlan *plan, st
         return x.s1 < y.s1;
     });
     std::vector<int> fid(S, -1), pair_of(S, -1);
-    plan->state_label.assign(S, 0); plan->state_pos.assign(S, 1); plan->orig_state.assign(S, 0); plan->final_lin.assign(S, 0.f);
-    int next = 0, n_pairs = 0;
-    for (auto &g : gk) {
-        if (g.s0 >= 0) { fid[(size_t)g.s0] = next++; pair_of[(size_t)g.s0] = n_pairs; pair_of[(size_t)g.s1] = n_pairs; }
-        fid[(size_t)g.s1] = next++;
-        if (g.s0 >= 0) ++n_pairs;
-    }
-    for (size_t s = 0; s < S; ++s) {
-        const int f = fid[s];
-        plan->state_label[(size_t)f] = sid_label[s];
-        plan->orig_state[(size_t)f] = sid_orig[s];
-        const float fw = fst.final_logw[(size_t)sid_orig[s]];
-        plan->final_lin[(size_t)f] = std::isinf(fw) ? 0.f : std::exp(fw);
-    }
-    for (auto &g : gk) if (g.s0 >= 0) plan->state_pos[(size_t)fid[(size_t)g.s0]] = 0;
+    std::vector<Group> fgroups, bgroups;
+    auto by_peer = [](const Arc &a, const Arc &b) { return a.peer < b.peer; };
+    struct Ent { int pair; uint32_t wb; int member; int peer_fid; float w; };
+    std::vector<Ent> ents;
+    struct OEnt { int q; uint32_t wb; float w; };
+    std::vector<OEnt> l0, l1;
+
+    // (re)number the states for a given group order and build both passes' segments
+    auto build = [&](const std::vector<GroupKey> &order) {
+        plan->state_label.assign(S, 0); plan->state_pos.assign(S, 1); plan->orig_state.assign(S, 0); plan->final_lin.assign(S, 0.f);
+        int next = 0, n_pairs = 0;
+        for (auto &g : order) {
+            if (g.s0 >= 0) { fid[(size_t)g.s0] = next++; pair_of[(size_t)g.s0] = n_pairs; pair_of[(size_t)g.s1] = n_pairs; }
+            fid[(size_t)g.s1] = next++;
+            if (g.s0 >= 0) ++n_pairs;
+        }
+        for (size_t s = 0; s < S; ++s) {
+            const int f = fid[s];
+            plan->state_label[(size_t)f] = sid_label[s];
+            plan->orig_state[(size_t)f] = sid_orig[s];
+            const float fw = fst.final_logw[(size_t)sid_orig[s]];
+            plan->final_lin[(size_t)f] = std::isinf(fw) ? 0.f : std::exp(fw);
+        }
+        for (auto &g : order) if (g.s0 >= 0) plan->state_pos[(size_t)fid[(size_t)g.s0]] = 0;
+        plan->num_pairs = n_pairs;
+        plan->start = fid[(size_t)sid_of[(size_t)fst.start][0]];   // all start mass on one copy (copies share out-arcs)
+        plan->start_arcs.clear();
+        for (auto &a : out_s[(size_t)sid_of[(size_t)fst.start][0]]) plan->start_arcs.push_back(Arc{(uint32_t)fid[(size_t)a.peer], a.w});
+
+        // forward rows: a pair's two arcs with equal weight become one arc to the pair's virtual row S + j
+        auto forward_row = [&](int s, std::vector<Arc> *row) {
+            ents.clear();
+            for (auto &a : in_s[(size_t)s]) {
+                const int pj = pair_of[(size_t)a.peer];
+                const int member = pj >= 0 ? plan->state_pos[(size_t)fid[(size_t)a.peer]] : 0;
+                ents.push_back(Ent{pj, Bits(a.w), member, fid[(size_t)a.peer], a.w});
+            }
+            std::sort(ents.begin(), ents.end(), [](const Ent &x, const Ent &y) {
+                if (x.pair != y.pair) return x.pair < y.pair;
+                if (x.wb != y.wb) return x.wb < y.wb;
+                return x.member < y.member;
+            });
+            row->clear();
+            for (size_t i = 0; i < ents.size();) {
+                if (ents[i].pair < 0) { row->push_back(Arc{(uint32_t)ents[i].peer_fid, ents[i].w}); ++i; continue; }
+                size_t j = i;
+                int n0 = 0, n1 = 0;
+                while (j < ents.size() && ents[j].pair == ents[i].pair && ents[j].wb == ents[i].wb) { (ents[j].member ? n1 : n0)++; ++j; }
+                const int merged = std::min(n0, n1);
+                for (int k = 0; k < merged; ++k) row->push_back(Arc{(uint32_t)(S + (size_t)ents[i].pair), ents[i].w});
+                // leftovers keep their own rows: member-0 entries come first in [i, j)
+                for (int k = merged; k < n0; ++k) row->push_back(Arc{(uint32_t)ents[i + (size_t)k].peer_fid, ents[i].w});
+                for (int k = merged; k < n1; ++k) row->push_back(Arc{(uint32_t)ents[i + (size_t)n0 + (size_t)k].peer_fid, ents[i].w});
+                i = j;
+            }
+            std::sort(row->begin(), row->end(), by_peer);
+        };
+        auto out_list = [&](int s, std::vector<OEnt> *l) {
+            l->clear();
+            for (auto &a : out_s[(size_t)s]) l->push_back(OEnt{fid[(size_t)a.peer], Bits(a.w), a.w});
+            std::sort(l->begin(), l->end(), [](const OEnt &x, const OEnt &y) { return x.q != y.q ? x.q < y.q : x.wb < y.wb; });
+        };
+        fgroups.clear(); bgroups.clear();
+        fgroups.reserve(order.size()); bgroups.reserve(order.size());
+        for (auto &g : order) {
+            Group fg, bg;
+            fg.first_state = bg.first_state = g.s0 >= 0 ? fid[(size_t)g.s0] : fid[(size_t)g.s1];
+            fg.rows = bg.rows = g.s0 >= 0 ? 2 : 1;
+            fg.pairs = bg.pairs = g.s0 >= 0 ? 1 : 0;
+            if (g.s0 < 0) {
+                Segment f, b;
+                forward_row(g.s1, &f.arcs);
+                f.event = kEvRow;
+                out_list(g.s1, &l1);
+                for (auto &e : l1) { b.arcs.push_back(Arc{(uint32_t)e.q, e.w}); b.w1.push_back(0.f); }
+                b.event = kEvRow;
+                b.rows = 1;
+                fg.segs.push_back(std::move(f));
+                bg.segs.push_back(std::move(b));
+            } else {
+                Segment f0, f1, b;
+                forward_row(g.s0, &f0.arcs); f0.event = kEvRowPos0;
+                forward_row(g.s1, &f1.arcs); f1.event = kEvRowPos1;
+                // backward: ONE segment for the pair; slot weights (w for p0, w1 for p1): shared arcs carry both
+                out_list(g.s0, &l0);
+                out_list(g.s1, &l1);
+                size_t i = 0, j = 0;
+                while (i < l0.size() || j < l1.size()) {
+                    if (i < l0.size() && j < l1.size() && l0[i].q == l1[j].q && l0[i].wb == l1[j].wb) {
+                        b.arcs.push_back(Arc{(uint32_t)l0[i].q, l0[i].w}); b.w1.push_back(l1[j].w); ++i; ++j;
+                    } else if (j >= l1.size() || (i < l0.size() && (l0[i].q < l1[j].q || (l0[i].q == l1[j].q && l0[i].wb < l1[j].wb)))) {
+                        b.arcs.push_back(Arc{(uint32_t)l0[i].q, l0[i].w}); b.w1.push_back(0.f); ++i;
+                    } else {
+                        b.arcs.push_back(Arc{(uint32_t)l1[j].q, 0.f}); b.w1.push_back(l1[j].w); ++j;
+                    }
+                }
+                b.event = kEvRowPos1;
+                b.rows = 2;
+                fg.segs.push_back(std::move(f0)); fg.segs.push_back(std::move(f1));
+                bg.segs.push_back(std::move(b));
+            }
+            fgroups.push_back(std::move(fg));
+            bgroups.push_back(std::move(bg));
+        }
+    };
+
     plan->file_states = S0;
     plan->file_arcs = (int)A0;
     plan->num_states = (int)S;
-    plan->num_pairs = n_pairs;
     plan->num_labels = max_label + 1;
-    plan->start = fid[(size_t)sid_of[(size_t)fst.start][0]];   // all start mass on one copy (copies share out-arcs)
     plan->n_ctas = n_ctas;
     plan->n_warps = n_warps;
-    plan->start_arcs.clear();
-    for (auto &a : out_s[(size_t)sid_of[(size_t)fst.start][0]]) plan->start_arcs.push_back(Arc{(uint32_t)fid[(size_t)a.peer], a.w});
 
-    auto by_peer = [](const Arc &a, const Arc &b) { return a.peer < b.peer; };
-
-    // 4a. forward rows: a pair's two arcs with equal weight become one arc to the pair's virtual row S + j
-    std::vector<Group> fgroups, bgroups;
-    fgroups.reserve(gk.size()); bgroups.reserve(gk.size());
-    struct Ent { int pair; uint32_t wb; int member; int peer_fid; float w; };
-    std::vector<Ent> ents;
-    auto forward_row = [&](int s, std::vector<Arc> *row) {
-        ents.clear();
-        for (auto &a : in_s[(size_t)s]) {
-            const int pj = pair_of[(size_t)a.peer];
-            const int member = pj >= 0 ? plan->state_pos[(size_t)fid[(size_t)a.peer]] : 0;
-            ents.push_back(Ent{pj, Bits(a.w), member, fid[(size_t)a.peer], a.w});
-        }
-        std::sort(ents.begin(), ents.end(), [](const Ent &x, const Ent &y) {
-            if (x.pair != y.pair) return x.pair < y.pair;
-            if (x.wb != y.wb) return x.wb < y.wb;
-            return x.member < y.member;
-        });
-        row->clear();
-        for (size_t i = 0; i < ents.size();) {
-            if (ents[i].pair < 0) { row->push_back(Arc{(uint32_t)ents[i].peer_fid, ents[i].w}); ++i; continue; }
-            size_t j = i;
-            int n0 = 0, n1 = 0;
-            while (j < ents.size() && ents[j].pair == ents[i].pair && ents[j].wb == ents[i].wb) { (ents[j].member ? n1 : n0)++; ++j; }
-            const int merged = std::min(n0, n1);
-            for (int k = 0; k < merged; ++k) row->push_back(Arc{(uint32_t)(S + (size_t)ents[i].pair), ents[i].w});
-            // leftovers keep their own rows: member-0 entries come first in [i, j)
-            for (int k = merged; k < n0; ++k) row->push_back(Arc{(uint32_t)ents[i + (size_t)k].peer_fid, ents[i].w});
-            for (int k = merged; k < n1; ++k) row->push_back(Arc{(uint32_t)ents[i + (size_t)n0 + (size_t)k].peer_fid, ents[i].w});
-            i = j;
-        }
-        std::sort(row->begin(), row->end(), by_peer);
-    };
-    // 4b. backward: out-arcs of a pair split into common (same destination, bit-equal weight) and private parts
-    struct OEnt { int q; uint32_t wb; float w; };
-    auto out_list = [&](int s, std::vector<OEnt> *l) {
-        l->clear();
-        for (auto &a : out_s[(size_t)s]) l->push_back(OEnt{fid[(size_t)a.peer], Bits(a.w), a.w});
-        std::sort(l->begin(), l->end(), [](const OEnt &x, const OEnt &y) { return x.q != y.q ? x.q < y.q : x.wb < y.wb; });
-    };
-    std::vector<OEnt> l0, l1;
-    for (auto &g : gk) {
-        Group fg, bg;
-        fg.first_state = bg.first_state = g.s0 >= 0 ? fid[(size_t)g.s0] : fid[(size_t)g.s1];
-        fg.rows = bg.rows = g.s0 >= 0 ? 2 : 1;
-        fg.pairs = bg.pairs = g.s0 >= 0 ? 1 : 0;
-        if (g.s0 < 0) {
-            Segment f, b;
-            forward_row(g.s1, &f.arcs);
-            f.event = kEvRow;
-            out_list(g.s1, &l1);
-            for (auto &e : l1) { b.arcs.push_back(Arc{(uint32_t)e.q, e.w}); b.w1.push_back(0.f); }
-            b.event = kEvRow;
-            b.rows = 1;
-            fg.segs.push_back(std::move(f));
-            bg.segs.push_back(std::move(b));
-        } else {
-            Segment f0, f1, b;
-            forward_row(g.s0, &f0.arcs); f0.event = kEvRowPos0;
-            forward_row(g.s1, &f1.arcs); f1.event = kEvRowPos1;
-            // backward: ONE segment for the pair; slot weights (w for p0, w1 for p1): shared arcs carry both
-            out_list(g.s0, &l0);
-            out_list(g.s1, &l1);
-            size_t i = 0, j = 0;
-            while (i < l0.size() || j < l1.size()) {
-                if (i < l0.size() && j < l1.size() && l0[i].q == l1[j].q && l0[i].wb == l1[j].wb) {
-                    b.arcs.push_back(Arc{(uint32_t)l0[i].q, l0[i].w}); b.w1.push_back(l1[j].w); ++i; ++j;
-                } else if (j >= l1.size() || (i < l0.size() && (l0[i].q < l1[j].q || (l0[i].q == l1[j].q && l0[i].wb < l1[j].wb)))) {
-                    b.arcs.push_back(Arc{(uint32_t)l0[i].q, l0[i].w}); b.w1.push_back(0.f); ++i;
-                } else {
-                    b.arcs.push_back(Arc{(uint32_t)l1[j].q, 0.f}); b.w1.push_back(l1[j].w); ++j;
-                }
-            }
-            b.event = kEvRowPos1;
-            b.rows = 2;
-            fg.segs.push_back(std::move(f0)); fg.segs.push_back(std::move(f1));
-            bg.segs.push_back(std::move(b));
-        }
-        fgroups.push_back(std::move(fg));
-        bgroups.push_back(std::move(bg));
+    // Phase 1: label-sorted order, to learn every group's cost in both passes.
+    build(gk);
+    const int G = (int)gk.size();
+    auto seg_quads = [](const Segment &sg) { return std::max<int64_t>(1, ((int64_t)sg.arcs.size() + kQuad - 1) / kQuad); };
+    // per-row costs in arc units, fitted to per-warp timelines on B200 (tools/timeline.py)
+    constexpr int64_t kRowCostFwd = 5, kRowCostBwd = 8;
+    std::vector<int64_t> cost((size_t)G, 0);
+    for (int g = 0; g < G; ++g) {
+        int64_t c = 0;
+        for (auto &sg : fgroups[(size_t)g].segs) c += seg_quads(sg) * kQuad;
+        for (auto &sg : bgroups[(size_t)g].segs) c += seg_quads(sg) * kQuad;
+        cost[(size_t)g] = c + (kRowCostFwd + kRowCostBwd) * fgroups[(size_t)g].rows;
     }
-    // row costs in arc units, fitted to per-warp timelines on B200 (tools/timeline.py)
-    Layout(fgroups, (int)S, plan->state_label, plan->state_pos, n_ctas, n_warps, 4, false, &plan->fwd);
-    Layout(bgroups, (int)S, plan->state_label, plan->state_pos, n_ctas, n_warps, 8, true, &plan->bwd);
+    // Phase 2: CTA tiles = contiguous ranges of the label-sorted order with equal total cost (both passes share the
+    // tiles); inside a tile the groups are dealt to the warps longest-first (LPT), then each warp's groups are put
+    // back in label order.  States are renumbered in that (tile, warp, label) order, which keeps every warp's rows
+    // contiguous while balancing the warps to within one small group.
+    std::vector<int64_t> prefix((size_t)G + 1, 0);
+    for (int g = 0; g < G; ++g) prefix[(size_t)g + 1] = prefix[(size_t)g] + cost[(size_t)g];
+    std::vector<int> tile((size_t)n_ctas + 1, 0);
+    for (int c = 1; c < n_ctas; ++c) {
+        const int64_t target = (prefix[(size_t)G] * c + n_ctas / 2) / n_ctas;
+        int g = (int)(std::lower_bound(prefix.begin(), prefix.end(), target) - prefix.begin());
+        tile[(size_t)c] = std::min(std::max(g, tile[(size_t)c - 1]), G);
+    }
+    tile[(size_t)n_ctas] = G;
+    std::vector<GroupKey> order;
+    order.reserve((size_t)G);
+    std::vector<int> chunk_group((size_t)n_ctas * n_warps + 1, 0);
+    std::vector<std::vector<int>> bins((size_t)n_warps);
+    std::vector<int64_t> load((size_t)n_warps);
+    std::vector<int> idx;
+    for (int c = 0; c < n_ctas; ++c) {
+        idx.clear();
+        for (int g = tile[(size_t)c]; g < tile[(size_t)c + 1]; ++g) idx.push_back(g);
+        std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return cost[(size_t)a] > cost[(size_t)b]; });
+        for (auto &b : bins) b.clear();
+        std::fill(load.begin(), load.end(), 0);
+        for (int g : idx) {
+            const int w = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+            bins[(size_t)w].push_back(g);
+            load[(size_t)w] += cost[(size_t)g];
+        }
+        for (int w = 0; w < n_warps; ++w) {
+            std::sort(bins[(size_t)w].begin(), bins[(size_t)w].end());   // label order (phase-1 index)
+            chunk_group[(size_t)c * n_warps + w] = (int)order.size();
+            for (int g : bins[(size_t)w]) order.push_back(gk[(size_t)g]);
+        }
+    }
+    chunk_group[(size_t)n_ctas * n_warps] = (int)order.size();
+    build(order);
+    Layout(fgroups, (int)S, plan->state_label, plan->state_pos, n_ctas, n_warps, chunk_group, false, &plan->fwd);
+    Layout(bgroups, (int)S, plan->state_label, plan->state_pos, n_ctas, n_warps, chunk_group, true, &plan->bwd);
     return true;
 }
 

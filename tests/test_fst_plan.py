@@ -59,11 +59,23 @@ def test_plan_invariants(tmp_graphs, n_ctas, n_warps):
         S, NP = P.num_states, P.num_pairs
         assert P.num_labels <= V
         assert set(np.unique(P.state_pos)) <= {0, 1} and int((P.state_pos == 0).sum()) == NP
-        # groups are ordered by the label of their last member; a pair is (pos0, pos1) on adjacent ids
-        last = P.state_label[P.state_pos == 1]
-        assert (np.diff(last) >= 0).all()
+        # a pair is (pos0, pos1) on adjacent ids; inside a warp chunk groups are ordered by the label of their last
+        # member, and CTA tiles are contiguous ranges of the global label order
         p0 = np.nonzero(P.state_pos == 0)[0]
         assert (P.state_pos[p0 + 1] == 1).all()
+        np.testing.assert_array_equal(P.fwd.chunk_state, P.bwd.chunk_state)     # both passes share the cut
+        cs_all = P.fwd.chunk_state
+        for c in range(len(cs_all) - 1):
+            st = np.arange(cs_all[c], cs_all[c + 1])
+            last = P.state_label[st][P.state_pos[st] == 1]
+            assert (np.diff(last) >= 0).all()
+        tile_max = -1
+        for c in range(n_ctas):
+            st = np.arange(cs_all[c * n_warps], cs_all[(c + 1) * n_warps])
+            last = P.state_label[st][P.state_pos[st] == 1]
+            if len(last):
+                assert last.min() >= tile_max
+                tile_max = last.max()
         for pv, is_fwd in ((P.fwd, True), (P.bwd, False)):
             segs = list(pv.segments())
             if is_fwd:
@@ -141,6 +153,8 @@ def test_plan_balance(tmp_path):
     for pv in (P.fwd, P.bwd):
         per_cta = np.diff(pv.chunk_arc[::16])
         assert per_cta.max() <= 1.3 * per_cta.mean() + 64
+        per_warp = np.diff(pv.chunk_arc).reshape(148, 16)
+        assert (per_warp.max(1) - per_warp.min(1)).max() <= 48          # LPT: warps of a CTA within a few quads
     assert P.max_tile_arcs * 8 < 200 * 1024
 
 

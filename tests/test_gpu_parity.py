@@ -157,6 +157,38 @@ def test_fused_vs_oracle_and_bf16(tmp_graphs):
     del ctx
 
 
+@pytest.mark.parametrize("N,T,lens,ly", [
+    (1, 1, [1], [0]),                       # single frame, empty label sequence
+    (1, 1, [1], [1]),                       # single frame, single label
+    (2, 6, [6, 0], [2, 0]),                 # an utterance of length zero rides along
+    (3, 9, [9, 9, 9], [9, 4, 0]),           # L == T (no blank can be emitted), and L = 0
+    (33, 5, None, None),                    # more utterances than one lane group, tiny T
+])
+def test_edge_shapes_vs_oracle(tmp_graphs, N, T, lens, ly):
+    """Degenerate shapes through the fused op against the oracle (empty labels, T=1, len=0, L=T, ragged lanes)."""
+    from oracle import oracle
+    path, g, V = tmp_graphs["tlm_small"]
+    ctx = _ctx(path)
+    rng = np.random.default_rng(17)
+    if lens is None:
+        lens = rng.integers(1, T + 1, size=N)
+        ly = np.minimum(lens // 2, 2)
+    y, _, lens, _ = oracle.synth_batch(N, T, V, seed=41, lens=lens)
+    ly = np.asarray(ly, np.int32)
+    labels = rng.integers(1, V, size=int(ly.sum())).astype(np.int32)
+    for i in range(1, len(labels)):          # no repeats, so that L == T stays feasible
+        if labels[i] == labels[i - 1]:
+            labels[i] = labels[i] % (V - 1) + 1
+    loss, grad = _run_ours(y, labels, lens, ly, 0.1)
+    oloss, ograd, parts = oracle.ctc_crf(g, y, labels, lens, ly, 0.1)
+    if np.isfinite(oloss):
+        _close_loss(loss, oloss)
+        assert np.abs(grad - ograd).max() < GRAD_ATOL
+    else:                                     # an infeasible utterance: +inf loss on both sides
+        assert not np.isfinite(loss)
+    del ctx
+
+
 def test_sliced_batches_and_padded_frames(tmp_graphs, monkeypatch):
     """Batches are processed in memory-bounded slices that walk only max(len) frames: same loss/grad as one call,
     and frames beyond every length (T padded past max len) cost nothing and stay zero."""
