@@ -59,7 +59,7 @@ int Upload(T **dst, const std::vector<T> &src) {
 
 void FreeDevice(DeviceGraph &d) {
     if (!d.loaded) return;
-    cudaFree(d.state_label); cudaFree(d.state_pos); cudaFree(d.final_lin); cudaFree(d.start_arcs);
+    cudaFree(d.state_label); cudaFree(d.state_pos); cudaFree(d.final_lin); cudaFree(d.start_arcs); cudaFree(d.hub_states);
     for (DevicePass *p : {&d.fwd, &d.bwd}) { cudaFree(p->arcs); cudaFree(p->chunk_state); cudaFree(p->chunk_arc); cudaFree(p->chunk_pair); cudaFree(p->cta_labels); cudaFree(p->w1); }
     d = DeviceGraph();
 }
@@ -126,8 +126,10 @@ int InitImpl(const char *fst_name, int n_gpus, const int *gpus) {
         d.max_smem_optin = (int)p2.sharedMemPerBlockOptin;
         rc = Upload(&d.state_label, g_plan.state_label) || Upload(&d.state_pos, g_plan.state_pos) ||
              Upload(&d.final_lin, g_plan.final_lin) || Upload(&d.start_arcs, g_plan.start_arcs) ||
+             Upload(&d.hub_states, g_plan.hub_states) ||
              UploadPass(g_plan.fwd, &d.fwd) || UploadPass(g_plan.bwd, &d.bwd);
         d.n_start_arcs = (int)g_plan.start_arcs.size();
+        d.n_hubs = (int)g_plan.hub_states.size();
         d.start_final = g_plan.final_lin[(size_t)g_plan.start];
         d.loaded = (rc == 0);
     }
@@ -159,6 +161,7 @@ DenParams BaseParams(const DeviceGraph &g, const void *y, int dtype, long sn, lo
     char *a = reinterpret_cast<char *>(aux);
     p.state_label = g.state_label; p.state_pos = g.state_pos; p.final_lin = g.final_lin;
     p.start_arcs = g.start_arcs; p.n_start_arcs = g.n_start_arcs;
+    p.hub_states = g.hub_states; p.n_hubs = g.n_hubs;
     p.S = g.S; p.num_pairs = g.P; p.start = g.start; p.n_warps = g.n_warps;
     p.start_final = g.start_final;
     p.y = y; p.y_bf16 = (dtype == CCB_DTYPE_BF16); p.sn = sn; p.st = st;
@@ -481,7 +484,7 @@ int ccb_plan_info(void *plan, long *info) {
     info[3] = (long)p->fwd.arcs.size(); info[4] = (long)p->bwd.arcs.size(); info[5] = p->start;
     info[6] = p->num_labels; info[7] = p->n_ctas; info[8] = p->n_warps;
     info[9] = std::max(p->fwd.max_tile_arcs, p->bwd.max_tile_arcs);
-    info[10] = p->num_pairs; info[11] = (long)p->start_arcs.size();
+    info[10] = p->num_pairs; info[11] = (long)p->start_arcs.size(); info[12] = (long)p->hub_states.size();
     return 0;
 }
 
@@ -507,6 +510,7 @@ int ccb_plan_copy(void *plan, int which, void *dst, size_t dst_bytes) {
         case 13: src = p->fwd.cta_labels.data(); bytes = p->fwd.cta_labels.size() * 4; break;
         case 14: src = p->bwd.cta_labels.data(); bytes = p->bwd.cta_labels.size() * 4; break;
         case 15: src = p->bwd.w1.data(); bytes = p->bwd.w1.size() * 4; break;
+        case 16: src = p->hub_states.data(); bytes = p->hub_states.size() * 4; break;
         default: return 1;
     }
     if (bytes > dst_bytes) return 2;

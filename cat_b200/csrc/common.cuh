@@ -37,6 +37,8 @@ struct DeviceGraph {
     DevicePass fwd, bwd;
     Arc *start_arcs = nullptr;   // out-arcs of the start state
     int n_start_arcs = 0;
+    int *hub_states = nullptr;   // states whose forward row is accumulated from parts
+    int n_hubs = 0;
     float start_final = 0.f;
     int max_smem_optin = 0;
 };
@@ -55,6 +57,8 @@ struct DenParams {
     const float *final_lin;
     const Arc *start_arcs;
     int n_start_arcs;
+    const int *hub_states;
+    int n_hubs;
     int S, num_pairs, start, n_warps;
     float start_final;
     // problem

@@ -141,7 +141,7 @@ void Layout(const std::vector<Group> &groups, int S, const std::vector<int> &sta
                 // the kernels then skip the label lookup / emission refresh on the common path.
                 // one-row segments: sign(w[0]); two-row (backward pair) segments: sign(w[0]) for p0, sign(w[1]) for p1.
                 bool chg0 = false, chg1 = false;
-                if (sg.rows == 1) {
+                if (sg.rows == 1 && sg.event != kEvPartial) {   // (partial rows bypass the kernels' emission cache)
                     const int k = sg.event == kEvRowPos0 ? 0 : 1;
                     chg0 = state_label[(size_t)row] != prev_label[k];
                     prev_label[k] = state_label[(size_t)row];
@@ -261,6 +261,19 @@ bool BuildDenPlan(const HostFst &fst, int n_ctas, int n_warps, DenPlan *plan, st
         }
     }
 
+    // hubs: states whose in-arc row is too long for one warp
+    std::vector<char> is_hub(S, 0);
+    {
+        const char *e = getenv("CCB_HUB_IN_ARCS");   // test hook
+        const size_t hub_thr = e ? (size_t)atoi(e) : (size_t)kHubInArcs;
+        for (size_t q = 0; q < S; ++q) is_hub[q] = in_s[q].size() > hub_thr;
+    }
+    int part_arcs = kPartArcs;
+    {
+        const char *e = getenv("CCB_PART_ARCS");     // test hook; must leave the last slot of a quad for the target
+        if (e && atoi(e) >= 3) part_arcs = atoi(e) / kQuad * kQuad + kQuad - 1;
+    }
+
     // 2. pair detection: two sources that enter a destination with bit-equal weights, counted over destinations
     std::vector<int> partner(S, -1);
     {
@@ -293,25 +306,35 @@ bool BuildDenPlan(const HostFst &fst, int n_ctas, int n_warps, DenPlan *plan, st
         });
         const char *nopair = getenv("CCB_NO_PAIRS");
         if (!(nopair && nopair[0] == '1'))
-            for (auto &c : cands)
+            for (auto &c : cands) {
+                if (is_hub[(size_t)c.p1] || is_hub[(size_t)c.p2]) continue;   // hub rows are accumulated from parts
                 if (partner[(size_t)c.p1] < 0 && partner[(size_t)c.p2] < 0) { partner[(size_t)c.p1] = c.p2; partner[(size_t)c.p2] = c.p1; }
+            }
     }
 
     // 3. groups and final state order ("fid")
-    struct GroupKey { int lab1, lab0, s0, s1; };   // s0 = pos0 sid or -1, s1 = pos1 sid
+    struct GroupKey { int lab1, lab0, s0, s1, part; };   // s0 = pos0 sid or -1, s1 = pos1 sid; part > 0: floating part of hub s1
     std::vector<GroupKey> gk;
     for (size_t s = 0; s < S; ++s) {
         const int o = partner[s];
-        if (o < 0) { gk.push_back(GroupKey{sid_label[s], -1, -1, (int)s}); continue; }
+        if (o < 0) {
+            gk.push_back(GroupKey{sid_label[s], -1, -1, (int)s, 0});
+            if (is_hub[s]) {
+                const int parts = (int)((in_s[s].size() + part_arcs - 1) / part_arcs);
+                for (int j = 1; j < parts; ++j) gk.push_back(GroupKey{sid_label[s], -1, -1, (int)s, j});
+            }
+            continue;
+        }
         if ((int)s > o) continue;   // handle each pair once
         int a = (int)s, b = o;      // pos0 = smaller label (ties: smaller sid)
         if (sid_label[(size_t)b] < sid_label[(size_t)a]) std::swap(a, b);
-        gk.push_back(GroupKey{sid_label[(size_t)b], sid_label[(size_t)a], a, b});
+        gk.push_back(GroupKey{sid_label[(size_t)b], sid_label[(size_t)a], a, b, 0});
     }
     std::sort(gk.begin(), gk.end(), [](const GroupKey &x, const GroupKey &y) {
         if (x.lab1 != y.lab1) return x.lab1 < y.lab1;
         if (x.lab0 != y.lab0) return x.lab0 < y.lab0;
-        return x.s1 < y.s1;
+        if (x.s1 != y.s1) return x.s1 < y.s1;
+        return x.part < y.part;
     });
     std::vector<int> fid(S, -1), pair_of(S, -1);
     std::vector<Group> fgroups, bgroups;
@@ -326,10 +349,13 @@ bool BuildDenPlan(const HostFst &fst, int n_ctas, int n_warps, DenPlan *plan, st
         plan->state_label.assign(S, 0); plan->state_pos.assign(S, 1); plan->orig_state.assign(S, 0); plan->final_lin.assign(S, 0.f);
         int next = 0, n_pairs = 0;
         for (auto &g : order) {
+            if (g.part > 0) continue;   // floating part of a hub row: no state of its own
             if (g.s0 >= 0) { fid[(size_t)g.s0] = next++; pair_of[(size_t)g.s0] = n_pairs; pair_of[(size_t)g.s1] = n_pairs; }
             fid[(size_t)g.s1] = next++;
             if (g.s0 >= 0) ++n_pairs;
         }
+        plan->hub_states.clear();
+        for (size_t s = 0; s < S; ++s) if (is_hub[s]) plan->hub_states.push_back(fid[s]);
         for (size_t s = 0; s < S; ++s) {
             const int f = fid[s];
             plan->state_label[(size_t)f] = sid_label[s];
@@ -378,11 +404,41 @@ bool BuildDenPlan(const HostFst &fst, int n_ctas, int n_warps, DenPlan *plan, st
         };
         fgroups.clear(); bgroups.clear();
         fgroups.reserve(order.size()); bgroups.reserve(order.size());
+        std::vector<Arc> hub_row;
+        int next_state = 0;
         for (auto &g : order) {
             Group fg, bg;
+            if (g.part > 0 || (g.s0 < 0 && is_hub[(size_t)g.s1])) {
+                // a PART of a hub's forward row: arcs [part*kPartArcs, ...) of the merged row + the target slot
+                forward_row(g.s1, &hub_row);
+                Segment f;
+                const size_t a0 = std::min(hub_row.size(), (size_t)g.part * part_arcs), a1 = std::min(hub_row.size(), a0 + (size_t)part_arcs);
+                for (size_t i = a0; i < a1; ++i) f.arcs.push_back(hub_row[i]);
+                while (f.arcs.size() % kQuad != kQuad - 1) f.arcs.push_back(Arc{f.arcs.empty() ? (uint32_t)fid[(size_t)g.s1] : f.arcs.back().peer, 0.f});
+                f.arcs.push_back(Arc{(uint32_t)fid[(size_t)g.s1], 0.f});   // last slot: the target row
+                f.event = kEvPartial;
+                f.rows = g.part == 0 ? 1 : 0;
+                fg.first_state = bg.first_state = g.part == 0 ? fid[(size_t)g.s1] : next_state;
+                fg.rows = bg.rows = f.rows;
+                fg.pairs = bg.pairs = 0;
+                fg.segs.push_back(std::move(f));
+                if (g.part == 0) {
+                    Segment b;
+                    out_list(g.s1, &l1);
+                    for (auto &e : l1) { b.arcs.push_back(Arc{(uint32_t)e.q, e.w}); b.w1.push_back(0.f); }
+                    b.event = kEvRow;
+                    b.rows = 1;
+                    bg.segs.push_back(std::move(b));
+                    next_state = fid[(size_t)g.s1] + 1;
+                }
+                fgroups.push_back(std::move(fg));
+                bgroups.push_back(std::move(bg));
+                continue;
+            }
             fg.first_state = bg.first_state = g.s0 >= 0 ? fid[(size_t)g.s0] : fid[(size_t)g.s1];
             fg.rows = bg.rows = g.s0 >= 0 ? 2 : 1;
             fg.pairs = bg.pairs = g.s0 >= 0 ? 1 : 0;
+            next_state = fg.first_state + fg.rows;
             if (g.s0 < 0) {
                 Segment f, b;
                 forward_row(g.s1, &f.arcs);
@@ -444,8 +500,10 @@ bool BuildDenPlan(const HostFst &fst, int n_ctas, int n_warps, DenPlan *plan, st
     // tiles); inside a tile the groups are dealt to the warps longest-first (LPT), then each warp's groups are put
     // back in label order.  States are renumbered in that (tile, warp, label) order, which keeps every warp's rows
     // contiguous while balancing the warps to within one small group.
+    // (floating parts of hub rows carry forward-pass work only: they are dealt over ALL tiles afterwards, to the tile
+    // with the least forward load, instead of piling up in the tiles around their hub)
     std::vector<int64_t> prefix((size_t)G + 1, 0);
-    for (int g = 0; g < G; ++g) prefix[(size_t)g + 1] = prefix[(size_t)g] + cost[(size_t)g];
+    for (int g = 0; g < G; ++g) prefix[(size_t)g + 1] = prefix[(size_t)g] + (gk[(size_t)g].part > 0 ? 0 : cost[(size_t)g]);
     std::vector<int> tile((size_t)n_ctas + 1, 0);
     for (int c = 1; c < n_ctas; ++c) {
         const int64_t target = (prefix[(size_t)G] * c + n_ctas / 2) / n_ctas;
@@ -453,6 +511,20 @@ bool BuildDenPlan(const HostFst &fst, int n_ctas, int n_warps, DenPlan *plan, st
         tile[(size_t)c] = std::min(std::max(g, tile[(size_t)c - 1]), G);
     }
     tile[(size_t)n_ctas] = G;
+    std::vector<std::vector<int>> tile_groups((size_t)n_ctas);
+    std::vector<int64_t> tile_fwd((size_t)n_ctas, 0);
+    std::vector<int> floating;
+    for (int c = 0; c < n_ctas; ++c)
+        for (int g = tile[(size_t)c]; g < tile[(size_t)c + 1]; ++g) {
+            if (gk[(size_t)g].part > 0) { floating.push_back(g); continue; }
+            tile_groups[(size_t)c].push_back(g);
+            for (auto &sg : fgroups[(size_t)g].segs) tile_fwd[(size_t)c] += seg_quads(sg) * kQuad;
+        }
+    for (int g : floating) {
+        const int c = (int)(std::min_element(tile_fwd.begin(), tile_fwd.end()) - tile_fwd.begin());
+        tile_groups[(size_t)c].push_back(g);
+        for (auto &sg : fgroups[(size_t)g].segs) tile_fwd[(size_t)c] += seg_quads(sg) * kQuad;
+    }
     std::vector<GroupKey> order;
     order.reserve((size_t)G);
     std::vector<int> chunk_group((size_t)n_ctas * n_warps + 1, 0);
@@ -460,8 +532,7 @@ bool BuildDenPlan(const HostFst &fst, int n_ctas, int n_warps, DenPlan *plan, st
     std::vector<int64_t> load((size_t)n_warps);
     std::vector<int> idx;
     for (int c = 0; c < n_ctas; ++c) {
-        idx.clear();
-        for (int g = tile[(size_t)c]; g < tile[(size_t)c + 1]; ++g) idx.push_back(g);
+        idx = tile_groups[(size_t)c];
         std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return cost[(size_t)a] > cost[(size_t)b]; });
         for (auto &b : bins) b.clear();
         std::fill(load.begin(), load.end(), 0);

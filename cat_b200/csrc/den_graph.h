@@ -27,7 +27,10 @@ static constexpr int kChunkArcPad = 16;  // every warp chunk's arc count is padd
 static constexpr int kEvRow = 0;         // end of the row of an unpaired state
 static constexpr int kEvRowPos0 = 1;     // end of the row of the first member of a pair
 static constexpr int kEvRowPos1 = 2;     // end of the row of the second member of a pair
-static constexpr int kEvCommon = 3;      // backward only: end of the arcs the two members of a pair share
+static constexpr int kEvPartial = 3;     // forward only: a PART of a high in-degree row; the last slot of the segment carries
+                                         // the target row (weight 0) and the result is added to it atomically
+static constexpr int kHubInArcs = 384;   // rows with more in-arcs than this are split into parts of kPartArcs arcs that
+static constexpr int kPartArcs = 191;    // any warp of the grid can own (real n-gram den graphs have such states)
 
 // Den graph as stored in the file, in the view fst_read.cc:40-59 gives the kernels.
 struct HostFst {
@@ -68,7 +71,9 @@ struct DenPlan {
     std::vector<float> final_lin;       // [S] exp(final_logw) (0 for non-final)
     std::vector<int> orig_state;        // [S] state id in the file
     std::vector<Arc> start_arcs;        // out-arcs of the start state (plain), for logZ recomputed from beta
-    // fwd: one segment per state (its in-arcs; peers may be virtual pair rows), events kEvRow / kEvRowPos0 / kEvRowPos1.
+    std::vector<int> hub_states;        // states whose forward row is accumulated from parts (rows zeroed before each frame)
+    // fwd: one segment per state (its in-arcs; peers may be virtual pair rows), events kEvRow / kEvRowPos0 / kEvRowPos1;
+    //      a high in-degree state has several kEvPartial segments instead (one in its own group, the others floating).
     // bwd: one segment per GROUP (an unpaired state, or a pair p0,p1): every slot carries two weights, arcs[i].w for the
     //      group's first row and w1[i] for its second row (0 when the arc does not belong to that row), so the arcs the
     //      two members share are gathered once.  Event kEvRow = one-row group, kEvRowPos1 = two-row group; the

@@ -167,7 +167,7 @@ __device__ __forceinline__ void walk_arcs(const uint4 *arcs, int n_batches, uint
                 acc[u] = fmaf(w3, v[g4 * kQuad + 3].v[u], acc[u]);
             }
             if ((int)wq.w < 0)   // warp-uniform: a segment ends at this quad; the callback owns the accumulators
-                seg_end(acc, (int)(((wq.z >> 31) << 1) | (wq.y >> 31)), (int)wq.x < 0);
+                seg_end(acc, (int)(((wq.z >> 31) << 1) | (wq.y >> 31)), (int)wq.x < 0, p + 2 * g4);
         }
     };
 
@@ -332,6 +332,13 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const DenParams P) {
         }
     }
     if (cta == 0) for (int n = tid; n < Npad; n += NT) __stcg(P.colsum_a + n, 1.f);
+    // rows of high in-degree states are accumulated with atomics from several parts: zero them one frame ahead
+    auto zero_hub_rows = [&](int frame) {
+        float *fr = P.alpha + (size_t)frame * frame_elems;
+        for (int i = cta * NT + tid; i < P.n_hubs * Npad; i += gridDim.x * NT)
+            __stcg(fr + (size_t)__ldg(P.hub_states + i / Npad) * Npad + (i % Npad), 0.f);
+    };
+    if (P.Tmax >= 1) zero_hub_rows(1);
     const int my_len = (cta == 0 && tid < P.N) ? __ldg(P.len + tid) : 0;   // CTA 0 keeps log-scale books
     int len0[U];   // lengths of this lane's utterances in lane group 0 (the only group for N <= 32*U)
 #pragma unroll
@@ -375,9 +382,28 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const DenParams P) {
             float *const out_base = a_cur + n0;
             Vec<U> cacc = vec_zero<U>();
             walk_arcs<U, BATCH, SMEM_ARCS>(arc4, n_batches, row_bytes, reinterpret_cast<const char *>(a_prev + n0), lane_act,
-                                           frame_scalars, [&](float *acc, int ev, bool new_label) {
+                                           frame_scalars, [&](float *acc, int ev, bool new_label, const uint4 *quad) {
                 const bool k1 = ev != kEvRowPos0;
                 if (P.debug & 1) { sum[0] += acc[0]; acc[0] = 0.f; return; }
+                if (ev == kEvPartial) {
+                    // a part of a high in-degree row: the segment's last slot names the target row; add into it
+                    const uint32_t tgt_off = load_quad_peers<SMEM_ARCS>(quad, row_bytes).w;   // byte offset of the row
+                    const int tgt = (int)(tgt_off / row_bytes);
+                    const int lab = __ldg(P.state_label + tgt);
+                    float *dst = reinterpret_cast<float *>(reinterpret_cast<char *>(out_base) + tgt_off);
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        if (act[u]) {
+                            const float ev_u = expf(load_y(P.y, P.y_bf16, (n0 + u) * P.sn + (long)(t - 1) * P.st + lab) - fm[u]);
+                            const float o = acc[u] * ev_u * r[u];
+                            sum[u] += o;
+                            if (o != 0.f) atomicAdd(dst + u, o);
+                        }
+                        acc[u] = 0.f;
+                    }
+                    if (tgt == (int)out_row) { ++out_row; ++ql; }   // the part that lives in the row's own group
+                    return;
+                }
                 if (new_label) {   // rare: a new label for this row position -> refresh its emission
                     const int lab = s_label[ql];
                     const int lp = k1 ? labp1 : labp0;
@@ -412,6 +438,7 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const DenParams P) {
                 if (act[u] && sum[u] != 0.f) atomicAdd(&s_sum[n0 + u], sum[u]);
         }
         tl_mark(P, t, chunk, n_chunks, 1, lane);
+        if (t < P.Tmax) zero_hub_rows(t + 1);
         __syncthreads();
         for (int i = tid; i < Npad; i += NT) {
             const float v = s_sum[i];

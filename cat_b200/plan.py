@@ -14,7 +14,8 @@ from . import _lib
 
 QUAD = 4            # arc segments are padded to whole quads (den_graph.h kQuad)
 CHUNK_ARC_PAD = 16  # chunk arc counts are padded to a multiple of this (kChunkArcPad)
-EV_ROW, EV_ROW_POS0, EV_ROW_POS1, EV_COMMON = 0, 1, 2, 3   # den_graph.h kEv*
+EV_ROW, EV_ROW_POS0, EV_ROW_POS1, EV_PARTIAL = 0, 1, 2, 3   # den_graph.h kEv*
+EV_COMMON = EV_PARTIAL   # (old name)
 ARC_DTYPE = np.dtype([("peer", "<u4"), ("w", "<f4")])
 
 
@@ -65,6 +66,7 @@ class PlanView:
     final_lin: np.ndarray
     orig_state: np.ndarray
     start_arcs: np.ndarray
+    hub_states: np.ndarray
     fwd: PassView
     bwd: PassView
 
@@ -75,9 +77,9 @@ def load_plan(path: str, n_ctas: int = 148, n_warps: int = 16) -> PlanView:
     if not h:
         raise RuntimeError(_lib.last_error())
     try:
-        info = (C.c_long * 12)()
+        info = (C.c_long * 13)()
         assert L.ccb_plan_info(h, info) == 0
-        S0, A0, S, Af, Ab, start, nl, nc, nw, mta, P, nsa = [int(x) for x in info]
+        S0, A0, S, Af, Ab, start, nl, nc, nw, mta, P, nsa, nh = [int(x) for x in info]
         n_chunks = nc * nw
 
         def get(which, dtype, count):
@@ -88,7 +90,7 @@ def load_plan(path: str, n_ctas: int = 148, n_warps: int = 16) -> PlanView:
 
         return PlanView(S0, A0, S, P, start, nl, nc, nw, mta,
                         get(0, np.int32, S), get(9, np.int32, S), get(1, np.float32, S), get(2, np.int32, S),
-                        get(12, ARC_DTYPE, nsa),
+                        get(12, ARC_DTYPE, nsa), get(16, np.int32, nh),
                         PassView(get(3, ARC_DTYPE, Af), get(4, np.int32, n_chunks + 1), get(5, np.int32, n_chunks + 1),
                                  get(10, np.int32, n_chunks + 1), get(13, np.int32, nc * 4).reshape(nc, 4)),
                         PassView(get(6, ARC_DTYPE, Ab), get(7, np.int32, n_chunks + 1), get(8, np.int32, n_chunks + 1),

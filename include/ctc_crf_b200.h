@@ -139,13 +139,14 @@ void ccb_debug_timeline(void *dev_buffer, int step0, int nsteps);
 /* Parse + plan without touching CUDA.  n_ctas/n_warps describe the persistent grid the plan is cut for. */
 void *ccb_plan_create(const char *fst_name, int n_ctas, int n_warps);
 void ccb_plan_destroy(void *plan);
-/* info[0..11] = S_file, A_file, S, A_fwd, A_bwd, start, num_labels, n_ctas, n_warps, max_tile_arcs, P (pairs), n_start_arcs */
+/* info[0..12] = S_file, A_file, S, A_fwd, A_bwd, start, num_labels, n_ctas, n_warps, max_tile_arcs, P (pairs), n_start_arcs,
+ *               n_hubs (states whose forward row is split into parts) */
 int ccb_plan_info(void *plan, long *info);
 /* which: 0 state_label[S] i32, 1 final_lin[S] f32, 2 orig_state[S] i32,
  *        3 fwd_arcs[A_fwd] {u32 peer, f32 w (sign bits = segment events)}, 4 fwd_chunk_state[n_ctas*n_warps+1] i32,
  *        5 fwd_chunk_arc[n_ctas*n_warps+1] i32, 6 bwd_arcs[A_bwd], 7 bwd_chunk_state, 8 bwd_chunk_arc,
  *        9 state_pos[S] i32, 10 fwd_chunk_pair, 11 bwd_chunk_pair, 12 start_arcs[n_start_arcs],
- *        13 fwd_cta_labels[n_ctas*4] i32, 14 bwd_cta_labels */
+ *        13 fwd_cta_labels[n_ctas*4] i32, 14 bwd_cta_labels, 15 bwd second weights f32[A_bwd], 16 hub_states[n_hubs] i32 */
 int ccb_plan_copy(void *plan, int which, void *dst, size_t dst_bytes);
 
 #ifdef __cplusplus

@@ -25,9 +25,18 @@ def _decode_forward(plan):
     pairs = []
     q = 0
     arcs = plan.fwd.arcs
+    hubs = set(int(h) for h in plan.hub_states)
     for a0, a1, ev, _chg in plan.fwd.segments():
-        assert ev != 3, "kEvCommon must not appear in the forward stream"
         n = a1 - a0
+        if ev == 3:     # a part of a high in-degree row: the last slot names the target row (weight 0)
+            tgt = int(arcs["peer"][a1 - 1])
+            assert tgt in hubs and arcs["w"][a1 - 1] == 0
+            row.append(np.full(n - 1, tgt)); peer.append(arcs["peer"][a0:a1 - 1].astype(np.int64)); w.append(np.abs(arcs["w"][a0:a1 - 1]).astype(np.float64))
+            if tgt == q:
+                assert plan.state_pos[q] == 1
+                q += 1
+            continue
+        assert q not in hubs
         row.append(np.full(n, q)); peer.append(arcs["peer"][a0:a1].astype(np.int64)); w.append(np.abs(arcs["w"][a0:a1]).astype(np.float64))
         if ev == 1:
             assert plan.state_pos[q] == 0

@@ -172,6 +172,26 @@ def test_kernel_arithmetic_emulation_matches_oracle(tmp_graphs, name, lens):
     assert np.abs(eg - gd).max() < 1e-6
 
 
+def test_hub_rows_split_into_parts(tmp_graphs, monkeypatch):
+    """States with a long in-arc row get their forward row computed in parts (any warp, atomically accumulated);
+    thresholds lowered through the test hooks so that small graphs exercise several parts per row."""
+    monkeypatch.setenv("CCB_HUB_IN_ARCS", "6")
+    monkeypatch.setenv("CCB_PART_ARCS", "7")
+    for name in ("tlm_small", "random_split"):
+        path, g, V = tmp_graphs[name]
+        P = plan.load_plan(path, 148, 16)
+        assert len(P.hub_states) > 0
+        parts = [x for x in P.fwd.segments() if x[2] == plan.EV_PARTIAL]
+        assert len(parts) > len(P.hub_states)                      # some rows have several parts
+        lens = [20, 13, 7, 2]
+        y, _, lens, _ = oracle.synth_batch(len(lens), max(lens), V, seed=6, lens=lens)
+        la, lb, gd = oracle.den(g, y, lens)
+        ea, eb, eg = emulate.den_emulate(P, y, lens)
+        np.testing.assert_allclose(ea, la, rtol=1e-7)
+        np.testing.assert_allclose(eb, lb, rtol=1e-7)
+        assert np.abs(eg - gd).max() < 1e-6
+
+
 def test_fixture_emulation(fixture_fst, fixture_inputs):
     P = plan.load_plan(fixture_fst, 148, 16)
     ea, eb, eg = emulate.den_emulate(P, fixture_inputs["y"], fixture_inputs["lx"])

@@ -113,13 +113,18 @@ def test_ctc_vs_oracle(N, T, V, lens, ly):
     assert np.abs(grads.transpose(0, 1).cpu().numpy() - gc).max() < GRAD_ATOL
 
 
-@pytest.mark.parametrize("env", ["CCB_ARCS_IN_GLOBAL", "CCB_NO_PAIRS"])
+@pytest.mark.parametrize("env", ["CCB_ARCS_IN_GLOBAL", "CCB_NO_PAIRS", "HUBS", "HUBS+CCB_ARCS_IN_GLOBAL"])
 def test_fallback_paths(tmp_graphs, monkeypatch, env):
-    """Arc tiles streamed from global memory (graphs too large for shared memory) and the un-paired plan give the
-    same answers as the default path."""
+    """Arc tiles streamed from global memory (graphs too large for shared memory), the un-paired plan and rows split
+    into parts give the same answers as the default path."""
     from oracle import oracle
     from cat_b200 import _C
-    monkeypatch.setenv(env, "1")
+    for e in env.split("+"):
+        if e == "HUBS":     # long in-arc rows computed in atomically accumulated parts
+            monkeypatch.setenv("CCB_HUB_IN_ARCS", "10")
+            monkeypatch.setenv("CCB_PART_ARCS", "7")
+        else:
+            monkeypatch.setenv(e, "1")
     path, g, V = tmp_graphs["tlm_mid"]
     ctx = _ctx(path)
     N, T = 40, 30
