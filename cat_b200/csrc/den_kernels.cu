@@ -273,10 +273,36 @@ __device__ __forceinline__ void tl_mark(const DenParams &P, int step_index, int 
     else rec[slot + 1] = clock64();
 }
 
+// One PART of a high in-degree forward row (den_graph.h kEvPartial): scale the partial sum like a row end and add it
+// into the target row with atomics (the row was zeroed one frame ahead).  Deliberately out of line and self-contained:
+// it recomputes the few per-frame scalars it needs so that the hot row-end path keeps its registers.
+template <int U>
+__device__ __noinline__ void forward_partial_row(const int *state_label, const int *len, const float *colsum_prev,
+                                                 const float *fmax_prev, const void *y, int y_bf16, long sn, long yt_off,
+                                                 int N, int t, int n0, Vec<U> part, uint32_t tgt_off, uint32_t row_bytes,
+                                                 float *a_cur, float *s_sum) {
+    const int tgt = (int)(tgt_off / row_bytes);
+    const int lab = __ldg(state_label + tgt);
+    float *dst = reinterpret_cast<float *>(reinterpret_cast<char *>(a_cur + n0) + tgt_off);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int n = n0 + u;
+        if (n < N && t <= __ldg(len + n)) {
+            int sh;
+            const float r = scale_from_sum(__ldcg(colsum_prev + n), &sh);
+            const float e = expf(load_y(y, y_bf16, n * sn + yt_off + lab) - __ldg(fmax_prev + n));
+            const float o = part.v[u] * e * r;
+            if (o != 0.f) { atomicAdd(dst + u, o); atomicAdd(&s_sum[n], o); }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // forward: alpha recursion + logZ
 // ------------------------------------------------------------------------------------------------
-template <int NT, int U, int BATCH, bool SMEM_ARCS>
+// HUBS: the plan contains high in-degree rows split into parts (kEvPartial segments); the common case compiles the
+// partial-row path out entirely so that it costs the hot row-end code nothing.
+template <int NT, int U, int BATCH, bool SMEM_ARCS, bool HUBS>
 __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const DenParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *s_sum = reinterpret_cast<float *>(smem_raw);                                  // [Npad]
@@ -338,7 +364,7 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const DenParams P) {
         for (int i = cta * NT + tid; i < P.n_hubs * Npad; i += gridDim.x * NT)
             __stcg(fr + (size_t)__ldg(P.hub_states + i / Npad) * Npad + (i % Npad), 0.f);
     };
-    if (P.Tmax >= 1) zero_hub_rows(1);
+    if (HUBS && P.Tmax >= 1) zero_hub_rows(1);
     const int my_len = (cta == 0 && tid < P.N) ? __ldg(P.len + tid) : 0;   // CTA 0 keeps log-scale books
     int len0[U];   // lengths of this lane's utterances in lane group 0 (the only group for N <= 32*U)
 #pragma unroll
@@ -385,23 +411,14 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const DenParams P) {
                                            frame_scalars, [&](float *acc, int ev, bool new_label, const uint4 *quad) {
                 const bool k1 = ev != kEvRowPos0;
                 if (P.debug & 1) { sum[0] += acc[0]; acc[0] = 0.f; return; }
-                if (ev == kEvPartial) {
-                    // a part of a high in-degree row: the segment's last slot names the target row; add into it
-                    const uint32_t tgt_off = load_quad_peers<SMEM_ARCS>(quad, row_bytes).w;   // byte offset of the row
-                    const int tgt = (int)(tgt_off / row_bytes);
-                    const int lab = __ldg(P.state_label + tgt);
-                    float *dst = reinterpret_cast<float *>(reinterpret_cast<char *>(out_base) + tgt_off);
+                if (HUBS && ev == kEvPartial) {   // high in-degree rows only: handled out of line, nothing hot is captured
+                    Vec<U> part;
 #pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        if (act[u]) {
-                            const float ev_u = expf(load_y(P.y, P.y_bf16, (n0 + u) * P.sn + (long)(t - 1) * P.st + lab) - fm[u]);
-                            const float o = acc[u] * ev_u * r[u];
-                            sum[u] += o;
-                            if (o != 0.f) atomicAdd(dst + u, o);
-                        }
-                        acc[u] = 0.f;
-                    }
-                    if (tgt == (int)out_row) { ++out_row; ++ql; }   // the part that lives in the row's own group
+                    for (int u = 0; u < U; ++u) { part.v[u] = acc[u]; acc[u] = 0.f; }
+                    const uint32_t tgt_off = load_quad_peers<SMEM_ARCS>(quad, row_bytes).w;   // byte offset of the target row
+                    forward_partial_row<U>(P.state_label, P.len, P.colsum_a + (size_t)(t - 1) * Npad, P.fmax + (size_t)(t - 1) * Npad,
+                                           P.y, P.y_bf16, P.sn, (long)(t - 1) * P.st, P.N, t, n0, part, tgt_off, row_bytes, a_cur, s_sum);
+                    if (tgt_off == out_row * row_bytes) { ++out_row; ++ql; }   // the part that lives in the row's own group
                     return;
                 }
                 if (new_label) {   // rare: a new label for this row position -> refresh its emission
@@ -438,7 +455,7 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const DenParams P) {
                 if (act[u] && sum[u] != 0.f) atomicAdd(&s_sum[n0 + u], sum[u]);
         }
         tl_mark(P, t, chunk, n_chunks, 1, lane);
-        if (t < P.Tmax) zero_hub_rows(t + 1);
+        if (HUBS && t < P.Tmax) zero_hub_rows(t + 1);
         __syncthreads();
         for (int i = tid; i < Npad; i += NT) {
             const float v = s_sum[i];
@@ -726,7 +743,8 @@ __global__ void den_grad_normalize_kernel(float *grad, long gsn, long gst, const
 template <int NT, int U, int BATCH, bool SMEM_ARCS>
 int LaunchOne(bool backward, const DenParams &p, int n_ctas, size_t smem, cudaStream_t stream, std::string *err) {
     const void *fn = backward ? (const void *)den_backward_kernel<NT, U, BATCH, SMEM_ARCS>
-                              : (const void *)den_forward_kernel<NT, U, BATCH, SMEM_ARCS>;
+                     : p.n_hubs > 0 ? (const void *)den_forward_kernel<NT, U, BATCH, SMEM_ARCS, true>
+                                    : (const void *)den_forward_kernel<NT, U, BATCH, SMEM_ARCS, false>;
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { *err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return (int)e; }
     int per_sm = 0;
