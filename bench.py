@@ -151,6 +151,7 @@ def run_reference(args, rank):
     _, g = den_graph_file(args.H, args.d, args.V)
     cores = os.cpu_count() or 1
     sN, sT = max(1, min(args.N, cores)), 64
+    cores = min(cores, sN)            # the port parallelises over utterances: threads actually used
     for _ in range(min(args.warmup, 1)):
         cpu_port(g, sN, sT, args.V, args.lamb, cores)
     t0 = time.perf_counter()
@@ -348,6 +349,7 @@ def main():
                     sN, sT = max(1, min(N, cores)), min(T, 96)
                 else:
                     sN, sT = [int(x) for x in args.cpu_sample.split(",")]
+                cores = min(cores, sN)    # the port parallelises over utterances: threads actually used
                 v, dt = cpu_port(graph, sN, sT, V, args.lamb, cores)
                 cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "seconds": dt,
                                 "sample": f"fp64 oracle port (reference has no CPU path), N={sN},T={sT} slice, same den graph/V/lamb, {cores} threads"}
