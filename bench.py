@@ -208,8 +208,13 @@ def main():
     frames_per_step = int(lens_np.sum())
     crit = ctc_crf.CTC_CRF_LOSS(lamb=args.lamb, size_average=True)
 
+    host_s = [0.0, 0]   # host-side enqueue time of the resident steps (diagnostic: the GPU must never wait for it)
+
     def step_resident():
+        t0 = time.perf_counter()
         loss, grad, _ = _C.ctc_crf_loss_fwd(y, labels, lx, ly, args.lamb, True)
+        host_s[0] += time.perf_counter() - t0
+        host_s[1] += 1
         if world > 1:
             v = torch.stack([loss.reshape(()) * N, torch.tensor(float(N), device=dev)])
             dist.all_reduce(v)
@@ -238,7 +243,7 @@ def main():
 
     # ---- value: whole-job throughput, inputs resident in HBM -------------------------------------------------
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("CCB_BENCH_NO_SAMPLER"):
         sampler.start()
     l0 = _C.launch_count()
     ms_total = timed(step_resident, args.steps, max(args.warmup, 3))
@@ -365,6 +370,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
                     "api": "ctc_crf.CTC_CRF_LOSS.forward on pinned-host logits copied H2D inside the step, loss.item() back"},
             "gpu_launches": int(launches),
+            "host_enqueue_ms_per_step": 1e3 * host_s[0] / max(host_s[1], 1),
             "clocks": clocks,
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,

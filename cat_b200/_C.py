@@ -200,12 +200,15 @@ def _plan_slices(L, lx, ly, N, V, dev):
 
 
 def ctc_crf_loss_fwd(logits: torch.Tensor, labels: torch.Tensor, lx: torch.Tensor, ly: torch.Tensor,
-                     lamb: float, size_average: bool, want_parts: bool = False
+                     lamb: float, size_average: bool, want_parts: bool = False, from_logits: bool = False
                      ) -> Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]:
     """Fused CTC-CRF loss.  logits (N,T,V) fp32 or bf16 CUDA contiguous log-probs; labels/lx/ly int32 CPU.
     Returns (loss[1] fp32 CUDA, grad (N,T,V) fp32 CUDA, parts[2N] or None).  Never synchronises the host.
-    Batches whose scratch does not fit the free memory (or > 512 utterances) are processed in slices."""
+    Batches whose scratch does not fit the free memory (or > 512 utterances) are processed in slices.
+    from_logits: `logits` are the RAW encoder outputs; log_softmax and its Jacobian are applied inside
+    (grad = d loss / d raw logits), replacing cat/ctc/train.py:173-174."""
     L = _lib.lib()
+    entry = L.ccb_ctc_crf_loss_logits_fwd if from_logits else L.ccb_ctc_crf_loss_fwd
     assert logits.is_cuda and logits.dim() == 3 and logits.is_contiguous()
     if logits.dtype not in _DTYPES:
         raise RuntimeError(f"unsupported logits dtype {logits.dtype}")
@@ -235,11 +238,11 @@ def ctc_crf_loss_fwd(logits: torch.Tensor, labels: torch.Tensor, lx: torch.Tenso
             aux_ws = torch.empty(int(L.ccb_den_aux_bytes(n, tmax)), dtype=torch.uint8, device=dev)
             ctc_ws = torch.empty(int(L.ccb_ctc_workspace_bytes(n, tmax, maxl)), dtype=torch.uint8, device=dev)
             sub_parts = torch.empty(2 * n, dtype=torch.float32, device=dev) if want_parts else None
-            rc = L.ccb_ctc_crf_loss_fwd(logits.data_ptr() + n0 * T * V * esz, _DTYPES[logits.dtype], n, T, V, tmax,
-                                        p_labels, p_off + 4 * n0, p_ly + 4 * n0, p_lx + 4 * n0, maxl, float(lamb),
-                                        float(scale), alpha_ws.data_ptr(), aux_ws.data_ptr(), ctc_ws.data_ptr(),
-                                        grad.data_ptr() + n0 * T * V * 4, losses.data_ptr() + 4 * i,
-                                        sub_parts.data_ptr() if want_parts else None, stream)
+            rc = entry(logits.data_ptr() + n0 * T * V * esz, _DTYPES[logits.dtype], n, T, V, tmax,
+                       p_labels, p_off + 4 * n0, p_ly + 4 * n0, p_lx + 4 * n0, maxl, float(lamb),
+                       float(scale), alpha_ws.data_ptr(), aux_ws.data_ptr(), ctc_ws.data_ptr(),
+                       grad.data_ptr() + n0 * T * V * 4, losses.data_ptr() + 4 * i,
+                       sub_parts.data_ptr() if want_parts else None, stream)
             _check(rc, "ctc_crf_loss_fwd")
             if want_parts:
                 parts[n0:n1] = sub_parts[:n]

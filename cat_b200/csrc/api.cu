@@ -190,14 +190,18 @@ int CheckDen(const DeviceGraph &g, int dtype, int N, int T, int V) {
 }
 
 // forward part: zero aux, frame max, alpha recursion; logz_a lands in aux
+// raw: `y` holds unnormalised logits; the log-normalisers go to aux (lz, lnorm) and logZ comes out normalised
 int DenForward(const DeviceGraph &g, const void *y, int dtype, long sn, long st, int N, int T, int V, const int *len,
-               float *alpha, void *aux, cudaStream_t stream) {
+               float *alpha, void *aux, cudaStream_t stream, bool raw = false) {
     const DenAuxLayout L = MakeDenAuxLayout(g.S, N, T);
     char *a = reinterpret_cast<char *>(aux);
     CCB_CUDA(cudaMemsetAsync(a, 0, L.zero_bytes, stream));
-    int rc = LaunchFrameMax(y, dtype == CCB_DTYPE_BF16, sn, st, N, T, V, len, reinterpret_cast<float *>(a + L.fmax), L.Npad, stream);
+    int rc = raw ? LaunchFrameLse(y, dtype == CCB_DTYPE_BF16, sn, st, N, T, V, len, reinterpret_cast<float *>(a + L.fmax),
+                                  reinterpret_cast<float *>(a + L.lz), reinterpret_cast<double *>(a + L.lnorm), L.Npad, stream)
+                 : LaunchFrameMax(y, dtype == CCB_DTYPE_BF16, sn, st, N, T, V, len, reinterpret_cast<float *>(a + L.fmax), L.Npad, stream);
     if (rc) return FailCuda("frame_max", (cudaError_t)rc);
     DenParams p = BaseParams(g, y, dtype, sn, st, N, T, V, len, alpha, aux, L);
+    if (raw) p.lnorm = reinterpret_cast<const double *>(a + L.lnorm);
     p.barrier = reinterpret_cast<unsigned *>(a + L.barrier);
     p.logz = reinterpret_cast<float *>(a + L.logz_a);
     std::string err;
@@ -207,10 +211,12 @@ int DenForward(const DeviceGraph &g, const void *y, int dtype, long sn, long st,
 }
 
 int DenBackward(const DeviceGraph &g, const void *y, int dtype, long sn, long st, int N, int T, int V, const int *len,
-                float *alpha, void *aux, float *grad, long gsn, long gst, float grad_scale, cudaStream_t stream) {
+                float *alpha, void *aux, float *grad, long gsn, long gst, float grad_scale, cudaStream_t stream,
+                bool raw = false) {
     const DenAuxLayout L = MakeDenAuxLayout(g.S, N, T);
     char *a = reinterpret_cast<char *>(aux);
     DenParams p = BaseParams(g, y, dtype, sn, st, N, T, V, len, alpha, aux, L);
+    if (raw) p.lnorm = reinterpret_cast<const double *>(a + L.lnorm);
     p.barrier = reinterpret_cast<unsigned *>(a + L.barrier + 128);
     p.logz = reinterpret_cast<float *>(a + L.logz_b);
     p.grad = grad; p.gsn = gsn; p.gst = gst;
@@ -359,16 +365,16 @@ int ccb_ctc_forward_backward(const void *logits, int dtype, long sn, long st, in
     std::string err;
     int rc = LaunchCtc(logits, dtype == CCB_DTYPE_BF16, sn, st, N, T, V, labels_dev, label_off_dev, label_len_dev,
                        len_dev, max_label_len, blank, reinterpret_cast<float *>(workspace), grad, gsn, gst, grad_scale,
-                       logp, (cudaStream_t)stream, &err);
+                       logp, nullptr, (cudaStream_t)stream, &err);
     if (rc) return Fail(err);
     return 0;
 }
 
-int ccb_ctc_crf_loss_fwd(const void *logits, int dtype, int N, int T, int V, int Tmax,
-                         const int *labels_dev, const int *label_off_dev, const int *label_len_dev,
-                         const int *len_dev, int max_label_len, float lamb, float scale,
-                         float *alpha_ws, void *aux_ws, void *ctc_ws, float *grad, float *loss, float *parts,
-                         void *stream) {
+static int LossFwdImpl(bool raw, const void *logits, int dtype, int N, int T, int V, int Tmax,
+                       const int *labels_dev, const int *label_off_dev, const int *label_len_dev,
+                       const int *len_dev, int max_label_len, float lamb, float scale,
+                       float *alpha_ws, void *aux_ws, void *ctc_ws, float *grad, float *loss, float *parts,
+                       void *stream) {
     g_err.clear();
     DeviceGraph *g;
     if (CurrentGraph(&g)) return 1;
@@ -378,15 +384,21 @@ int ccb_ctc_crf_loss_fwd(const void *logits, int dtype, int N, int T, int V, int
     cudaStream_t s = (cudaStream_t)stream;
     const long sn = (long)T * V, st = V;     // the (N,T,V) block is addressed in place; only Tmax frames are walked
     CCB_CUDA(cudaMemsetAsync(grad, 0, sizeof(float) * (size_t)N * T * V, s));
-    if (DenForward(*g, logits, dtype, sn, st, N, Tmax, V, len_dev, alpha_ws, aux_ws, s)) return 1;
-    if (DenBackward(*g, logits, dtype, sn, st, N, Tmax, V, len_dev, alpha_ws, aux_ws, grad, sn, st, scale, s)) return 1;
+    if (DenForward(*g, logits, dtype, sn, st, N, Tmax, V, len_dev, alpha_ws, aux_ws, s, raw)) return 1;
+    if (DenBackward(*g, logits, dtype, sn, st, N, Tmax, V, len_dev, alpha_ws, aux_ws, grad, sn, st, scale, s, raw)) return 1;
     const DenAuxLayout L = MakeDenAuxLayout(g->S, N, Tmax);
     float *logz = reinterpret_cast<float *>((char *)aux_ws + L.logz_a);
     float *logp = reinterpret_cast<float *>((char *)aux_ws + L.logz_b);   // logZ(beta) no longer needed: reuse
+    const double *lnorm = raw ? reinterpret_cast<const double *>((char *)aux_ws + L.lnorm) : nullptr;
     std::string err;
     int rc = LaunchCtc(logits, dtype == CCB_DTYPE_BF16, sn, st, N, Tmax, V, labels_dev, label_off_dev, label_len_dev, len_dev,
-                       max_label_len, 0, reinterpret_cast<float *>(ctc_ws), grad, sn, st, -(1.f + lamb) * scale, logp, s, &err);
+                       max_label_len, 0, reinterpret_cast<float *>(ctc_ws), grad, sn, st, -(1.f + lamb) * scale, logp, lnorm, s, &err);
     if (rc) return Fail(err);
+    if (raw) {   // chain through log_softmax: dL/dz = g - softmax(z) * sum_k g_k
+        rc = LaunchLogitGrad(logits, dtype == CCB_DTYPE_BF16, sn, st, N, Tmax, V, len_dev,
+                             reinterpret_cast<const float *>((char *)aux_ws + L.lz), L.Npad, grad, sn, st, s);
+        if (rc) return FailCuda("logit_grad", (cudaError_t)rc);
+    }
     rc = LaunchAssembleLoss(logz, logp, N, lamb, scale, loss, s);
     if (rc) return FailCuda("assemble_loss", (cudaError_t)rc);
     if (parts) {
@@ -394,6 +406,24 @@ int ccb_ctc_crf_loss_fwd(const void *logits, int dtype, int N, int T, int V, int
         CCB_CUDA(cudaMemcpyAsync(parts + N, logp, sizeof(float) * N, cudaMemcpyDeviceToDevice, s));
     }
     return 0;
+}
+
+int ccb_ctc_crf_loss_fwd(const void *logits, int dtype, int N, int T, int V, int Tmax,
+                         const int *labels_dev, const int *label_off_dev, const int *label_len_dev,
+                         const int *len_dev, int max_label_len, float lamb, float scale,
+                         float *alpha_ws, void *aux_ws, void *ctc_ws, float *grad, float *loss, float *parts,
+                         void *stream) {
+    return LossFwdImpl(false, logits, dtype, N, T, V, Tmax, labels_dev, label_off_dev, label_len_dev, len_dev, max_label_len,
+                       lamb, scale, alpha_ws, aux_ws, ctc_ws, grad, loss, parts, stream);
+}
+
+int ccb_ctc_crf_loss_logits_fwd(const void *logits, int dtype, int N, int T, int V, int Tmax,
+                                const int *labels_dev, const int *label_off_dev, const int *label_len_dev,
+                                const int *len_dev, int max_label_len, float lamb, float scale,
+                                float *alpha_ws, void *aux_ws, void *ctc_ws, float *grad, float *loss, float *parts,
+                                void *stream) {
+    return LossFwdImpl(true, logits, dtype, N, T, V, Tmax, labels_dev, label_off_dev, label_len_dev, len_dev, max_label_len,
+                       lamb, scale, alpha_ws, aux_ws, ctc_ws, grad, loss, parts, stream);
 }
 
 /* ---- gpu_ctc/ctc.h surface ------------------------------------------------------------------- */
@@ -457,7 +487,7 @@ ctcStatus_t compute_ctc_loss(const float *const activations, float *gradients, c
     // (T,N,V) layout: element (n,t,k) at t*(N*V) + n*V + k
     int rc = LaunchCtc(activations, 0, (long)alphabet_size, (long)minibatch * alphabet_size, minibatch, maxT, alphabet_size,
                        d_labels, d_off, d_llen, d_len, maxL, options.blank_label, alpha_ws, gradients,
-                       (long)alphabet_size, (long)minibatch * alphabet_size, 1.f, d_costs, s, &err);
+                       (long)alphabet_size, (long)minibatch * alphabet_size, 1.f, d_costs, nullptr, s, &err);
     if (rc) { g_err = err; return CTC_STATUS_EXECUTION_FAILED; }
     if (cudaMemcpyAsync(costs, d_costs, sizeof(float) * minibatch, cudaMemcpyDeviceToHost, s) != cudaSuccess) return CTC_STATUS_MEMOPS_FAILED;
     if (cudaStreamSynchronize(s) != cudaSuccess) return CTC_STATUS_EXECUTION_FAILED;   // costs are host memory (gpu_ctc.h:365-368)

@@ -78,6 +78,7 @@ struct DenParams {
     const float *fmax;    // [Tmax][Npad]          per-frame max of y (emission shift)
     unsigned *barrier;    // grid barrier counter (zeroed before launch)
     float *logz;          // [N] out (forward: logZ from alpha; backward: logZ from beta)
+    const double *lnorm;  // [N] or null: sum_t log-normaliser of raw logits, subtracted from logZ (raw-logit entry)
     // gradient (backward)
     float *grad;          // raw accumulation target, element (n,t,k) at n*gsn + t*gst + k
     long gsn, gst;
@@ -93,7 +94,7 @@ struct DenParams {
 struct DenAuxLayout {
     int Npad = 0;
     size_t colsum_a = 0, colsum_b = 0, absum = 0, zsum = 0, b0 = 0, barrier = 0, zero_bytes = 0;
-    size_t fmax = 0, bh = 0, logz_a = 0, logz_b = 0, total = 0;
+    size_t fmax = 0, bh = 0, logz_a = 0, logz_b = 0, lz = 0, lnorm = 0, total = 0;
 };
 DenAuxLayout MakeDenAuxLayout(int S, int N, int T);
 inline int PadLanes(int N) {
@@ -106,6 +107,10 @@ inline int LaneWidth(int Npad) { int g = Npad / 32; return g >= 4 ? 4 : g; }
 // host launchers; return cudaError_t-compatible int (0 = ok) and fill *err
 int LaunchFrameMax(const void *y, int y_bf16, long sn, long st, int N, int T, int V, const int *len, float *fmax,
                    int Npad, cudaStream_t stream);
+int LaunchFrameLse(const void *y, int y_bf16, long sn, long st, int N, int T, int V, const int *len, float *fmax,
+                   float *lz, double *lnorm, int Npad, cudaStream_t stream);
+int LaunchLogitGrad(const void *z, int z_bf16, long sn, long st, int N, int T, int V, const int *len, const float *lz,
+                    int Npad, float *grad, long gsn, long gst, cudaStream_t stream);
 int LaunchDenForward(const DeviceGraph &g, DenParams p, cudaStream_t stream, std::string *err);
 int LaunchDenBackward(const DeviceGraph &g, DenParams p, cudaStream_t stream, std::string *err);
 int LaunchDenGradNormalize(float *grad, long gsn, long gst, const float *absum, const int *len, int N, int Npad,
@@ -113,7 +118,7 @@ int LaunchDenGradNormalize(float *grad, long gsn, long gst, const float *absum, 
 int LaunchCtc(const void *y, int y_bf16, long sn, long st, int N, int T, int V, const int *labels,
               const int *label_off, const int *label_len, const int *len, int max_label_len, int blank,
               float *alpha_ws, float *grad, long gsn, long gst, float grad_scale, float *logp,
-              cudaStream_t stream, std::string *err);
+              const double *lnorm, cudaStream_t stream, std::string *err);
 int LaunchAssembleLoss(const float *logz, const float *logp, int N, float lamb, float scale, float *loss,
                        cudaStream_t stream);
 void CountLaunch(int n = 1);

@@ -42,7 +42,8 @@ __device__ __forceinline__ float block_max_from(const float *s_wmax, int nwarps)
 __global__ void ctc_fwd_bwd_kernel(const void *y, int y_bf16, long sn, long st, int T, int V,
                                    const int *labels, const int *label_off, const int *label_len, const int *len,
                                    int max_label_len, int blank, float *alpha_ws,
-                                   float *grad, long gsn, long gst, float grad_scale, float *logp_out) {
+                                   float *grad, long gsn, long gst, float grad_scale, float *logp_out,
+                                   const double *lnorm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = blockIdx.x;
     const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = NT >> 5;
@@ -159,7 +160,8 @@ __global__ void ctc_fwd_bwd_kernel(const void *y, int y_bf16, long sn, long st, 
         if (Sc > 1) lp = log_add(lp, last[Sc - 2]);
         logp_d = (double)lp + C;
     }
-    if (tid == 0) logp_out[n] = (float)logp_d;
+    // raw-logit entry: the reported log-likelihood is normalised; everything below stays in the raw domain
+    if (tid == 0) logp_out[n] = (float)(logp_d - (lnorm ? lnorm[n] : 0.0));
     if (grad == nullptr || !(logp_d > -INFINITY)) return;
     __syncthreads();
 
@@ -290,7 +292,7 @@ __global__ void assemble_loss_kernel(const float *logz, const float *logp, int N
 int LaunchCtc(const void *y, int y_bf16, long sn, long st, int N, int T, int V, const int *labels,
               const int *label_off, const int *label_len, const int *len, int max_label_len, int blank,
               float *alpha_ws, float *grad, long gsn, long gst, float grad_scale, float *logp,
-              cudaStream_t stream, std::string *err) {
+              const double *lnorm, cudaStream_t stream, std::string *err) {
     if (N == 0) return 0;
     const int ScMax = 2 * max_label_len + 1;
     const size_t smem = (size_t)(max_label_len + 1) * 4 + (size_t)2 * ScMax * 4 + (size_t)4 * V * 4 + 64 * 4;
@@ -300,7 +302,7 @@ int LaunchCtc(const void *y, int y_bf16, long sn, long st, int N, int T, int V, 
     cudaError_t e = cudaFuncSetAttribute(ctc_fwd_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { *err = std::string("cudaFuncSetAttribute(ctc): ") + cudaGetErrorString(e); return (int)e; }
     ctc_fwd_bwd_kernel<<<N, threads, smem, stream>>>(y, y_bf16, sn, st, T, V, labels, label_off, label_len, len,
-                                                     max_label_len, blank, alpha_ws, grad, gsn, gst, grad_scale, logp);
+                                                     max_label_len, blank, alpha_ws, grad, gsn, gst, grad_scale, logp, lnorm);
     CountLaunch();
     e = cudaGetLastError();
     if (e != cudaSuccess) { *err = std::string("ctc launch: ") + cudaGetErrorString(e); return (int)e; }

@@ -489,12 +489,14 @@ bool BuildDenPlan(const HostFst &fst, int n_ctas, int n_warps, DenPlan *plan, st
     auto seg_quads = [](const Segment &sg) { return std::max<int64_t>(1, ((int64_t)sg.arcs.size() + kQuad - 1) / kQuad); };
     // per-row costs in arc units, fitted to per-warp timelines on B200 (tools/timeline.py)
     constexpr int64_t kRowCostFwd = 5, kRowCostBwd = 8;
-    std::vector<int64_t> cost((size_t)G, 0);
+    std::vector<int64_t> cost((size_t)G, 0), cost_f((size_t)G, 0), cost_b((size_t)G, 0);
     for (int g = 0; g < G; ++g) {
-        int64_t c = 0;
-        for (auto &sg : fgroups[(size_t)g].segs) c += seg_quads(sg) * kQuad;
-        for (auto &sg : bgroups[(size_t)g].segs) c += seg_quads(sg) * kQuad;
-        cost[(size_t)g] = c + (kRowCostFwd + kRowCostBwd) * fgroups[(size_t)g].rows;
+        int64_t cf = 0, cb = 0;
+        for (auto &sg : fgroups[(size_t)g].segs) cf += seg_quads(sg) * kQuad;
+        for (auto &sg : bgroups[(size_t)g].segs) cb += seg_quads(sg) * kQuad;
+        cost_f[(size_t)g] = cf + kRowCostFwd * fgroups[(size_t)g].rows;
+        cost_b[(size_t)g] = cb + kRowCostBwd * fgroups[(size_t)g].rows;
+        cost[(size_t)g] = cost_f[(size_t)g] + cost_b[(size_t)g];
     }
     // Phase 2: CTA tiles = contiguous ranges of the label-sorted order with equal total cost (both passes share the
     // tiles); inside a tile the groups are dealt to the warps longest-first (LPT), then each warp's groups are put
@@ -529,17 +531,93 @@ bool BuildDenPlan(const HostFst &fst, int n_ctas, int n_warps, DenPlan *plan, st
     order.reserve((size_t)G);
     std::vector<int> chunk_group((size_t)n_ctas * n_warps + 1, 0);
     std::vector<std::vector<int>> bins((size_t)n_warps);
-    std::vector<int64_t> load((size_t)n_warps);
+    std::vector<double> load_f((size_t)n_warps), load_b((size_t)n_warps);
+    const bool balance_sum = getenv("CCB_BALANCE_SUM") != nullptr;
     std::vector<int> idx;
     for (int c = 0; c < n_ctas; ++c) {
+        // Both passes walk the same warp -> rows assignment but their costs differ per group, and a frame of either
+        // pass lasts as long as its slowest warp: balance the two loads as a vector (greedy: heaviest group first,
+        // into the warp whose larger normalised load stays smallest), not their sum.
         idx = tile_groups[(size_t)c];
-        std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return cost[(size_t)a] > cost[(size_t)b]; });
+        double tot_f = 1e-9, tot_b = 1e-9;
+        for (int g : idx) { tot_f += (double)cost_f[(size_t)g]; tot_b += (double)cost_b[(size_t)g]; }
+        // CCB_BALANCE_SUM (tuning hook): balance the sum of the two passes' costs instead (the round-1 behaviour)
+        auto nf = [&](int g) { return balance_sum ? (double)cost[(size_t)g] / (tot_f + tot_b) : (double)cost_f[(size_t)g] / tot_f; };
+        auto nb = [&](int g) { return balance_sum ? (double)cost[(size_t)g] / (tot_f + tot_b) : (double)cost_b[(size_t)g] / tot_b; };
+        std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return std::max(nf(a), nb(a)) > std::max(nf(b), nb(b)); });
         for (auto &b : bins) b.clear();
-        std::fill(load.begin(), load.end(), 0);
+        std::fill(load_f.begin(), load_f.end(), 0.0);
+        std::fill(load_b.begin(), load_b.end(), 0.0);
         for (int g : idx) {
-            const int w = (int)(std::min_element(load.begin(), load.end()) - load.begin());
-            bins[(size_t)w].push_back(g);
-            load[(size_t)w] += cost[(size_t)g];
+            int best = 0;
+            double best_max = 1e300, best_sum = 1e300;
+            for (int w = 0; w < n_warps; ++w) {
+                const double f = load_f[(size_t)w] + nf(g), b = load_b[(size_t)w] + nb(g);
+                const double m = std::max(f, b);
+                if (m < best_max - 1e-12 || (m < best_max + 1e-12 && f + b < best_sum)) { best = w; best_max = m; best_sum = f + b; }
+            }
+            bins[(size_t)best].push_back(g);
+            load_f[(size_t)best] += nf(g);
+            load_b[(size_t)best] += nb(g);
+        }
+        // Local search on top of the greedy.  A warp's chunk is padded to whole batches of kChunkArcPad slots and the
+        // grid barrier makes every frame of a pass wait for the longest chunk of the whole grid, so what counts is the
+        // PADDED maximum per pass: move / swap groups out of the critical warps while that (then the number of warps
+        // sitting at it, then the spread) improves.
+        if (!balance_sum && idx.size() <= 320) {   // (big tiles: a group is a small fraction of a chunk, and the search is O(groups^2))
+            std::vector<int64_t> sf((size_t)n_warps, 0), sb((size_t)n_warps, 0);   // slots per warp and pass
+            auto slots_f = [&](int g) { int64_t c = 0; for (auto &sg : fgroups[(size_t)g].segs) c += seg_quads(sg) * kQuad; return c; };
+            auto slots_b = [&](int g) { int64_t c = 0; for (auto &sg : bgroups[(size_t)g].segs) c += seg_quads(sg) * kQuad; return c; };
+            for (int w = 0; w < n_warps; ++w)
+                for (int g : bins[(size_t)w]) { sf[(size_t)w] += slots_f(g); sb[(size_t)w] += slots_b(g); }
+            auto pad = [](int64_t x) { return (x + kChunkArcPad - 1) / kChunkArcPad; };
+            struct Score { int64_t mx; int64_t at_max; int64_t sq; };
+            auto score = [&]() {
+                int64_t mf = 0, mb = 0;
+                for (int w = 0; w < n_warps; ++w) { mf = std::max(mf, pad(sf[(size_t)w])); mb = std::max(mb, pad(sb[(size_t)w])); }
+                Score sc{mf + mb, 0, 0};
+                for (int w = 0; w < n_warps; ++w) {
+                    sc.at_max += (pad(sf[(size_t)w]) == mf) + (pad(sb[(size_t)w]) == mb);
+                    sc.sq += sf[(size_t)w] * sf[(size_t)w] + sb[(size_t)w] * sb[(size_t)w];
+                }
+                return sc;
+            };
+            auto better = [](const Score &a, const Score &b) {
+                if (a.mx != b.mx) return a.mx < b.mx;
+                if (a.at_max != b.at_max) return a.at_max < b.at_max;
+                return a.sq < b.sq;
+            };
+            for (int iter = 0; iter < 300; ++iter) {
+                const Score cur = score();
+                int64_t mf = 0, mb = 0;
+                for (int w = 0; w < n_warps; ++w) { mf = std::max(mf, pad(sf[(size_t)w])); mb = std::max(mb, pad(sb[(size_t)w])); }
+                Score best = cur;
+                int b_hw = -1, b_i = -1, b_w = -1, b_j = -1;
+                for (int hw = 0; hw < n_warps; ++hw) {
+                    if (pad(sf[(size_t)hw]) != mf && pad(sb[(size_t)hw]) != mb) continue;   // only critical warps give
+                    for (int i = 0; i < (int)bins[(size_t)hw].size(); ++i) {
+                        const int g = bins[(size_t)hw][(size_t)i];
+                        const int64_t gf = slots_f(g), gb = slots_b(g);
+                        for (int w = 0; w < n_warps; ++w) {
+                            if (w == hw) continue;
+                            for (int j = -1; j < (int)bins[(size_t)w].size(); ++j) {
+                                const int64_t of = j < 0 ? 0 : slots_f(bins[(size_t)w][(size_t)j]), ob = j < 0 ? 0 : slots_b(bins[(size_t)w][(size_t)j]);
+                                sf[(size_t)hw] += of - gf; sb[(size_t)hw] += ob - gb; sf[(size_t)w] += gf - of; sb[(size_t)w] += gb - ob;
+                                const Score sc = score();
+                                sf[(size_t)hw] -= of - gf; sb[(size_t)hw] -= ob - gb; sf[(size_t)w] -= gf - of; sb[(size_t)w] -= gb - ob;
+                                if (better(sc, best)) { best = sc; b_hw = hw; b_i = i; b_w = w; b_j = j; }
+                            }
+                        }
+                    }
+                }
+                if (b_hw < 0) break;
+                const int g = bins[(size_t)b_hw][(size_t)b_i];
+                const int o = b_j < 0 ? -1 : bins[(size_t)b_w][(size_t)b_j];
+                const int64_t gf = slots_f(g), gb = slots_b(g), of = o < 0 ? 0 : slots_f(o), ob = o < 0 ? 0 : slots_b(o);
+                sf[(size_t)b_hw] += of - gf; sb[(size_t)b_hw] += ob - gb; sf[(size_t)b_w] += gf - of; sb[(size_t)b_w] += gb - ob;
+                if (o >= 0) { bins[(size_t)b_hw][(size_t)b_i] = o; bins[(size_t)b_w][(size_t)b_j] = g; }
+                else { bins[(size_t)b_hw].erase(bins[(size_t)b_hw].begin() + b_i); bins[(size_t)b_w].push_back(g); }
+            }
         }
         for (int w = 0; w < n_warps; ++w) {
             std::sort(bins[(size_t)w].begin(), bins[(size_t)w].end());   // label order (phase-1 index)

@@ -26,16 +26,27 @@ namespace {
 constexpr int kScaleExp = 32;        // per-frame column sums are renormalised to ~2^32
 constexpr unsigned kFull = 0xffffffffu;
 
+// Row gathers read data that another SM wrote one frame earlier.  Plain (L1-allocating) loads are coherent here: every
+// frame ends in the grid barrier's gpu-scope acquire fence + bar.sync, after which ordinary loads must observe the other
+// CTAs' released writes (the same contract cooperative-groups grid.sync() gives), and no row is re-read within a frame
+// after being rewritten.  Against ld.global.cg this makes the zero-weight padding slots (which repeat the address of
+// the preceding arc) L1 hits: forward pass -5.6 % on B200 (profiles/r01_experiments.md).  -DCCB_GATHER_CG restores
+// the L2-only loads for A/B runs.
+#ifdef CCB_GATHER_CG
+#define CCB_GATHER_LOAD(p) __ldcg(p)
+#else
+#define CCB_GATHER_LOAD(p) (*(p))
+#endif
 template <int U> struct Vec;
 template <> struct Vec<1> {
     float v[1];
-    __device__ __forceinline__ static Vec ldcg(const float *p) { Vec r; r.v[0] = __ldcg(p); return r; }
+    __device__ __forceinline__ static Vec ldcg(const float *p) { Vec r; r.v[0] = CCB_GATHER_LOAD(p); return r; }
     __device__ __forceinline__ void stcg(float *p) const { __stcg(p, v[0]); }
 };
 template <> struct Vec<2> {
     float v[2];
     __device__ __forceinline__ static Vec ldcg(const float *p) {
-        float2 t = __ldcg(reinterpret_cast<const float2 *>(p));
+        float2 t = CCB_GATHER_LOAD(reinterpret_cast<const float2 *>(p));
         Vec r; r.v[0] = t.x; r.v[1] = t.y; return r;
     }
     __device__ __forceinline__ void stcg(float *p) const { __stcg(reinterpret_cast<float2 *>(p), make_float2(v[0], v[1])); }
@@ -43,7 +54,7 @@ template <> struct Vec<2> {
 template <> struct Vec<4> {
     float v[4];
     __device__ __forceinline__ static Vec ldcg(const float *p) {
-        float4 t = __ldcg(reinterpret_cast<const float4 *>(p));
+        float4 t = CCB_GATHER_LOAD(reinterpret_cast<const float4 *>(p));
         Vec r; r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w; return r;
     }
     __device__ __forceinline__ void stcg(float *p) const {
@@ -90,6 +101,16 @@ template <int U>
 __device__ __forceinline__ Vec<U> gather_row(const char *lane_base, uint32_t byte_off) {
     return Vec<U>::ldcg(reinterpret_cast<const float *>(lane_base + byte_off));
 }
+// The gathers of one quad.  (Skipping the zero-weight padding slots -- ~17 % of the forward stream -- was tried with a
+// per-quad count in the last offset: the extra branches cost 10 % of the forward pass and the saved gathers returned
+// 1.6 %; measured on B200, profiles/r01_experiments.md.)
+template <int U>
+__device__ __forceinline__ void gather_quad(const char *lane_base, const uint4 pr, Vec<U> *v) {
+    v[0] = gather_row<U>(lane_base, pr.x);
+    v[1] = gather_row<U>(lane_base, pr.y);
+    v[2] = gather_row<U>(lane_base, pr.z);
+    v[3] = gather_row<U>(lane_base, pr.w);
+}
 template <int U>
 __device__ __forceinline__ float *row_ptr(float *lane_base, uint32_t row, uint32_t row_bytes) {
     return reinterpret_cast<float *>(reinterpret_cast<char *>(lane_base) + (size_t)row * row_bytes);
@@ -118,6 +139,64 @@ __global__ void frame_max_kernel(const void *y, int bf16, long sn, long st, int 
     if (lane == 0) fmax[(size_t)t * Npad + n] = (m == -INFINITY) ? 0.f : m;
 }
 
+// Raw-logit entry: per valid frame the max AND the log-normaliser lz = log sum_k exp(z_k) of the raw
+// encoder outputs.  The recursions then run on z as if it were log-probs (emissions are shifted by the row max either
+// way, and a per-frame constant does not change any occupancy); only the log-likelihoods need lz, summed per utterance.
+__global__ void frame_lse_kernel(const void *y, int bf16, long sn, long st, int N, int T, int V,
+                                 const int *len, float *fmax, float *lz, int Npad) {
+    const int warps_per_block = blockDim.x >> 5;
+    const long row = (long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= (long)N * T) return;
+    const int n = (int)(row / T), t = (int)(row % T);
+    if (t >= len[n]) return;
+    float m = -INFINITY;
+    const long base = n * sn + t * st;
+    for (int k = lane; k < V; k += 32) m = fmaxf(m, load_y(y, bf16, base + k));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(kFull, m, o));
+    if (m == -INFINITY) m = 0.f;
+    float s = 0.f;
+    for (int k = lane; k < V; k += 32) s += expf(load_y(y, bf16, base + k) - m);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(kFull, s, o);
+    if (lane == 0) {
+        fmax[(size_t)t * Npad + n] = m;
+        lz[(size_t)t * Npad + n] = m + logf(s);
+    }
+}
+
+// lnorm[n] = sum_{t < len[n]} lz[t][n] in fp64, fixed order (one warp per utterance)
+__global__ void lnorm_kernel(const float *lz, const int *len, int N, int Npad, double *lnorm) {
+    const int n = blockIdx.x, lane = threadIdx.x;
+    double acc = 0.0;
+    const int ln = len[n];
+    for (int t = lane; t < ln; t += 32) acc += (double)lz[(size_t)t * Npad + n];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(kFull, acc, o);
+    if (lane == 0) lnorm[n] = acc;
+}
+
+// Softmax Jacobian of the raw-logit entry: g = dL/dy (y = log_softmax z) -> dL/dz_k = g_k - softmax(z)_k * sum_j g_j,
+// in place, one warp per valid frame (cat/ctc/train.py:173-174 does this through autograd of log_softmax).
+__global__ void logit_grad_kernel(const void *z, int bf16, long sn, long st, int N, int T, int V, const int *len,
+                                  const float *lz, int Npad, float *grad, long gsn, long gst) {
+    const int warps_per_block = blockDim.x >> 5;
+    const long row = (long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= (long)N * T) return;
+    const int n = (int)(row / T), t = (int)(row % T);
+    if (t >= len[n]) return;
+    float *g = grad + n * gsn + t * gst;
+    float gs = 0.f;
+    for (int k = lane; k < V; k += 32) gs += g[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) gs += __shfl_xor_sync(kFull, gs, o);
+    const float l = lz[(size_t)t * Npad + n];
+    const long base = n * sn + t * st;
+    for (int k = lane; k < V; k += 32) g[k] -= expf(load_y(z, bf16, base + k) - l) * gs;
+}
+
 // ------------------------------------------------------------------------------------------------
 // The arc walk shared by both passes: a software-pipelined stream over the warp's chunk of arcs.
 //   * arcs come a quad at a time: one LDS.128 of four peers for the gathers, one LDS.128 of four weights for the FMAs;
@@ -143,14 +222,13 @@ __device__ __forceinline__ void walk_arcs(const uint4 *arcs, int n_batches, uint
     // 2*BATCH gathers stay in flight without holding 2*BATCH arc words in registers.
     auto issue = [&](const uint4 *p, Vec<U> *v) {
         if (do_load) {
+            // all offset words first: the per-quad padding branch below must not sit between a quad's shared-memory
+            // load and the next one (that exposed the LDS latency once per quad)
+            uint4 pr[BATCH / kQuad];
 #pragma unroll
-            for (int g4 = 0; g4 < BATCH / kQuad; ++g4) {
-                const uint4 pr = load_quad_peers<SMEM_ARCS>(p + 2 * g4, row_bytes);
-                v[g4 * kQuad + 0] = gather_row<U>(lane_base, pr.x);
-                v[g4 * kQuad + 1] = gather_row<U>(lane_base, pr.y);
-                v[g4 * kQuad + 2] = gather_row<U>(lane_base, pr.z);
-                v[g4 * kQuad + 3] = gather_row<U>(lane_base, pr.w);
-            }
+            for (int g4 = 0; g4 < BATCH / kQuad; ++g4) pr[g4] = load_quad_peers<SMEM_ARCS>(p + 2 * g4, row_bytes);
+#pragma unroll
+            for (int g4 = 0; g4 < BATCH / kQuad; ++g4) gather_quad<U>(lane_base, pr[g4], v + g4 * kQuad);
         }
     };
     auto consume = [&](const uint4 *p, const Vec<U> *v) {
@@ -204,14 +282,12 @@ __device__ __forceinline__ void walk_arcs_dual(const uint4 *arcs, const float4 *
 
     auto issue = [&](const uint4 *p, Vec<U> *v) {
         if (do_load) {
+            // (the global-memory fallback keeps all four gathers: its second weights live in another array)
+            uint4 pr[BATCH / kQuad];
 #pragma unroll
-            for (int g4 = 0; g4 < BATCH / kQuad; ++g4) {
-                const uint4 pr = SMEM_ARCS ? p[kWordsPerQuad * g4] : load_quad_peers<false>(p + 2 * g4, row_bytes);
-                v[g4 * kQuad + 0] = gather_row<U>(lane_base, pr.x);
-                v[g4 * kQuad + 1] = gather_row<U>(lane_base, pr.y);
-                v[g4 * kQuad + 2] = gather_row<U>(lane_base, pr.z);
-                v[g4 * kQuad + 3] = gather_row<U>(lane_base, pr.w);
-            }
+            for (int g4 = 0; g4 < BATCH / kQuad; ++g4) pr[g4] = SMEM_ARCS ? p[kWordsPerQuad * g4] : load_quad_peers<false>(p + 2 * g4, row_bytes);
+#pragma unroll
+            for (int g4 = 0; g4 < BATCH / kQuad; ++g4) gather_quad<U>(lane_base, pr[g4], v + g4 * kQuad);
         }
     };
     auto consume = [&](const uint4 *p, const float4 *pw1, const Vec<U> *v) {
@@ -335,11 +411,12 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const DenParams P) {
     for (int i = tid; i < tile_s1 - tile_s0; i += NT) s_label[i] = __ldg(P.state_label + tile_s0 + i);
     const uint32_t row_bytes = (uint32_t)Npad * 4u;
     if (SMEM_ARCS) {   // stage the tile once, quad-wise transposed: {byte offset 0..3}{w0..3}
-        uint32_t *sq = reinterpret_cast<uint32_t *>(s_arcs);
-        for (int i = tid; i < tile_a1 - tile_a0; i += NT) {
-            const Arc k = P.arcs[tile_a0 + i];
-            sq[(i >> 2) * 8 + (i & 3)] = k.peer * row_bytes;   // byte offset of the gathered row
-            sq[(i >> 2) * 8 + 4 + (i & 3)] = __float_as_uint(k.w);
+        uint4 *sq = reinterpret_cast<uint4 *>(s_arcs);
+        const uint4 *src = reinterpret_cast<const uint4 *>(P.arcs + tile_a0);
+        for (int i = tid; i < (tile_a1 - tile_a0) / kQuad; i += NT) {
+            const uint4 m0 = __ldg(src + 2 * i), m1 = __ldg(src + 2 * i + 1);
+            sq[2 * i] = make_uint4(m0.x * row_bytes, m0.z * row_bytes, m1.x * row_bytes, m1.z * row_bytes);   // byte offsets of the gathered rows
+            sq[2 * i + 1] = make_uint4(m0.y, m0.w, m1.y, m1.w);
         }
     }
     for (int i = tid; i < Npad; i += NT) s_sum[i] = 0.f;
@@ -489,7 +566,7 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const DenParams P) {
         if (v != 0.f) atomicAdd(P.zsum + i, v);
     }
     grid_barrier(P.barrier, (++epoch) * gridDim.x);
-    if (cta == 0 && tid < P.N) P.logz[tid] = (float)(log((double)__ldcg(P.zsum + tid)) + runlog);
+    if (cta == 0 && tid < P.N) P.logz[tid] = (float)(log((double)__ldcg(P.zsum + tid)) + runlog - (P.lnorm ? P.lnorm[tid] : 0.0));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -536,12 +613,14 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const DenParams P) 
     }
     const uint32_t row_bytes = (uint32_t)Npad * 4u;
     if (SMEM_ARCS) {   // stage the tile once, quad-wise transposed: {byte offset 0..3}{w0 0..3}{w1 0..3}
-        uint32_t *sq = reinterpret_cast<uint32_t *>(s_arcs);
-        for (int i = tid; i < tile_a1 - tile_a0; i += NT) {
-            const Arc k = P.arcs[tile_a0 + i];
-            sq[(i >> 2) * 12 + (i & 3)] = k.peer * row_bytes;
-            sq[(i >> 2) * 12 + 4 + (i & 3)] = __float_as_uint(k.w);
-            sq[(i >> 2) * 12 + 8 + (i & 3)] = __float_as_uint(__ldg(P.w1 + tile_a0 + i));
+        uint4 *sq = reinterpret_cast<uint4 *>(s_arcs);
+        const uint4 *src = reinterpret_cast<const uint4 *>(P.arcs + tile_a0);
+        const uint4 *src1 = reinterpret_cast<const uint4 *>(P.w1 + tile_a0);
+        for (int i = tid; i < (tile_a1 - tile_a0) / kQuad; i += NT) {
+            const uint4 m0 = __ldg(src + 2 * i), m1 = __ldg(src + 2 * i + 1), w1 = __ldg(src1 + i);
+            sq[3 * i] = make_uint4(m0.x * row_bytes, m0.z * row_bytes, m1.x * row_bytes, m1.z * row_bytes);
+            sq[3 * i + 1] = make_uint4(m0.y, m0.w, m1.y, m1.w);
+            sq[3 * i + 2] = w1;
         }
     }
     for (int i = tid; i < (2 + P.gacc_rows) * Npad; i += NT) s_sum[i] = 0.f;
@@ -722,7 +801,7 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const DenParams P) 
         runlog += (double)__ldg(P.fmax + tid) - (double)sh * 0.6931471805599453;
     }
     grid_barrier(P.barrier, (++epoch) * gridDim.x);
-    if (cta == 0 && tid < P.N) P.logz[tid] = (float)(log((double)__ldcg(P.b0 + tid)) + runlog);
+    if (cta == 0 && tid < P.N) P.logz[tid] = (float)(log((double)__ldcg(P.b0 + tid)) + runlog - (P.lnorm ? P.lnorm[tid] : 0.0));
 }
 
 // grad[n][t][:] *= scale / absum[t+1][n]   for t < len[n]
@@ -821,6 +900,8 @@ DenAuxLayout MakeDenAuxLayout(int S, int N, int T) {
     L.fmax = off; off = up(off + (size_t)(T + 1) * L.Npad * 4);
     L.logz_a = off; off = up(off + (size_t)L.Npad * 4);
     L.logz_b = off; off = up(off + (size_t)L.Npad * 4);
+    L.lz = off; off = up(off + (size_t)(T + 1) * L.Npad * 4);
+    L.lnorm = off; off = up(off + (size_t)L.Npad * 8);
     L.bh = off; off = up(off + (size_t)2 * S * L.Npad * 4);
     L.total = off;
     return L;
@@ -832,6 +913,27 @@ int LaunchFrameMax(const void *y, int y_bf16, long sn, long st, int N, int T, in
     if (rows == 0) return 0;
     const int wpb = 8;
     frame_max_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, stream>>>(y, y_bf16, sn, st, N, T, V, len, fmax, Npad);
+    CountLaunch();
+    return (int)cudaGetLastError();
+}
+
+int LaunchFrameLse(const void *y, int y_bf16, long sn, long st, int N, int T, int V, const int *len, float *fmax,
+                   float *lz, double *lnorm, int Npad, cudaStream_t stream) {
+    const long rows = (long)N * T;
+    if (rows == 0) return 0;
+    const int wpb = 8;
+    frame_lse_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, stream>>>(y, y_bf16, sn, st, N, T, V, len, fmax, lz, Npad);
+    lnorm_kernel<<<N, 32, 0, stream>>>(lz, len, N, Npad, lnorm);
+    CountLaunch(2);
+    return (int)cudaGetLastError();
+}
+
+int LaunchLogitGrad(const void *z, int z_bf16, long sn, long st, int N, int T, int V, const int *len, const float *lz,
+                    int Npad, float *grad, long gsn, long gst, cudaStream_t stream) {
+    const long rows = (long)N * T;
+    if (rows == 0) return 0;
+    const int wpb = 8;
+    logit_grad_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, stream>>>(z, z_bf16, sn, st, N, T, V, len, lz, Npad, grad, gsn, gst);
     CountLaunch();
     return (int)cudaGetLastError();
 }

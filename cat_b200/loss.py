@@ -68,16 +68,40 @@ class _CTC_CRF(Function):
         return ctx.grads * grad_output.to(ctx.grads.device), None, None, None, None, None, None
 
 
+class _CTC_CRF_LOGITS(Function):
+    """the same loss taken on the RAW encoder outputs.  Replaces, in one native call,
+    ``logits = net_out.float().log_softmax(-1); loss = _CTC_CRF(logits, ...)`` and the autograd backward of the cast
+    and of log_softmax (cat/ctc/train.py:173-174,184-190): no normalised fp32 copy is materialised and the gradient
+    comes back already chained through the softmax Jacobian, in the dtype of the input."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, input_lengths, label_lengths, lamb=0.1, size_average=True):
+        logits = logits.contiguous()
+        costs, grads, _ = core.ctc_crf_loss_fwd(logits, labels, input_lengths, label_lengths, lamb, size_average,
+                                                from_logits=True)
+        ctx.grads = grads
+        ctx.in_dtype = logits.dtype
+        return costs
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        g = ctx.grads * grad_output.to(ctx.grads.device)
+        return g.to(ctx.in_dtype), None, None, None, None, None, None
+
+
 class CTC_CRF_LOSS(Module):
-    def __init__(self, lamb: float = 0.1, size_average: bool = True):
+    def __init__(self, lamb: float = 0.1, size_average: bool = True, from_logits: bool = False):
         """
         lamb (float): weight for auxiliary CTC loss, final loss = lamb * loss_ctc + loss_crf
         size_average (bool): whether to do average over batch size dimension.
+        from_logits (bool): addition to the reference signature -- ``forward`` takes the raw encoder outputs and
+            applies log_softmax (and its backward) inside the fused call.  Default False = reference behaviour.
         """
         super(CTC_CRF_LOSS, self).__init__()
-        self.ctc_crf = _CTC_CRF.apply
+        self.ctc_crf = _CTC_CRF_LOGITS.apply if from_logits else _CTC_CRF.apply
         self.lamb = lamb
         self.size_average = size_average
+        self.from_logits = from_logits
 
     def forward(self, logits, labels, lx, ly) -> torch.FloatTensor:
         """

@@ -125,6 +125,16 @@ int ccb_ctc_crf_loss_fwd(const void *logits, int dtype, int N, int T, int V, int
                          float *alpha_ws, void *aux_ws, void *ctc_ws,
                          float *grad, float *loss, float *parts, void *stream);
 
+/* Same, taking the RAW encoder outputs z (N,T,V) instead of log-probs (replaces the caller's
+ * `logits.log_softmax(-1)` + its autograd backward, cat/ctc/train.py:173-174,184-190):
+ *   loss as above evaluated on y = log_softmax(z);   grad = d loss / d z = g - softmax(z) * sum_k g_k.
+ * No normalised copy of the logits is materialised. */
+int ccb_ctc_crf_loss_logits_fwd(const void *logits, int dtype, int N, int T, int V, int Tmax,
+                                const int *labels_dev, const int *label_off_dev, const int *label_len_dev,
+                                const int *len_dev, int max_label_len, float lamb, float scale,
+                                float *alpha_ws, void *aux_ws, void *ctc_ws,
+                                float *grad, float *loss, float *parts, void *stream);
+
 /* number of kernels launched by this library since load (bench.py's gpu_launches) */
 long ccb_launch_count(void);
 

@@ -162,6 +162,50 @@ def test_fused_vs_oracle_and_bf16(tmp_graphs):
     del ctx
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_raw_logit_entry(tmp_graphs, dtype):
+    """CTC_CRF_LOSS(from_logits=True) on raw encoder outputs == log_softmax + loss + autograd chain, against
+    the oracle and against our own two-step path (torch log_softmax -> CTC_CRF_LOSS) on the same inputs."""
+    import ctc_crf
+    from oracle import oracle
+    path, g, V = tmp_graphs["tlm_mid"]
+    ctx = _ctx(path)
+    N, T = 8, 60
+    lens = [60, 60, 55, 41, 33, 20, 9, 3]
+    _, labels, lens, ly = oracle.synth_batch(N, T, V, seed=23, lens=lens)
+    rng = np.random.default_rng(5)
+    z = (4.0 * rng.standard_normal((N, T, V)) + 7.0).astype(np.float32)      # unnormalised, offset on purpose
+    zt = torch.tensor(z, device="cuda").to(dtype)
+    z_used = zt.float().cpu().numpy()                                           # the values the kernel actually sees
+    lab_t, lx_t, ly_t = (torch.tensor(a, dtype=torch.int32) for a in (labels, lens, ly))
+    for sa in (True, False):
+        oloss, odz, oparts = oracle.ctc_crf_from_logits(g, z_used, labels, lens, ly, 0.1, size_average=sa)
+        zin = zt.clone().requires_grad_(True)
+        loss = ctc_crf.CTC_CRF_LOSS(lamb=0.1, size_average=sa, from_logits=True)(zin, lab_t, lx_t, ly_t)
+        loss.backward()
+        assert zin.grad.dtype == dtype
+        _close_loss(float(loss.item()), oloss)
+        tol = GRAD_ATOL * (1 if sa else N) * (4 if dtype == torch.bfloat16 else 1)   # bf16: the returned grad is rounded
+        assert np.abs(zin.grad.float().cpu().numpy() - odz).max() < tol
+        # rows past each length stay zero; every valid row of d loss/d z sums to ~0 (softmax Jacobian)
+        gz = zin.grad.float().cpu().numpy()
+        for n in range(N):
+            assert np.all(gz[n, lens[n]:] == 0)
+        assert np.abs(gz.sum(-1)).max() < (2e-2 if dtype == torch.bfloat16 else 1e-4) * (1 if sa else N)
+        # two-step path through torch autograd (what cat/ctc/train.py does)
+        z2 = zt.clone().requires_grad_(True)
+        loss2 = ctc_crf.CTC_CRF_LOSS(lamb=0.1, size_average=sa)(z2.float().log_softmax(-1), lab_t, lx_t, ly_t)
+        loss2.backward()
+        _close_loss(float(loss.item()), float(loss2.item()))
+        assert np.abs(gz - z2.grad.float().cpu().numpy()).max() < tol
+    # parts are reported normalised
+    _, _, parts = ctc_crf._C.ctc_crf_loss_fwd(zt.contiguous(), lab_t, lx_t, ly_t, 0.1, True, want_parts=True, from_logits=True)
+    parts = parts.cpu().numpy()
+    np.testing.assert_allclose(parts[:N], oparts["logz_alpha"], rtol=1e-4, atol=1e-3)
+    np.testing.assert_allclose(parts[N:], oparts["logp_ctc"], rtol=1e-4, atol=1e-3)
+    del ctx
+
+
 @pytest.mark.parametrize("N,T,lens,ly", [
     (1, 1, [1], [0]),                       # single frame, empty label sequence
     (1, 1, [1], [1]),                       # single frame, single label

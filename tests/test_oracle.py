@@ -106,3 +106,26 @@ def test_against_reference_cuda_golden():
         assert np.abs(grad - z[f"{c}/ref_grad"]).max() < 1e-3, c
         np.testing.assert_allclose(parts["logz_alpha"], z[f"{c}/ref_logz_alpha"], rtol=1e-4, atol=1e-4)
         np.testing.assert_allclose(parts["logp_ctc"], z[f"{c}/ref_logp_ctc"], rtol=1e-4, atol=1e-4)
+
+
+def test_oracle_from_logits_matches_autograd_chain(fixture_fst):
+    """oracle.ctc_crf_from_logits (raw encoder outputs) == torch autograd through log_softmax of the
+    oracle's own d loss / d y, and a per-frame constant added to the logits changes nothing."""
+    from cat_b200 import fst
+    from oracle import oracle
+    g = fst.read_fst(fixture_fst)
+    rng = np.random.default_rng(3)
+    N, T, V = 2, 7, 5
+    z = (2.0 * rng.standard_normal((N, T, V)) + 3.0).astype(np.float32)
+    labels = np.array([1, 2, 3, 2], np.int32)
+    lx, ly = np.array([7, 5], np.int32), np.array([3, 1], np.int32)
+    loss, dz, _ = oracle.ctc_crf_from_logits(g, z, labels, lx, ly, 0.05)
+    zt = torch.tensor(z, dtype=torch.float64, requires_grad=True)
+    y = zt.log_softmax(-1)
+    oloss, gy, _ = oracle.ctc_crf(g, y.detach().numpy().astype(np.float32), labels, lx, ly, 0.05)
+    y.backward(torch.tensor(gy))
+    assert abs(loss - oloss) < 1e-9
+    np.testing.assert_allclose(dz, zt.grad.numpy(), atol=1e-9)
+    loss2, dz2, _ = oracle.ctc_crf_from_logits(g, z + rng.standard_normal((N, T, 1)).astype(np.float32), labels, lx, ly, 0.05)
+    assert abs(loss - loss2) < 1e-5
+    np.testing.assert_allclose(dz, dz2, atol=1e-5)
