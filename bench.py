@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--d", type=int, default=24)
     ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"])
     ap.add_argument("--lamb", type=float, default=0.01)
+    ap.add_argument("--varlen", action="store_true", help="variable-length batch (len ~ U{200..T}, sorted); not the headline workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true")
     ap.add_argument("--cpu-sample", default="auto", help="N,T of the CPU sample (default sized for ~15 s)")
@@ -72,9 +73,11 @@ def den_graph_file(H, d, V):
     return path, g
 
 
-def synth_labels(N, T, V, seed):
+def synth_labels(N, T, V, seed, varlen=False):
     rng = np.random.default_rng(seed)
     lens = np.full(N, T, np.int32)
+    if varlen:   # len ~ U{200..T}, sorted descending as sortedPadCollateASR does
+        lens = np.sort(rng.integers(min(200, T), T + 1, size=N).astype(np.int32))[::-1].copy()
     ly = np.minimum(lens // 6, 400).astype(np.int32)
     labels = rng.integers(1, V, size=int(ly.sum())).astype(np.int32)
     return labels, lens, ly
@@ -203,7 +206,7 @@ def main():
 
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     y = torch.log_softmax(3.0 * torch.randn(N, T, V, device=dev, generator=gen), -1).to(dtype).contiguous()
-    labels_np, lens_np, ly_np = synth_labels(N, T, V, 1234 + rank)
+    labels_np, lens_np, ly_np = synth_labels(N, T, V, 1234 + rank, args.varlen)
     labels, lx, ly = torch.tensor(labels_np), torch.tensor(lens_np), torch.tensor(ly_np)
     frames_per_step = int(lens_np.sum())
     crit = ctc_crf.CTC_CRF_LOSS(lamb=args.lamb, size_average=True)
@@ -320,6 +323,27 @@ def main():
     }
     del alpha_ws, aux_ws, gden
 
+    # ---- raw-logit entry vs the caller's two-step path (log_softmax + loss + autograd), fwd+bwd ----
+    raw_entry = None
+    if world == 1:
+        z = (3.0 * torch.randn(N, T, V, device=dev, generator=gen)).to(dtype)
+        crit_raw = ctc_crf.CTC_CRF_LOSS(lamb=args.lamb, size_average=True, from_logits=True)
+
+        def two_step():
+            zz = z.detach().requires_grad_(True)
+            crit(zz.float().log_softmax(-1), labels, lx, ly).backward()
+
+        def fused():
+            zz = z.detach().requires_grad_(True)
+            crit_raw(zz, labels, lx, ly).backward()
+
+        reps = max(2, min(args.steps, 5))
+        ms_two = timed(two_step, reps, 2) / reps
+        ms_fused = timed(fused, reps, 2) / reps
+        raw_entry = {"two_step_ms": ms_two, "fused_ms": ms_fused,
+                     "what": "forward+backward from raw encoder outputs: torch log_softmax + CTC_CRF_LOSS + autograd vs CTC_CRF_LOSS(from_logits=True)"}
+        del z
+
     out = None
     if rank == 0:
         # ---- reference CUDA build (B0) on the same GPU, and the CPU port on the host cores (N=1 run only) ----
@@ -362,7 +386,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": f"CTC-CRF loss+grad N={N}/GPU,T={T},V={V} (BASELINE configs headline)",
+            "config": {"workload": f"CTC-CRF loss+grad N={N}/GPU,T={T},V={V} " + ("(variable lengths, SURVEY config 5 shape)" if args.varlen else "(BASELINE configs headline)"),
                        "den_graph": f"synthetic T-compose-LM H={args.H},d={args.d}: file S={graph.num_states} A={graph.num_arcs}; plan S={info['states']} pairs={info['pairs']} gathered arcs fwd/bwd={info['fwd_arcs']}/{info['bwd_arcs']}",
                        "global_batch": N * world, "parallelism": f"minibatch sharded x{world}, den graph replicated, 1 all-reduce of [cost,count]",
                        "lamb": args.lamb,
@@ -375,6 +399,7 @@ def main():
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
             "reference_cuda_same_gpu": ref_cuda_res,
+            "raw_logit_entry": raw_entry,
         }
     if world > 1:
         dist.barrier()

@@ -178,7 +178,9 @@ _WS_FRACTION = 0.85              # of the currently free device memory a call ma
 def _plan_slices(L, lx, ly, N, V, dev):
     """Split the batch into contiguous slices whose scratch (alpha spill etc.) fits the free device memory.
     Each slice walks only max(lx[slice]) frames."""
+    # what a torch allocation can get: free device memory plus what the caching allocator holds but is not using
     free, _ = torch.cuda.mem_get_info(dev)
+    free += max(0, torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev))
     budget = int(free * _WS_FRACTION)
     slices, n0 = [], 0
     while n0 < N:

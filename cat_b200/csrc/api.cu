@@ -289,8 +289,9 @@ size_t ccb_den_aux_bytes(int N, int T) {
 }
 
 size_t ccb_ctc_workspace_bytes(int N, int T, int max_label_len) {
-    // per utterance: alpha_rel [T][2L+1] floats (rounded up to an even count) + per-frame fp64 offsets [T]
-    const size_t per_utt = ((size_t)T * (2 * (size_t)max_label_len + 1) + 1) / 2 * 2 + 2 * (size_t)T;
+    // per utterance: alpha_rel and beta_rel [T][2L+1] floats each (rounded up to an even count) + two per-frame fp64
+    // offset arrays [T] + the fp64 log-likelihood (ctc_kernels.cu)
+    const size_t per_utt = 2 * (((size_t)T * (2 * (size_t)max_label_len + 1) + 1) / 2 * 2) + 4 * (size_t)T + 2;
     return ((size_t)N * per_utt + 64) * sizeof(float);
 }
 

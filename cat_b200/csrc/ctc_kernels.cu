@@ -2,8 +2,12 @@
 //
 // Replaces src/ctc_crf/gpu_ctc (compute_alpha_kernel gpu_ctc_kernels.h:87-213,
 // compute_betas_and_grad_kernel :218-458, host driver gpu_ctc.h:100-400).  Differences by design:
-//   * one kernel does forward, backward and the gradient (the reference launches two and synchronises
-//     the stream twice, gpu_ctc.h:272,368); nothing here touches the host;
+//   * one launch does forward, backward and the gradient (the reference launches two kernels and synchronises
+//     the stream twice, gpu_ctc.h:272,368); nothing here touches the host.  Each utterance gets a CLUSTER OF TWO
+//     CTAs: rank 0 walks alpha forwards while rank 1 walks beta backwards at the same time (both recursions are
+//     latency-bound chains of T frames, so this halves the critical path), each spilling its cells relative to a
+//     per-frame fp64 offset; after one cluster barrier both CTAs turn the spills into occupancies, a warp per frame,
+//     with no further block-wide synchronisation;
 //   * thread i owns lattice cells 2i (blank) and 2i+1 (label i): the 2-/3-way log-sum of a frame needs
 //     one value from the neighbouring thread, exchanged through a shared-memory ping-pong, one
 //     __syncthreads per frame; the label row y[n][t][:] is staged coalesced one frame ahead;
@@ -38,14 +42,25 @@ __device__ __forceinline__ float block_max_from(const float *s_wmax, int nwarps)
 // fp64), so fp32 log-add rounding stays ~1e-6 absolute instead of growing with |alpha| (the reference's plain fp32
 // log domain loses ~1e-2 relative on the occupancies at T ~ 1000).  alpha_true_t(s) = a_rel_t(s) + C_t,
 // beta_true_t(s) = b_rel_t(s) + D_t, occupancy = exp(a_rel + b_rel - y + (C_t + D_t - log p)).
-// shared memory carve-up: lab[Lmax+1] ints | a[2][ScMax] | yrow[2][V] | gk[2][V] | wmax[2][32]
-__global__ void ctc_fwd_bwd_kernel(const void *y, int y_bf16, long sn, long st, int T, int V,
-                                   const int *labels, const int *label_off, const int *label_len, const int *len,
-                                   int max_label_len, int blank, float *alpha_ws,
-                                   float *grad, long gsn, long gst, float grad_scale, float *logp_out,
-                                   const double *lnorm) {
+__device__ __forceinline__ unsigned cluster_rank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync() {   // release/acquire at cluster scope: the partner's spills are visible
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// shared memory carve-up: lab[Lmax+1] ints | a[2][ScMax] | yrow[2][V] | wmax[2][32] | gw[gwarps][V]
+__global__ void __cluster_dims__(2, 1, 1)
+ctc_fwd_bwd_kernel(const void *y, int y_bf16, long sn, long st, int T, int V,
+                   const int *labels, const int *label_off, const int *label_len, const int *len,
+                   int max_label_len, int blank, float *alpha_ws, int gwarps,
+                   float *grad, long gsn, long gst, float grad_scale, float *logp_out,
+                   const double *lnorm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int n = blockIdx.x;
+    const int n = blockIdx.x >> 1;
+    const unsigned role = cluster_rank();   // 0: alpha pass, 1: beta pass
     const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = NT >> 5;
     const int L = label_len[n], Tn = len[n];
     const int Sc = 2 * L + 1, L1 = L + 1;
@@ -53,8 +68,8 @@ __global__ void ctc_fwd_bwd_kernel(const void *y, int y_bf16, long sn, long st, 
     int *s_lab = reinterpret_cast<int *>(smem_raw);                 // [max_label_len + 1] label of cell 2i+1
     float *s_a = reinterpret_cast<float *>(s_lab + max_label_len + 1);   // [2][ScMax]
     float *s_y = s_a + 2 * ScMax;                                   // [2][V]
-    float *s_g = s_y + 2 * V;                                       // [2][V]
-    float *s_wmax = s_g + 2 * V;                                    // [2][32]
+    float *s_wmax = s_y + 2 * V;                                    // [2][32]
+    float *s_gw = s_wmax + 64;                                      // [gwarps][V] per-warp label accumulators
     const int *lab = labels + label_off[n];
 
     // feasibility (gpu_ctc_kernels.h:108-109)
@@ -65,18 +80,28 @@ __global__ void ctc_fwd_bwd_kernel(const void *y, int y_bf16, long sn, long st, 
     __syncthreads();
     if (rep) atomicAdd(&s_rep, rep);
     __syncthreads();
-    if (Tn <= 0 || L + s_rep > Tn) {
-        if (tid == 0) logp_out[n] = -INFINITY;
+    if (Tn <= 0 || L + s_rep > Tn) {   // both CTAs of the pair take this exit: nobody waits at the cluster barrier
+        if (tid == 0 && role == 0) logp_out[n] = -INFINITY;
         return;
     }
+    if (grad == nullptr && role == 1) return;   // likelihood only: the alpha CTA never reaches the cluster barrier either
     for (int i = tid; i < L; i += NT) s_lab[i] = lab[i];
-    for (int k = tid; k < 2 * V; k += NT) s_g[k] = 0.f;
-    // per-utterance workspace: alpha_rel [T][ScMax] floats, then C_t [T] doubles
-    const size_t per_utt = ((size_t)T * ScMax + 1) / 2 * 2 + 2 * (size_t)T;
+    for (int k = tid; k < gwarps * V; k += NT) s_gw[k] = 0.f;
+    // per-utterance workspace: alpha_rel [T][ScMax] | beta_rel [T][ScMax] floats, then C_t [T] | D_t [T] doubles, log p
+    const size_t cells = ((size_t)T * ScMax + 1) / 2 * 2;
+    const size_t per_utt = 2 * cells + 4 * (size_t)T + 2;
     float *ws = alpha_ws + (size_t)n * per_utt;
-    double *coff = reinterpret_cast<double *>(ws + ((size_t)T * ScMax + 1) / 2 * 2);
+    float *wsb = ws + cells;
+    double *coff = reinterpret_cast<double *>(ws + 2 * cells);
+    double *doff = coff + T;
+    double *logp_slot = doff + T;
     const long ybase = n * sn;
+    constexpr int kRowRegs = 4;
+    const bool row_in_regs = V <= kRowRegs * NT;
+    float yreg[kRowRegs];
+    double logp_d = 0.0;
 
+    if (role == 0) {
     // ---- forward ---------------------------------------------------------------------------------
     for (int k = tid; k < V; k += NT) s_y[k] = load_y(y, y_bf16, ybase + k);
     __syncthreads();
@@ -98,9 +123,6 @@ __global__ void ctc_fwd_bwd_kernel(const void *y, int y_bf16, long sn, long st, 
     double C = 0.0;
     // Row prefetch: the emission row of frame t+1 is loaded into registers while frame t is computed and parked in
     // shared memory afterwards, so no frame waits on a global-memory round trip (V <= kRowRegs * blockDim).
-    constexpr int kRowRegs = 4;
-    const bool row_in_regs = V <= kRowRegs * NT;
-    float yreg[kRowRegs];
     if (row_in_regs && Tn > 1) {
 #pragma unroll
         for (int j = 0; j < kRowRegs; ++j) { const int k = tid + j * NT; yreg[j] = k < V ? load_y(y, y_bf16, ybase + st + k) : 0.f; }
@@ -153,7 +175,6 @@ __global__ void ctc_fwd_bwd_kernel(const void *y, int y_bf16, long sn, long st, 
         }
     }
     __syncthreads();
-    double logp_d;
     {
         const float *last = s_a + ((Tn - 1) & 1) * ScMax;
         float lp = last[Sc - 1];
@@ -161,102 +182,67 @@ __global__ void ctc_fwd_bwd_kernel(const void *y, int y_bf16, long sn, long st, 
         logp_d = (double)lp + C;
     }
     // raw-logit entry: the reported log-likelihood is normalised; everything below stays in the raw domain
-    if (tid == 0) logp_out[n] = (float)(logp_d - (lnorm ? lnorm[n] : 0.0));
-    if (grad == nullptr || !(logp_d > -INFINITY)) return;
-    __syncthreads();
-
-    // ---- backward + occupancies ------------------------------------------------------------------
-    // beta ping-pong reuses s_a (slot t&1 holds beta_rel_t) and s_wmax.
+    if (tid == 0) { logp_out[n] = (float)(logp_d - (lnorm ? lnorm[n] : 0.0)); *logp_slot = logp_d; }
+    if (grad == nullptr) return;
+    } else {
+    // ---- beta pass (cluster rank 1), concurrent with the alpha pass ---------------------------------
+    // beta_true_t(s) = b_rel_t(s) + D_t; ping-pong in s_a (slot t&1 holds beta_rel_t), maxima in s_wmax.
     double D = 0.0;
-    // prefetch state: emission row and this thread's two alpha cells of the NEXT frame to be processed (t-1)
-    const bool cells_in_regs = L1 <= NT;
-    float a_sb = -INFINITY, a_sl = -INFINITY;   // alpha_rel of cells 2*tid, 2*tid+1 for the current frame
     {
         const int t = Tn - 1;
         float *yc = s_y + (t & 1) * V;
         for (int k = tid; k < V; k += NT) yc[k] = load_y(y, y_bf16, ybase + (long)t * st + k);
-        if (cells_in_regs && tid < L1) {
-            a_sb = ws[(size_t)t * ScMax + 2 * tid];
-            if (tid < L) a_sl = ws[(size_t)t * ScMax + 2 * tid + 1];
-        }
     }
     for (int t = Tn - 1; t >= 0; --t) {
         float *yc = s_y + (t & 1) * V;
         float *cur = s_a + (t & 1) * ScMax;
         const float *nxt = s_a + ((t + 1) & 1) * ScMax;
-        float *gk = s_g + (t & 1) * V;
-        // issue the loads for frame t-1 now; they are consumed after this frame's work
-        float an_sb = -INFINITY, an_sl = -INFINITY;
-        if (t > 0) {
-            if (row_in_regs) {
+        if (t > 0 && row_in_regs) {   // issue the loads for frame t-1 now; they are parked after this frame's work
 #pragma unroll
-                for (int j = 0; j < kRowRegs; ++j) { const int k = tid + j * NT; yreg[j] = k < V ? load_y(y, y_bf16, ybase + (long)(t - 1) * st + k) : 0.f; }
-            }
-            if (cells_in_regs && tid < L1) {
-                an_sb = ws[(size_t)(t - 1) * ScMax + 2 * tid];
-                if (tid < L) an_sl = ws[(size_t)(t - 1) * ScMax + 2 * tid + 1];
-            }
+            for (int j = 0; j < kRowRegs; ++j) { const int k = tid + j * NT; yreg[j] = k < V ? load_y(y, y_bf16, ybase + (long)(t - 1) * st + k) : 0.f; }
         }
-        const double Ct = coff[t];
-        __syncthreads();   // the only barrier of the frame: publishes row t, beta_{t+1}, its maxima and gk(t+1)
-        if (t + 1 < Tn) {  // flush the (now complete) occupancies of frame t+1 and clear their slot
-            float *gp = s_g + ((t + 1) & 1) * V;
-            float *grow = grad + n * gsn + (long)(t + 1) * gst;
-            for (int k = tid; k < V; k += NT) {
-                const float g = gp[k];
-                if (g != 0.f) { atomicAdd(grow + k, grad_scale * g); gp[k] = 0.f; }
-            }
-        }
+        __syncthreads();   // the only barrier of the frame: publishes row t, beta_{t+1} and its maxima
         float m = 0.f;
         if (t < Tn - 1) {
             m = block_max_from(s_wmax + ((t + 1) & 1) * 32, nwarps);
             D += (double)m;
         }
-        const float K = (float)(Ct + D - logp_d);
-        const float *al = ws + (size_t)t * ScMax;
+        if (tid == 0) doff[t] = D;
+        float *bl = wsb + (size_t)t * ScMax;
         float mx = -INFINITY;
-        for (int i0 = 0; i0 < L1; i0 += NT) {
-            const int i = i0 + tid;
-            float occ_blank = 0.f;
-            if (i < L1) {
-                const int sb = 2 * i;
-                float vb;
-                if (t == Tn - 1) {
-                    vb = (sb == Sc - 1) ? yc[blank] : -INFINITY;
-                } else {
-                    vb = nxt[sb];
-                    if (sb + 1 < Sc) vb = log_add(vb, nxt[sb + 1]);
-                    vb += yc[blank] - m;
-                }
-                cur[sb] = vb;
-                mx = fmaxf(mx, vb);
-                const float ob = (cells_in_regs ? a_sb : al[sb]) + vb - yc[blank] + K;
-                occ_blank = (ob == -INFINITY || ob != ob) ? 0.f : expf(ob);
-                if (i < L) {
-                    const int sl = sb + 1;
-                    const int li = s_lab[i];
-                    float vl;
-                    if (t == Tn - 1) {
-                        vl = (sl == Sc - 2) ? yc[li] : -INFINITY;
-                    } else {
-                        vl = log_add(nxt[sl], nxt[sl + 1]);
-                        if (i + 1 < L && li != s_lab[i + 1]) vl = log_add(vl, nxt[sl + 2]);
-                        vl += yc[li] - m;
-                    }
-                    cur[sl] = vl;
-                    mx = fmaxf(mx, vl);
-                    const float ol = (cells_in_regs ? a_sl : al[sl]) + vl - yc[li] + K;
-                    if (ol != -INFINITY && ol == ol) atomicAdd(&gk[li], expf(ol));
-                }
+        for (int i = tid; i < L1; i += NT) {
+            const int sb = 2 * i;
+            float vb;
+            if (t == Tn - 1) {
+                vb = (sb == Sc - 1) ? yc[blank] : -INFINITY;
+            } else {
+                vb = nxt[sb];
+                if (sb + 1 < Sc) vb = log_add(vb, nxt[sb + 1]);
+                vb += yc[blank] - m;
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) occ_blank += __shfl_xor_sync(kFull, occ_blank, o);
-            if (lane == 0 && occ_blank != 0.f) atomicAdd(&gk[blank], occ_blank);
+            cur[sb] = vb;
+            bl[sb] = vb;
+            mx = fmaxf(mx, vb);
+            if (i < L) {
+                const int sl = sb + 1;
+                const int li = s_lab[i];
+                float vl;
+                if (t == Tn - 1) {
+                    vl = (sl == Sc - 2) ? yc[li] : -INFINITY;
+                } else {
+                    vl = log_add(nxt[sl], nxt[sl + 1]);
+                    if (i + 1 < L && li != s_lab[i + 1]) vl = log_add(vl, nxt[sl + 2]);
+                    vl += yc[li] - m;
+                }
+                cur[sl] = vl;
+                bl[sl] = vl;
+                mx = fmaxf(mx, vl);
+            }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, o));
         if (lane == 0) s_wmax[(t & 1) * 32 + warp] = mx;
-        if (t > 0) {   // park row t-1 (slot last read during frame t+1) and rotate the alpha cells
+        if (t > 0) {   // park row t-1 in the slot last read during frame t+1
             float *yn = s_y + ((t - 1) & 1) * V;
             if (row_in_regs) {
 #pragma unroll
@@ -264,16 +250,39 @@ __global__ void ctc_fwd_bwd_kernel(const void *y, int y_bf16, long sn, long st, 
             } else {
                 for (int k = tid; k < V; k += NT) yn[k] = load_y(y, y_bf16, ybase + (long)(t - 1) * st + k);
             }
-            a_sb = an_sb; a_sl = an_sl;
         }
     }
-    __syncthreads();
-    {   // flush frame 0
-        float *gp = s_g;
-        float *grow = grad + n * gsn;
-        for (int k = tid; k < V; k += NT) {
-            const float g = gp[k];
-            if (g != 0.f) atomicAdd(grow + k, grad_scale * g);
+    }
+
+    // ---- occupancies: both CTAs, one warp per frame ------------------------------------------------
+    cluster_sync();
+    logp_d = *reinterpret_cast<volatile double *>(logp_slot);
+    if (!(logp_d > -INFINITY)) return;
+    if (warp < gwarps) {
+        float *g = s_gw + warp * V;
+        for (int t = warp + gwarps * (int)role; t < Tn; t += 2 * gwarps) {
+            const float K = (float)(coff[t] + doff[t] - logp_d);
+            const float *al = ws + (size_t)t * ScMax, *bl = wsb + (size_t)t * ScMax;
+            const long yrow = ybase + (long)t * st;
+            float occ_blank = 0.f;
+            for (int s = lane; s < Sc; s += 32) {   // lane parity == cell parity: even lanes take blanks, odd lanes labels
+                const int li = (s & 1) ? s_lab[s >> 1] : blank;
+                const float o = al[s] + bl[s] - load_y(y, y_bf16, yrow + li) + K;
+                const float e = (o == -INFINITY || o != o) ? 0.f : expf(o);
+                if (s & 1) { if (e != 0.f) atomicAdd(&g[li], e); }
+                else occ_blank += e;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) occ_blank += __shfl_xor_sync(kFull, occ_blank, o);
+            __syncwarp();
+            if (lane == 0 && occ_blank != 0.f) g[blank] += occ_blank;
+            __syncwarp();
+            float *grow = grad + n * gsn + (long)t * gst;
+            for (int k = lane; k < V; k += 32) {
+                const float gv = g[k];
+                if (gv != 0.f) { atomicAdd(grow + k, grad_scale * gv); g[k] = 0.f; }
+            }
+            __syncwarp();
         }
     }
 }
@@ -295,14 +304,18 @@ int LaunchCtc(const void *y, int y_bf16, long sn, long st, int N, int T, int V, 
               const double *lnorm, cudaStream_t stream, std::string *err) {
     if (N == 0) return 0;
     const int ScMax = 2 * max_label_len + 1;
-    const size_t smem = (size_t)(max_label_len + 1) * 4 + (size_t)2 * ScMax * 4 + (size_t)4 * V * 4 + 64 * 4;
     int threads = ((max_label_len + 1 + 31) / 32) * 32;
     threads = threads < 64 ? 64 : (threads > 1024 ? 1024 : threads);
-    if (smem > 200 * 1024) { *err = "label sequence too long for the numerator kernel's shared memory"; return 1; }
+    const size_t fixed = (size_t)(max_label_len + 1) * 4 + (size_t)2 * ScMax * 4 + (size_t)2 * V * 4 + 64 * 4;
+    if (fixed + (size_t)V * 4 > 200 * 1024) { *err = "label sequence too long for the numerator kernel's shared memory"; return 1; }
+    // occupancy phase: one label accumulator [V] per participating warp, as many warps as fit
+    int gwarps = threads / 32;
+    while (gwarps > 1 && fixed + (size_t)gwarps * V * 4 > 160 * 1024) --gwarps;
+    const size_t smem = fixed + (size_t)gwarps * V * 4;
     cudaError_t e = cudaFuncSetAttribute(ctc_fwd_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { *err = std::string("cudaFuncSetAttribute(ctc): ") + cudaGetErrorString(e); return (int)e; }
-    ctc_fwd_bwd_kernel<<<N, threads, smem, stream>>>(y, y_bf16, sn, st, T, V, labels, label_off, label_len, len,
-                                                     max_label_len, blank, alpha_ws, grad, gsn, gst, grad_scale, logp, lnorm);
+    ctc_fwd_bwd_kernel<<<2 * N, threads, smem, stream>>>(y, y_bf16, sn, st, T, V, labels, label_off, label_len, len,
+                                                         max_label_len, blank, alpha_ws, gwarps, grad, gsn, gst, grad_scale, logp, lnorm);
     CountLaunch();
     e = cudaGetLastError();
     if (e != cudaSuccess) { *err = std::string("ctc launch: ") + cudaGetErrorString(e); return (int)e; }

@@ -202,3 +202,109 @@ def make_random_den(S: int, A: int, V: int, seed: int = 0, n_final: int = 2) -> 
     final[S - 1] = 0.3
     return DenGraph(num_states=S, start=0, src=src, dst=dst, ilabel=lab + 1, olabel=lab.copy(),
                     weight=w, final=final)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Den-graph construction without Kaldi/OpenFst: T o LM for an epsilon-free phone LM
+# ---------------------------------------------------------------------------------------------------
+@dataclass
+class PhoneLm:
+    """Epsilon-free weighted acceptor over phone ids 1..V-1 (0 is the CTC blank and never appears):
+    what ``chain-est-phone-lm`` produces for ``cat/utils/tool/prep_den_lm.sh:40-45`` (no back-off arcs)."""
+    num_states: int
+    start: int
+    src: np.ndarray      # int32 [A]
+    dst: np.ndarray      # int32 [A]
+    phone: np.ndarray    # int32 [A] in [1, V-1]
+    weight: np.ndarray   # float32 [A] tropical (-log p)
+    final: np.ndarray    # float32 [S] tropical, +inf = non-final
+
+
+def compose_ctc_lm(lm: PhoneLm) -> DenGraph:
+    """den graph = T o LM, with T the CTC topology of ``cat/utils/tool/build_ctc_topo.py:47-66`` (state 0 = blank,
+    state i = token i; every arc INTO token state i reads label i and emits phone i, arcs into the blank state and
+    token self loops emit nothing), i.e. the composition ``prep_den_lm.sh:46-51`` performs with OpenFst.
+
+    States of the result: (h,B) "LM state h, last frame was blank or nothing yet" for every reachable h, and (h,i)
+    "LM state h reached by phone i, last frame was i" for every phone i entering h.  Because T emits a phone exactly
+    when a token state is entered, the composition needs no epsilon handling for an epsilon-free LM, and for a
+    deterministic LM the result is already deterministic (what fstdeterminizestar would return up to state order)."""
+    S, A = lm.num_states, int(lm.src.shape[0])
+    # token states: one per distinct (destination, phone)
+    key = lm.dst.astype(np.int64) * (int(lm.phone.max(initial=0)) + 1) + lm.phone
+    uniq, tok_of_arc = np.unique(key, return_inverse=True)
+    n_tok = int(uniq.shape[0])
+    tok_h = (uniq // (int(lm.phone.max(initial=0)) + 1)).astype(np.int32)
+    tok_p = (uniq % (int(lm.phone.max(initial=0)) + 1)).astype(np.int32)
+    B = lambda h: np.asarray(h, np.int64)                   # (h,B) -> h
+    TK = lambda k: S + np.asarray(k, np.int64)             # token state k -> S + k
+    src, dst, lab, w = [], [], [], []
+    hs = np.arange(S)
+    ks = np.arange(n_tok)
+    # blank self loop, token self loop, token -> blank
+    src += [B(hs), TK(ks), TK(ks)]
+    dst += [B(hs), TK(ks), B(tok_h)]
+    lab += [np.zeros(S, np.int32), tok_p, np.zeros(n_tok, np.int32)]
+    w += [np.zeros(S, np.float32), np.zeros(n_tok, np.float32), np.zeros(n_tok, np.float32)]
+    # per LM arc h -p-> h': from (h,B), and from every token state (h,i) with i != p
+    src.append(B(lm.src)); dst.append(TK(tok_of_arc)); lab.append(lm.phone); w.append(lm.weight)
+    by_h = [[] for _ in range(S)]
+    for k in range(n_tok):
+        by_h[int(tok_h[k])].append(k)
+    s2, d2, l2, w2 = [], [], [], []
+    for a in range(A):
+        for k in by_h[int(lm.src[a])]:
+            if tok_p[k] != lm.phone[a]:
+                s2.append(S + k); d2.append(S + int(tok_of_arc[a])); l2.append(int(lm.phone[a])); w2.append(float(lm.weight[a]))
+    src.append(np.asarray(s2, np.int64)); dst.append(np.asarray(d2, np.int64))
+    lab.append(np.asarray(l2, np.int32)); w.append(np.asarray(w2, np.float32))
+    src = np.concatenate(src); dst = np.concatenate(dst)
+    lab = np.concatenate(lab).astype(np.int32); w = np.concatenate(w).astype(np.float32)
+    final = np.concatenate([lm.final, lm.final[tok_h]]).astype(np.float32)
+    # keep what is reachable from (start,B), renumbered in discovery order
+    n_all = S + n_tok
+    order = np.argsort(src, kind="stable")
+    starts = np.searchsorted(src[order], np.arange(n_all + 1))
+    new_id = np.full(n_all, -1, np.int64)
+    new_id[lm.start] = 0
+    stack, n_new = [int(lm.start)], 1
+    while stack:
+        q = stack.pop()
+        for a in order[starts[q]:starts[q + 1]]:
+            t = int(dst[a])
+            if new_id[t] < 0:
+                new_id[t] = n_new; n_new += 1; stack.append(t)
+    keep = new_id[src] >= 0
+    inv = np.argsort(np.where(new_id >= 0, new_id, n_all), kind="stable")[:n_new]
+    return DenGraph(num_states=n_new, start=0, src=new_id[src[keep]].astype(np.int32), dst=new_id[dst[keep]].astype(np.int32),
+                    ilabel=(lab[keep] + 1).astype(np.int32), olabel=lab[keep].copy(), weight=w[keep], final=final[inv])
+
+
+def lm_logprob(lm: PhoneLm, phones) -> float:
+    """log p_LM(l) of one phone sequence under a deterministic LM (the per-utterance path weight CAT adds to the
+    numerator, docs/toolkitworkflow.md:124-135); -inf if the LM does not accept it."""
+    h, lp = int(lm.start), 0.0
+    for p in phones:
+        m = np.nonzero((lm.src == h) & (lm.phone == int(p)))[0]
+        if m.size == 0:
+            return float("-inf")
+        assert m.size == 1, "lm_logprob needs a deterministic LM"
+        lp -= float(lm.weight[m[0]]); h = int(lm.dst[m[0]])
+    return lp - float(lm.final[h]) if np.isfinite(lm.final[h]) else float("-inf")
+
+
+def make_random_lm(H: int, V: int, d: int, seed: int = 0, p_final: float = 0.2) -> PhoneLm:
+    """Small deterministic phone LM for tests: every state has d out-arcs with distinct phones, random targets."""
+    rng = np.random.default_rng(seed)
+    assert 1 <= d <= V - 1
+    src, dst, ph, w = [], [], [], []
+    final = np.full(H, np.inf, np.float32)
+    for h in range(H):
+        fin = h > 0 and rng.random() < 0.7
+        pr = rng.dirichlet(np.ones(d)) * (1.0 - (p_final if fin else 0.0))
+        for p, q in zip(rng.choice(np.arange(1, V), size=d, replace=False), pr):
+            src.append(h); dst.append(int(rng.integers(0, H))); ph.append(int(p)); w.append(-np.log(q))
+        if fin:
+            final[h] = -np.log(p_final)
+    return PhoneLm(H, 0, np.asarray(src, np.int32), np.asarray(dst, np.int32), np.asarray(ph, np.int32),
+                   np.asarray(w, np.float32), final)

@@ -196,3 +196,38 @@ def test_fixture_emulation(fixture_fst, fixture_inputs):
     P = plan.load_plan(fixture_fst, 148, 16)
     ea, eb, eg = emulate.den_emulate(P, fixture_inputs["y"], fixture_inputs["lx"])
     assert abs(ea[0] + 6.25832785) < 1e-6 and abs(eb[0] + 6.25832785) < 1e-6
+
+
+def test_compose_ctc_lm_is_the_lm_weighted_sum_of_ctc(tmp_path):
+    """den graph built natively as T o LM.  Property (what the denominator *means*,
+    docs/toolkitworkflow.md:124-135): logZ_den(x) = log sum_l p_LM(l) p_CTC(l|x) over every label sequence l --
+    enumerated exhaustively here with the oracle's CTC, and the composed file round-trips through both FST readers."""
+    import itertools
+    from oracle import oracle
+    V, T = 4, 4
+    lm = fst.make_random_lm(H=3, V=V, d=2, seed=5)
+    g = fst.compose_ctc_lm(lm)
+    rng = np.random.default_rng(2)
+    x = rng.standard_normal((1, T, V))
+    y = (x - np.log(np.exp(x).sum(-1, keepdims=True))).astype(np.float32)
+    la, lb, gamma = oracle.den(g, y, [T])
+    total = -np.inf
+    n_acc = 0
+    for L in range(0, T + 1):
+        for l in itertools.product(range(1, V), repeat=L):
+            lp_lm = fst.lm_logprob(lm, l)
+            if not np.isfinite(lp_lm):
+                continue
+            lp, _ = oracle.ctc(y, np.asarray(l, np.int32), [L], [T], want_grad=False)
+            if np.isfinite(lp[0]):
+                total = np.logaddexp(total, lp_lm + lp[0]); n_acc += 1
+    assert n_acc > 3
+    assert abs(la[0] - total) < 1e-5 and abs(lb[0] - total) < 1e-5
+    # the file the product loads: same plan semantics as any other den graph
+    p = str(tmp_path / "tlm.fst")
+    fst.write_fst(p, g)
+    g2 = fst.read_fst(p)
+    assert g2.num_states == g.num_states and g2.num_arcs == g.num_arcs
+    pv = plan.load_plan(p, 4, 2)
+    ea, eb, eg = emulate.den_emulate(pv, y, [T])
+    assert abs(ea[0] - total) < 1e-4 and abs(eb[0] - total) < 1e-4

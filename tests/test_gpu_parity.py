@@ -162,6 +162,37 @@ def test_fused_vs_oracle_and_bf16(tmp_graphs):
     del ctx
 
 
+def test_composed_den_graph_is_lm_weighted_ctc_sum(tmp_path):
+    """SURVEY 8f-2 on the GPU: a den graph composed natively (fst.compose_ctc_lm, no Kaldi/OpenFst) loaded through
+    CRFContext; logZ_den must equal log sum_l p_LM(l) p_CTC(l|x), both factors from this library's own kernels
+    (den via _C.gpu_den, every p_CTC via _C.gpu_ctc), enumerated over all label sequences."""
+    import itertools
+    import ctc_crf
+    from cat_b200 import fst
+    V, T = 4, 5
+    lm = fst.make_random_lm(H=3, V=V, d=2, seed=11)
+    path = str(tmp_path / "tlm_native.fst")
+    fst.write_fst(path, fst.compose_ctc_lm(lm))
+    ctx = _ctx(path)
+    y = torch.log_softmax(torch.randn(1, T, V, generator=torch.Generator().manual_seed(3)), -1).cuda()
+    grad = torch.zeros_like(y)
+    ca, cb = torch.zeros(1, device="cuda"), torch.zeros(1, device="cuda")
+    ctc_crf._C.gpu_den(y, grad, torch.tensor([T], dtype=torch.int32, device="cuda"), ca, cb)
+    seqs = [l for L in range(T + 1) for l in itertools.product(range(1, V), repeat=L) if np.isfinite(fst.lm_logprob(lm, l))]
+    seqs = [l for l in seqs if len(l) + sum(a == b for a, b in zip(l, l[1:])) <= T]      # CTC-feasible in T frames
+    act = y.transpose(0, 1).repeat(1, len(seqs), 1).contiguous()                           # (T, n_seqs, V)
+    costs = torch.zeros(len(seqs))
+    labels = torch.tensor([p for l in seqs for p in l], dtype=torch.int32)
+    ctc_crf._C.gpu_ctc(act, torch.zeros_like(act), labels, torch.tensor([len(l) for l in seqs], dtype=torch.int32),
+                       torch.full((len(seqs),), T, dtype=torch.int32), len(seqs), costs, 0)
+    torch.cuda.synchronize()
+    total = np.logaddexp.reduce([fst.lm_logprob(lm, l) + float(c) for l, c in zip(seqs, costs)])
+    assert len(seqs) > 5
+    assert abs(float(ca.item()) - total) < 1e-4 * max(1.0, abs(total))
+    assert abs(float(cb.item()) - total) < 1e-4 * max(1.0, abs(total))
+    del ctx
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_raw_logit_entry(tmp_graphs, dtype):
     """CTC_CRF_LOSS(from_logits=True) on raw encoder outputs == log_softmax + loss + autograd chain, against
