@@ -37,7 +37,7 @@ UNIT = "frames/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     # workload overrides (development only; the defaults are the headline configuration)
@@ -338,9 +338,11 @@ def main():
             crit_raw(zz, labels, lx, ly).backward()
 
         reps = max(2, min(args.steps, 5))
-        ms_two = timed(two_step, reps, 2) / reps
-        ms_fused = timed(fused, reps, 2) / reps
-        raw_entry = {"two_step_ms": ms_two, "fused_ms": ms_fused,
+        ms_two, ms_fused = [], []
+        for _ in range(2):   # alternate the two arms so that neither owns the warmer allocator / clocks
+            ms_two.append(timed(two_step, reps, 2) / reps)
+            ms_fused.append(timed(fused, reps, 2) / reps)
+        raw_entry = {"two_step_ms": min(ms_two), "fused_ms": min(ms_fused), "all_ms": {"two_step": ms_two, "fused": ms_fused},
                      "what": "forward+backward from raw encoder outputs: torch log_softmax + CTC_CRF_LOSS + autograd vs CTC_CRF_LOSS(from_logits=True)"}
         del z
 

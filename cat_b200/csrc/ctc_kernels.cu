@@ -2,12 +2,11 @@
 //
 // Replaces src/ctc_crf/gpu_ctc (compute_alpha_kernel gpu_ctc_kernels.h:87-213,
 // compute_betas_and_grad_kernel :218-458, host driver gpu_ctc.h:100-400).  Differences by design:
-//   * one launch does forward, backward and the gradient (the reference launches two kernels and synchronises
-//     the stream twice, gpu_ctc.h:272,368); nothing here touches the host.  Each utterance gets a CLUSTER OF TWO
-//     CTAs: rank 0 walks alpha forwards while rank 1 walks beta backwards at the same time (both recursions are
-//     latency-bound chains of T frames, so this halves the critical path), each spilling its cells relative to a
-//     per-frame fp64 offset; after one cluster barrier both CTAs turn the spills into occupancies, a warp per frame,
-//     with no further block-wide synchronisation;
+//   * nothing here touches the host (the reference synchronises the stream twice, gpu_ctc.h:272,368).  Each utterance
+//     gets TWO CTAs in one launch: one walks alpha forwards while the other walks beta backwards at the same time
+//     (both recursions are latency-bound chains of T frames, so this halves the critical path), each spilling its
+//     cells relative to a per-frame fp64 offset; a second, fully parallel kernel (one warp per frame, all SMs) turns
+//     the two spills into occupancies;
 //   * thread i owns lattice cells 2i (blank) and 2i+1 (label i): the 2-/3-way log-sum of a frame needs
 //     one value from the neighbouring thread, exchanged through a shared-memory ping-pong, one
 //     __syncthreads per frame; the label row y[n][t][:] is staged coalesced one frame ahead;
@@ -42,25 +41,29 @@ __device__ __forceinline__ float block_max_from(const float *s_wmax, int nwarps)
 // fp64), so fp32 log-add rounding stays ~1e-6 absolute instead of growing with |alpha| (the reference's plain fp32
 // log domain loses ~1e-2 relative on the occupancies at T ~ 1000).  alpha_true_t(s) = a_rel_t(s) + C_t,
 // beta_true_t(s) = b_rel_t(s) + D_t, occupancy = exp(a_rel + b_rel - y + (C_t + D_t - log p)).
-__device__ __forceinline__ unsigned cluster_rank() {
-    unsigned r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync() {   // release/acquire at cluster scope: the partner's spills are visible
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
+// per-utterance workspace: alpha_rel [T][ScMax] | beta_rel [T][ScMax] floats, then C_t [T] | D_t [T] doubles, log p
+struct CtcWorkspace {
+    float *a, *b;
+    double *coff, *doff, *logp;
+    __device__ CtcWorkspace(float *base, int n, int T, int ScMax) {
+        const size_t cells = ((size_t)T * ScMax + 1) / 2 * 2;
+        const size_t per_utt = 2 * cells + 4 * (size_t)T + 2;
+        a = base + (size_t)n * per_utt;
+        b = a + cells;
+        coff = reinterpret_cast<double *>(a + 2 * cells);
+        doff = coff + T;
+        logp = doff + T;
+    }
+};
 
-// shared memory carve-up: lab[Lmax+1] ints | a[2][ScMax] | yrow[2][V] | wmax[2][32] | gw[gwarps][V]
-__global__ void __cluster_dims__(2, 1, 1)
-ctc_fwd_bwd_kernel(const void *y, int y_bf16, long sn, long st, int T, int V,
-                   const int *labels, const int *label_off, const int *label_len, const int *len,
-                   int max_label_len, int blank, float *alpha_ws, int gwarps,
-                   float *grad, long gsn, long gst, float grad_scale, float *logp_out,
-                   const double *lnorm) {
+// shared memory carve-up: lab[Lmax+1] ints | a[2][ScMax] | yrow[2][V] | wmax[2][32]
+__global__ void ctc_alpha_beta_kernel(const void *y, int y_bf16, long sn, long st, int T, int V,
+                                      const int *labels, const int *label_off, const int *label_len, const int *len,
+                                      int max_label_len, int blank, float *alpha_ws, bool want_beta, float *logp_out,
+                                      const double *lnorm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = blockIdx.x >> 1;
-    const unsigned role = cluster_rank();   // 0: alpha pass, 1: beta pass
+    const unsigned role = blockIdx.x & 1;   // 0: alpha pass, 1: beta pass
     const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = NT >> 5;
     const int L = label_len[n], Tn = len[n];
     const int Sc = 2 * L + 1, L1 = L + 1;
@@ -69,7 +72,7 @@ ctc_fwd_bwd_kernel(const void *y, int y_bf16, long sn, long st, int T, int V,
     float *s_a = reinterpret_cast<float *>(s_lab + max_label_len + 1);   // [2][ScMax]
     float *s_y = s_a + 2 * ScMax;                                   // [2][V]
     float *s_wmax = s_y + 2 * V;                                    // [2][32]
-    float *s_gw = s_wmax + 64;                                      // [gwarps][V] per-warp label accumulators
+    CtcWorkspace W(alpha_ws, n, T, ScMax);
     const int *lab = labels + label_off[n];
 
     // feasibility (gpu_ctc_kernels.h:108-109)
@@ -80,21 +83,14 @@ ctc_fwd_bwd_kernel(const void *y, int y_bf16, long sn, long st, int T, int V,
     __syncthreads();
     if (rep) atomicAdd(&s_rep, rep);
     __syncthreads();
-    if (Tn <= 0 || L + s_rep > Tn) {   // both CTAs of the pair take this exit: nobody waits at the cluster barrier
-        if (tid == 0 && role == 0) logp_out[n] = -INFINITY;
+    if (Tn <= 0 || L + s_rep > Tn) {
+        if (tid == 0 && role == 0) { logp_out[n] = -INFINITY; *W.logp = -INFINITY; }
         return;
     }
-    if (grad == nullptr && role == 1) return;   // likelihood only: the alpha CTA never reaches the cluster barrier either
+    if (!want_beta && role == 1) return;   // likelihood only
     for (int i = tid; i < L; i += NT) s_lab[i] = lab[i];
-    for (int k = tid; k < gwarps * V; k += NT) s_gw[k] = 0.f;
-    // per-utterance workspace: alpha_rel [T][ScMax] | beta_rel [T][ScMax] floats, then C_t [T] | D_t [T] doubles, log p
-    const size_t cells = ((size_t)T * ScMax + 1) / 2 * 2;
-    const size_t per_utt = 2 * cells + 4 * (size_t)T + 2;
-    float *ws = alpha_ws + (size_t)n * per_utt;
-    float *wsb = ws + cells;
-    double *coff = reinterpret_cast<double *>(ws + 2 * cells);
-    double *doff = coff + T;
-    double *logp_slot = doff + T;
+    float *ws = W.a, *wsb = W.b;
+    double *coff = W.coff, *doff = W.doff;
     const long ybase = n * sn;
     constexpr int kRowRegs = 4;
     const bool row_in_regs = V <= kRowRegs * NT;
@@ -182,8 +178,7 @@ ctc_fwd_bwd_kernel(const void *y, int y_bf16, long sn, long st, int T, int V,
         logp_d = (double)lp + C;
     }
     // raw-logit entry: the reported log-likelihood is normalised; everything below stays in the raw domain
-    if (tid == 0) { logp_out[n] = (float)(logp_d - (lnorm ? lnorm[n] : 0.0)); *logp_slot = logp_d; }
-    if (grad == nullptr) return;
+    if (tid == 0) { logp_out[n] = (float)(logp_d - (lnorm ? lnorm[n] : 0.0)); *W.logp = logp_d; }
     } else {
     // ---- beta pass (cluster rank 1), concurrent with the alpha pass ---------------------------------
     // beta_true_t(s) = b_rel_t(s) + D_t; ping-pong in s_a (slot t&1 holds beta_rel_t), maxima in s_wmax.
@@ -254,36 +249,49 @@ ctc_fwd_bwd_kernel(const void *y, int y_bf16, long sn, long st, int T, int V,
     }
     }
 
-    // ---- occupancies: both CTAs, one warp per frame ------------------------------------------------
-    cluster_sync();
-    logp_d = *reinterpret_cast<volatile double *>(logp_slot);
-    if (!(logp_d > -INFINITY)) return;
-    if (warp < gwarps) {
-        float *g = s_gw + warp * V;
-        for (int t = warp + gwarps * (int)role; t < Tn; t += 2 * gwarps) {
-            const float K = (float)(coff[t] + doff[t] - logp_d);
-            const float *al = ws + (size_t)t * ScMax, *bl = wsb + (size_t)t * ScMax;
-            const long yrow = ybase + (long)t * st;
-            float occ_blank = 0.f;
-            for (int s = lane; s < Sc; s += 32) {   // lane parity == cell parity: even lanes take blanks, odd lanes labels
-                const int li = (s & 1) ? s_lab[s >> 1] : blank;
-                const float o = al[s] + bl[s] - load_y(y, y_bf16, yrow + li) + K;
-                const float e = (o == -INFINITY || o != o) ? 0.f : expf(o);
-                if (s & 1) { if (e != 0.f) atomicAdd(&g[li], e); }
-                else occ_blank += e;
-            }
+}
+
+// Occupancies from the two spills: one warp per (utterance, frame), label accumulator [V] per warp in shared memory.
+//   gamma_t[k] = sum_{s: l'_s = k} exp(a_rel_t(s) + b_rel_t(s) - y_t(k) + C_t + D_t - log p)   (gpu_ctc_kernels.h:337-453)
+// accumulated with the caller's scale into grad[n][t][:] (which may already hold the denominator part).
+__global__ void ctc_gamma_kernel(const void *y, int y_bf16, long sn, long st, int N, int T, int V,
+                                 const int *labels, const int *label_off, const int *label_len, const int *len,
+                                 int max_label_len, int blank, float *alpha_ws,
+                                 float *grad, long gsn, long gst, float grad_scale) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const long row = (long)blockIdx.x * wpb + warp;
+    if (row >= (long)N * T) return;
+    const int n = (int)(row / T), t = (int)(row % T);
+    if (t >= len[n]) return;
+    const int L = label_len[n], Sc = 2 * L + 1, ScMax = 2 * max_label_len + 1;
+    CtcWorkspace W(alpha_ws, n, T, ScMax);
+    const double logp_d = *W.logp;
+    if (!(logp_d > -INFINITY)) return;       // infeasible utterance: no gradient
+    float *g = reinterpret_cast<float *>(smem_raw) + (size_t)warp * V;
+    for (int k = lane; k < V; k += 32) g[k] = 0.f;
+    __syncwarp();
+    const float K = (float)(W.coff[t] + W.doff[t] - logp_d);
+    const float *al = W.a + (size_t)t * ScMax, *bl = W.b + (size_t)t * ScMax;
+    const int *lab = labels + label_off[n];
+    const long yrow = n * sn + (long)t * st;
+    float occ_blank = 0.f;
+    for (int s = lane; s < Sc; s += 32) {   // lane parity == cell parity: even lanes take blanks, odd lanes labels
+        const int li = (s & 1) ? __ldg(lab + (s >> 1)) : blank;
+        const float o = al[s] + bl[s] - load_y(y, y_bf16, yrow + li) + K;
+        const float e = (o == -INFINITY || o != o) ? 0.f : expf(o);
+        if (s & 1) { if (e != 0.f) atomicAdd(&g[li], e); }
+        else occ_blank += e;
+    }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) occ_blank += __shfl_xor_sync(kFull, occ_blank, o);
-            __syncwarp();
-            if (lane == 0 && occ_blank != 0.f) g[blank] += occ_blank;
-            __syncwarp();
-            float *grow = grad + n * gsn + (long)t * gst;
-            for (int k = lane; k < V; k += 32) {
-                const float gv = g[k];
-                if (gv != 0.f) { atomicAdd(grow + k, grad_scale * gv); g[k] = 0.f; }
-            }
-            __syncwarp();
-        }
+    for (int o = 16; o > 0; o >>= 1) occ_blank += __shfl_xor_sync(kFull, occ_blank, o);
+    __syncwarp();
+    if (lane == 0 && occ_blank != 0.f) g[blank] += occ_blank;
+    __syncwarp();
+    float *grow = grad + n * gsn + (long)t * gst;
+    for (int k = lane; k < V; k += 32) {
+        const float gv = g[k];
+        if (gv != 0.f) atomicAdd(grow + k, grad_scale * gv);
     }
 }
 
@@ -306,17 +314,24 @@ int LaunchCtc(const void *y, int y_bf16, long sn, long st, int N, int T, int V, 
     const int ScMax = 2 * max_label_len + 1;
     int threads = ((max_label_len + 1 + 31) / 32) * 32;
     threads = threads < 64 ? 64 : (threads > 1024 ? 1024 : threads);
-    const size_t fixed = (size_t)(max_label_len + 1) * 4 + (size_t)2 * ScMax * 4 + (size_t)2 * V * 4 + 64 * 4;
-    if (fixed + (size_t)V * 4 > 200 * 1024) { *err = "label sequence too long for the numerator kernel's shared memory"; return 1; }
-    // occupancy phase: one label accumulator [V] per participating warp, as many warps as fit
-    int gwarps = threads / 32;
-    while (gwarps > 1 && fixed + (size_t)gwarps * V * 4 > 160 * 1024) --gwarps;
-    const size_t smem = fixed + (size_t)gwarps * V * 4;
-    cudaError_t e = cudaFuncSetAttribute(ctc_fwd_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = (size_t)(max_label_len + 1) * 4 + (size_t)2 * ScMax * 4 + (size_t)2 * V * 4 + 64 * 4;
+    if (smem > 200 * 1024 || (size_t)V * 4 > 200 * 1024) { *err = "label sequence too long for the numerator kernel's shared memory"; return 1; }
+    cudaError_t e = cudaFuncSetAttribute(ctc_alpha_beta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { *err = std::string("cudaFuncSetAttribute(ctc): ") + cudaGetErrorString(e); return (int)e; }
-    ctc_fwd_bwd_kernel<<<2 * N, threads, smem, stream>>>(y, y_bf16, sn, st, T, V, labels, label_off, label_len, len,
-                                                         max_label_len, blank, alpha_ws, gwarps, grad, gsn, gst, grad_scale, logp, lnorm);
+    ctc_alpha_beta_kernel<<<2 * N, threads, smem, stream>>>(y, y_bf16, sn, st, T, V, labels, label_off, label_len, len,
+                                                            max_label_len, blank, alpha_ws, grad != nullptr, logp, lnorm);
     CountLaunch();
+    if (grad != nullptr) {
+        int wpb = 8;   // warps (= frames) per CTA of the occupancy kernel, bounded by the [V] accumulators
+        while (wpb > 1 && (size_t)wpb * V * 4 > 48 * 1024) wpb >>= 1;
+        const size_t gsm = (size_t)wpb * V * 4;
+        e = cudaFuncSetAttribute(ctc_gamma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm);
+        if (e != cudaSuccess) { *err = std::string("cudaFuncSetAttribute(ctc gamma): ") + cudaGetErrorString(e); return (int)e; }
+        const long rows = (long)N * T;
+        ctc_gamma_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, gsm, stream>>>(
+            y, y_bf16, sn, st, N, T, V, labels, label_off, label_len, len, max_label_len, blank, alpha_ws, grad, gsn, gst, grad_scale);
+        CountLaunch();
+    }
     e = cudaGetLastError();
     if (e != cudaSuccess) { *err = std::string("ctc launch: ") + cudaGetErrorString(e); return (int)e; }
     return 0;

@@ -840,6 +840,8 @@ int LaunchOne(bool backward, const DenParams &p, int n_ctas, size_t smem, cudaSt
     return 0;
 }
 
+constexpr int kBwdMaxLaneWidth = 2;   // N=256: bwd 163 ms at 2 vs 248 ms at 4 (profiles/r01_experiments.md)
+
 template <int NT>
 int Dispatch(bool backward, const DeviceGraph &g, const DenParams &p, size_t fixed_smem, cudaStream_t stream,
              std::string *err) {
@@ -849,7 +851,15 @@ int Dispatch(bool backward, const DeviceGraph &g, const DenParams &p, size_t fix
     const char *force_global = getenv("CCB_ARCS_IN_GLOBAL");   // test hook: exercise the large-graph fallback
     const bool smem_arcs = fixed_smem + arc_bytes <= budget && !(force_global && force_global[0] == '1');
     const size_t smem = fixed_smem + (smem_arcs ? arc_bytes : 0);
-    const int U = LaneWidth(p.Npad);
+    // utterances per lane: the widest row segment the batch allows, except that the backward pass (two accumulators per
+    // utterance) runs out of registers at 4 -- it walks 64-utterance groups instead.  CCB_U_FWD / CCB_U_BWD: tuning override.
+    int U = LaneWidth(p.Npad);
+    if (backward && U == 4) U = kBwdMaxLaneWidth;
+    {
+        const char *e = getenv(backward ? "CCB_U_BWD" : "CCB_U_FWD");
+        const int u = e ? atoi(e) : 0;
+        if ((u == 1 || u == 2 || u == 4) && p.Npad % (32 * u) == 0) U = u;
+    }
     // gathers per batch (two batches are in flight per warp); bounded by the register budget of the variant.
     // CCB_BATCH_FWD / CCB_BATCH_BWD (8 or 16) override the 512-thread defaults for tuning.
     int want = NT == 512 ? (U == 4 ? 8 : (backward ? 8 : 16)) : (U == 1 ? 8 : 4);
