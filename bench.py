@@ -93,6 +93,7 @@ class ClockSampler:
         self.index = index
         self.rows = []
         self.proc = None
+        self.skip = 0
 
     def start(self):
         try:
@@ -100,6 +101,12 @@ class ClockSampler:
                                           "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            # nvidia-smi's own start-up (NVML init) stalls CUDA launches for tens of ms: let it finish BEFORE the
+            # timed region starts, then drop what it printed while the GPU was idle
+            t0 = time.time()
+            while not self.rows and time.time() - t0 < 3.0:
+                time.sleep(0.02)
+            self.skip = len(self.rows)
         except Exception:
             self.proc = None
 
@@ -118,7 +125,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in self.rows[self.skip:]:
             if len(r) < 8:
                 continue
             try:
@@ -233,6 +240,7 @@ def main():
         for _ in range(warmup):
             fn()
         barrier()
+        timed.launches_before = _C.launch_count()     # so that gpu_launches counts the timed steps only
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
@@ -248,9 +256,8 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0 and not os.environ.get("CCB_BENCH_NO_SAMPLER"):
         sampler.start()
-    l0 = _C.launch_count()
     ms_total = timed(step_resident, args.steps, max(args.warmup, 3))
-    launches = _C.launch_count() - l0
+    launches = _C.launch_count() - timed.launches_before
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = ms_total / args.steps
     value = world * frames_per_step / (ms_per_step * 1e-3)

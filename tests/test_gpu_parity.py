@@ -243,6 +243,7 @@ def test_raw_logit_entry(tmp_graphs, dtype):
     (2, 6, [6, 0], [2, 0]),                 # an utterance of length zero rides along
     (3, 9, [9, 9, 9], [9, 4, 0]),           # L == T (no blank can be emitted), and L = 0
     (33, 5, None, None),                    # more utterances than one lane group, tiny T
+    (130, 7, None, None),                   # 256 lanes: forward walks 4 utterances per lane, backward 2 (4 lane groups)
 ])
 def test_edge_shapes_vs_oracle(tmp_graphs, N, T, lens, ly):
     """Degenerate shapes through the fused op against the oracle (empty labels, T=1, len=0, L=T, ragged lanes)."""
