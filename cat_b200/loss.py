@@ -158,5 +158,8 @@ class CRFContext:
 
     def __del__(self):
         if hasattr(self, '_gpus'):
-            core.release_env(self._gpus)
+            try:
+                core.release_env(self._gpus)
+            except Exception:      # interpreter shutdown: module globals may already be gone
+                pass
             del self._gpus
