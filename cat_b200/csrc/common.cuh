@@ -153,6 +153,24 @@ __device__ __forceinline__ void grid_barrier(unsigned *counter, unsigned target)
     __syncthreads();
 }
 
+// The same barrier in two halves: work placed between them (by any thread of the CTA) overlaps the barrier latency.
+// Only writes made BEFORE the arrive are guaranteed visible to the other CTAs after their wait; writes made in between
+// are ordered by the NEXT barrier's release (use them for data nobody reads in the next frame).
+__device__ __forceinline__ void grid_barrier_arrive(unsigned *counter) {
+    __syncthreads();
+    if (threadIdx.x == 0) red_release_add_u32(counter, 1u);
+}
+__device__ __forceinline__ void grid_barrier_wait(unsigned *counter, unsigned target) {
+    if (threadIdx.x == 0) {
+        unsigned v;
+        do {
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+        } while (v < target);
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    }
+    __syncthreads();
+}
+
 // log-semiring add in fp32 (numerator only), same formula as den_calculate.cu:28-35 / ctc_helper.h.  The operands
 // are kept relative to a per-frame offset (|values| stay small), so the hardware ex2/lg2 approximations
 // (abs. error ~1e-7 here) are as accurate as the libm versions were on the reference's un-normalised values.

@@ -750,9 +750,16 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const DenParams P) 
         }
         tl_mark(P, P.Tmax - tau, chunk, n_chunks, 1, lane);
         __syncthreads();
-        for (int i = tid; i < Npad; i += NT) {
-            const float vb = s_sum[i], vab = s_sum[Npad + i];
+        for (int i = tid; i < Npad; i += NT) {   // the next frame's scale: must be out before this CTA arrives
+            const float vb = s_sum[i];
             if (vb != 0.f) { atomicAdd(P.colsum_b + (size_t)tau * Npad + i, vb); s_sum[i] = 0.f; }
+        }
+        // Everything the next frame reads is written: arrive now, and flush what only the end of the kernel needs
+        // (occupancy sums, the label accumulator) in the shadow of the barrier latency.
+        const bool split_barrier = !(P.debug & 2) && !(P.debug & 8);
+        if (split_barrier) grid_barrier_arrive(P.barrier);
+        for (int i = tid; i < Npad; i += NT) {
+            const float vab = s_sum[Npad + i];
             if (vab != 0.f) { atomicAdd(P.absum + (size_t)tau * Npad + i, vab); s_sum[Npad + i] = 0.f; }
         }
         if (use_gacc) {
@@ -772,7 +779,9 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const DenParams P) 
             (void)scale_from_sum(__ldcg(P.colsum_b + (size_t)(tau + 1) * Npad + tid), &sh);
             runlog += (double)__ldg(P.fmax + (size_t)tau * Npad + tid) - (double)sh * 0.6931471805599453;
         }
-        if (!(P.debug & 2)) grid_barrier(P.barrier, (++epoch) * gridDim.x); else __syncthreads();
+        if (split_barrier) grid_barrier_wait(P.barrier, (++epoch) * gridDim.x);
+        else if (!(P.debug & 2)) grid_barrier(P.barrier, (++epoch) * gridDim.x);
+        else __syncthreads();
         tl_mark(P, P.Tmax - tau, chunk, n_chunks, 2, lane);
     }
 
