@@ -404,6 +404,7 @@ def main():
                     "api": "ctc_crf.CTC_CRF_LOSS.forward on pinned-host logits copied H2D inside the step, loss.item() back"},
             "gpu_launches": int(launches),
             "host_enqueue_ms_per_step": 1e3 * host_s[0] / max(host_s[1], 1),
+            "host_note": "host time inside the call; in the resident loop it is mostly the 4-slot pinned staging ring throttling the host to 4 steps ahead of the GPU (0.2 ms of real work per call, tools/host_probe.py)",
             "clocks": clocks,
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,

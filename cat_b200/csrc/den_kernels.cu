@@ -11,7 +11,7 @@
 //     power-of-two scale (exact), so the arc loop has no transcendental at all; the emission
 //     exp(y - max_k y) is applied once per (state, frame) thanks to the loader's single-in-label states.
 //   * one cooperative launch per pass; frames are separated by a hand-rolled grid barrier
-//     (red.release / ld.acquire), not by kernel launches.
+//     (red.release arrive, relaxed polling, one acquire fence), not by kernel launches.
 //   * gradient without arc atomics: gamma_t[k] = sum_{q: lab(q)=k} alpha_t(q) beta_t(q) / sum_q alpha_t(q) beta_t(q),
 //     accumulated per CTA in shared memory (states are sorted by label) and flushed with a few REDs.
 #include <cstdio>
@@ -40,12 +40,12 @@ constexpr unsigned kFull = 0xffffffffu;
 template <int U> struct Vec;
 template <> struct Vec<1> {
     float v[1];
-    __device__ __forceinline__ static Vec ldcg(const float *p) { Vec r; r.v[0] = CCB_GATHER_LOAD(p); return r; }
+    __device__ __forceinline__ static Vec ld_row(const float *p) { Vec r; r.v[0] = CCB_GATHER_LOAD(p); return r; }
     __device__ __forceinline__ void stcg(float *p) const { __stcg(p, v[0]); }
 };
 template <> struct Vec<2> {
     float v[2];
-    __device__ __forceinline__ static Vec ldcg(const float *p) {
+    __device__ __forceinline__ static Vec ld_row(const float *p) {
         float2 t = CCB_GATHER_LOAD(reinterpret_cast<const float2 *>(p));
         Vec r; r.v[0] = t.x; r.v[1] = t.y; return r;
     }
@@ -53,7 +53,7 @@ template <> struct Vec<2> {
 };
 template <> struct Vec<4> {
     float v[4];
-    __device__ __forceinline__ static Vec ldcg(const float *p) {
+    __device__ __forceinline__ static Vec ld_row(const float *p) {
         float4 t = CCB_GATHER_LOAD(reinterpret_cast<const float4 *>(p));
         Vec r; r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w; return r;
     }
@@ -99,7 +99,7 @@ __device__ __forceinline__ uint4 load_quad_weights(const uint4 *quad) {
 // instructions, so the multiplication by the row pitch is done once, when the tile is staged / in the fallback loader).
 template <int U>
 __device__ __forceinline__ Vec<U> gather_row(const char *lane_base, uint32_t byte_off) {
-    return Vec<U>::ldcg(reinterpret_cast<const float *>(lane_base + byte_off));
+    return Vec<U>::ld_row(reinterpret_cast<const float *>(lane_base + byte_off));
 }
 // The gathers of one quad.  (Skipping the zero-weight padding slots -- ~17 % of the forward stream -- was tried with a
 // per-quad count in the last offset: the extra branches cost 10 % of the forward pass and the saved gathers returned
@@ -200,7 +200,7 @@ __global__ void logit_grad_kernel(const void *z, int bf16, long sn, long st, int
 // ------------------------------------------------------------------------------------------------
 // The arc walk shared by both passes: a software-pipelined stream over the warp's chunk of arcs.
 //   * arcs come a quad at a time: one LDS.128 of four peers for the gathers, one LDS.128 of four weights for the FMAs;
-//   * BATCH row gathers (ld.global.cg, 32*U*4 bytes each, one per arc) are issued for batch k+1 BEFORE batch k
+//   * BATCH row gathers (CCB_GATHER_LOAD, 32*U*4 bytes each, one per arc) are issued for batch k+1 BEFORE batch k
 //     is consumed, so a warp keeps BATCH..2*BATCH loads in flight (the recursion is latency-bound on L2);
 //   * weights are applied as |w|; the sign bit of a quad's 4th weight marks the end of a segment and the sign bits
 //     of its 3rd/2nd weights the event code (den_graph.h kEv*): `seg_end(acc, event)` runs (warp-uniform branch).
@@ -538,12 +538,17 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const DenParams P) {
             const float v = s_sum[i];
             if (v != 0.f) { atomicAdd(P.colsum_a + (size_t)t * Npad + i, v); s_sum[i] = 0.f; }
         }
+        // arrive first, then the log-scale books of CTA 0 (two L2 round trips nobody waits for) in the barrier's shadow
+        const bool split_barrier = !(P.debug & 2) && !(P.debug & 8);
+        if (split_barrier) grid_barrier_arrive(P.barrier);
         if (cta == 0 && tid < P.N && t <= my_len) {
             int sh;
             (void)scale_from_sum(__ldcg(P.colsum_a + (size_t)(t - 1) * Npad + tid), &sh);
             runlog += (double)__ldg(P.fmax + (size_t)(t - 1) * Npad + tid) - (double)sh * 0.6931471805599453;
         }
-        if (!(P.debug & 2)) grid_barrier(P.barrier, (++epoch) * gridDim.x); else __syncthreads();
+        if (split_barrier) grid_barrier_wait(P.barrier, (++epoch) * gridDim.x);
+        else if (!(P.debug & 2)) grid_barrier(P.barrier, (++epoch) * gridDim.x);
+        else __syncthreads();
         tl_mark(P, t, chunk, n_chunks, 2, lane);
     }
 

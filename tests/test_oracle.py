@@ -129,3 +129,41 @@ def test_oracle_from_logits_matches_autograd_chain(fixture_fst):
     loss2, dz2, _ = oracle.ctc_crf_from_logits(g, z + rng.standard_normal((N, T, 1)).astype(np.float32), labels, lx, ly, 0.05)
     assert abs(loss - loss2) < 1e-5
     np.testing.assert_allclose(dz, dz2, atol=1e-5)
+
+
+def test_den_oracle_equals_brute_force_path_sum(fixture_fst):
+    """The denominator restatement against first principles on the reference's own den_lm.fst: logZ = log of the sum over
+    EVERY start->final path of exp(sum of arc weights + emissions + final weight) (den_calculate.cu:75-161 computes the
+    same sum by dynamic programming), enumerated path by path; the occupancies likewise."""
+    g = fst.read_fst(fixture_fst)
+    src, dst, lab, lw = g.log_arcs()
+    ew = g.end_weight()
+    out = [[] for _ in range(g.num_states)]
+    for a in range(g.num_arcs):
+        out[src[a]].append(a)
+    rng = np.random.default_rng(9)
+    T, V = 8, 5
+    x = rng.standard_normal((1, T, V))
+    y = (x - np.log(np.exp(x).sum(-1, keepdims=True))).astype(np.float32)
+    total = 0.0
+    occ = np.zeros((T, V))
+    n_paths = 0
+
+    def walk(q, t, score, labs):
+        nonlocal total, n_paths
+        if t == T:
+            if np.isfinite(ew[q]):
+                p = float(np.exp(np.float64(score) + np.float64(ew[q])))
+                total += p
+                n_paths += 1
+                for tt, k in enumerate(labs):
+                    occ[tt, k] += p
+            return
+        for a in out[q]:
+            walk(dst[a], t + 1, score + float(lw[a]) + float(y[0, t, lab[a]]), labs + [int(lab[a])])
+
+    walk(g.start, 0, 0.0, [])
+    assert n_paths > 20
+    la, lb, gamma = oracle.den(g, y, [T])
+    assert abs(la[0] - np.log(total)) < 1e-9 and abs(lb[0] - np.log(total)) < 1e-9
+    np.testing.assert_allclose(gamma[0], occ / total, atol=1e-9)
