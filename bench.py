@@ -266,8 +266,14 @@ def main():
     y_host = y.cpu().pin_memory()
     y_dev = torch.empty_like(y)
 
+    h2d_ev = []
+
     def step_e2e():
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record()
         y_dev.copy_(y_host, non_blocking=True)
+        eb.record()
+        h2d_ev.append((ea, eb))
         loss = crit(y_dev.requires_grad_(False), labels, lx, ly)
         if world > 1:
             v = torch.stack([loss.reshape(()) * N, torch.tensor(float(N), device=dev)])
@@ -277,6 +283,7 @@ def main():
     e2e_steps = max(3, min(args.steps, 10))
     ms_e2e = timed(step_e2e, e2e_steps, 2) / e2e_steps
     e2e_value = world * frames_per_step / (ms_e2e * 1e-3)
+    h2d_ms = sorted(a.elapsed_time(b) for a, b in h2d_ev[-e2e_steps:])   # the logits copy alone, per timed step
     meta_bytes = 4 * (labels.numel() + 3 * N + 1)
     h2d = y_host.numel() * y_host.element_size() + meta_bytes
 
@@ -401,6 +408,7 @@ def main():
                        "lamb": args.lamb,
                        "l2": "no explicit flush: each step streams a 15.4 GB alpha spill (>> 126 MB L2)" if N * T >= 20000 else "small dev workload"},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
+                    "h2d_ms_median": h2d_ms[len(h2d_ms) // 2], "h2d_ms_max": h2d_ms[-1],
                     "api": "ctc_crf.CTC_CRF_LOSS.forward on pinned-host logits copied H2D inside the step, loss.item() back"},
             "gpu_launches": int(launches),
             "host_enqueue_ms_per_step": 1e3 * host_s[0] / max(host_s[1], 1),
