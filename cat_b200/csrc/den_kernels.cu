@@ -269,10 +269,12 @@ __device__ __forceinline__ void walk_arcs(const uint4 *arcs, int n_batches, uint
 // its second row -- so the arcs shared by the two members of a pair are gathered once and feed two accumulators.
 // Shared-memory quads are three 16-byte words {byte offsets}{w0}{w1}; the global fallback reads the plan's AoS arcs
 // plus the separate w1 array.  `group_end(acc0, acc1, pair, new_label0, new_label1)` runs at the last quad of a group.
-template <int U, int BATCH, bool SMEM_ARCS, typename Prologue, typename GroupEnd>
+// W1_SMEM = false with SMEM_ARCS = true is the middle tier for graphs whose 12-byte backward slots do not fit shared
+// memory: byte offsets and first weights stay in shared memory (8 bytes per slot), the second weights stream from L2.
+template <int U, int BATCH, bool SMEM_ARCS, bool W1_SMEM, typename Prologue, typename GroupEnd>
 __device__ __forceinline__ void walk_arcs_dual(const uint4 *arcs, const float4 *w1g, int n_batches, uint32_t row_bytes,
                                                const char *lane_base, bool do_load, Prologue &&prologue, GroupEnd &&group_end) {
-    constexpr int kWordsPerQuad = SMEM_ARCS ? 3 : 2;
+    constexpr int kWordsPerQuad = (SMEM_ARCS && W1_SMEM) ? 3 : 2;
     Vec<U> vA[BATCH], vB[BATCH];
 #pragma unroll
     for (int i = 0; i < BATCH; ++i) { vA[i] = vec_zero<U>(); vB[i] = vec_zero<U>(); }
@@ -295,7 +297,7 @@ __device__ __forceinline__ void walk_arcs_dual(const uint4 *arcs, const float4 *
         for (int g4 = 0; g4 < BATCH / kQuad; ++g4) {
             const uint4 wq = SMEM_ARCS ? p[kWordsPerQuad * g4 + 1] : load_quad_weights<false>(p + 2 * g4);
             float4 w1;
-            if (SMEM_ARCS) { const uint4 t = p[kWordsPerQuad * g4 + 2]; w1 = make_float4(__uint_as_float(t.x), __uint_as_float(t.y), __uint_as_float(t.z), __uint_as_float(t.w)); }
+            if (SMEM_ARCS && W1_SMEM) { const uint4 t = p[kWordsPerQuad * g4 + 2]; w1 = make_float4(__uint_as_float(t.x), __uint_as_float(t.y), __uint_as_float(t.z), __uint_as_float(t.w)); }
             else w1 = __ldg(pw1 + g4);
             const float a0 = fabsf(__uint_as_float(wq.x)), a1 = fabsf(__uint_as_float(wq.y));
             const float a2 = fabsf(__uint_as_float(wq.z)), a3 = fabsf(__uint_as_float(wq.w));
@@ -577,7 +579,7 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const DenParams P) {
 // ------------------------------------------------------------------------------------------------
 // backward: beta recursion, occupancies, logZ from beta
 // ------------------------------------------------------------------------------------------------
-template <int NT, int U, int BATCH, bool SMEM_ARCS>
+template <int NT, int U, int BATCH, bool SMEM_ARCS, bool W1_SMEM = SMEM_ARCS>
 __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const DenParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int Npad = P.Npad, S = P.S;
@@ -604,7 +606,8 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const DenParams P) 
     for (int q = se - 1; q >= sb; --q) { if (__ldg(P.state_pos + q)) labp1 = __ldg(P.state_label + q); else labp0 = __ldg(P.state_label + q); }
     const int n_batches = (ae - ab) / BATCH;
     // shared memory: 3 words of 16 bytes per quad {byte offsets}{w0}{w1}; global fallback: AoS arcs + w1 array
-    const uint4 *const arc4 = SMEM_ARCS ? reinterpret_cast<const uint4 *>(s_arcs) + 3 * ((ab - tile_a0) / kQuad)
+    constexpr int kW = W1_SMEM ? 3 : 2;   // 16-byte words per staged quad
+    const uint4 *const arc4 = SMEM_ARCS ? reinterpret_cast<const uint4 *>(s_arcs) + kW * ((ab - tile_a0) / kQuad)
                                         : reinterpret_cast<const uint4 *>(P.arcs + ab);
     const float4 *const w1g = reinterpret_cast<const float4 *>(P.w1 + ab);
     const bool use_gacc = P.gacc_rows > 0;
@@ -617,15 +620,15 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const DenParams P) 
         s_final[i] = __ldg(P.final_lin + tile_s0 + i);
     }
     const uint32_t row_bytes = (uint32_t)Npad * 4u;
-    if (SMEM_ARCS) {   // stage the tile once, quad-wise transposed: {byte offset 0..3}{w0 0..3}{w1 0..3}
+    if (SMEM_ARCS) {   // stage the tile once, quad-wise transposed: {byte offset 0..3}{w0 0..3}[{w1 0..3}]
         uint4 *sq = reinterpret_cast<uint4 *>(s_arcs);
         const uint4 *src = reinterpret_cast<const uint4 *>(P.arcs + tile_a0);
         const uint4 *src1 = reinterpret_cast<const uint4 *>(P.w1 + tile_a0);
         for (int i = tid; i < (tile_a1 - tile_a0) / kQuad; i += NT) {
-            const uint4 m0 = __ldg(src + 2 * i), m1 = __ldg(src + 2 * i + 1), w1 = __ldg(src1 + i);
-            sq[3 * i] = make_uint4(m0.x * row_bytes, m0.z * row_bytes, m1.x * row_bytes, m1.z * row_bytes);
-            sq[3 * i + 1] = make_uint4(m0.y, m0.w, m1.y, m1.w);
-            sq[3 * i + 2] = w1;
+            const uint4 m0 = __ldg(src + 2 * i), m1 = __ldg(src + 2 * i + 1);
+            sq[kW * i] = make_uint4(m0.x * row_bytes, m0.z * row_bytes, m1.x * row_bytes, m1.z * row_bytes);
+            sq[kW * i + 1] = make_uint4(m0.y, m0.w, m1.y, m1.w);
+            if (W1_SMEM) sq[kW * i + 2] = __ldg(src1 + i);
         }
     }
     for (int i = tid; i < (2 + P.gacc_rows) * Npad; i += NT) s_sum[i] = 0.f;
@@ -728,7 +731,7 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const DenParams P) 
                 ++out_row;
                 ++ql;
             };
-            walk_arcs_dual<U, BATCH, SMEM_ARCS>(arc4, w1g, n_batches, row_bytes, reinterpret_cast<const char *>(bh_next + n0),
+            walk_arcs_dual<U, BATCH, SMEM_ARCS, W1_SMEM>(arc4, w1g, n_batches, row_bytes, reinterpret_cast<const char *>(bh_next + n0),
                                                 lane_gat, frame_scalars,
                                                 [&](float *acc0, float *acc1, bool pair, bool new0, bool new1) {
                 if (P.debug & 1) { sum_b[0] += acc0[0] + acc1[0]; acc0[0] = 0.f; acc1[0] = 0.f; return; }
@@ -834,8 +837,9 @@ __global__ void den_grad_normalize_kernel(float *grad, long gsn, long gst, const
 // launch plumbing
 // ------------------------------------------------------------------------------------------------
 template <int NT, int U, int BATCH, bool SMEM_ARCS>
-int LaunchOne(bool backward, const DenParams &p, int n_ctas, size_t smem, cudaStream_t stream, std::string *err) {
-    const void *fn = backward ? (const void *)den_backward_kernel<NT, U, BATCH, SMEM_ARCS>
+int LaunchOne(bool backward, bool w1_smem, const DenParams &p, int n_ctas, size_t smem, cudaStream_t stream, std::string *err) {
+    const void *fn = backward ? (SMEM_ARCS && !w1_smem ? (const void *)den_backward_kernel<NT, U, BATCH, SMEM_ARCS, false>
+                                                       : (const void *)den_backward_kernel<NT, U, BATCH, SMEM_ARCS>)
                      : p.n_hubs > 0 ? (const void *)den_forward_kernel<NT, U, BATCH, SMEM_ARCS, true>
                                     : (const void *)den_forward_kernel<NT, U, BATCH, SMEM_ARCS, false>;
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -860,10 +864,16 @@ template <int NT>
 int Dispatch(bool backward, const DeviceGraph &g, const DenParams &p, size_t fixed_smem, cudaStream_t stream,
              std::string *err) {
     const DevicePass &pass = backward ? g.bwd : g.fwd;
-    const size_t arc_bytes = (size_t)pass.max_tile_arcs * (backward ? 12 : sizeof(Arc));
+    // three tiers by graph size: the whole arc stream in shared memory (8 bytes per forward slot, 12 per backward slot);
+    // backward only: offsets + first weights in shared memory, second weights streamed from L2; everything from L2
     const size_t budget = (size_t)g.max_smem_optin > 2048 ? (size_t)g.max_smem_optin - 1024 : 0;
-    const char *force_global = getenv("CCB_ARCS_IN_GLOBAL");   // test hook: exercise the large-graph fallback
-    const bool smem_arcs = fixed_smem + arc_bytes <= budget && !(force_global && force_global[0] == '1');
+    const char *force_global = getenv("CCB_ARCS_IN_GLOBAL");   // test hooks: exercise the large-graph tiers
+    const char *force_w1 = getenv("CCB_W1_IN_GLOBAL");
+    const bool no_smem = force_global && force_global[0] == '1';
+    bool w1_smem = backward && !(force_w1 && force_w1[0] == '1');
+    size_t arc_bytes = (size_t)pass.max_tile_arcs * (backward && w1_smem ? 12 : sizeof(Arc));
+    if (backward && w1_smem && fixed_smem + arc_bytes > budget) { w1_smem = false; arc_bytes = (size_t)pass.max_tile_arcs * sizeof(Arc); }
+    const bool smem_arcs = fixed_smem + arc_bytes <= budget && !no_smem;
     const size_t smem = fixed_smem + (smem_arcs ? arc_bytes : 0);
     // utterances per lane: the widest row segment the batch allows, except that the backward pass (two accumulators per
     // utterance) runs out of registers at 4 -- it walks 64-utterance groups instead.  CCB_U_FWD / CCB_U_BWD: tuning override.
@@ -882,8 +892,8 @@ int Dispatch(bool backward, const DeviceGraph &g, const DenParams &p, size_t fix
         if (e && (atoi(e) == 8 || atoi(e) == 16)) want = atoi(e);
     }
 #define CCB_LAUNCH(UU, BB)                                                                               \
-    return smem_arcs ? LaunchOne<NT, UU, BB, true>(backward, p, g.n_ctas, smem, stream, err)            \
-                     : LaunchOne<NT, UU, BB, false>(backward, p, g.n_ctas, smem, stream, err)
+    return smem_arcs ? LaunchOne<NT, UU, BB, true>(backward, w1_smem, p, g.n_ctas, smem, stream, err)   \
+                     : LaunchOne<NT, UU, BB, false>(backward, w1_smem, p, g.n_ctas, smem, stream, err)
 #define CCB_GO(UU)                                                                                      \
     {                                                                                                   \
         if (NT == 512 && UU != 4 && want == 16) { CCB_LAUNCH(UU, 16); }                                 \

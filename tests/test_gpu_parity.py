@@ -113,7 +113,7 @@ def test_ctc_vs_oracle(N, T, V, lens, ly):
     assert np.abs(grads.transpose(0, 1).cpu().numpy() - gc).max() < GRAD_ATOL
 
 
-@pytest.mark.parametrize("env", ["CCB_ARCS_IN_GLOBAL", "CCB_NO_PAIRS", "HUBS", "HUBS+CCB_ARCS_IN_GLOBAL"])
+@pytest.mark.parametrize("env", ["CCB_ARCS_IN_GLOBAL", "CCB_W1_IN_GLOBAL", "CCB_NO_PAIRS", "HUBS", "HUBS+CCB_ARCS_IN_GLOBAL"])
 def test_fallback_paths(tmp_graphs, monkeypatch, env):
     """Arc tiles streamed from global memory (graphs too large for shared memory), the un-paired plan and rows split
     into parts give the same answers as the default path."""
