@@ -275,16 +275,26 @@ template <int U, int BATCH, bool SMEM_ARCS, bool W1_SMEM, typename Prologue, typ
 __device__ __forceinline__ void walk_arcs_dual(const uint4 *arcs, const float4 *w1g, int n_batches, uint32_t row_bytes,
                                                const char *lane_base, bool do_load, Prologue &&prologue, GroupEnd &&group_end) {
     constexpr int kWordsPerQuad = (SMEM_ARCS && W1_SMEM) ? 3 : 2;
+    // middle tier, one utterance per lane (the registers allow it): the second weights of a batch are fetched from L2
+    // together with its gathers instead of at consume time
+    constexpr bool kPrefW1 = SMEM_ARCS && !W1_SMEM && U == 1;
+    constexpr int kQ = BATCH / kQuad;
     Vec<U> vA[BATCH], vB[BATCH];
+    float4 wA[kPrefW1 ? kQ : 1], wB[kPrefW1 ? kQ : 1];
 #pragma unroll
     for (int i = 0; i < BATCH; ++i) { vA[i] = vec_zero<U>(); vB[i] = vec_zero<U>(); }
+#pragma unroll
+    for (int i = 0; i < (kPrefW1 ? kQ : 1); ++i) { wA[i] = make_float4(0.f, 0.f, 0.f, 0.f); wB[i] = wA[i]; }
     float acc0[U], acc1[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) { acc0[u] = 0.f; acc1[u] = 0.f; }
 
-    auto issue = [&](const uint4 *p, Vec<U> *v) {
+    auto issue = [&](const uint4 *p, const float4 *pw1, Vec<U> *v, float4 *wpre) {
         if (do_load) {
-            // (the global-memory fallback keeps all four gathers: its second weights live in another array)
+            if (kPrefW1) {
+#pragma unroll
+                for (int g4 = 0; g4 < kQ; ++g4) wpre[g4] = __ldg(pw1 + g4);
+            }
             uint4 pr[BATCH / kQuad];
 #pragma unroll
             for (int g4 = 0; g4 < BATCH / kQuad; ++g4) pr[g4] = SMEM_ARCS ? p[kWordsPerQuad * g4] : load_quad_peers<false>(p + 2 * g4, row_bytes);
@@ -292,12 +302,13 @@ __device__ __forceinline__ void walk_arcs_dual(const uint4 *arcs, const float4 *
             for (int g4 = 0; g4 < BATCH / kQuad; ++g4) gather_quad<U>(lane_base, pr[g4], v + g4 * kQuad);
         }
     };
-    auto consume = [&](const uint4 *p, const float4 *pw1, const Vec<U> *v) {
+    auto consume = [&](const uint4 *p, const float4 *pw1, const Vec<U> *v, const float4 *wpre) {
 #pragma unroll
         for (int g4 = 0; g4 < BATCH / kQuad; ++g4) {
             const uint4 wq = SMEM_ARCS ? p[kWordsPerQuad * g4 + 1] : load_quad_weights<false>(p + 2 * g4);
             float4 w1;
-            if (SMEM_ARCS && W1_SMEM) { const uint4 t = p[kWordsPerQuad * g4 + 2]; w1 = make_float4(__uint_as_float(t.x), __uint_as_float(t.y), __uint_as_float(t.z), __uint_as_float(t.w)); }
+            if (kPrefW1) w1 = wpre[g4];
+            else if (SMEM_ARCS && W1_SMEM) { const uint4 t = p[kWordsPerQuad * g4 + 2]; w1 = make_float4(__uint_as_float(t.x), __uint_as_float(t.y), __uint_as_float(t.z), __uint_as_float(t.w)); }
             else w1 = __ldg(pw1 + g4);
             const float a0 = fabsf(__uint_as_float(wq.x)), a1 = fabsf(__uint_as_float(wq.y));
             const float a2 = fabsf(__uint_as_float(wq.z)), a3 = fabsf(__uint_as_float(wq.w));
@@ -319,19 +330,19 @@ __device__ __forceinline__ void walk_arcs_dual(const uint4 *arcs, const float4 *
 
     constexpr int kStep = kWordsPerQuad * (BATCH / kQuad);   // 16-byte words per batch
     const uint4 *pi = arcs, *pc = arcs;
-    const float4 *pw = w1g;
+    const float4 *pw = w1g, *pwi = w1g;
     int nb = n_batches;
     if (nb <= 0) { prologue(); return; }
-    issue(pi, vA); pi += kStep;
-    if (nb > 1) { issue(pi, vB); pi += kStep; }
+    issue(pi, pwi, vA, wA); pi += kStep; pwi += kQ;
+    if (nb > 1) { issue(pi, pwi, vB, wB); pi += kStep; pwi += kQ; }
     prologue();
     while (true) {
-        consume(pc, pw, vA); pc += kStep; pw += BATCH / kQuad;
+        consume(pc, pw, vA, wA); pc += kStep; pw += kQ;
         if (--nb == 0) break;
-        if (nb > 1) { issue(pi, vA); pi += kStep; }
-        consume(pc, pw, vB); pc += kStep; pw += BATCH / kQuad;
+        if (nb > 1) { issue(pi, pwi, vA, wA); pi += kStep; pwi += kQ; }
+        consume(pc, pw, vB, wB); pc += kStep; pw += kQ;
         if (--nb == 0) break;
-        if (nb > 1) { issue(pi, vB); pi += kStep; }
+        if (nb > 1) { issue(pi, pwi, vB, wB); pi += kStep; pwi += kQ; }
     }
 }
 
