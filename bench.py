@@ -153,14 +153,15 @@ def cpu_port(graph, N, T, V, lamb, threads, seed=1234):
 def run_reference(args, rank):
     """--impl reference: the reference path on the host cores.  The reference ships no CPU implementation
     (src/ctc_crf/setup.py:15-16), so this is the oracle port (kind "port"), all host threads, each step a
-    bounded sample (N=cores, T=64) of the same workload: same den graph, V, label density, lamb."""
+    bounded sample (N=cores, T<=64) of the same workload: same den graph, V, label density, lamb."""
     if rank != 0:
         return
     from oracle import oracle
     oracle.build()
     _, g = den_graph_file(args.H, args.d, args.V)
     cores = os.cpu_count() or 1
-    sN, sT = max(1, min(args.N, cores)), 64
+    sN = max(1, min(args.N, cores))
+    sT = max(16, min(64, 640 // max(args.steps, 1)))   # bounded sample: the whole run stays within ~2 minutes for any --steps
     cores = min(cores, sN)            # the port parallelises over utterances: threads actually used
     for _ in range(min(args.warmup, 1)):
         cpu_port(g, sN, sT, args.V, args.lamb, cores)
