@@ -175,13 +175,28 @@ MAX_UTTS_PER_CALL = 512          # bookkeeping CTA of the den kernels handles on
 _WS_FRACTION = 0.85              # of the currently free device memory a call may use for scratch
 
 
-def _plan_slices(L, lx, ly, N, V, dev):
-    """Split the batch into contiguous slices whose scratch (alpha spill etc.) fits the free device memory.
-    Each slice walks only max(lx[slice]) frames."""
-    # what a torch allocation can get: free device memory plus what the caching allocator holds but is not using
+_budget_cache = {}    # device index -> [calls until the next refresh, budget in bytes]
+
+
+def _scratch_budget(dev, need: int = 0) -> int:
+    """What a torch allocation can get now: free device memory plus what the caching allocator holds but is not using.
+    cudaMemGetInfo costs ~0.6 ms, so the answer is reused for a few calls unless the request does not fit it."""
+    key = torch.device(dev).index
+    ent = _budget_cache.get(key)
+    if ent is not None and ent[0] > 0 and need <= ent[1]:
+        ent[0] -= 1
+        return ent[1]
     free, _ = torch.cuda.mem_get_info(dev)
     free += max(0, torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev))
     budget = int(free * _WS_FRACTION)
+    _budget_cache[key] = [16, budget]
+    return budget
+
+
+def _plan_slices(L, lx, ly, N, V, dev):
+    """Split the batch into contiguous slices whose scratch (alpha spill etc.) fits the free device memory.
+    Each slice walks only max(lx[slice]) frames."""
+    budget = _scratch_budget(dev)
     slices, n0 = [], 0
     while n0 < N:
         n1 = min(N, n0 + MAX_UTTS_PER_CALL)
@@ -190,6 +205,8 @@ def _plan_slices(L, lx, ly, N, V, dev):
             maxl = int(ly[n0:n1].max())
             need = (int(L.ccb_den_alpha_floats(n1 - n0, tmax)) * 4 + int(L.ccb_den_aux_bytes(n1 - n0, tmax))
                     + int(L.ccb_ctc_workspace_bytes(n1 - n0, tmax, maxl)))
+            if need > budget:
+                budget = _scratch_budget(dev, need)     # a stale (cached) figure must not split a batch needlessly
             if need <= budget or n1 - n0 == 1:
                 break
             n1 = n0 + max(1, (n1 - n0) // 2)
@@ -231,25 +248,35 @@ def ctc_crf_loss_fwd(logits: torch.Tensor, labels: torch.Tensor, lx: torch.Tenso
         p_ly, p_lx = p_off + 4 * (N + 1), p_off + 4 * (2 * N + 1)
         grad = torch.empty((N, T, V), dtype=torch.float32, device=dev)
         parts = torch.empty(2 * N, dtype=torch.float32, device=dev) if want_parts else None
-        slices = _plan_slices(L, lx, ly, N, V, dev)
-        losses = torch.empty(len(slices), dtype=torch.float32, device=dev)
         stream = _stream(dev)
-        for i, (n0, n1, tmax, maxl) in enumerate(slices):
-            n = n1 - n0
-            alpha_ws = torch.empty(int(L.ccb_den_alpha_floats(n, tmax)), dtype=torch.float32, device=dev)
-            aux_ws = torch.empty(int(L.ccb_den_aux_bytes(n, tmax)), dtype=torch.uint8, device=dev)
-            ctc_ws = torch.empty(int(L.ccb_ctc_workspace_bytes(n, tmax, maxl)), dtype=torch.uint8, device=dev)
-            sub_parts = torch.empty(2 * n, dtype=torch.float32, device=dev) if want_parts else None
-            rc = entry(logits.data_ptr() + n0 * T * V * esz, _DTYPES[logits.dtype], n, T, V, tmax,
-                       p_labels, p_off + 4 * n0, p_ly + 4 * n0, p_lx + 4 * n0, maxl, float(lamb),
-                       float(scale), alpha_ws.data_ptr(), aux_ws.data_ptr(), ctc_ws.data_ptr(),
-                       grad.data_ptr() + n0 * T * V * 4, losses.data_ptr() + 4 * i,
-                       sub_parts.data_ptr() if want_parts else None, stream)
-            _check(rc, "ctc_crf_loss_fwd")
-            if want_parts:
-                parts[n0:n1] = sub_parts[:n]
-                parts[N + n0:N + n1] = sub_parts[n:]
-            del alpha_ws, aux_ws, ctc_ws      # stream-ordered reuse by the caching allocator for the next slice
+
+        def run_slices():
+            slices = _plan_slices(L, lx, ly, N, V, dev)
+            losses = torch.empty(len(slices), dtype=torch.float32, device=dev)
+            for i, (n0, n1, tmax, maxl) in enumerate(slices):
+                n = n1 - n0
+                alpha_ws = torch.empty(int(L.ccb_den_alpha_floats(n, tmax)), dtype=torch.float32, device=dev)
+                aux_ws = torch.empty(int(L.ccb_den_aux_bytes(n, tmax)), dtype=torch.uint8, device=dev)
+                ctc_ws = torch.empty(int(L.ccb_ctc_workspace_bytes(n, tmax, maxl)), dtype=torch.uint8, device=dev)
+                sub_parts = torch.empty(2 * n, dtype=torch.float32, device=dev) if want_parts else None
+                rc = entry(logits.data_ptr() + n0 * T * V * esz, _DTYPES[logits.dtype], n, T, V, tmax,
+                           p_labels, p_off + 4 * n0, p_ly + 4 * n0, p_lx + 4 * n0, maxl, float(lamb),
+                           float(scale), alpha_ws.data_ptr(), aux_ws.data_ptr(), ctc_ws.data_ptr(),
+                           grad.data_ptr() + n0 * T * V * 4, losses.data_ptr() + 4 * i,
+                           sub_parts.data_ptr() if want_parts else None, stream)
+                _check(rc, "ctc_crf_loss_fwd")
+                if want_parts:
+                    parts[n0:n1] = sub_parts[:n]
+                    parts[N + n0:N + n1] = sub_parts[n:]
+                del alpha_ws, aux_ws, ctc_ws      # stream-ordered reuse by the caching allocator for the next slice
+            return slices, losses
+
+        try:
+            slices, losses = run_slices()
+        except torch.cuda.OutOfMemoryError:       # the cached memory figure was stale: measure again, slice finer, redo
+            _budget_cache.pop(torch.device(dev).index, None)
+            torch.cuda.empty_cache()
+            slices, losses = run_slices()
         loss = losses.sum().reshape(1) if len(slices) > 1 else losses
         meta.record_stream(torch.cuda.current_stream(dev))
     return loss, grad, parts

@@ -291,6 +291,21 @@ def test_sliced_batches_and_padded_frames(tmp_graphs, monkeypatch):
     assert np.abs(grad - ograd).max() < GRAD_ATOL
     for n in range(N):
         assert not grad[n, lens[n]:].any()
+    # memory-bounded slicing: 40 utterances need 64 lanes of scratch; with room for 32 lanes only they go in two halves
+    from cat_b200 import _lib
+    monkeypatch.setattr(_C, "MAX_UTTS_PER_CALL", 512)
+    N2, T2 = 40, 20
+    y2, labels2, lens2, ly2 = oracle.synth_batch(N2, T2, V, seed=32)
+    ref_loss, ref_grad = _run_ours(y2, labels2, lens2, ly2, 0.05)
+    L = _lib.lib()
+    need32 = (int(L.ccb_den_alpha_floats(32, T2)) * 4 + int(L.ccb_den_aux_bytes(32, T2))
+              + int(L.ccb_ctc_workspace_bytes(32, T2, int(ly2.max()))))
+    calls = []
+    monkeypatch.setattr(_C, "_scratch_budget", lambda dev, need=0: (calls.append(need), need32 + 4096)[1])
+    loss, grad = _run_ours(y2, labels2, lens2, ly2, 0.05)
+    assert calls, "the budget hook was not consulted"
+    _close_loss(loss, ref_loss, 1e-6)
+    assert np.abs(grad - ref_grad).max() < 1e-6
     del ctx
 
 
