@@ -79,3 +79,29 @@ def test_no_cpu_fallback():
         ctc_crf.CTC_CRF_LOSS()(torch.zeros(1, 2, 3).log_softmax(-1), lab, torch.tensor([2], dtype=torch.int32), lab)
     src = open(os.path.join(ROOT, "cat_b200", "loss.py")).read() + open(os.path.join(ROOT, "cat_b200", "_C.py")).read()
     assert "oracle" not in src
+
+
+def test_scratch_budget_is_cached_and_refreshed(monkeypatch):
+    """Host logic of the batch slicer: the device-memory query is reused for a few calls, refreshed when a request does
+    not fit the cached figure, and counts what the caching allocator holds but is not using."""
+    import torch
+    from cat_b200 import _C
+    calls = []
+    state = {"free": 100 << 20, "reserved": 30 << 20, "allocated": 10 << 20}
+    monkeypatch.setattr(torch.cuda, "mem_get_info", lambda dev=None: (calls.append(1), (state["free"], 1 << 40))[1])
+    monkeypatch.setattr(torch.cuda, "memory_reserved", lambda dev=None: state["reserved"])
+    monkeypatch.setattr(torch.cuda, "memory_allocated", lambda dev=None: state["allocated"])
+    _C._budget_cache.clear()
+    dev = torch.device("cuda", 0)
+    b0 = _C._scratch_budget(dev)
+    assert b0 == int((120 << 20) * _C._WS_FRACTION) and len(calls) == 1
+    for _ in range(5):
+        assert _C._scratch_budget(dev) == b0
+    assert len(calls) == 1                                   # served from the cache
+    state["free"] = 500 << 20
+    assert _C._scratch_budget(dev, need=b0 + 1) > b0         # a request that does not fit forces a fresh query
+    assert len(calls) == 2
+    for _ in range(40):
+        _C._scratch_budget(dev)
+    assert len(calls) >= 4                                   # and it expires on its own after a few calls
+    _C._budget_cache.clear()
