@@ -59,3 +59,5 @@ json.dump(traffic, open("profiles/traffic.json", "w"), indent=1)
 os.makedirs("profiles", exist_ok=True)
 open(f"profiles/{tag}_summary.md", "w").write("\n".join(out) + "\n")
 print("wrote", f"profiles/{tag}_summary.md")
+import shutil
+shutil.copyfile(launches, f"profiles/{tag}_launches.csv")   # the launch list the summary table was made from
