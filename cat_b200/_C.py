@@ -171,7 +171,10 @@ def upload_meta(labels: torch.Tensor, lx: torch.Tensor, ly: torch.Tensor, device
     return meta, sum_l, int(ly.max()) if N else 0
 
 
-MAX_UTTS_PER_CALL = 512          # bookkeeping CTA of the den kernels handles one utterance per thread
+MAX_UTTS_PER_CALL = 64           # utterances per native call: the den kernels are fastest per utterance at two utterances
+                                 # per lane (N=64: 35 us per frame; N=128 in one call: 79 us), and a slice of a
+                                 # length-sorted batch walks only its own longest utterance (N=256, len~U{200..3000}:
+                                 # 7.8 k frame steps in four slices instead of 12 k in one).  Hard limit of the kernels: 512.
 _WS_FRACTION = 0.85              # of the currently free device memory a call may use for scratch
 
 
@@ -231,14 +234,8 @@ def ctc_crf_loss_fwd(logits: torch.Tensor, labels: torch.Tensor, lx: torch.Tenso
     assert logits.is_cuda and logits.dim() == 3 and logits.is_contiguous()
     if logits.dtype not in _DTYPES:
         raise RuntimeError(f"unsupported logits dtype {logits.dtype}")
-    N, T, V = logits.shape
+    N, T, V = _check_batch_args(logits, labels, lx, ly)
     dev = logits.device
-    if int(lx.numel()) != N or int(ly.numel()) != N:
-        raise RuntimeError("lx / ly must have one entry per utterance")
-    if N and (int(lx.max()) > T or int(lx.min()) < 0):
-        raise RuntimeError("input lengths must lie in [0, T]")
-    if labels.numel() and (int(labels.min()) < 0 or int(labels.max()) >= V):
-        raise RuntimeError("label out of range")
     esz = logits.element_size()
     scale = 1.0 / N if size_average else 1.0
     with torch.cuda.device(dev):
@@ -280,6 +277,74 @@ def ctc_crf_loss_fwd(logits: torch.Tensor, labels: torch.Tensor, lx: torch.Tenso
         loss = losses.sum().reshape(1) if len(slices) > 1 else losses
         meta.record_stream(torch.cuda.current_stream(dev))
     return loss, grad, parts
+
+
+def _check_batch_args(logits, labels, lx, ly):
+    assert logits.is_cuda and logits.dim() == 3 and logits.is_contiguous()
+    if logits.dtype not in _DTYPES:
+        raise RuntimeError(f"unsupported logits dtype {logits.dtype}")
+    N, T, V = logits.shape
+    if N == 0:
+        raise RuntimeError("empty batch")
+    if int(lx.numel()) != N or int(ly.numel()) != N:
+        raise RuntimeError("lx / ly must have one entry per utterance")
+    if int(lx.max()) > T or int(lx.min()) < 0:
+        raise RuntimeError("input lengths must lie in [0, T]")
+    if int(ly.min()) < 0:
+        raise RuntimeError("label lengths must be non-negative")
+    if labels.numel() and (int(labels.min()) < 0 or int(labels.max()) >= V):
+        raise RuntimeError("label out of range")
+    return N, T, V
+
+
+def ctc_loss_fwd(logits: torch.Tensor, labels: torch.Tensor, lx: torch.Tensor, ly: torch.Tensor,
+                 size_average: bool, blank: int = 0) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """CTC-only loss on the (N,T,V) log-probs in place (the native counterpart of ``_WARP_CTC_GPU``,
+    ctc_crf/__init__.py:25-56): no (T,N,V) transpose copy, no zero fill, no host round trip for the costs.
+    Returns (loss[1], grad (N,T,V) fp32 = d loss / d logits, logp[N]) on the device; never synchronises the host."""
+    L = _lib.lib()
+    N, T, V = _check_batch_args(logits, labels, lx, ly)
+    dev = logits.device
+    scale = 1.0 / N if size_average else 1.0
+    with torch.cuda.device(dev):
+        meta, sum_l, maxl = upload_meta(labels, lx, ly, dev)
+        base = meta.data_ptr()
+        p_labels, p_off = base, base + 4 * sum_l
+        p_ly, p_lx = p_off + 4 * (N + 1), p_off + 4 * (2 * N + 1)
+        tmax = max(1, int(lx.max()))
+        grad = torch.empty((N, T, V), dtype=torch.float32, device=dev)
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        logp = torch.empty(N, dtype=torch.float32, device=dev)
+        ws = torch.empty(int(L.ccb_ctc_workspace_bytes(N, tmax, maxl)), dtype=torch.uint8, device=dev)
+        rc = L.ccb_ctc_loss_fwd(logits.data_ptr(), _DTYPES[logits.dtype], N, T, V, tmax, p_labels, p_off, p_ly, p_lx, maxl,
+                                int(blank), float(scale), ws.data_ptr(), grad.data_ptr(), loss.data_ptr(), logp.data_ptr(),
+                                _stream(dev))
+        _check(rc, "ctc_loss_fwd")
+        meta.record_stream(torch.cuda.current_stream(dev))
+    return loss, grad, logp
+
+
+def ctc_align(logits: torch.Tensor, labels: torch.Tensor, lx: torch.Tensor, ly: torch.Tensor, blank: int = 0
+              ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Best-path (Viterbi) forced alignment over the numerator lattice.  logits (N,T,V) fp32/bf16 CUDA
+    log-probs; labels/lx/ly int32 CPU as for the loss.  Returns (align (N,T) int32 CUDA: the token of every frame
+    t < lx[n], blank included, -1 beyond; score (N,) fp32 CUDA: log-probability of that path, -inf if infeasible)."""
+    L = _lib.lib()
+    N, T, V = _check_batch_args(logits, labels, lx, ly)
+    dev = logits.device
+    with torch.cuda.device(dev):
+        meta, sum_l, maxl = upload_meta(labels, lx, ly, dev)
+        base = meta.data_ptr()
+        p_labels, p_off = base, base + 4 * sum_l
+        p_ly, p_lx = p_off + 4 * (N + 1), p_off + 4 * (2 * N + 1)
+        align = torch.empty((N, T), dtype=torch.int32, device=dev)
+        score = torch.empty(N, dtype=torch.float32, device=dev)
+        ws = torch.empty(int(L.ccb_ctc_align_workspace_bytes(N, T, maxl)), dtype=torch.uint8, device=dev)
+        rc = L.ccb_ctc_align(logits.data_ptr(), _DTYPES[logits.dtype], T * V, V, N, T, V, p_labels, p_off, p_ly, p_lx, maxl,
+                             int(blank), ws.data_ptr(), align.data_ptr(), score.data_ptr(), _stream(dev))
+        _check(rc, "ctc_align")
+        meta.record_stream(torch.cuda.current_stream(dev))
+    return align, score
 
 
 def launch_count() -> int:

@@ -4,4 +4,4 @@
 implementation: ``csrc/`` (sm_100a CUDA kernels + C ABI), ``_C`` (mirror of binding.cpp), ``loss``
 (mirror of ctc_crf/__init__.py), ``fst`` (den-graph files), ``dist`` (minibatch sharding over GPUs).
 """
-from .loss import CRFContext, CTC_CRF_LOSS, WARP_CTC_LOSS, __version__  # noqa: F401
+from .loss import CRFContext, CTC_CRF_LOSS, WARP_CTC_LOSS, ctc_align, __version__  # noqa: F401

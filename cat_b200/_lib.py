@@ -22,7 +22,7 @@ SYMBOLS = [
     "Init", "Release", "compute_alpha", "compute_beta_and_grad", "compute_ctc_loss", "get_workspace_size",
     "ctcGetStatusString", "ccb_last_error", "ccb_den_loaded", "ccb_den_info", "ccb_den_alpha_floats", "ccb_den_aux_bytes",
     "ccb_ctc_workspace_bytes", "ccb_den_forward_backward", "ccb_ctc_forward_backward", "ccb_ctc_crf_loss_fwd",
-    "ccb_ctc_crf_loss_logits_fwd",
+    "ccb_ctc_crf_loss_logits_fwd", "ccb_ctc_loss_fwd", "ccb_ctc_align_workspace_bytes", "ccb_ctc_align",
     "ccb_launch_count", "ccb_debug_timeline", "ccb_plan_create", "ccb_plan_destroy", "ccb_plan_info", "ccb_plan_copy",
 ]
 GLOBALS = ["DEN_NUM_ARCS", "DEN_NUM_STATES"]
@@ -66,6 +66,14 @@ def lib() -> C.CDLL:
     L.ccb_ctc_crf_loss_fwd.restype = C.c_int
     L.ccb_ctc_crf_loss_logits_fwd.argtypes = L.ccb_ctc_crf_loss_fwd.argtypes
     L.ccb_ctc_crf_loss_logits_fwd.restype = C.c_int
+    L.ccb_ctc_loss_fwd.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, C.c_int, C.c_int,
+                                   C.c_float, vp, vp, vp, vp, vp]
+    L.ccb_ctc_loss_fwd.restype = C.c_int
+    L.ccb_ctc_align_workspace_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
+    L.ccb_ctc_align_workspace_bytes.restype = C.c_size_t
+    L.ccb_ctc_align.argtypes = [vp, C.c_int, C.c_long, C.c_long, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, C.c_int, C.c_int,
+                                vp, vp, vp, vp]
+    L.ccb_ctc_align.restype = C.c_int
     L.ccb_launch_count.argtypes = []; L.ccb_launch_count.restype = C.c_long
     L.ccb_debug_timeline.argtypes = [vp, C.c_int, C.c_int]; L.ccb_debug_timeline.restype = None
     L.ccb_plan_create.argtypes = [C.c_char_p, C.c_int, C.c_int]; L.ccb_plan_create.restype = vp

@@ -87,11 +87,7 @@ int CurrentGraph(DeviceGraph **out) {
     return 0;
 }
 
-int DenWarps() {
-    const char *e = getenv("CCB_DEN_WARPS");
-    int w = e ? atoi(e) : 16;
-    return (w == 32) ? 32 : 16;
-}
+int DenWarps() { return 16; }   // warps per CTA of the persistent den kernels (512 threads, one CTA per SM)
 
 int InitImpl(const char *fst_name, int n_gpus, const int *gpus) {
     std::lock_guard<std::mutex> lk(g_mu);
@@ -122,12 +118,17 @@ int InitImpl(const char *fst_name, int n_gpus, const int *gpus) {
         if (p2.multiProcessorCount != prop.multiProcessorCount) { rc = Fail("Init: heterogeneous GPUs are not supported"); break; }
         d.device = gpus[i];
         d.S = g_plan.num_states; d.P = g_plan.num_pairs; d.start = g_plan.start; d.num_labels = g_plan.num_labels;
+        d.scale_exp = g_plan.scale_exp;
         d.n_ctas = g_plan.n_ctas; d.n_warps = g_plan.n_warps;
         d.max_smem_optin = (int)p2.sharedMemPerBlockOptin;
         rc = Upload(&d.state_label, g_plan.state_label) || Upload(&d.state_pos, g_plan.state_pos) ||
              Upload(&d.final_lin, g_plan.final_lin) || Upload(&d.start_arcs, g_plan.start_arcs) ||
              Upload(&d.hub_states, g_plan.hub_states) ||
              UploadPass(g_plan.fwd, &d.fwd) || UploadPass(g_plan.bwd, &d.bwd);
+        { const char *e = getenv("CCB_ARCS_IN_GLOBAL"); d.tune_arcs_in_global = e && e[0] == '1'; }
+        { const char *e = getenv("CCB_W1_IN_GLOBAL"); d.tune_w1_in_global = e && e[0] == '1'; }
+        if (d.tune_arcs_in_global || d.tune_w1_in_global)
+            fprintf(stderr, "ctc_crf_b200: CCB_ARCS_IN_GLOBAL / CCB_W1_IN_GLOBAL set -- den arc tiles forced out of shared memory (test hook, slow)\n");
         d.n_start_arcs = (int)g_plan.start_arcs.size();
         d.n_hubs = (int)g_plan.hub_states.size();
         d.start_final = g_plan.final_lin[(size_t)g_plan.start];
@@ -163,6 +164,7 @@ DenParams BaseParams(const DeviceGraph &g, const void *y, int dtype, long sn, lo
     p.start_arcs = g.start_arcs; p.n_start_arcs = g.n_start_arcs;
     p.hub_states = g.hub_states; p.n_hubs = g.n_hubs;
     p.S = g.S; p.num_pairs = g.P; p.start = g.start; p.n_warps = g.n_warps;
+    p.scale_exp = g.scale_exp;
     p.start_final = g.start_final;
     p.y = y; p.y_bf16 = (dtype == CCB_DTYPE_BF16); p.sn = sn; p.st = st;
     p.N = N; p.Npad = L.Npad; p.Tmax = T; p.V = V; p.len = len;
@@ -175,7 +177,9 @@ DenParams BaseParams(const DeviceGraph &g, const void *y, int dtype, long sn, lo
     p.b0 = reinterpret_cast<float *>(a + L.b0);
     p.fmax = reinterpret_cast<float *>(a + L.fmax);
     p.timeline = g_timeline; p.tl_step0 = g_tl_step0; p.tl_steps = g_tl_steps;
+#ifdef CCB_TUNING   // timing-experiment switches (skip row ends / barriers: WRONG RESULTS) exist in tuning builds only
     { const char *e = getenv("CCB_DEBUG"); p.debug = e ? atoi(e) : 0; }
+#endif
     return p;
 }
 
@@ -184,7 +188,7 @@ int CheckDen(const DeviceGraph &g, int dtype, int N, int T, int V) {
     if (dtype != CCB_DTYPE_F32 && dtype != CCB_DTYPE_BF16) return Fail("den: unsupported logits dtype");
     if (V < g.num_labels)
         return Fail("den graph uses label " + std::to_string(g.num_labels - 1) + " but logits have only " + std::to_string(V) + " classes");
-    if ((size_t)(g.S + g.P) * (size_t)PadLanes(N) * 4 >= ((size_t)1 << 32)) return Fail("den: states x batch too large for 32-bit row offsets; split the batch");
+    if ((size_t)(2 * (size_t)g.S + g.P) * (size_t)PadLanes(N) * 4 >= ((size_t)1 << 32)) return Fail("den: states x batch too large for 32-bit row offsets; split the batch");
     if (PadLanes(N) > g.n_warps * 32) return Fail("den: batch larger than " + std::to_string(g.n_warps * 32) + " utterances per call; split the batch");
     return 0;
 }
@@ -280,7 +284,9 @@ void Release(int n_gpus, int *gpus) { ReleaseImpl(n_gpus, gpus); }
 
 size_t ccb_den_alpha_floats(int N, int T) {
     if (!g_plan_valid) return 0;
-    return (size_t)(T + 1) * (size_t)(g_plan.num_states + g_plan.num_pairs) * (size_t)PadLanes(N);
+    // T+1 frames of S real rows; the virtual pair-sum rows of a frame are parked two frames ahead (den_kernels.cu), so two
+    // more frames at the end when the plan has pairs
+    return (size_t)(T + 1 + (g_plan.num_pairs > 0 ? 2 : 0)) * (size_t)g_plan.num_states * (size_t)PadLanes(N);
 }
 
 size_t ccb_den_aux_bytes(int N, int T) {
@@ -367,6 +373,47 @@ int ccb_ctc_forward_backward(const void *logits, int dtype, long sn, long st, in
     int rc = LaunchCtc(logits, dtype == CCB_DTYPE_BF16, sn, st, N, T, V, labels_dev, label_off_dev, label_len_dev,
                        len_dev, max_label_len, blank, reinterpret_cast<float *>(workspace), grad, gsn, gst, grad_scale,
                        logp, nullptr, (cudaStream_t)stream, &err);
+    if (rc) return Fail(err);
+    return 0;
+}
+
+/* CTC-only loss (WARP_CTC_LOSS, ctc_crf/__init__.py:25-56) on the (N,T,V) block in place: one numerator pass, the gradient
+ * rows all written by the occupancy kernel (no zero fill), the scalar assembled on the device (no host round trip). */
+int ccb_ctc_loss_fwd(const void *logits, int dtype, int N, int T, int V, int Tmax,
+                     const int *labels_dev, const int *label_off_dev, const int *label_len_dev, const int *len_dev,
+                     int max_label_len, int blank, float scale, void *ctc_ws, float *grad, float *loss, float *logp,
+                     void *stream) {
+    g_err.clear();
+    if (N <= 0 || T <= 0 || V <= 0 || !logits || !ctc_ws || !grad || !loss || !logp) return Fail("ctc_loss_fwd: bad arguments");
+    if (Tmax <= 0 || Tmax > T) return Fail("ctc_loss_fwd: Tmax must lie in [1, T]");
+    if (dtype != CCB_DTYPE_F32 && dtype != CCB_DTYPE_BF16) return Fail("ctc_loss_fwd: unsupported logits dtype");
+    if (blank < 0 || blank >= V) return Fail("ctc: blank label out of range");
+    cudaStream_t s = (cudaStream_t)stream;
+    const long sn = (long)T * V, st = V;
+    std::string err;
+    int rc = LaunchCtc(logits, dtype == CCB_DTYPE_BF16, sn, st, N, Tmax, V, labels_dev, label_off_dev, label_len_dev, len_dev,
+                       max_label_len, blank, reinterpret_cast<float *>(ctc_ws), grad, sn, st, -scale, logp, nullptr, s, &err,
+                       /*overwrite=*/1, /*Tfull=*/T);
+    if (rc) return Fail(err);
+    rc = LaunchSumScale(logp, N, -scale, loss, s);
+    if (rc) return FailCuda("sum_scale", (cudaError_t)rc);
+    return 0;
+}
+
+size_t ccb_ctc_align_workspace_bytes(int N, int T, int max_label_len) {
+    return (size_t)N * (size_t)T * (2 * (size_t)max_label_len + 1) + 256;
+}
+
+int ccb_ctc_align(const void *logits, int dtype, long sn, long st, int N, int T, int V,
+                  const int *labels_dev, const int *label_off_dev, const int *label_len_dev, const int *len_dev,
+                  int max_label_len, int blank, void *workspace, int *align, float *score, void *stream) {
+    g_err.clear();
+    if (N <= 0 || T <= 0 || V <= 0 || !logits || !workspace || !align) return Fail("ctc_align: bad arguments");
+    if (dtype != CCB_DTYPE_F32 && dtype != CCB_DTYPE_BF16) return Fail("ctc_align: unsupported logits dtype");
+    if (blank < 0 || blank >= V) return Fail("ctc: blank label out of range");
+    std::string err;
+    int rc = LaunchCtcViterbi(logits, dtype == CCB_DTYPE_BF16, sn, st, N, T, V, labels_dev, label_off_dev, label_len_dev, len_dev,
+                              max_label_len, blank, reinterpret_cast<unsigned char *>(workspace), align, score, (cudaStream_t)stream, &err);
     if (rc) return Fail(err);
     return 0;
 }

@@ -29,7 +29,8 @@ struct DevicePass {
 struct DeviceGraph {
     bool loaded = false;
     int device = -1;
-    int S = 0, P = 0, start = 0, num_labels = 0;   // S states, P pairs (virtual rows S..S+P-1 of the alpha frames)
+    int S = 0, P = 0, start = 0, num_labels = 0;   // S states, P pairs (gather-table rows S..S+P-1 = virtual pair-sum rows)
+    int scale_exp = 56;
     int n_ctas = 0, n_warps = 0;
     int *state_label = nullptr;
     int *state_pos = nullptr;
@@ -41,6 +42,8 @@ struct DeviceGraph {
     int n_hubs = 0;
     float start_final = 0.f;
     int max_smem_optin = 0;
+    // test hooks, read ONCE at Init (never on the per-call path): force the large-graph tiers on a small graph
+    bool tune_arcs_in_global = false, tune_w1_in_global = false;
 };
 
 // Kernel parameter block shared by the two persistent den kernels.
@@ -60,6 +63,7 @@ struct DenParams {
     const int *hub_states;
     int n_hubs;
     int S, num_pairs, start, n_warps;
+    int scale_exp;        // column sums are renormalised to ~2^scale_exp (DenPlan::scale_exp)
     float start_final;
     // problem
     const void *y;        // (N,T,V) log-probs, fp32 or bf16
@@ -68,7 +72,7 @@ struct DenParams {
     int N, Npad, Tmax, V;
     const int *len;       // [N] device
     // workspaces
-    float *alpha;         // [(Tmax+1)][S+P][Npad] scaled-linear alpha spill (+ pair-sum rows)
+    float *alpha;         // [(Tmax+3)][S][Npad] scaled-linear alpha spill; the pair-sum rows of frame t are parked in frame t+2
     float *bh;            // [2][S][Npad]          backward ping-pong (emission-weighted beta)
     float *colsum_a;      // [(Tmax+2)][Npad]
     float *colsum_b;      // [(Tmax+2)][Npad]
@@ -118,7 +122,11 @@ int LaunchDenGradNormalize(float *grad, long gsn, long gst, const float *absum, 
 int LaunchCtc(const void *y, int y_bf16, long sn, long st, int N, int T, int V, const int *labels,
               const int *label_off, const int *label_len, const int *len, int max_label_len, int blank,
               float *alpha_ws, float *grad, long gsn, long gst, float grad_scale, float *logp,
-              const double *lnorm, cudaStream_t stream, std::string *err);
+              const double *lnorm, cudaStream_t stream, std::string *err, int overwrite = 0, int Tfull = 0);
+int LaunchSumScale(const float *logp, int N, float scale, float *loss, cudaStream_t stream);
+int LaunchCtcViterbi(const void *y, int y_bf16, long sn, long st, int N, int T, int V, const int *labels,
+                     const int *label_off, const int *label_len, const int *len, int max_label_len, int blank,
+                     unsigned char *bp_ws, int *align, float *score, cudaStream_t stream, std::string *err);
 int LaunchAssembleLoss(const float *logz, const float *logp, int N, float lamb, float scale, float *loss,
                        cudaStream_t stream);
 void CountLaunch(int n = 1);

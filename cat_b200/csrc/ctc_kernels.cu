@@ -257,17 +257,22 @@ __global__ void ctc_alpha_beta_kernel(const void *y, int y_bf16, long sn, long s
 __global__ void ctc_gamma_kernel(const void *y, int y_bf16, long sn, long st, int N, int T, int V,
                                  const int *labels, const int *label_off, const int *label_len, const int *len,
                                  int max_label_len, int blank, float *alpha_ws,
-                                 float *grad, long gsn, long gst, float grad_scale) {
+                                 float *grad, long gsn, long gst, float grad_scale, int overwrite, int Tfull) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const long row = (long)blockIdx.x * wpb + warp;
-    if (row >= (long)N * T) return;
-    const int n = (int)(row / T), t = (int)(row % T);
-    if (t >= len[n]) return;
+    // overwrite mode (CTC-only loss): every row of the (N, Tfull, V) gradient is WRITTEN, zeros included, so the caller
+    // needs no zero-fill pass; accumulate mode adds into a buffer that already holds the denominator part.
+    const int Trows = overwrite ? Tfull : T;
+    if (row >= (long)N * Trows) return;
+    const int n = (int)(row / Trows), t = (int)(row % Trows);
     const int L = label_len[n], Sc = 2 * L + 1, ScMax = 2 * max_label_len + 1;
     CtcWorkspace W(alpha_ws, n, T, ScMax);
     const double logp_d = *W.logp;
-    if (!(logp_d > -INFINITY)) return;       // infeasible utterance: no gradient
+    if (t >= len[n] || !(logp_d > -INFINITY)) {      // padding frame / infeasible utterance: no gradient
+        if (overwrite) { float *gz = grad + n * gsn + (long)t * gst; for (int k = lane; k < V; k += 32) gz[k] = 0.f; }
+        return;
+    }
     float *g = reinterpret_cast<float *>(smem_raw) + (size_t)warp * V;
     for (int k = lane; k < V; k += 32) g[k] = 0.f;
     __syncwarp();
@@ -291,7 +296,91 @@ __global__ void ctc_gamma_kernel(const void *y, int y_bf16, long sn, long st, in
     float *grow = grad + n * gsn + (long)t * gst;
     for (int k = lane; k < V; k += 32) {
         const float gv = g[k];
-        if (gv != 0.f) atomicAdd(grow + k, grad_scale * gv);
+        if (overwrite) grow[k] = grad_scale * gv;
+        else if (gv != 0.f) atomicAdd(grow + k, grad_scale * gv);
+    }
+}
+
+// loss[0] = scale * sum_n logp[n]   (CTC-only loss, ctc_crf/__init__.py:41-47: costs = -sum log p, / batch when averaging)
+__global__ void sum_scale_kernel(const float *logp, int N, float scale, float *loss) {
+    double acc = 0.0;
+    for (int n = threadIdx.x; n < N; n += 32) acc += (double)logp[n];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(kFull, acc, o);
+    if (threadIdx.x == 0) loss[0] = (float)(acc * (double)scale);
+}
+
+// Best-path (Viterbi) alignment over the same blank-expanded lattice: the forced alignment that is a by-product of the
+// numerator.  One CTA per utterance; thread i owns cells 2i and 2i+1 as in the alpha pass; max replaces
+// log-add; a 2-bit back-pointer per cell and frame (0: stay, 1: from s-1, 2: from s-2) goes to the workspace, and thread 0
+// walks it back.  align[n][t] = the token emitted at frame t (blank included), -1 for t >= len or an infeasible utterance.
+// Ties are broken towards the smaller predecessor index (stay < s-1 < s-2).
+// shared memory: lab[Lmax] ints | v[2][ScMax] floats
+__global__ void ctc_viterbi_kernel(const void *y, int y_bf16, long sn, long st, int T, int V,
+                                   const int *labels, const int *label_off, const int *label_len, const int *len,
+                                   int max_label_len, int blank, unsigned char *bp_ws, int *align, float *score) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = blockIdx.x, tid = threadIdx.x, NT = blockDim.x;
+    const int L = label_len[n], Tn = len[n];
+    const int Sc = 2 * L + 1, L1 = L + 1, ScMax = 2 * max_label_len + 1;
+    int *s_lab = reinterpret_cast<int *>(smem_raw);
+    float *s_v = reinterpret_cast<float *>(s_lab + max_label_len + 1);
+    unsigned char *bp = bp_ws + (size_t)n * T * ScMax;
+    const int *lab = labels + label_off[n];
+    int *arow = align + (size_t)n * T;
+    for (int t = tid; t < T; t += NT) arow[t] = -1;
+    int rep = 0;
+    for (int i = tid + 1; i < L; i += NT) rep += (lab[i] == lab[i - 1]);
+    __shared__ int s_rep;
+    if (tid == 0) s_rep = 0;
+    __syncthreads();
+    if (rep) atomicAdd(&s_rep, rep);
+    __syncthreads();
+    if (Tn <= 0 || L + s_rep > Tn) { if (tid == 0 && score) score[n] = -INFINITY; return; }
+    for (int i = tid; i < L; i += NT) s_lab[i] = lab[i];
+    __syncthreads();
+    const long ybase = n * sn;
+    for (int s = tid; s < Sc; s += NT) {
+        float v = -INFINITY;
+        if (s == 0) v = load_y(y, y_bf16, ybase + blank);
+        else if (s == 1) v = load_y(y, y_bf16, ybase + s_lab[0]);
+        s_v[s] = v;
+        bp[s] = 0;
+    }
+    for (int t = 1; t < Tn; ++t) {
+        __syncthreads();
+        const float *prev = s_v + ((t - 1) & 1) * ScMax;
+        float *cur = s_v + (t & 1) * ScMax;
+        unsigned char *b = bp + (size_t)t * ScMax;
+        const long yrow = ybase + (long)t * st;
+        for (int i = tid; i < L1; i += NT) {
+            const int sb = 2 * i;
+            float vb = prev[sb];
+            unsigned char kb = 0;
+            if (i > 0 && prev[sb - 1] > vb) { vb = prev[sb - 1]; kb = 1; }
+            cur[sb] = vb + load_y(y, y_bf16, yrow + blank);
+            b[sb] = kb;
+            if (i < L) {
+                const int sl = sb + 1, li = s_lab[i];
+                float vl = prev[sl];
+                unsigned char kl = 0;
+                if (prev[sb] > vl) { vl = prev[sb]; kl = 1; }
+                if (i > 0 && li != s_lab[i - 1] && prev[sl - 2] > vl) { vl = prev[sl - 2]; kl = 2; }
+                cur[sl] = vl + load_y(y, y_bf16, yrow + li);
+                b[sl] = kl;
+            }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const float *last = s_v + ((Tn - 1) & 1) * ScMax;
+        int s = Sc - 1;
+        if (Sc > 1 && last[Sc - 2] > last[Sc - 1]) s = Sc - 2;
+        if (score) score[n] = last[s];
+        for (int t = Tn - 1; t >= 0; --t) {
+            arow[t] = (s & 1) ? s_lab[s >> 1] : blank;
+            s -= bp[(size_t)t * ScMax + s];
+        }
     }
 }
 
@@ -309,7 +398,7 @@ __global__ void assemble_loss_kernel(const float *logz, const float *logp, int N
 int LaunchCtc(const void *y, int y_bf16, long sn, long st, int N, int T, int V, const int *labels,
               const int *label_off, const int *label_len, const int *len, int max_label_len, int blank,
               float *alpha_ws, float *grad, long gsn, long gst, float grad_scale, float *logp,
-              const double *lnorm, cudaStream_t stream, std::string *err) {
+              const double *lnorm, cudaStream_t stream, std::string *err, int overwrite, int Tfull) {
     if (N == 0) return 0;
     const int ScMax = 2 * max_label_len + 1;
     int threads = ((max_label_len + 1 + 31) / 32) * 32;
@@ -327,13 +416,39 @@ int LaunchCtc(const void *y, int y_bf16, long sn, long st, int N, int T, int V, 
         const size_t gsm = (size_t)wpb * V * 4;
         e = cudaFuncSetAttribute(ctc_gamma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm);
         if (e != cudaSuccess) { *err = std::string("cudaFuncSetAttribute(ctc gamma): ") + cudaGetErrorString(e); return (int)e; }
-        const long rows = (long)N * T;
+        const long rows = (long)N * (overwrite ? Tfull : T);
         ctc_gamma_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, gsm, stream>>>(
-            y, y_bf16, sn, st, N, T, V, labels, label_off, label_len, len, max_label_len, blank, alpha_ws, grad, gsn, gst, grad_scale);
+            y, y_bf16, sn, st, N, T, V, labels, label_off, label_len, len, max_label_len, blank, alpha_ws, grad, gsn, gst, grad_scale,
+            overwrite, Tfull);
         CountLaunch();
     }
     e = cudaGetLastError();
     if (e != cudaSuccess) { *err = std::string("ctc launch: ") + cudaGetErrorString(e); return (int)e; }
+    return 0;
+}
+
+int LaunchSumScale(const float *logp, int N, float scale, float *loss, cudaStream_t stream) {
+    sum_scale_kernel<<<1, 32, 0, stream>>>(logp, N, scale, loss);
+    CountLaunch();
+    return (int)cudaGetLastError();
+}
+
+int LaunchCtcViterbi(const void *y, int y_bf16, long sn, long st, int N, int T, int V, const int *labels,
+                     const int *label_off, const int *label_len, const int *len, int max_label_len, int blank,
+                     unsigned char *bp_ws, int *align, float *score, cudaStream_t stream, std::string *err) {
+    if (N == 0) return 0;
+    const int ScMax = 2 * max_label_len + 1;
+    int threads = ((max_label_len + 1 + 31) / 32) * 32;
+    threads = threads < 64 ? 64 : (threads > 1024 ? 1024 : threads);
+    const size_t smem = (size_t)(max_label_len + 1) * 4 + (size_t)2 * ScMax * 4;
+    if (smem > 200 * 1024) { *err = "label sequence too long for the alignment kernel's shared memory"; return 1; }
+    cudaError_t e = cudaFuncSetAttribute(ctc_viterbi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { *err = std::string("cudaFuncSetAttribute(ctc viterbi): ") + cudaGetErrorString(e); return (int)e; }
+    ctc_viterbi_kernel<<<N, threads, smem, stream>>>(y, y_bf16, sn, st, T, V, labels, label_off, label_len, len, max_label_len,
+                                                     blank, bp_ws, align, score);
+    CountLaunch();
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { *err = std::string("ctc viterbi launch: ") + cudaGetErrorString(e); return (int)e; }
     return 0;
 }
 

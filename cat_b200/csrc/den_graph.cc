@@ -476,6 +476,19 @@ bool BuildDenPlan(const HostFst &fst, int n_ctas, int n_warps, DenPlan *plan, st
         }
     };
 
+    // largest total weight leaving a state (final weight included): the per-frame growth bound of a column sum
+    {
+        std::vector<double> out_sum((size_t)S0, 0.0);
+        for (size_t a = 0; a < A0; ++a) out_sum[(size_t)fst.src[a]] += std::exp((double)fst.logw[a]);
+        double G = 1.0;
+        for (int q = 0; q < S0; ++q) {
+            const float fw = fst.final_logw[(size_t)q];
+            G = std::max(G, out_sum[(size_t)q] + (std::isinf(fw) ? 0.0 : std::exp((double)fw)));
+        }
+        const int e = (int)std::floor(61.0 - std::log2(G));
+        if (e < 16) { *err = "den graph: a state's out-weights sum to " + std::to_string(G) + " -- not a probability-like graph"; return false; }
+        plan->scale_exp = std::min(56, e);
+    }
     plan->file_states = S0;
     plan->file_arcs = (int)A0;
     plan->num_states = (int)S;

@@ -66,6 +66,8 @@ struct DenPlan {
     int start = 0;                      // renumbered start state
     int num_labels = 0;                 // max label + 1
     int n_ctas = 0, n_warps = 0;
+    int scale_exp = 56;                 // the kernels renormalise every column sum to ~2^scale_exp: 56, lowered when a state's
+                                        // out-weight sum G is large so that alpha * beta <= 2^(2E+2) G^2 stays below 2^127
     std::vector<int> state_label;       // [S] the single label carried by every arc INTO the state
     std::vector<int> state_pos;         // [S] 0 = first member of a pair, 1 = second member or unpaired
     std::vector<float> final_lin;       // [S] exp(final_logw) (0 for non-final)

@@ -23,7 +23,12 @@ namespace ccb {
 
 namespace {
 
-constexpr int kScaleExp = 32;        // per-frame column sums are renormalised to ~2^32
+// Per-frame column sums are renormalised to ~2^E with E = DenParams::scale_exp (56 unless the graph's out-weight sums are
+// large, den_graph.cc): the scale a frame is written with comes from the PREVIOUS column, so a frame whose emissions are all
+// tiny (one-hot rows with -60 floors cost 2^-87) sits that far below 2^E for one frame; values live down to 2^-149, which
+// leaves 2^-(E+149) / drop of dynamic range inside such a column.  E = 32 lost 6e-2 on the occupancies there (measured,
+// tests/test_gpu_atsize.py::test_peaky_logits), E >= 48 is exact to 4e-6; the ceiling is the occupancy product
+// alpha * beta <= 2^(2E+2) * G^2 < 2^127 (G = largest out-weight sum of a state).
 constexpr unsigned kFull = 0xffffffffu;
 
 // Row gathers read data that another SM wrote one frame earlier.  Plain (L1-allocating) loads are coherent here: every
@@ -68,12 +73,12 @@ template <int U> __device__ __forceinline__ Vec<U> vec_zero() {
     return r;
 }
 
-// r = 2^shift with shift = kScaleExp - floor(log2(s)); exact power of two, so rescaling never rounds.
-__device__ __forceinline__ float scale_from_sum(float s, int *shift) {
+// r = 2^shift with shift = E - floor(log2(s)); exact power of two, so rescaling never rounds.
+__device__ __forceinline__ float scale_from_sum(float s, int *shift, int E) {
     if (!(s > 0.f) || s > 3.0e38f) { *shift = 0; return 1.f; }
     int field = (__float_as_int(s) >> 23) & 0xff;
     int ex = (field == 0 ? 1 : field) - 127;
-    int sh = kScaleExp - ex;
+    int sh = E - ex;
     sh = max(-126, min(127, sh));
     *shift = sh;
     return __int_as_float((sh + 127) << 23);
@@ -82,11 +87,15 @@ __device__ __forceinline__ float scale_from_sum(float s, int *shift) {
 // One quad of arcs as two 16-byte words: {peer0..3} and {w0..3}.  In shared memory the tile is staged quad-wise in
 // exactly this (SoA) form, so each word is one LDS.128 whose four lanes are all used; the global-memory fallback
 // (tiles too large for shared memory) reads the plan's AoS arcs.
+// forward gather rows: peers >= S name virtual pair-sum rows, parked at 2S + j of the frame (see den_forward_kernel)
+__device__ __forceinline__ uint32_t fwd_row(uint32_t peer, int S) { return peer < (uint32_t)S ? peer : peer + (uint32_t)S; }
+// virt_from: peers >= virt_from are shifted by virt_from (forward pass: S; backward pass: no virtual rows, 0xffffffff)
 template <bool SMEM_ARCS>
-__device__ __forceinline__ uint4 load_quad_peers(const uint4 *quad, uint32_t row_bytes) {
+__device__ __forceinline__ uint4 load_quad_peers(const uint4 *quad, uint32_t row_bytes, uint32_t virt_from = 0xffffffffu) {
     if (SMEM_ARCS) return quad[0];   // already byte offsets
     const uint4 m0 = __ldg(quad), m1 = __ldg(quad + 1);
-    return make_uint4(m0.x * row_bytes, m0.z * row_bytes, m1.x * row_bytes, m1.z * row_bytes);
+    auto row = [&](uint32_t p) { return (p >= virt_from ? p + virt_from : p) * row_bytes; };
+    return make_uint4(row(m0.x), row(m0.z), row(m1.x), row(m1.z));
 }
 template <bool SMEM_ARCS>
 __device__ __forceinline__ uint4 load_quad_weights(const uint4 *quad) {
@@ -207,7 +216,7 @@ __global__ void logit_grad_kernel(const void *z, int bf16, long sn, long st, int
 // `arcs` points at the chunk's first quad (two 16-byte words per quad), n_batches = chunk arcs / BATCH.
 // ------------------------------------------------------------------------------------------------
 template <int U, int BATCH, bool SMEM_ARCS, typename Prologue, typename SegEnd>
-__device__ __forceinline__ void walk_arcs(const uint4 *arcs, int n_batches, uint32_t row_bytes, const char *lane_base,
+__device__ __forceinline__ void walk_arcs(const uint4 *arcs, int n_batches, uint32_t row_bytes, uint32_t virt_from, const char *lane_base,
                                           bool do_load, Prologue &&prologue, SegEnd &&seg_end) {
     Vec<U> vA[BATCH], vB[BATCH];
 #pragma unroll
@@ -226,7 +235,7 @@ __device__ __forceinline__ void walk_arcs(const uint4 *arcs, int n_batches, uint
             // load and the next one (that exposed the LDS latency once per quad)
             uint4 pr[BATCH / kQuad];
 #pragma unroll
-            for (int g4 = 0; g4 < BATCH / kQuad; ++g4) pr[g4] = load_quad_peers<SMEM_ARCS>(p + 2 * g4, row_bytes);
+            for (int g4 = 0; g4 < BATCH / kQuad; ++g4) pr[g4] = load_quad_peers<SMEM_ARCS>(p + 2 * g4, row_bytes, virt_from);
 #pragma unroll
             for (int g4 = 0; g4 < BATCH / kQuad; ++g4) gather_quad<U>(lane_base, pr[g4], v + g4 * kQuad);
         }
@@ -369,7 +378,7 @@ template <int U>
 __device__ __noinline__ void forward_partial_row(const int *state_label, const int *len, const float *colsum_prev,
                                                  const float *fmax_prev, const void *y, int y_bf16, long sn, long yt_off,
                                                  int N, int t, int n0, Vec<U> part, uint32_t tgt_off, uint32_t row_bytes,
-                                                 float *a_cur, float *s_sum) {
+                                                 float *a_cur, float *s_sum, int scale_exp) {
     const int tgt = (int)(tgt_off / row_bytes);
     const int lab = __ldg(state_label + tgt);
     float *dst = reinterpret_cast<float *>(reinterpret_cast<char *>(a_cur + n0) + tgt_off);
@@ -378,7 +387,7 @@ __device__ __noinline__ void forward_partial_row(const int *state_label, const i
         const int n = n0 + u;
         if (n < N && t <= __ldg(len + n)) {
             int sh;
-            const float r = scale_from_sum(__ldcg(colsum_prev + n), &sh);
+            const float r = scale_from_sum(__ldcg(colsum_prev + n), &sh, scale_exp);
             const float e = expf(load_y(y, y_bf16, n * sn + yt_off + lab) - __ldg(fmax_prev + n));
             const float o = part.v[u] * e * r;
             if (o != 0.f) { atomicAdd(dst + u, o); atomicAdd(&s_sum[n], o); }
@@ -410,7 +419,13 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const DenParams P) {
     const int tile_s1 = __ldg(P.chunk_state + (cta + 1) * P.n_warps);
     const int vj0 = __ldg(P.chunk_pair + chunk);   // first virtual (pair-sum) row written by this warp
     const int S = P.S, Npad = P.Npad;
-    const size_t frame_elems = (size_t)(S + P.num_pairs) * Npad;   // real rows, then one virtual row per pair
+    // Spill layout: frame t holds the S real rows only (what the backward pass reads back from HBM).  The virtual pair-sum
+    // rows of frame t -- read by frame t+1 only -- are parked where the real rows of frame t+2 will be written: gather
+    // peer S + j maps to row 2S + j of the frame, so one base pointer still addresses everything a frame gathers, the parked
+    // rows are overwritten in L2 two frames later and never reach HBM, and the spill is (T+3) * S rows instead of
+    // (T+1) * (S+P)  (N=64, T=1500, 1 M arcs: 15.4 GB instead of 23 GB; forward DRAM writes 10.2 MB instead of 15 MB a frame).
+    const size_t frame_elems = (size_t)S * Npad;
+    const uint32_t virt0 = 2u * (uint32_t)S;                       // first parked virtual row, relative to the frame
     // first label of each row position in this chunk (pair first members / everything else): emission prefetch
     int labp0 = -1, labp1 = -1;
     for (int q = se - 1; q >= sb; --q) { if (__ldg(P.state_pos + q)) labp1 = __ldg(P.state_label + q); else labp0 = __ldg(P.state_label + q); }
@@ -428,7 +443,8 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const DenParams P) {
         const uint4 *src = reinterpret_cast<const uint4 *>(P.arcs + tile_a0);
         for (int i = tid; i < (tile_a1 - tile_a0) / kQuad; i += NT) {
             const uint4 m0 = __ldg(src + 2 * i), m1 = __ldg(src + 2 * i + 1);
-            sq[2 * i] = make_uint4(m0.x * row_bytes, m0.z * row_bytes, m1.x * row_bytes, m1.z * row_bytes);   // byte offsets of the gathered rows
+            sq[2 * i] = make_uint4(fwd_row(m0.x, S) * row_bytes, fwd_row(m0.z, S) * row_bytes,
+                                   fwd_row(m1.x, S) * row_bytes, fwd_row(m1.z, S) * row_bytes);   // byte offsets of the gathered rows
             sq[2 * i + 1] = make_uint4(m0.y, m0.w, m1.y, m1.w);
         }
     }
@@ -442,7 +458,7 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const DenParams P) {
         for (int q = sb; q < se; ++q) {
             if (__ldg(P.state_pos + q) == 0) {   // q, q+1 are a pair
                 const float v = (q == P.start || q + 1 == P.start) ? 1.f : 0.f;
-                for (int n = lane; n < Npad; n += 32) __stcg(P.alpha + (size_t)(S + vj) * Npad + n, v);
+                for (int n = lane; n < Npad; n += 32) __stcg(P.alpha + (size_t)(virt0 + vj) * Npad + n, v);
                 ++vj;
             }
         }
@@ -484,7 +500,7 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const DenParams P) {
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     int sh;
-                    r[u] = scale_from_sum(__ldcg(P.colsum_a + (size_t)(t - 1) * Npad + n0 + u), &sh);
+                    r[u] = scale_from_sum(__ldcg(P.colsum_a + (size_t)(t - 1) * Npad + n0 + u), &sh, P.scale_exp);
                     fm[u] = act[u] ? __ldg(P.fmax + (size_t)(t - 1) * Npad + n0 + u) : 0.f;
                     // emissions of the chunk's first labels: issued now, consumed at the first row ends
                     const long yb = (n0 + u) * P.sn + (long)(t - 1) * P.st;
@@ -494,10 +510,10 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const DenParams P) {
             };
             int ql = sb - tile_s0;                               // row index inside the CTA tile
             uint32_t out_row = (uint32_t)sb;                     // row q of the frame
-            uint32_t virt_row = (uint32_t)(S + vj0);             // the next virtual row
+            uint32_t virt_row = virt0 + (uint32_t)vj0;           // the next virtual row (parked two frames ahead)
             float *const out_base = a_cur + n0;
             Vec<U> cacc = vec_zero<U>();
-            walk_arcs<U, BATCH, SMEM_ARCS>(arc4, n_batches, row_bytes, reinterpret_cast<const char *>(a_prev + n0), lane_act,
+            walk_arcs<U, BATCH, SMEM_ARCS>(arc4, n_batches, row_bytes, (uint32_t)S, reinterpret_cast<const char *>(a_prev + n0), lane_act,
                                            frame_scalars, [&](float *acc, int ev, bool new_label, const uint4 *quad) {
                 const bool k1 = ev != kEvRowPos0;
                 if (P.debug & 1) { sum[0] += acc[0]; acc[0] = 0.f; return; }
@@ -505,9 +521,9 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const DenParams P) {
                     Vec<U> part;
 #pragma unroll
                     for (int u = 0; u < U; ++u) { part.v[u] = acc[u]; acc[u] = 0.f; }
-                    const uint32_t tgt_off = load_quad_peers<SMEM_ARCS>(quad, row_bytes).w;   // byte offset of the target row
+                    const uint32_t tgt_off = load_quad_peers<SMEM_ARCS>(quad, row_bytes, (uint32_t)S).w;   // byte offset of the target row
                     forward_partial_row<U>(P.state_label, P.len, P.colsum_a + (size_t)(t - 1) * Npad, P.fmax + (size_t)(t - 1) * Npad,
-                                           P.y, P.y_bf16, P.sn, (long)(t - 1) * P.st, P.N, t, n0, part, tgt_off, row_bytes, a_cur, s_sum);
+                                           P.y, P.y_bf16, P.sn, (long)(t - 1) * P.st, P.N, t, n0, part, tgt_off, row_bytes, a_cur, s_sum, P.scale_exp);
                     if (tgt_off == out_row * row_bytes) { ++out_row; ++ql; }   // the part that lives in the row's own group
                     return;
                 }
@@ -556,7 +572,7 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const DenParams P) {
         if (split_barrier) grid_barrier_arrive(P.barrier);
         if (cta == 0 && tid < P.N && t <= my_len) {
             int sh;
-            (void)scale_from_sum(__ldcg(P.colsum_a + (size_t)(t - 1) * Npad + tid), &sh);
+            (void)scale_from_sum(__ldcg(P.colsum_a + (size_t)(t - 1) * Npad + tid), &sh, P.scale_exp);
             runlog += (double)__ldg(P.fmax + (size_t)(t - 1) * Npad + tid) - (double)sh * 0.6931471805599453;
         }
         if (split_barrier) grid_barrier_wait(P.barrier, (++epoch) * gridDim.x);
@@ -623,7 +639,7 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const DenParams P) 
     const float4 *const w1g = reinterpret_cast<const float4 *>(P.w1 + ab);
     const bool use_gacc = P.gacc_rows > 0;
     const size_t frame_elems = (size_t)S * Npad;                         // beta ping-pong: real rows only
-    const size_t alpha_frame = (size_t)(S + P.num_pairs) * Npad;          // alpha spill: real + virtual rows
+    const size_t alpha_frame = (size_t)S * Npad;                          // alpha spill: real rows only (see den_forward_kernel)
     unsigned epoch = 0;
 
     for (int i = tid; i < tile_s1 - tile_s0; i += NT) {
@@ -683,7 +699,7 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const DenParams P) 
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     int sh;
-                    rb[u] = gat[u] ? scale_from_sum(__ldcg(P.colsum_b + (size_t)(tau + 1) * Npad + n0 + u), &sh) : 1.f;
+                    rb[u] = gat[u] ? scale_from_sum(__ldcg(P.colsum_b + (size_t)(tau + 1) * Npad + n0 + u), &sh, P.scale_exp) : 1.f;
                     fm[u] = act[u] ? __ldg(P.fmax + (size_t)(tau - 1) * Npad + n0 + u) : 0.f;
                     const long yb = (n0 + u) * P.sn + (long)(tau - 1) * P.st;
                     ypre0[u] = (act[u] && labp0 >= 0) ? load_y(P.y, P.y_bf16, yb + labp0) : 0.f;
@@ -795,7 +811,7 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const DenParams P) 
         // log-scale of beta: LB_tau = LB_{tau+1} + m_tau - log rb_{tau+1}   (applies for tau < len)
         if (cta == 0 && tid < P.N && tau < my_len) {
             int sh;
-            (void)scale_from_sum(__ldcg(P.colsum_b + (size_t)(tau + 1) * Npad + tid), &sh);
+            (void)scale_from_sum(__ldcg(P.colsum_b + (size_t)(tau + 1) * Npad + tid), &sh, P.scale_exp);
             runlog += (double)__ldg(P.fmax + (size_t)tau * Npad + tid) - (double)sh * 0.6931471805599453;
         }
         if (split_barrier) grid_barrier_wait(P.barrier, (++epoch) * gridDim.x);
@@ -812,7 +828,7 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const DenParams P) 
             float b = P.start_final;
             if (ln > 0) {
                 int sh;
-                const float rb = scale_from_sum(__ldcg(P.colsum_b + (size_t)1 * Npad + n), &sh);
+                const float rb = scale_from_sum(__ldcg(P.colsum_b + (size_t)1 * Npad + n), &sh, P.scale_exp);
                 float acc = 0.f;
                 for (int a = 0; a < P.n_start_arcs; ++a) {
                     const Arc k = P.start_arcs[a];
@@ -825,7 +841,7 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const DenParams P) 
     }
     if (cta == 0 && tid < P.N && 0 < my_len) {
         int sh;
-        (void)scale_from_sum(__ldcg(P.colsum_b + (size_t)1 * Npad + tid), &sh);
+        (void)scale_from_sum(__ldcg(P.colsum_b + (size_t)1 * Npad + tid), &sh, P.scale_exp);
         runlog += (double)__ldg(P.fmax + tid) - (double)sh * 0.6931471805599453;
     }
     grid_barrier(P.barrier, (++epoch) * gridDim.x);
@@ -871,6 +887,21 @@ int LaunchOne(bool backward, bool w1_smem, const DenParams &p, int n_ctas, size_
 
 constexpr int kBwdMaxLaneWidth = 2;   // N=256: bwd 163 ms at 2 vs 248 ms at 4 (profiles/r01_experiments.md)
 
+// Gathers per batch (two batches are in flight per warp), fixed per variant by the register budget at 512 threads
+// (profiles/r01_experiments.md #4/#5): forward 2x16 rows (2x8 at four utterances per lane), backward 2x8.
+template <int U> struct FwdBatch { static constexpr int value = U == 4 ? 8 : 16; };
+constexpr int kBwdBatch = 8;
+
+template <int NT, int U>
+int DispatchU(bool backward, bool smem_arcs, bool w1_smem, const DenParams &p, int n_ctas, size_t smem, cudaStream_t stream,
+              std::string *err) {
+    if (backward)
+        return smem_arcs ? LaunchOne<NT, U, kBwdBatch, true>(true, w1_smem, p, n_ctas, smem, stream, err)
+                         : LaunchOne<NT, U, kBwdBatch, false>(true, w1_smem, p, n_ctas, smem, stream, err);
+    return smem_arcs ? LaunchOne<NT, U, FwdBatch<U>::value, true>(false, w1_smem, p, n_ctas, smem, stream, err)
+                     : LaunchOne<NT, U, FwdBatch<U>::value, false>(false, w1_smem, p, n_ctas, smem, stream, err);
+}
+
 template <int NT>
 int Dispatch(bool backward, const DeviceGraph &g, const DenParams &p, size_t fixed_smem, cudaStream_t stream,
              std::string *err) {
@@ -878,52 +909,26 @@ int Dispatch(bool backward, const DeviceGraph &g, const DenParams &p, size_t fix
     // three tiers by graph size: the whole arc stream in shared memory (8 bytes per forward slot, 12 per backward slot);
     // backward only: offsets + first weights in shared memory, second weights streamed from L2; everything from L2
     const size_t budget = (size_t)g.max_smem_optin > 2048 ? (size_t)g.max_smem_optin - 1024 : 0;
-    const char *force_global = getenv("CCB_ARCS_IN_GLOBAL");   // test hooks: exercise the large-graph tiers
-    const char *force_w1 = getenv("CCB_W1_IN_GLOBAL");
-    const bool no_smem = force_global && force_global[0] == '1';
-    bool w1_smem = backward && !(force_w1 && force_w1[0] == '1');
+    const bool no_smem = g.tune_arcs_in_global;   // test hooks (read once at Init): exercise the large-graph tiers
+    bool w1_smem = backward && !g.tune_w1_in_global;
     size_t arc_bytes = (size_t)pass.max_tile_arcs * (backward && w1_smem ? 12 : sizeof(Arc));
     if (backward && w1_smem && fixed_smem + arc_bytes > budget) { w1_smem = false; arc_bytes = (size_t)pass.max_tile_arcs * sizeof(Arc); }
     const bool smem_arcs = fixed_smem + arc_bytes <= budget && !no_smem;
     const size_t smem = fixed_smem + (smem_arcs ? arc_bytes : 0);
     // utterances per lane: the widest row segment the batch allows, except that the backward pass (two accumulators per
-    // utterance) runs out of registers at 4 -- it walks 64-utterance groups instead.  CCB_U_FWD / CCB_U_BWD: tuning override.
+    // utterance) runs out of registers at 4 -- it walks 64-utterance groups instead.
     int U = LaneWidth(p.Npad);
     if (backward && U == 4) U = kBwdMaxLaneWidth;
-    {
-        const char *e = getenv(backward ? "CCB_U_BWD" : "CCB_U_FWD");
-        const int u = e ? atoi(e) : 0;
-        if ((u == 1 || u == 2 || u == 4) && p.Npad % (32 * u) == 0) U = u;
-    }
-    // gathers per batch (two batches are in flight per warp); bounded by the register budget of the variant.
-    // CCB_BATCH_FWD / CCB_BATCH_BWD (8 or 16) override the 512-thread defaults for tuning.
-    int want = NT == 512 ? (U == 4 ? 8 : (backward ? 8 : 16)) : (U == 1 ? 8 : 4);
-    if (NT == 512 && U != 4) {
-        const char *e = getenv(backward ? "CCB_BATCH_BWD" : "CCB_BATCH_FWD");
-        if (e && (atoi(e) == 8 || atoi(e) == 16)) want = atoi(e);
-    }
-#define CCB_LAUNCH(UU, BB)                                                                               \
-    return smem_arcs ? LaunchOne<NT, UU, BB, true>(backward, w1_smem, p, g.n_ctas, smem, stream, err)   \
-                     : LaunchOne<NT, UU, BB, false>(backward, w1_smem, p, g.n_ctas, smem, stream, err)
-#define CCB_GO(UU)                                                                                      \
-    {                                                                                                   \
-        if (NT == 512 && UU != 4 && want == 16) { CCB_LAUNCH(UU, 16); }                                 \
-        if (NT == 512 || UU == 1) { CCB_LAUNCH(UU, 8); }                                                \
-        CCB_LAUNCH(UU, 4);                                                                              \
-    }
-    if (U == 1) { CCB_GO(1); }
-    if (U == 2) { CCB_GO(2); }
-    CCB_GO(4);
-#undef CCB_LAUNCH
-#undef CCB_GO
+    if (U == 1) return DispatchU<NT, 1>(backward, smem_arcs, w1_smem, p, g.n_ctas, smem, stream, err);
+    if (U == 2) return DispatchU<NT, 2>(backward, smem_arcs, w1_smem, p, g.n_ctas, smem, stream, err);
+    return DispatchU<NT, 4>(backward, smem_arcs, w1_smem, p, g.n_ctas, smem, stream, err);
 }
 
 int DispatchThreads(bool backward, const DeviceGraph &g, const DenParams &p, size_t fixed_smem, cudaStream_t stream,
                     std::string *err) {
     if (p.Npad > g.n_warps * 32) { *err = "batch too large for the den kernel's bookkeeping CTA (N <= " + std::to_string(g.n_warps * 32) + ")"; return 1; }
-    if (g.n_warps == 32) return Dispatch<1024>(backward, g, p, fixed_smem, stream, err);
     if (g.n_warps == 16) return Dispatch<512>(backward, g, p, fixed_smem, stream, err);
-    *err = "unsupported warps per CTA for den kernels (16 or 32)";
+    *err = "unsupported warps per CTA for den kernels (16)";
     return 1;
 }
 

@@ -25,26 +25,16 @@ def _assert_no_grad(tensor):
 
 
 class _WARP_CTC_GPU(Function):
-    """__init__.py:25-56: CTC loss on log-softmax inputs through ``gpu_ctc`` (kept with the reference's
-    (T,N,V) transposed call so that ``_C.gpu_ctc`` is exercised exactly as the reference exercises it)."""
+    """__init__.py:25-56: CTC loss on log-softmax inputs.  Same arguments, result and gradient as the reference's
+    Function; underneath it is ONE native call on the (N,T,V) tensor in place -- no (T,N,V) transpose copy (:31), no
+    zero-filled gradient (:32), no host round trip for the per-utterance costs (:33-35) -- see ``_C.ctc_loss_fwd``.
+    (``_C.gpu_ctc`` keeps the reference's pybind signature for callers that use it directly.)"""
 
     @staticmethod
     def forward(ctx, logits, labels, input_lengths, label_lengths, size_average=True):
         logits = logits.contiguous()
-        batch_size = logits.size(0)
-        costs_ctc = torch.zeros(logits.size(0))
-        act = torch.transpose(logits, 0, 1).contiguous()
-        grad_ctc = torch.zeros(act.size()).type_as(logits)
-        core.gpu_ctc(act, grad_ctc, labels, label_lengths, input_lengths, logits.size(0), costs_ctc, 0)
-        grad_ctc = torch.transpose(grad_ctc, 0, 1)
-        costs_ctc = costs_ctc.to(logits.get_device())
-        grad_all = -grad_ctc
-        costs_all = -costs_ctc
-        costs = costs_all.sum().reshape(1).to(logits.device)
-        if size_average:
-            grad_all = grad_all / batch_size
-            costs = costs / batch_size
-        ctx.grads = grad_all
+        costs, grads, _ = core.ctc_loss_fwd(logits, labels, input_lengths, label_lengths, size_average)
+        ctx.grads = grads
         return costs
 
     @staticmethod
@@ -137,6 +127,14 @@ class WARP_CTC_LOSS(Module):
         _assert_no_grad(input_lengths)
         _assert_no_grad(label_lengths)
         return self.ctc(logits, labels, input_lengths, label_lengths, self.size_average)
+
+
+def ctc_align(logits, labels, input_lengths, label_lengths):
+    """Best-path forced alignment of every utterance to its label sequence over the CTC lattice -- the alignment that comes
+    with the numerator (cat/ctc/train_jsa.py consumes frame-level paths).  Arguments as for WARP_CTC_LOSS.
+    Returns (align (N,T) int32 on the GPU, token per frame incl. blank 0, -1 past each length; score (N,) fp32)."""
+    assert len(labels.size()) == 1
+    return core.ctc_align(logits.contiguous(), labels, input_lengths, label_lengths)
 
 
 class CRFContext:

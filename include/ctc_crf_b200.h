@@ -135,6 +135,26 @@ int ccb_ctc_crf_loss_logits_fwd(const void *logits, int dtype, int N, int T, int
                                 float *alpha_ws, void *aux_ws, void *ctc_ws,
                                 float *grad, float *loss, float *parts, void *stream);
 
+/* CTC-only loss (replaces the numerator-only path ctc_crf/__init__.py:25-56 = WARP_CTC_LOSS) on an (N,T,V) block of
+ * log-probs, read in place (no (T,N,V) transpose copy, cf. __init__.py:31):
+ *   logp[n] = log p(l_n | x_n)  (N,) device out;   loss[0] = -scale * sum_n logp[n];
+ *   grad    = -scale * gamma_ctc, (N,T,V) fp32, every row WRITTEN here (zeros for t >= len and infeasible utterances), so
+ *             the caller needs no zero fill (cf. __init__.py:32) and no host round trip for the costs (:35).
+ * ctc_ws: ccb_ctc_workspace_bytes(N, Tmax, max_label_len). */
+int ccb_ctc_loss_fwd(const void *logits, int dtype, int N, int T, int V, int Tmax,
+                     const int *labels_dev, const int *label_off_dev, const int *label_len_dev, const int *len_dev,
+                     int max_label_len, int blank, float scale, void *ctc_ws, float *grad, float *loss, float *logp,
+                     void *stream);
+
+/* Best-path (Viterbi) alignment over the numerator lattice -- the forced alignment that comes with the CTC numerator
+ * (SURVEY.md 8f-4).  align: (N,T) int32 device out, the token emitted at every frame t < len (blank included), -1 beyond
+ * the length and for infeasible utterances; score (optional, may be NULL): (N,) log-probability of the best path.
+ * workspace: ccb_ctc_align_workspace_bytes(N, T, max_label_len) bytes. */
+size_t ccb_ctc_align_workspace_bytes(int N, int T, int max_label_len);
+int ccb_ctc_align(const void *logits, int dtype, long sn, long st, int N, int T, int V,
+                  const int *labels_dev, const int *label_off_dev, const int *label_len_dev, const int *len_dev,
+                  int max_label_len, int blank, void *workspace, int *align, float *score, void *stream);
+
 /* number of kernels launched by this library since load (bench.py's gpu_launches) */
 long ccb_launch_count(void);
 

@@ -40,9 +40,11 @@ def _p(a, t):
     return a.ctypes.data_as(C.POINTER(t))
 
 
-def den(graph, y: np.ndarray, lens, nthreads: int = 0):
+def den(graph, y: np.ndarray, lens, nthreads: int = 0, fast: bool = False):
     """Denominator forward-backward.  y: (N,T,V) float32 log-probs.
-    Returns (logz_alpha[N], logz_beta[N], gamma_den[N,T,V]) in float64."""
+    Returns (logz_alpha[N], logz_beta[N], gamma_den[N,T,V]) in float64.
+    fast: the fp64 scaled-linear evaluation (oracle_den_linear, pinned against the log-domain restatement by
+    tests/test_oracle.py) -- seconds instead of minutes per utterance at the benchmark sizes."""
     y = np.ascontiguousarray(y, dtype=np.float32)
     N, T, V = y.shape
     lens = np.ascontiguousarray(lens, dtype=np.int32)
@@ -53,12 +55,13 @@ def den(graph, y: np.ndarray, lens, nthreads: int = 0):
     lb = np.zeros(N, np.float64)
     g = np.zeros((N, T, V), np.float64)
     nt = nthreads or os.cpu_count()
-    rc = lib().oracle_den(C.c_int(graph.num_states), C.c_long(graph.num_arcs),
-                          _p(src, C.c_int), _p(dst, C.c_int), _p(lab, C.c_int), _p(lw, C.c_float),
-                          _p(sw, C.c_float), _p(ew, C.c_float), _p(y, C.c_float),
-                          C.c_long(T * V), C.c_long(V), C.c_int(N), C.c_int(T), C.c_int(V),
-                          _p(lens, C.c_int), _p(la, C.c_double), _p(lb, C.c_double),
-                          _p(g, C.c_double), C.c_int(nt))
+    fn = lib().oracle_den_linear if fast else lib().oracle_den
+    rc = fn(C.c_int(graph.num_states), C.c_long(graph.num_arcs),
+            _p(src, C.c_int), _p(dst, C.c_int), _p(lab, C.c_int), _p(lw, C.c_float),
+            _p(sw, C.c_float), _p(ew, C.c_float), _p(y, C.c_float),
+            C.c_long(T * V), C.c_long(V), C.c_int(N), C.c_int(T), C.c_int(V),
+            _p(lens, C.c_int), _p(la, C.c_double), _p(lb, C.c_double),
+            _p(g, C.c_double), C.c_int(nt))
     assert rc == 0, f"oracle_den failed ({rc})"
     return la, lb, g
 
@@ -83,11 +86,12 @@ def ctc(y: np.ndarray, labels, label_lens, lens, blank: int = 0, nthreads: int =
     return lp, g
 
 
-def ctc_crf(graph, y, labels, lx, ly, lamb: float = 0.1, size_average: bool = True, nthreads: int = 0):
+def ctc_crf(graph, y, labels, lx, ly, lamb: float = 0.1, size_average: bool = True, nthreads: int = 0,
+            fast: bool = False):
     """Full loss: returns (loss, grad[N,T,V], parts) following ctc_crf/__init__.py:58-90."""
     y = np.ascontiguousarray(y, dtype=np.float32)
     N = y.shape[0]
-    la, lb, gden = den(graph, y, lx, nthreads)
+    la, lb, gden = den(graph, y, lx, nthreads, fast=fast)
     lp, gctc = ctc(y, labels, ly, lx, 0, nthreads)
     grad = gden.copy()
     loss = lib().oracle_assemble(C.c_int(N), C.c_long(grad.size), _p(la, C.c_double), _p(lp, C.c_double),

@@ -7,7 +7,7 @@ disagreement with the oracle is a plan/algorithm error, not rounding.
 import numpy as np
 
 
-SCALE_EXP = 32
+SCALE_EXP = 56      # DenPlan::scale_exp for probability-like graphs (den_graph.cc)
 
 
 def _scale(s):

@@ -410,3 +410,96 @@ def test_error_paths(fixture_fst, tmp_path):
         crit(torch.zeros(1, 4, 3, device="cuda").log_softmax(-1), torch.tensor([1], dtype=torch.int32),
              torch.tensor([4], dtype=torch.int32), torch.tensor([1], dtype=torch.int32))
     del ctx
+
+
+def _viterbi_ref(y, lab, blank=0):
+    """Textbook best path over the blank-expanded CTC lattice (float64, python loops): token per frame, path score."""
+    T = y.shape[0]
+    ext = [blank]
+    for k in lab:
+        ext += [int(k), blank]
+    S = len(ext)
+    v = np.full((T, S), -np.inf)
+    bp = np.zeros((T, S), np.int64)
+    v[0, 0] = y[0, blank]
+    if S > 1:
+        v[0, 1] = y[0, ext[1]]
+    for t in range(1, T):
+        for s in range(S):
+            best, k = v[t - 1, s], 0
+            if s >= 1 and v[t - 1, s - 1] > best:
+                best, k = v[t - 1, s - 1], 1
+            if s >= 2 and ext[s] != blank and ext[s] != ext[s - 2] and v[t - 1, s - 2] > best:
+                best, k = v[t - 1, s - 2], 2
+            v[t, s] = best + y[t, ext[s]]
+            bp[t, s] = k
+    s = S - 1
+    if S > 1 and v[T - 1, S - 2] > v[T - 1, S - 1]:
+        s = S - 2
+    score = v[T - 1, s]
+    out = np.zeros(T, np.int64)
+    for t in range(T - 1, -1, -1):
+        out[t] = ext[s]
+        s -= bp[t, s]
+    return out, score
+
+
+def test_ctc_align_best_path():
+    """SURVEY 8f-4 by-product: ctc_crf.ctc_align == textbook Viterbi over the numerator lattice (tokens per frame and the
+    path score), collapses back to the label sequence, and marks padding / infeasible utterances with -1."""
+    import ctc_crf
+    from oracle import oracle
+    N, T, V = 5, 40, 9
+    lens = [40, 33, 12, 7, 3]
+    y, _, lens, _ = oracle.synth_batch(N, T, V, seed=19, lens=lens)
+    ly = np.array([9, 6, 0, 3, 5], np.int32)                      # L=0; the last one is infeasible (5 labels in 3 frames)
+    rng = np.random.default_rng(2)
+    labels = rng.integers(1, V, size=int(ly.sum())).astype(np.int32)
+    labels[1] = labels[0]                                          # a repeat: needs a blank in between
+    align, score = ctc_crf.ctc_align(torch.tensor(y, device="cuda"), torch.tensor(labels), torch.tensor(lens), torch.tensor(ly))
+    align, score = align.cpu().numpy(), score.cpu().numpy()
+    off = np.concatenate([[0], np.cumsum(ly)])
+    for n in range(N):
+        lab = labels[off[n]:off[n + 1]]
+        if n == N - 1:
+            assert np.isinf(score[n]) and score[n] < 0 and (align[n] == -1).all()
+            continue
+        ref, sc = _viterbi_ref(y[n, :lens[n]].astype(np.float64), lab)
+        assert (align[n, lens[n]:] == -1).all()
+        assert abs(score[n] - sc) < 1e-4 * max(1.0, abs(sc))
+        got = align[n, :lens[n]]
+        if not np.array_equal(got, ref):                           # ties may be broken differently in fp32: same score then
+            assert abs(float(sum(y[n, t, got[t]] for t in range(lens[n]))) - sc) < 1e-3
+        collapsed = [int(k) for i, k in enumerate(got) if k != 0 and (i == 0 or got[i - 1] != k)]
+        assert collapsed == [int(k) for k in lab]
+
+
+def test_warp_ctc_loss_native_path_matches_gpu_ctc():
+    """WARP_CTC_LOSS (one native call on (N,T,V), no transpose / zero fill / host costs) against the reference-signature
+    route through _C.gpu_ctc on the transposed copy, and against the oracle; infeasible utterance -> +inf loss."""
+    import ctc_crf
+    from oracle import oracle
+    from cat_b200 import _C
+    N, T, V = 6, 50, 20
+    y, labels, lens, ly = oracle.synth_batch(N, T, V, seed=29, lens=[50, 50, 44, 31, 18, 6])
+    yt = torch.tensor(y, device="cuda")
+    for sa in (True, False):
+        logits = yt.clone().requires_grad_(True)
+        loss = ctc_crf.WARP_CTC_LOSS(size_average=sa)(logits, torch.tensor(labels), torch.tensor(lens), torch.tensor(ly))
+        loss.backward()
+        act = yt.transpose(0, 1).contiguous()
+        grads = torch.zeros_like(act)
+        costs = torch.zeros(N)
+        _C.gpu_ctc(act, grads, torch.tensor(labels), torch.tensor(ly), torch.tensor(lens), N, costs, 0)
+        sc = 1.0 / N if sa else 1.0
+        assert abs(float(loss.item()) + float(costs.sum()) * sc) <= 1e-5 * max(1.0, abs(float(costs.sum())))
+        assert float((logits.grad + grads.transpose(0, 1) * sc).abs().max()) < 1e-6
+        lp, gc = oracle.ctc(y, labels, ly, lens)
+        _close_loss(float(loss.item()), -lp.sum() * sc)
+        assert np.abs(logits.grad.cpu().numpy() + gc * sc).max() < GRAD_ATOL
+        for n in range(N):
+            assert not bool(logits.grad[n, lens[n]:].any())
+    ly_bad = ly.copy(); ly_bad[-1] = 7                               # 7 labels in 6 frames
+    labels_bad = np.concatenate([labels, np.ones(int(ly_bad.sum() - ly.sum()), np.int32)])
+    loss = ctc_crf.WARP_CTC_LOSS()(yt, torch.tensor(labels_bad), torch.tensor(lens), torch.tensor(ly_bad))
+    assert np.isinf(float(loss.item())) and float(loss.item()) > 0

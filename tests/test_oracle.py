@@ -167,3 +167,24 @@ def test_den_oracle_equals_brute_force_path_sum(fixture_fst):
     la, lb, gamma = oracle.den(g, y, [T])
     assert abs(la[0] - np.log(total)) < 1e-9 and abs(lb[0] - np.log(total)) < 1e-9
     np.testing.assert_allclose(gamma[0], occ / total, atol=1e-9)
+
+
+@pytest.mark.parametrize("name,scale", [("tlm_small", 3.0), ("random_split", 3.0), ("tlm_mid", 3.0), ("tlm_mid", 20.0)])
+def test_linear_domain_oracle_equals_log_domain_oracle(tmp_graphs, fixture_fst, fixture_inputs, name, scale):
+    """The fp64 scaled-linear evaluation used by the at-size GPU tests (oracle_den_linear) is the same function as the
+    log-domain restatement of den_calculate.cu (oracle_den): logZ from alpha, logZ from beta and every occupancy, on
+    structured, unstructured and peaky inputs, ragged lengths included, plus the reference's own fixture."""
+    path, g, V = tmp_graphs[name]
+    y, _, lens, _ = oracle.synth_batch(5, 40, V, seed=13, lens=[40, 33, 17, 2, 1], scale=scale)
+    la, lb, gd = oracle.den(g, y, lens)
+    fa, fb, fg = oracle.den(g, y, lens, fast=True)
+    np.testing.assert_allclose(fa, la, rtol=1e-11, atol=1e-9)
+    np.testing.assert_allclose(fb, lb, rtol=1e-11, atol=1e-9)
+    np.testing.assert_allclose(fg, gd, atol=1e-10)
+    fi = fixture_inputs
+    gf = fst.read_fst(fixture_fst)
+    a = oracle.den(gf, fi["y"], fi["lx"])
+    b = oracle.den(gf, fi["y"], fi["lx"], fast=True)
+    for u, v in zip(a, b):
+        np.testing.assert_allclose(v, u, rtol=1e-12, atol=1e-12)
+    assert abs(b[0][0] - (-6.25832785)) < 1e-6
