@@ -26,6 +26,8 @@ std::mutex g_mu;
 DenPlan g_plan;                       // host copy (one den graph per process, like den_calculate.cu:263-273)
 bool g_plan_valid = false;
 DeviceGraph g_dev[kMaxDevices];
+int g_refs[kMaxDevices] = {0};        // Init() calls not yet matched by Release(), per device: `ctx = CRFContext(new_graph)` runs the
+                                      // old context's __del__ AFTER the new Init -- that Release must not free the new graph
 std::atomic<long> g_launches{0};
 
 // scratch owned by the library for the reference-signature entry points (Section 1)
@@ -34,6 +36,9 @@ struct LegacyScratch {
     float *alpha = nullptr; size_t alpha_floats = 0;
     void *ctc = nullptr; size_t ctc_bytes = 0;
     int N = 0, T = 0;
+    bool fwd_valid = false;            // compute_alpha ran and compute_beta_and_grad has not consumed it yet
+    cudaStream_t stream = nullptr;     // stream the scratch was last allocated / used on (stream-ordered allocation)
+    bool used = false;
 };
 LegacyScratch g_legacy[kMaxDevices];
 
@@ -127,12 +132,14 @@ int InitImpl(const char *fst_name, int n_gpus, const int *gpus) {
              UploadPass(g_plan.fwd, &d.fwd) || UploadPass(g_plan.bwd, &d.bwd);
         { const char *e = getenv("CCB_ARCS_IN_GLOBAL"); d.tune_arcs_in_global = e && e[0] == '1'; }
         { const char *e = getenv("CCB_W1_IN_GLOBAL"); d.tune_w1_in_global = e && e[0] == '1'; }
+        { const char *e = getenv("CCB_NO_TMA"); d.tune_no_tma = e && e[0] == '1'; }   // A/B: register gathers instead of TMA gather4
         if (d.tune_arcs_in_global || d.tune_w1_in_global)
             fprintf(stderr, "ctc_crf_b200: CCB_ARCS_IN_GLOBAL / CCB_W1_IN_GLOBAL set -- den arc tiles forced out of shared memory (test hook, slow)\n");
         d.n_start_arcs = (int)g_plan.start_arcs.size();
         d.n_hubs = (int)g_plan.hub_states.size();
         d.start_final = g_plan.final_lin[(size_t)g_plan.start];
         d.loaded = (rc == 0);
+        if (rc == 0) ++g_refs[gpus[i]];
     }
     cudaSetDevice(prev);
     return rc;
@@ -144,6 +151,7 @@ int ReleaseImpl(int n_gpus, const int *gpus) {
     cudaGetDevice(&prev);
     for (int i = 0; i < n_gpus; ++i) {
         if (gpus[i] < 0 || gpus[i] >= kMaxDevices) continue;
+        if (g_refs[gpus[i]] > 0 && --g_refs[gpus[i]] > 0) continue;   // a newer Init() still owns this device's graph
         if (cudaSetDevice(gpus[i]) != cudaSuccess) continue;
         cudaDeviceSynchronize();
         FreeDevice(g_dev[gpus[i]]);
@@ -232,23 +240,31 @@ int DenBackward(const DeviceGraph &g, const void *y, int dtype, long sn, long st
     return 0;
 }
 
-int EnsureLegacy(int dev, const DeviceGraph &g, int N, int T, float *caller_alpha, size_t caller_floats, float **alpha_out) {
+// Scratch of the reference-signature route, taken STREAM-ORDERED from the device's default memory pool
+// (cudaMallocAsync / cudaFreeAsync on the caller's stream): growing it never synchronises the device.  It is kept
+// between calls and returned by Release().  If the caller moves to another stream the old stream is drained first.
+int GrowAsync(void **ptr, size_t *have, size_t need, cudaStream_t s) {
+    if (*have >= need) return 0;
+    if (*ptr) CCB_CUDA(cudaFreeAsync(*ptr, s));
+    *ptr = nullptr; *have = 0;
+    CCB_CUDA(cudaMallocAsync(ptr, need, s));
+    *have = need;
+    return 0;
+}
+
+int EnsureLegacy(int dev, const DeviceGraph &g, int N, int T, float *caller_alpha, size_t caller_floats, float **alpha_out,
+                 cudaStream_t s) {
     LegacyScratch &ls = g_legacy[dev];
+    if (ls.used && ls.stream != s) CCB_CUDA(cudaStreamSynchronize(ls.stream));
+    ls.stream = s; ls.used = true;
     const DenAuxLayout L = MakeDenAuxLayout(g.S, N, T);
-    if (ls.aux_bytes < L.total) {
-        CCB_CUDA(cudaDeviceSynchronize());
-        cudaFree(ls.aux); ls.aux = nullptr; ls.aux_bytes = 0;
-        CCB_CUDA(cudaMalloc(&ls.aux, L.total));
-        ls.aux_bytes = L.total;
-    }
+    if (GrowAsync(&ls.aux, &ls.aux_bytes, L.total, s)) return 1;
     const size_t need = ccb_den_alpha_floats(N, T);
     if (caller_alpha && caller_floats >= need) { *alpha_out = caller_alpha; return 0; }
-    if (ls.alpha_floats < need) {
-        CCB_CUDA(cudaDeviceSynchronize());
-        cudaFree(ls.alpha); ls.alpha = nullptr; ls.alpha_floats = 0;
-        CCB_CUDA(cudaMalloc((void **)&ls.alpha, need * sizeof(float)));
-        ls.alpha_floats = need;
-    }
+    size_t have_bytes = ls.alpha_floats * sizeof(float);
+    void *ap = ls.alpha;
+    if (GrowAsync(&ap, &have_bytes, need * sizeof(float), s)) { ls.alpha = nullptr; ls.alpha_floats = 0; return 1; }
+    ls.alpha = reinterpret_cast<float *>(ap); ls.alpha_floats = have_bytes / sizeof(float);
     *alpha_out = ls.alpha;
     return 0;
 }
@@ -282,23 +298,33 @@ void Init(const char *fst_name, int n_gpus, int *gpus) {
 
 void Release(int n_gpus, int *gpus) { ReleaseImpl(n_gpus, gpus); }
 
+// (S, P) of the graph on the CURRENT device when one is loaded there (devices may hold different graphs if Init was
+// called per device with different files), else of the last plan built
+static void CurrentSizes(int *S, int *P) {
+    int dev = -1;
+    if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < kMaxDevices && g_dev[dev].loaded) { *S = g_dev[dev].S; *P = g_dev[dev].P; return; }
+    cudaGetLastError();
+    *S = g_plan_valid ? g_plan.num_states : 0; *P = g_plan_valid ? g_plan.num_pairs : 0;
+}
+
 size_t ccb_den_alpha_floats(int N, int T) {
-    if (!g_plan_valid) return 0;
+    int S, P;
+    CurrentSizes(&S, &P);
     // T+1 frames of S real rows; the virtual pair-sum rows of a frame are parked two frames ahead (den_kernels.cu), so two
     // more frames at the end when the plan has pairs
-    return (size_t)(T + 1 + (g_plan.num_pairs > 0 ? 2 : 0)) * (size_t)g_plan.num_states * (size_t)PadLanes(N);
+    return (size_t)(T + 1 + (P > 0 ? 2 : 0)) * (size_t)S * (size_t)PadLanes(N);
 }
 
 size_t ccb_den_aux_bytes(int N, int T) {
-    if (!g_plan_valid) return 0;
-    return MakeDenAuxLayout(g_plan.num_states, N, T).total;
+    int S, P;
+    CurrentSizes(&S, &P);
+    return S ? MakeDenAuxLayout(S, N, T).total : 0;
 }
 
 size_t ccb_ctc_workspace_bytes(int N, int T, int max_label_len) {
-    // per utterance: alpha_rel and beta_rel [T][2L+1] floats each (rounded up to an even count) + two per-frame fp64
-    // offset arrays [T] + the fp64 log-likelihood (ctc_kernels.cu)
-    const size_t per_utt = 2 * (((size_t)T * (2 * (size_t)max_label_len + 1) + 1) / 2 * 2) + 4 * (size_t)T + 2;
-    return ((size_t)N * per_utt + 64) * sizeof(float);
+    // per utterance: alpha and beta cells [T][2L+1] in double + the fp64 log-likelihood (ctc_kernels.cu)
+    const size_t per_utt = 2 * (size_t)T * (2 * (size_t)max_label_len + 1) + 1;
+    return ((size_t)N * per_utt + 32) * sizeof(double);
 }
 
 void compute_alpha(float *alpha, float *logits, const int batch_size, int T, const int alpha_size,
@@ -309,12 +335,13 @@ void compute_alpha(float *alpha, float *logits, const int batch_size, int T, con
     if (CheckDen(*g, CCB_DTYPE_F32, batch_size, T, logits_size)) return;
     float *al = nullptr;
     const size_t caller = (size_t)(T + 1) * (size_t)batch_size * (size_t)(alpha_size > 0 ? alpha_size : 0);
-    if (EnsureLegacy(g->device, *g, batch_size, T, alpha, caller, &al)) return;
-    LegacyScratch &ls = g_legacy[g->device];
-    ls.N = batch_size; ls.T = T;
     cudaStream_t s = (cudaStream_t)stream;
+    if (EnsureLegacy(g->device, *g, batch_size, T, alpha, caller, &al, s)) return;
+    LegacyScratch &ls = g_legacy[g->device];
+    ls.N = batch_size; ls.T = T; ls.fwd_valid = false;
     if (DenForward(*g, logits, CCB_DTYPE_F32, (long)T * logits_size, logits_size, batch_size, T, logits_size,
                    input_lengths, al, ls.aux, s)) return;
+    ls.fwd_valid = true;
     const DenAuxLayout L = MakeDenAuxLayout(g->S, batch_size, T);
     cudaError_t e = cudaMemcpyAsync(loglikelihood, (char *)ls.aux + L.logz_a, sizeof(float) * batch_size, cudaMemcpyDeviceToDevice, s);
     if (e != cudaSuccess) FailCuda("copy logZ", e);
@@ -329,11 +356,14 @@ void compute_beta_and_grad(float *beta, const float *const alpha, const float *c
     DeviceGraph *g;
     if (CurrentGraph(&g)) return;
     LegacyScratch &ls = g_legacy[g->device];
-    if (ls.N != batch_size || ls.T != T || !ls.aux) { Fail("compute_beta_and_grad: call compute_alpha on the same batch first"); return; }
+    // the backward pass continues from the forward pass's column sums / barrier words in the scratch: exactly one
+    // compute_beta_and_grad per compute_alpha, same batch
+    if (ls.N != batch_size || ls.T != T || !ls.aux || !ls.fwd_valid) { Fail("compute_beta_and_grad: call compute_alpha on the same batch first (once per backward call)"); return; }
+    ls.fwd_valid = false;
     float *al = nullptr;
     const size_t caller = (size_t)(T + 1) * (size_t)batch_size * (size_t)(beta_size > 0 ? beta_size : 0);
-    if (EnsureLegacy(g->device, *g, batch_size, T, const_cast<float *>(alpha), caller, &al)) return;
     cudaStream_t s = (cudaStream_t)stream;
+    if (EnsureLegacy(g->device, *g, batch_size, T, const_cast<float *>(alpha), caller, &al, s)) return;
     if (DenBackward(*g, logits, CCB_DTYPE_F32, (long)T * logits_size, logits_size, batch_size, T, logits_size,
                     input_lengths, al, ls.aux, grad_net, (long)T * logits_size, logits_size, 1.f, s)) return;
     if (loglikelihood) {

@@ -1,5 +1,6 @@
 // Shared device helpers and the internal host-side launch interface (not part of the C ABI).
 #pragma once
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
@@ -43,11 +44,18 @@ struct DeviceGraph {
     float start_final = 0.f;
     int max_smem_optin = 0;
     // test hooks, read ONCE at Init (never on the per-call path): force the large-graph tiers on a small graph
-    bool tune_arcs_in_global = false, tune_w1_in_global = false;
+    bool tune_arcs_in_global = false, tune_w1_in_global = false, tune_no_tma = false;
 };
 
-// Kernel parameter block shared by the two persistent den kernels.
-struct DenParams {
+// Kernel parameter block shared by the two persistent den kernels (passed as a __grid_constant__ kernel parameter: the TMA
+// descriptor inside it is read by the hardware straight from parameter memory and must sit on a 64-byte boundary).
+struct alignas(64) DenParams {
+    // TMA view of the pass's gather table (forward: the alpha spill, backward: the beta ping-pong) as a 2-D tensor
+    // [rows][Npad] of fp32 with a box of one row x (32 * utterances per lane) columns; used by the gather4 kernels only
+    CUtensorMap tmap;
+    int use_tma;          // 1: rows are staged in shared memory by TMA gather4 (den_kernels.cu), 0: register gathers
+    int ring_off;         // byte offset of the per-warp row rings in dynamic shared memory (128-byte aligned)
+    int bar_off;          // byte offset of the rings' mbarriers
     // graph
     const Arc *arcs;
     const float *w1;      // backward pass only
@@ -115,8 +123,11 @@ int LaunchFrameLse(const void *y, int y_bf16, long sn, long st, int N, int T, in
                    float *lz, double *lnorm, int Npad, cudaStream_t stream);
 int LaunchLogitGrad(const void *z, int z_bf16, long sn, long st, int N, int T, int V, const int *len, const float *lz,
                     int Npad, float *grad, long gsn, long gst, cudaStream_t stream);
-int LaunchDenForward(const DeviceGraph &g, DenParams p, cudaStream_t stream, std::string *err);
-int LaunchDenBackward(const DeviceGraph &g, DenParams p, cudaStream_t stream, std::string *err);
+int LaunchDenForward(const DeviceGraph &g, DenParams &p, cudaStream_t stream, std::string *err);
+int LaunchDenBackward(const DeviceGraph &g, DenParams &p, cudaStream_t stream, std::string *err);
+// fills *tm with the 2-D view [rows][Npad] fp32 of `base`, box = 1 row x box_cols columns; false if the driver entry
+// point is unavailable or refuses the shape (the callers then keep the register-gather kernels)
+bool EncodeRowTensorMap(CUtensorMap *tm, const float *base, size_t rows, int Npad, int box_cols);
 int LaunchDenGradNormalize(float *grad, long gsn, long gst, const float *absum, const int *len, int N, int Npad,
                            int T, int V, float scale, cudaStream_t stream);
 int LaunchCtc(const void *y, int y_bf16, long sn, long st, int N, int T, int V, const int *labels,

@@ -28,35 +28,34 @@ namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
 
-// Block-wide max of the values the warps published for the previous frame (one LDS + 5 shuffles).
-__device__ __forceinline__ float block_max_from(const float *s_wmax, int nwarps) {
-    const int lane = threadIdx.x & 31;
-    float m = lane < nwarps ? s_wmax[lane] : -INFINITY;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(kFull, m, o));
-    return m == -INFINITY ? 0.f : m;
+// Precision: lattice cells are carried in DOUBLE, the log-add's transcendental part in float:
+//     log_add(a, b) = max(a, b) + (double) log1pf(expf((float)(min(a, b) - max(a, b))))
+// The float part is a number in (0, ln 2] with ~1e-7 absolute error whatever the magnitude of the cells, and the double
+// sum does not quantise.  fp32 cells (round 1, relative to a per-frame offset) were not enough: at the cells that carry
+// the occupancy mass, alpha lies ~ln C(t, t/2) - ln C(t, t/6) ~ 700 nats below the frame's alpha maximum at t = 3000
+// (most alpha mass sits on paths that are ahead of the alignment), so |a_rel| ~ 700, ulp = 6e-5 per frame, and the
+// occupancies came out 1.3e-3 (GPU) / 5e-3 (numpy float32 emulation) off the fp64 oracle at T = 3000.  With double cells
+// the emulation gives 4e-7 at T = 3000.  (the reference's plain fp32 log domain: ~1e-2 at T ~ 1000.)
+// per-utterance workspace: alpha [T][ScMax] | beta [T][ScMax] doubles, then log p
+__device__ __forceinline__ double log_add_d(double a, double b) {
+    const double m = fmax(a, b);
+    if (m == -INFINITY) return m;
+    const float d = (float)(fmin(a, b) - m);          // <= 0; -inf when one side is empty: exp -> 0, log1p -> 0
+    return m + (double)log1pf(expf(d));
 }
 
-// Precision: cells are kept RELATIVE to a per-frame offset (the block max of the previous frame, accumulated in
-// fp64), so fp32 log-add rounding stays ~1e-6 absolute instead of growing with |alpha| (the reference's plain fp32
-// log domain loses ~1e-2 relative on the occupancies at T ~ 1000).  alpha_true_t(s) = a_rel_t(s) + C_t,
-// beta_true_t(s) = b_rel_t(s) + D_t, occupancy = exp(a_rel + b_rel - y + (C_t + D_t - log p)).
-// per-utterance workspace: alpha_rel [T][ScMax] | beta_rel [T][ScMax] floats, then C_t [T] | D_t [T] doubles, log p
 struct CtcWorkspace {
-    float *a, *b;
-    double *coff, *doff, *logp;
+    double *a, *b, *logp;
     __device__ CtcWorkspace(float *base, int n, int T, int ScMax) {
-        const size_t cells = ((size_t)T * ScMax + 1) / 2 * 2;
-        const size_t per_utt = 2 * cells + 4 * (size_t)T + 2;
-        a = base + (size_t)n * per_utt;
-        b = a + cells;
-        coff = reinterpret_cast<double *>(a + 2 * cells);
-        doff = coff + T;
-        logp = doff + T;
+        const size_t cells = (size_t)T * ScMax;
+        double *p = reinterpret_cast<double *>(base) + (size_t)n * (2 * cells + 1);
+        a = p;
+        b = p + cells;
+        logp = p + 2 * cells;
     }
 };
 
-// shared memory carve-up: lab[Lmax+1] ints | a[2][ScMax] | yrow[2][V] | wmax[2][32]
+// shared memory carve-up: a[2][ScMax] doubles | lab[Lmax+1] ints | yrow[2][V] floats
 __global__ void ctc_alpha_beta_kernel(const void *y, int y_bf16, long sn, long st, int T, int V,
                                       const int *labels, const int *label_off, const int *label_len, const int *len,
                                       int max_label_len, int blank, float *alpha_ws, bool want_beta, float *logp_out,
@@ -64,14 +63,13 @@ __global__ void ctc_alpha_beta_kernel(const void *y, int y_bf16, long sn, long s
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = blockIdx.x >> 1;
     const unsigned role = blockIdx.x & 1;   // 0: alpha pass, 1: beta pass
-    const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = NT >> 5;
+    const int tid = threadIdx.x, NT = blockDim.x;
     const int L = label_len[n], Tn = len[n];
     const int Sc = 2 * L + 1, L1 = L + 1;
     const int ScMax = 2 * max_label_len + 1;
-    int *s_lab = reinterpret_cast<int *>(smem_raw);                 // [max_label_len + 1] label of cell 2i+1
-    float *s_a = reinterpret_cast<float *>(s_lab + max_label_len + 1);   // [2][ScMax]
-    float *s_y = s_a + 2 * ScMax;                                   // [2][V]
-    float *s_wmax = s_y + 2 * V;                                    // [2][32]
+    double *s_a = reinterpret_cast<double *>(smem_raw);                        // [2][ScMax]
+    int *s_lab = reinterpret_cast<int *>(s_a + 2 * ScMax);                     // [max_label_len + 1] label of cell 2i+1
+    float *s_y = reinterpret_cast<float *>(s_lab + max_label_len + 1);         // [2][V]
     CtcWorkspace W(alpha_ws, n, T, ScMax);
     const int *lab = labels + label_off[n];
 
@@ -89,34 +87,23 @@ __global__ void ctc_alpha_beta_kernel(const void *y, int y_bf16, long sn, long s
     }
     if (!want_beta && role == 1) return;   // likelihood only
     for (int i = tid; i < L; i += NT) s_lab[i] = lab[i];
-    float *ws = W.a, *wsb = W.b;
-    double *coff = W.coff, *doff = W.doff;
+    double *ws = W.a, *wsb = W.b;
     const long ybase = n * sn;
     constexpr int kRowRegs = 4;
     const bool row_in_regs = V <= kRowRegs * NT;
     float yreg[kRowRegs];
-    double logp_d = 0.0;
 
     if (role == 0) {
     // ---- forward ---------------------------------------------------------------------------------
     for (int k = tid; k < V; k += NT) s_y[k] = load_y(y, y_bf16, ybase + k);
     __syncthreads();
-    {
-        float mx = -INFINITY;
-        for (int s = tid; s < Sc; s += NT) {
-            float v = -INFINITY;
-            if (s == 0) v = s_y[blank];
-            else if (s == 1) v = s_y[s_lab[0]];
-            s_a[s] = v;
-            ws[s] = v;
-            mx = fmaxf(mx, v);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, o));
-        if (lane == 0) s_wmax[warp] = mx;
-        if (tid == 0) coff[0] = 0.0;
+    for (int s = tid; s < Sc; s += NT) {
+        double v = -INFINITY;
+        if (s == 0) v = (double)s_y[blank];
+        else if (s == 1) v = (double)s_y[s_lab[0]];
+        s_a[s] = v;
+        ws[s] = v;
     }
-    double C = 0.0;
     // Row prefetch: the emission row of frame t+1 is loaded into registers while frame t is computed and parked in
     // shared memory afterwards, so no frame waits on a global-memory round trip (V <= kRowRegs * blockDim).
     if (row_in_regs && Tn > 1) {
@@ -126,44 +113,34 @@ __global__ void ctc_alpha_beta_kernel(const void *y, int y_bf16, long sn, long s
         for (int j = 0; j < kRowRegs; ++j) { const int k = tid + j * NT; if (k < V) s_y[V + k] = yreg[j]; }
     }
     for (int t = 1; t < Tn; ++t) {
-        // One barrier per frame: it publishes row t (parked in slot t&1 during the previous frame), the previous
-        // frame's cells and their per-warp maxima.
+        // One barrier per frame: it publishes row t (parked in slot t&1 during the previous frame) and the previous cells.
         float *yc = s_y + (t & 1) * V;
-        const float *prev = s_a + ((t - 1) & 1) * ScMax;
-        float *cur = s_a + (t & 1) * ScMax;
+        const double *prev = s_a + ((t - 1) & 1) * ScMax;
+        double *cur = s_a + (t & 1) * ScMax;
         if (!row_in_regs) for (int k = tid; k < V; k += NT) yc[k] = load_y(y, y_bf16, ybase + (long)t * st + k);
         else if (t + 1 < Tn) {
 #pragma unroll
             for (int j = 0; j < kRowRegs; ++j) { const int k = tid + j * NT; yreg[j] = k < V ? load_y(y, y_bf16, ybase + (long)(t + 1) * st + k) : 0.f; }
         }
         __syncthreads();
-        const float m = block_max_from(s_wmax + ((t - 1) & 1) * 32, nwarps);
-        C += (double)m;
-        if (tid == 0) coff[t] = C;
-        float mx = -INFINITY;
         for (int i = tid; i < L1; i += NT) {
             // blank cell 2i
             const int sb = 2 * i;
-            float vb = prev[sb];
-            if (i > 0) vb = log_add(vb, prev[sb - 1]);
-            vb += yc[blank] - m;
+            double vb = prev[sb];
+            if (i > 0) vb = log_add_d(vb, prev[sb - 1]);
+            vb += (double)yc[blank];
             cur[sb] = vb;
             ws[(size_t)t * ScMax + sb] = vb;
-            mx = fmaxf(mx, vb);
             if (i < L) {   // label cell 2i+1
                 const int sl = sb + 1;
                 const int li = s_lab[i];
-                float vl = log_add(prev[sl], prev[sb]);
-                if (i > 0 && li != s_lab[i - 1]) vl = log_add(vl, prev[sl - 2]);
-                vl += yc[li] - m;
+                double vl = log_add_d(prev[sl], prev[sb]);
+                if (i > 0 && li != s_lab[i - 1]) vl = log_add_d(vl, prev[sl - 2]);
+                vl += (double)yc[li];
                 cur[sl] = vl;
                 ws[(size_t)t * ScMax + sl] = vl;
-                mx = fmaxf(mx, vl);
             }
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, o));
-        if (lane == 0) s_wmax[(t & 1) * 32 + warp] = mx;
         if (row_in_regs && t + 1 < Tn) {   // park row t+1 in the slot last read during frame t-1
             float *yn = s_y + ((t + 1) & 1) * V;
 #pragma unroll
@@ -171,18 +148,16 @@ __global__ void ctc_alpha_beta_kernel(const void *y, int y_bf16, long sn, long s
         }
     }
     __syncthreads();
-    {
-        const float *last = s_a + ((Tn - 1) & 1) * ScMax;
-        float lp = last[Sc - 1];
-        if (Sc > 1) lp = log_add(lp, last[Sc - 2]);
-        logp_d = (double)lp + C;
+    if (tid == 0) {
+        const double *last = s_a + ((Tn - 1) & 1) * ScMax;
+        double lp = last[Sc - 1];
+        if (Sc > 1) lp = log_add_d(lp, last[Sc - 2]);
+        // raw-logit entry: the reported log-likelihood is normalised; everything else stays in the raw domain
+        logp_out[n] = (float)(lp - (lnorm ? lnorm[n] : 0.0));
+        *W.logp = lp;
     }
-    // raw-logit entry: the reported log-likelihood is normalised; everything below stays in the raw domain
-    if (tid == 0) { logp_out[n] = (float)(logp_d - (lnorm ? lnorm[n] : 0.0)); *W.logp = logp_d; }
     } else {
-    // ---- beta pass (cluster rank 1), concurrent with the alpha pass ---------------------------------
-    // beta_true_t(s) = b_rel_t(s) + D_t; ping-pong in s_a (slot t&1 holds beta_rel_t), maxima in s_wmax.
-    double D = 0.0;
+    // ---- beta pass (the utterance's second CTA), concurrent with the alpha pass -------------------------
     {
         const int t = Tn - 1;
         float *yc = s_y + (t & 1) * V;
@@ -190,53 +165,41 @@ __global__ void ctc_alpha_beta_kernel(const void *y, int y_bf16, long sn, long s
     }
     for (int t = Tn - 1; t >= 0; --t) {
         float *yc = s_y + (t & 1) * V;
-        float *cur = s_a + (t & 1) * ScMax;
-        const float *nxt = s_a + ((t + 1) & 1) * ScMax;
+        double *cur = s_a + (t & 1) * ScMax;
+        const double *nxt = s_a + ((t + 1) & 1) * ScMax;
         if (t > 0 && row_in_regs) {   // issue the loads for frame t-1 now; they are parked after this frame's work
 #pragma unroll
             for (int j = 0; j < kRowRegs; ++j) { const int k = tid + j * NT; yreg[j] = k < V ? load_y(y, y_bf16, ybase + (long)(t - 1) * st + k) : 0.f; }
         }
-        __syncthreads();   // the only barrier of the frame: publishes row t, beta_{t+1} and its maxima
-        float m = 0.f;
-        if (t < Tn - 1) {
-            m = block_max_from(s_wmax + ((t + 1) & 1) * 32, nwarps);
-            D += (double)m;
-        }
-        if (tid == 0) doff[t] = D;
-        float *bl = wsb + (size_t)t * ScMax;
-        float mx = -INFINITY;
+        __syncthreads();   // the only barrier of the frame: publishes row t and beta_{t+1}
+        double *bl = wsb + (size_t)t * ScMax;
         for (int i = tid; i < L1; i += NT) {
             const int sb = 2 * i;
-            float vb;
+            double vb;
             if (t == Tn - 1) {
-                vb = (sb == Sc - 1) ? yc[blank] : -INFINITY;
+                vb = (sb == Sc - 1) ? (double)yc[blank] : -INFINITY;
             } else {
                 vb = nxt[sb];
-                if (sb + 1 < Sc) vb = log_add(vb, nxt[sb + 1]);
-                vb += yc[blank] - m;
+                if (sb + 1 < Sc) vb = log_add_d(vb, nxt[sb + 1]);
+                vb += (double)yc[blank];
             }
             cur[sb] = vb;
             bl[sb] = vb;
-            mx = fmaxf(mx, vb);
             if (i < L) {
                 const int sl = sb + 1;
                 const int li = s_lab[i];
-                float vl;
+                double vl;
                 if (t == Tn - 1) {
-                    vl = (sl == Sc - 2) ? yc[li] : -INFINITY;
+                    vl = (sl == Sc - 2) ? (double)yc[li] : -INFINITY;
                 } else {
-                    vl = log_add(nxt[sl], nxt[sl + 1]);
-                    if (i + 1 < L && li != s_lab[i + 1]) vl = log_add(vl, nxt[sl + 2]);
-                    vl += yc[li] - m;
+                    vl = log_add_d(nxt[sl], nxt[sl + 1]);
+                    if (i + 1 < L && li != s_lab[i + 1]) vl = log_add_d(vl, nxt[sl + 2]);
+                    vl += (double)yc[li];
                 }
                 cur[sl] = vl;
                 bl[sl] = vl;
-                mx = fmaxf(mx, vl);
             }
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, o));
-        if (lane == 0) s_wmax[(t & 1) * 32 + warp] = mx;
         if (t > 0) {   // park row t-1 in the slot last read during frame t+1
             float *yn = s_y + ((t - 1) & 1) * V;
             if (row_in_regs) {
@@ -252,7 +215,7 @@ __global__ void ctc_alpha_beta_kernel(const void *y, int y_bf16, long sn, long s
 }
 
 // Occupancies from the two spills: one warp per (utterance, frame), label accumulator [V] per warp in shared memory.
-//   gamma_t[k] = sum_{s: l'_s = k} exp(a_rel_t(s) + b_rel_t(s) - y_t(k) + C_t + D_t - log p)   (gpu_ctc_kernels.h:337-453)
+//   gamma_t[k] = sum_{s: l'_s = k} exp(alpha_t(s) + beta_t(s) - y_t(k) - log p)   (gpu_ctc_kernels.h:337-453)
 // accumulated with the caller's scale into grad[n][t][:] (which may already hold the denominator part).
 __global__ void ctc_gamma_kernel(const void *y, int y_bf16, long sn, long st, int N, int T, int V,
                                  const int *labels, const int *label_off, const int *label_len, const int *len,
@@ -276,14 +239,13 @@ __global__ void ctc_gamma_kernel(const void *y, int y_bf16, long sn, long st, in
     float *g = reinterpret_cast<float *>(smem_raw) + (size_t)warp * V;
     for (int k = lane; k < V; k += 32) g[k] = 0.f;
     __syncwarp();
-    const float K = (float)(W.coff[t] + W.doff[t] - logp_d);
-    const float *al = W.a + (size_t)t * ScMax, *bl = W.b + (size_t)t * ScMax;
+    const double *al = W.a + (size_t)t * ScMax, *bl = W.b + (size_t)t * ScMax;
     const int *lab = labels + label_off[n];
     const long yrow = n * sn + (long)t * st;
     float occ_blank = 0.f;
     for (int s = lane; s < Sc; s += 32) {   // lane parity == cell parity: even lanes take blanks, odd lanes labels
         const int li = (s & 1) ? __ldg(lab + (s >> 1)) : blank;
-        const float o = al[s] + bl[s] - load_y(y, y_bf16, yrow + li) + K;
+        const float o = (float)(al[s] + bl[s] - (double)load_y(y, y_bf16, yrow + li) - logp_d);
         const float e = (o == -INFINITY || o != o) ? 0.f : expf(o);
         if (s & 1) { if (e != 0.f) atomicAdd(&g[li], e); }
         else occ_blank += e;
@@ -403,7 +365,7 @@ int LaunchCtc(const void *y, int y_bf16, long sn, long st, int N, int T, int V, 
     const int ScMax = 2 * max_label_len + 1;
     int threads = ((max_label_len + 1 + 31) / 32) * 32;
     threads = threads < 64 ? 64 : (threads > 1024 ? 1024 : threads);
-    const size_t smem = (size_t)(max_label_len + 1) * 4 + (size_t)2 * ScMax * 4 + (size_t)2 * V * 4 + 64 * 4;
+    const size_t smem = (size_t)2 * ScMax * 8 + (size_t)(max_label_len + 1) * 4 + (size_t)2 * V * 4 + 16;
     if (smem > 200 * 1024 || (size_t)V * 4 > 200 * 1024) { *err = "label sequence too long for the numerator kernel's shared memory"; return 1; }
     cudaError_t e = cudaFuncSetAttribute(ctc_alpha_beta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { *err = std::string("cudaFuncSetAttribute(ctc): ") + cudaGetErrorString(e); return (int)e; }

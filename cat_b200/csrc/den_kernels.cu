@@ -355,6 +355,109 @@ __device__ __forceinline__ void walk_arcs_dual(const uint4 *arcs, const float4 *
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// TMA row gathers (sm_100a): `cp.async.bulk.tensor.2d ... tile::gather4` (SASS UTMALDG.2D.GATHER4) copies FOUR rows of
+// the gather table, named by four row coordinates, into shared memory with one instruction issued by one lane -- exactly
+// one arc quad.  The rows of a batch land in a per-warp ring (STAGES stages of R rows) and complete an mbarrier; the warp
+// then reads them with LDS.  Measured on this B200 (tools/l2_gather4_bench.cu, profiles/r02_l2_gather4_microbench.txt):
+// random 256-byte rows from an L2-resident table at 62 G rows/s = 15.9 TB/s with 512 threads (1-D bulk copies, one
+// instruction per row: 43 G rows/s; the register path of round 1: 42 G rows/s inside the kernels), and the rows in flight
+// cost no registers and 5 instructions per arc slot instead of 13.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap *tm, int col, int r0, int r1, int r2, int r3, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+                 ::"r"(dst), "l"(tm), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar) : "memory");
+}
+// rows written with ordinary stores by other CTAs are read through the async proxy (TMA) one frame later: order the two
+// proxies on both sides of the grid barrier
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+
+// per-warp ring state: shared-memory address of the ring, of its first mbarrier, and the parity to wait for per stage
+struct TmaRing {
+    uint32_t buf, bar, phase;
+};
+template <int U> struct TmaShape;   // rows per batch / stages per warp: 8 KB (4 KB at U=1) of rows in flight per warp
+template <> struct TmaShape<1> { static constexpr int R = 16, STAGES = 2; };
+template <> struct TmaShape<2> { static constexpr int R = 16, STAGES = 2; };
+template <> struct TmaShape<4> { static constexpr int R = 8, STAGES = 2; };
+
+template <int U> __device__ __forceinline__ Vec<U> lds_row(uint32_t addr);
+template <> __device__ __forceinline__ Vec<1> lds_row<1>(uint32_t addr) {
+    Vec<1> r;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r.v[0]) : "r"(addr));
+    return r;
+}
+template <> __device__ __forceinline__ Vec<2> lds_row<2>(uint32_t addr) {
+    Vec<2> r;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(r.v[0]), "=f"(r.v[1]) : "r"(addr));
+    return r;
+}
+template <> __device__ __forceinline__ Vec<4> lds_row<4>(uint32_t addr) {
+    Vec<4> r;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]) : "r"(addr));
+    return r;
+}
+
+// The arc walk with TMA-staged rows.  `arcs`: the chunk's quads in shared memory, WPQ 16-byte words per quad
+// {row index 0..3}{w0..3}[{w1 0..3}]; n_batches = chunk arcs / R.  One batch = R/4 quads, issued by lanes 0..R/4-1 (one
+// gather4 each).  `consume_quad(words of the quad, rows v[4])` does the FMAs and the segment-end work.
+template <int U, int WPQ, typename Prologue, typename ConsumeQuad>
+__device__ __forceinline__ void walk_arcs_tma(const uint4 *arcs, int n_batches, const CUtensorMap *tm, int col, int row_base,
+                                              TmaRing &ring, int lane, Prologue &&prologue, ConsumeQuad &&consume_quad) {
+    constexpr int R = TmaShape<U>::R, STAGES = TmaShape<U>::STAGES, QB = R / kQuad;
+    constexpr uint32_t ROWB = 32u * U * 4u;
+    static_assert(STAGES == 2, "the loop below is unrolled for two stages");
+    auto issue = [&](int k, int s) {
+        const uint32_t bar = ring.bar + 8u * s;
+        if (lane == 0) mbar_expect_tx(bar, R * ROWB);
+        __syncwarp();
+        if (lane < QB) {
+            const uint4 pr = arcs[(size_t)WPQ * (k * QB + lane)];
+            tma_gather4(ring.buf + (uint32_t)(s * R + kQuad * lane) * ROWB, tm, col, row_base + (int)pr.x, row_base + (int)pr.y,
+                        row_base + (int)pr.z, row_base + (int)pr.w, bar);
+        }
+    };
+    auto consume = [&](int k, int s) {
+        mbar_wait(ring.bar + 8u * s, (ring.phase >> s) & 1u);
+        ring.phase ^= 1u << s;
+        const uint32_t base = ring.buf + (uint32_t)(s * R) * ROWB + (uint32_t)lane * (U * 4u);
+#pragma unroll
+        for (int q = 0; q < QB; ++q) {
+            Vec<U> v[kQuad];
+#pragma unroll
+            for (int j = 0; j < kQuad; ++j) v[j] = lds_row<U>(base + (uint32_t)(q * kQuad + j) * ROWB);
+            consume_quad(arcs + (size_t)WPQ * (k * QB + q), v);
+        }
+        __syncwarp();   // every lane is done with the stage before it is refilled
+    };
+    if (n_batches <= 0) { prologue(); return; }
+    issue(0, 0);
+    if (n_batches > 1) issue(1, 1);
+    prologue();   // per-frame scalars are fetched while the first rows are in flight
+    for (int k = 0; k < n_batches; k += 2) {
+        consume(k, 0);
+        if (k + 2 < n_batches) issue(k + 2, 0);
+        if (k + 1 < n_batches) {
+            consume(k + 1, 1);
+            if (k + 3 < n_batches) issue(k + 3, 1);
+        }
+    }
+}
+
 __device__ __forceinline__ unsigned long long global_timer() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -400,9 +503,12 @@ __device__ __noinline__ void forward_partial_row(const int *state_label, const i
 // ------------------------------------------------------------------------------------------------
 // HUBS: the plan contains high in-degree rows split into parts (kEvPartial segments); the common case compiles the
 // partial-row path out entirely so that it costs the hot row-end code nothing.
-template <int NT, int U, int BATCH, bool SMEM_ARCS, bool HUBS>
-__global__ void __launch_bounds__(NT, 1) den_forward_kernel(const DenParams P) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+// TMA: the gathered rows are staged in shared memory by gather4 copies (walk_arcs_tma) instead of register gathers; needs
+// the arc tile in shared memory (SMEM_ARCS) and DenParams::tmap.
+template <int NT, int U, int BATCH, bool SMEM_ARCS, bool HUBS, bool TMA = false>
+__global__ void __launch_bounds__(NT, 1) den_forward_kernel(const __grid_constant__ DenParams P) {
+    static_assert(!TMA || SMEM_ARCS, "the TMA walk reads the arc tile from shared memory");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     float *s_sum = reinterpret_cast<float *>(smem_raw);                                  // [Npad]
     int *s_label = reinterpret_cast<int *>(s_sum + P.Npad);                              // [tile_rows] label per row
     Arc *s_arcs = reinterpret_cast<Arc *>(smem_raw + (((size_t)(P.Npad + P.tile_rows) * 4 + 15) & ~(size_t)15));
@@ -430,9 +536,20 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const DenParams P) {
     int labp0 = -1, labp1 = -1;
     for (int q = se - 1; q >= sb; --q) { if (__ldg(P.state_pos + q)) labp1 = __ldg(P.state_label + q); else labp0 = __ldg(P.state_label + q); }
     unsigned epoch = 0;
-    const int n_batches = (ae - ab) / BATCH;
+    const int n_batches = (ae - ab) / (TMA ? TmaShape<U>::R : BATCH);
     const uint4 *const arc4 = SMEM_ARCS ? reinterpret_cast<const uint4 *>(s_arcs + (ab - tile_a0))
                                         : reinterpret_cast<const uint4 *>(P.arcs + ab);
+    TmaRing ring{0u, 0u, 0u};
+    if (TMA) {
+        constexpr uint32_t kRingBytes = (uint32_t)TmaShape<U>::STAGES * TmaShape<U>::R * 32u * U * 4u;
+        ring.buf = smem_u32(smem_raw + P.ring_off) + (uint32_t)warp * kRingBytes;
+        ring.bar = smem_u32(smem_raw + P.bar_off) + (uint32_t)warp * 8u * TmaShape<U>::STAGES;
+        if (lane == 0) {
+            for (int st = 0; st < TmaShape<U>::STAGES; ++st) mbar_init(ring.bar + 8u * st, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+    }
 
     // per-row metadata lives in shared memory: L1 is invalidated at every grid barrier, and a global load on the
     // row-end path would cost an L2 round trip per row
@@ -443,8 +560,8 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const DenParams P) {
         const uint4 *src = reinterpret_cast<const uint4 *>(P.arcs + tile_a0);
         for (int i = tid; i < (tile_a1 - tile_a0) / kQuad; i += NT) {
             const uint4 m0 = __ldg(src + 2 * i), m1 = __ldg(src + 2 * i + 1);
-            sq[2 * i] = make_uint4(fwd_row(m0.x, S) * row_bytes, fwd_row(m0.z, S) * row_bytes,
-                                   fwd_row(m1.x, S) * row_bytes, fwd_row(m1.z, S) * row_bytes);   // byte offsets of the gathered rows
+            const uint32_t mul = TMA ? 1u : row_bytes;   // TMA: row coordinates; register gathers: byte offsets
+            sq[2 * i] = make_uint4(fwd_row(m0.x, S) * mul, fwd_row(m0.z, S) * mul, fwd_row(m1.x, S) * mul, fwd_row(m1.z, S) * mul);
             sq[2 * i + 1] = make_uint4(m0.y, m0.w, m1.y, m1.w);
         }
     }
@@ -476,10 +593,12 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const DenParams P) {
 #pragma unroll
     for (int u = 0; u < U; ++u) len0[u] = (lane * U + u < P.N) ? __ldg(P.len + lane * U + u) : 0;
     double runlog = 0.0;
+    if (TMA) fence_proxy_async_global();
     grid_barrier(P.barrier, (++epoch) * gridDim.x);
 
     for (int t = 1; t <= P.Tmax; ++t) {
         tl_mark(P, t, chunk, n_chunks, 0, lane);
+        if (TMA) fence_proxy_async_global();
         const float *a_prev = P.alpha + (size_t)(t - 1) * frame_elems;
         float *a_cur = P.alpha + (size_t)t * frame_elems;
         for (int gc = 0; gc < Npad / (32 * U); ++gc) {
@@ -513,15 +632,15 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const DenParams P) {
             uint32_t virt_row = virt0 + (uint32_t)vj0;           // the next virtual row (parked two frames ahead)
             float *const out_base = a_cur + n0;
             Vec<U> cacc = vec_zero<U>();
-            walk_arcs<U, BATCH, SMEM_ARCS>(arc4, n_batches, row_bytes, (uint32_t)S, reinterpret_cast<const char *>(a_prev + n0), lane_act,
-                                           frame_scalars, [&](float *acc, int ev, bool new_label, const uint4 *quad) {
+            auto seg_end = [&](float *acc, int ev, bool new_label, const uint4 *quad) {
                 const bool k1 = ev != kEvRowPos0;
                 if (P.debug & 1) { sum[0] += acc[0]; acc[0] = 0.f; return; }
                 if (HUBS && ev == kEvPartial) {   // high in-degree rows only: handled out of line, nothing hot is captured
                     Vec<U> part;
 #pragma unroll
                     for (int u = 0; u < U; ++u) { part.v[u] = acc[u]; acc[u] = 0.f; }
-                    const uint32_t tgt_off = load_quad_peers<SMEM_ARCS>(quad, row_bytes, (uint32_t)S).w;   // byte offset of the target row
+                    // byte offset of the target row (last slot of the segment)
+                    const uint32_t tgt_off = TMA ? quad[0].w * row_bytes : load_quad_peers<SMEM_ARCS>(quad, row_bytes, (uint32_t)S).w;
                     forward_partial_row<U>(P.state_label, P.len, P.colsum_a + (size_t)(t - 1) * Npad, P.fmax + (size_t)(t - 1) * Npad,
                                            P.y, P.y_bf16, P.sn, (long)(t - 1) * P.st, P.N, t, n0, part, tgt_off, row_bytes, a_cur, s_sum, P.scale_exp);
                     if (tgt_off == out_row * row_bytes) { ++out_row; ++ql; }   // the part that lives in the row's own group
@@ -542,26 +661,53 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const DenParams P) {
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     out.v[u] = acc[u] * (k1 ? ec1[u] : ec0[u]) * r[u];   // ec is 0 for inactive utterances
+                    // TMA rows are read by every lane, whatever its utterances do: inactive columns are kept at a clean 0
+                    // (the register path never loads them)
+                    if (TMA && !act[u]) out.v[u] = 0.f;
                     sum[u] += out.v[u];
                     acc[u] = 0.f;
                 }
-                if (lane_act) out.stcg(row_ptr<U>(out_base, out_row, row_bytes));
+                if (TMA || lane_act) out.stcg(row_ptr<U>(out_base, out_row, row_bytes));
                 if (ev == kEvRowPos0) cacc = out;
                 else if (ev == kEvRowPos1) {   // the pair's virtual row: what the next frame gathers instead of both
 #pragma unroll
                     for (int u = 0; u < U; ++u) cacc.v[u] += out.v[u];
-                    if (lane_act) cacc.stcg(row_ptr<U>(out_base, virt_row, row_bytes));
+                    if (TMA || lane_act) cacc.stcg(row_ptr<U>(out_base, virt_row, row_bytes));
                     ++virt_row;
                 }
                 ++out_row;
                 ++ql;
-            });
+            };
+            if (TMA) {
+                float acc[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) acc[u] = 0.f;
+                walk_arcs_tma<U, 2>(arc4, n_batches, &P.tmap, gc * 32 * U, (t - 1) * S, ring, lane, frame_scalars,
+                                    [&](const uint4 *quad, const Vec<U> *v) {
+                    const uint4 wq = quad[1];
+                    const float w0 = fabsf(__uint_as_float(wq.x)), w1 = fabsf(__uint_as_float(wq.y));
+                    const float w2 = fabsf(__uint_as_float(wq.z)), w3 = fabsf(__uint_as_float(wq.w));
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        acc[u] = fmaf(w0, v[0].v[u], acc[u]);
+                        acc[u] = fmaf(w1, v[1].v[u], acc[u]);
+                        acc[u] = fmaf(w2, v[2].v[u], acc[u]);
+                        acc[u] = fmaf(w3, v[3].v[u], acc[u]);
+                    }
+                    if ((int)wq.w < 0)   // warp-uniform: a segment ends at this quad
+                        seg_end(acc, (int)(((wq.z >> 31) << 1) | (wq.y >> 31)), (int)wq.x < 0, quad);
+                });
+            } else {
+                walk_arcs<U, BATCH, SMEM_ARCS>(arc4, n_batches, row_bytes, (uint32_t)S, reinterpret_cast<const char *>(a_prev + n0), lane_act,
+                                               frame_scalars, seg_end);
+            }
 #pragma unroll
             for (int u = 0; u < U; ++u)
                 if (act[u] && sum[u] != 0.f) atomicAdd(&s_sum[n0 + u], sum[u]);
         }
         tl_mark(P, t, chunk, n_chunks, 1, lane);
         if (HUBS && t < P.Tmax) zero_hub_rows(t + 1);
+        if (TMA) fence_proxy_async_global();   // this frame's rows are read through the async proxy after the barrier
         __syncthreads();
         for (int i = tid; i < Npad; i += NT) {
             const float v = s_sum[i];
@@ -606,9 +752,10 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const DenParams P) {
 // ------------------------------------------------------------------------------------------------
 // backward: beta recursion, occupancies, logZ from beta
 // ------------------------------------------------------------------------------------------------
-template <int NT, int U, int BATCH, bool SMEM_ARCS, bool W1_SMEM = SMEM_ARCS>
-__global__ void __launch_bounds__(NT, 1) den_backward_kernel(const DenParams P) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+template <int NT, int U, int BATCH, bool SMEM_ARCS, bool W1_SMEM = SMEM_ARCS, bool TMA = false>
+__global__ void __launch_bounds__(NT, 1) den_backward_kernel(const __grid_constant__ DenParams P) {
+    static_assert(!TMA || (SMEM_ARCS && W1_SMEM), "the TMA walk reads offsets and both weights from shared memory");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int Npad = P.Npad, S = P.S;
     float *s_sum = reinterpret_cast<float *>(smem_raw);            // [2][Npad]: colsum_b, absum
     float *s_gacc = s_sum + 2 * Npad;                              // [gacc_rows][Npad]
@@ -631,7 +778,7 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const DenParams P) 
     const int cl_lab1 = __ldg(P.cta_labels + cta * 4 + 2), cl_n1 = __ldg(P.cta_labels + cta * 4 + 3);
     int labp0 = -1, labp1 = -1;
     for (int q = se - 1; q >= sb; --q) { if (__ldg(P.state_pos + q)) labp1 = __ldg(P.state_label + q); else labp0 = __ldg(P.state_label + q); }
-    const int n_batches = (ae - ab) / BATCH;
+    const int n_batches = (ae - ab) / (TMA ? TmaShape<U>::R : BATCH);
     // shared memory: 3 words of 16 bytes per quad {byte offsets}{w0}{w1}; global fallback: AoS arcs + w1 array
     constexpr int kW = W1_SMEM ? 3 : 2;   // 16-byte words per staged quad
     const uint4 *const arc4 = SMEM_ARCS ? reinterpret_cast<const uint4 *>(s_arcs) + kW * ((ab - tile_a0) / kQuad)
@@ -653,10 +800,22 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const DenParams P) 
         const uint4 *src1 = reinterpret_cast<const uint4 *>(P.w1 + tile_a0);
         for (int i = tid; i < (tile_a1 - tile_a0) / kQuad; i += NT) {
             const uint4 m0 = __ldg(src + 2 * i), m1 = __ldg(src + 2 * i + 1);
-            sq[kW * i] = make_uint4(m0.x * row_bytes, m0.z * row_bytes, m1.x * row_bytes, m1.z * row_bytes);
+            const uint32_t mul = TMA ? 1u : row_bytes;   // TMA: row coordinates; register gathers: byte offsets
+            sq[kW * i] = make_uint4(m0.x * mul, m0.z * mul, m1.x * mul, m1.z * mul);
             sq[kW * i + 1] = make_uint4(m0.y, m0.w, m1.y, m1.w);
             if (W1_SMEM) sq[kW * i + 2] = __ldg(src1 + i);
         }
+    }
+    TmaRing ring{0u, 0u, 0u};
+    if (TMA) {
+        constexpr uint32_t kRingBytes = (uint32_t)TmaShape<U>::STAGES * TmaShape<U>::R * 32u * U * 4u;
+        ring.buf = smem_u32(smem_raw + P.ring_off) + (uint32_t)warp * kRingBytes;
+        ring.bar = smem_u32(smem_raw + P.bar_off) + (uint32_t)warp * 8u * TmaShape<U>::STAGES;
+        if (lane == 0) {
+            for (int st = 0; st < TmaShape<U>::STAGES; ++st) mbar_init(ring.bar + 8u * st, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
     }
     for (int i = tid; i < (2 + P.gacc_rows) * Npad; i += NT) s_sum[i] = 0.f;
     const int my_len = (cta == 0 && tid < P.N) ? __ldg(P.len + tid) : 0;
@@ -668,6 +827,7 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const DenParams P) 
 
     for (int tau = P.Tmax; tau >= 1; --tau) {
         tl_mark(P, P.Tmax - tau, chunk, n_chunks, 0, lane);
+        if (TMA) fence_proxy_async_global();
         const float *bh_next = P.bh + (size_t)((tau + 1) & 1) * frame_elems;
         float *bh_cur = P.bh + (size_t)(tau & 1) * frame_elems;
         const float *a_row = P.alpha + (size_t)tau * alpha_frame;
@@ -754,13 +914,11 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const DenParams P) 
                     sum_b[u] += out.v[u];
                     acc[u] = 0.f;
                 }
-                if (lane_act) out.stcg(row_ptr<U>(out_base, out_row, row_bytes));
+                if (TMA || lane_act) out.stcg(row_ptr<U>(out_base, out_row, row_bytes));   // (TMA: every lane reads the row later)
                 ++out_row;
                 ++ql;
             };
-            walk_arcs_dual<U, BATCH, SMEM_ARCS, W1_SMEM>(arc4, w1g, n_batches, row_bytes, reinterpret_cast<const char *>(bh_next + n0),
-                                                lane_gat, frame_scalars,
-                                                [&](float *acc0, float *acc1, bool pair, bool new0, bool new1) {
+            auto group_end = [&](float *acc0, float *acc1, bool pair, bool new0, bool new1) {
                 if (P.debug & 1) { sum_b[0] += acc0[0] + acc1[0]; acc0[0] = 0.f; acc1[0] = 0.f; return; }
                 if (pair) {
                     do_row(false, new0, acc0, a_q);
@@ -772,7 +930,33 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const DenParams P) 
                 }
                 a_q = ((int)out_row < se && lane_act) ? gather_row<U>(a_base, out_row * row_bytes) : vec_zero<U>();
                 a_q1 = ((int)out_row + 1 < se && lane_act) ? gather_row<U>(a_base, (out_row + 1) * row_bytes) : vec_zero<U>();
-            });
+            };
+            if (TMA) {
+                float acc0[U], acc1[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) { acc0[u] = 0.f; acc1[u] = 0.f; }
+                // (the first backward frame of an utterance takes beta from the final weights, not from these sums: whatever
+                // the ring holds then is never selected, see do_row)
+                walk_arcs_tma<U, 3>(arc4, n_batches, &P.tmap, gc * 32 * U, ((tau + 1) & 1) * S, ring, lane, frame_scalars,
+                                    [&](const uint4 *quad, const Vec<U> *v) {
+                    const uint4 wq = quad[1], t1 = quad[2];
+                    const float a0 = fabsf(__uint_as_float(wq.x)), a1 = fabsf(__uint_as_float(wq.y));
+                    const float a2 = fabsf(__uint_as_float(wq.z)), a3 = fabsf(__uint_as_float(wq.w));
+                    const float b0 = __uint_as_float(t1.x), b1 = __uint_as_float(t1.y), b2 = __uint_as_float(t1.z), b3 = __uint_as_float(t1.w);
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        acc0[u] = fmaf(a0, v[0].v[u], acc0[u]); acc1[u] = fmaf(b0, v[0].v[u], acc1[u]);
+                        acc0[u] = fmaf(a1, v[1].v[u], acc0[u]); acc1[u] = fmaf(b1, v[1].v[u], acc1[u]);
+                        acc0[u] = fmaf(a2, v[2].v[u], acc0[u]); acc1[u] = fmaf(b2, v[2].v[u], acc1[u]);
+                        acc0[u] = fmaf(a3, v[3].v[u], acc0[u]); acc1[u] = fmaf(b3, v[3].v[u], acc1[u]);
+                    }
+                    if ((int)wq.w < 0)   // warp-uniform: the group ends at this quad
+                        group_end(acc0, acc1, (int)wq.z < 0, (int)wq.x < 0, (int)wq.y < 0);
+                });
+            } else {
+                walk_arcs_dual<U, BATCH, SMEM_ARCS, W1_SMEM>(arc4, w1g, n_batches, row_bytes, reinterpret_cast<const char *>(bh_next + n0),
+                                                             lane_gat, frame_scalars, group_end);
+            }
             if (curlab0 >= 0) flush_gsum(false);
             if (curlab1 >= 0) flush_gsum(true);
 #pragma unroll
@@ -784,6 +968,7 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const DenParams P) 
             }
         }
         tl_mark(P, P.Tmax - tau, chunk, n_chunks, 1, lane);
+        if (TMA) fence_proxy_async_global();   // this frame's rows are read through the async proxy after the barrier
         __syncthreads();
         for (int i = tid; i < Npad; i += NT) {   // the next frame's scale: must be out before this CTA arrives
             const float vb = s_sum[i];
@@ -863,12 +1048,7 @@ __global__ void den_grad_normalize_kernel(float *grad, long gsn, long gst, const
 // ------------------------------------------------------------------------------------------------
 // launch plumbing
 // ------------------------------------------------------------------------------------------------
-template <int NT, int U, int BATCH, bool SMEM_ARCS>
-int LaunchOne(bool backward, bool w1_smem, const DenParams &p, int n_ctas, size_t smem, cudaStream_t stream, std::string *err) {
-    const void *fn = backward ? (SMEM_ARCS && !w1_smem ? (const void *)den_backward_kernel<NT, U, BATCH, SMEM_ARCS, false>
-                                                       : (const void *)den_backward_kernel<NT, U, BATCH, SMEM_ARCS>)
-                     : p.n_hubs > 0 ? (const void *)den_forward_kernel<NT, U, BATCH, SMEM_ARCS, true>
-                                    : (const void *)den_forward_kernel<NT, U, BATCH, SMEM_ARCS, false>;
+int LaunchCoop(const void *fn, int NT, const DenParams &p, int n_ctas, size_t smem, cudaStream_t stream, std::string *err) {
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { *err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return (int)e; }
     int per_sm = 0;
@@ -885,6 +1065,29 @@ int LaunchOne(bool backward, bool w1_smem, const DenParams &p, int n_ctas, size_
     return 0;
 }
 
+template <int NT, int U, int BATCH, bool SMEM_ARCS>
+int LaunchFwd(const DenParams &p, int n_ctas, size_t smem, cudaStream_t stream, std::string *err) {
+    const void *fn = p.n_hubs > 0 ? (const void *)den_forward_kernel<NT, U, BATCH, SMEM_ARCS, true>
+                                  : (const void *)den_forward_kernel<NT, U, BATCH, SMEM_ARCS, false>;
+    return LaunchCoop(fn, NT, p, n_ctas, smem, stream, err);
+}
+template <int NT, int U, int BATCH, bool SMEM_ARCS>
+int LaunchBwd(bool w1_smem, const DenParams &p, int n_ctas, size_t smem, cudaStream_t stream, std::string *err) {
+    const void *fn = SMEM_ARCS && !w1_smem ? (const void *)den_backward_kernel<NT, U, BATCH, SMEM_ARCS, false>
+                                           : (const void *)den_backward_kernel<NT, U, BATCH, SMEM_ARCS>;
+    return LaunchCoop(fn, NT, p, n_ctas, smem, stream, err);
+}
+
+// TMA gather4 variants (arc tile and, backward, both weights in shared memory)
+template <int NT, int U>
+int LaunchTma(bool backward, const DenParams &p, int n_ctas, size_t smem, cudaStream_t stream, std::string *err) {
+    constexpr int R = TmaShape<U>::R;
+    const void *fn = backward ? (const void *)den_backward_kernel<NT, U, R, true, true, true>
+                     : p.n_hubs > 0 ? (const void *)den_forward_kernel<NT, U, R, true, true, true>
+                                    : (const void *)den_forward_kernel<NT, U, R, true, false, true>;
+    return LaunchCoop(fn, NT, p, n_ctas, smem, stream, err);
+}
+
 constexpr int kBwdMaxLaneWidth = 2;   // N=256: bwd 163 ms at 2 vs 248 ms at 4 (profiles/r01_experiments.md)
 
 // Gathers per batch (two batches are in flight per warp), fixed per variant by the register budget at 512 threads
@@ -893,38 +1096,60 @@ template <int U> struct FwdBatch { static constexpr int value = U == 4 ? 8 : 16;
 constexpr int kBwdBatch = 8;
 
 template <int NT, int U>
-int DispatchU(bool backward, bool smem_arcs, bool w1_smem, const DenParams &p, int n_ctas, size_t smem, cudaStream_t stream,
+int DispatchU(bool backward, bool tma, bool smem_arcs, bool w1_smem, const DenParams &p, int n_ctas, size_t smem, cudaStream_t stream,
               std::string *err) {
+    if (tma) return LaunchTma<NT, U>(backward, p, n_ctas, smem, stream, err);
     if (backward)
-        return smem_arcs ? LaunchOne<NT, U, kBwdBatch, true>(true, w1_smem, p, n_ctas, smem, stream, err)
-                         : LaunchOne<NT, U, kBwdBatch, false>(true, w1_smem, p, n_ctas, smem, stream, err);
-    return smem_arcs ? LaunchOne<NT, U, FwdBatch<U>::value, true>(false, w1_smem, p, n_ctas, smem, stream, err)
-                     : LaunchOne<NT, U, FwdBatch<U>::value, false>(false, w1_smem, p, n_ctas, smem, stream, err);
+        return smem_arcs ? LaunchBwd<NT, U, kBwdBatch, true>(w1_smem, p, n_ctas, smem, stream, err)
+                         : LaunchBwd<NT, U, kBwdBatch, false>(w1_smem, p, n_ctas, smem, stream, err);
+    return smem_arcs ? LaunchFwd<NT, U, FwdBatch<U>::value, true>(p, n_ctas, smem, stream, err)
+                     : LaunchFwd<NT, U, FwdBatch<U>::value, false>(p, n_ctas, smem, stream, err);
+}
+
+size_t TmaRingBytes(int U) {   // per warp
+    return U == 1 ? (size_t)TmaShape<1>::STAGES * TmaShape<1>::R * 128 : U == 2 ? (size_t)TmaShape<2>::STAGES * TmaShape<2>::R * 256
+                                                                               : (size_t)TmaShape<4>::STAGES * TmaShape<4>::R * 512;
 }
 
 template <int NT>
-int Dispatch(bool backward, const DeviceGraph &g, const DenParams &p, size_t fixed_smem, cudaStream_t stream,
+int Dispatch(bool backward, const DeviceGraph &g, DenParams &p, size_t fixed_smem, cudaStream_t stream,
              std::string *err) {
     const DevicePass &pass = backward ? g.bwd : g.fwd;
-    // three tiers by graph size: the whole arc stream in shared memory (8 bytes per forward slot, 12 per backward slot);
-    // backward only: offsets + first weights in shared memory, second weights streamed from L2; everything from L2
+    // Tiers by graph size.  (1) TMA: the whole arc stream in shared memory (8 bytes per forward slot, 12 per backward slot)
+    // next to the per-warp row rings the gather4 copies fill; (2) the same stream with register gathers (no ring);
+    // (3) backward only: offsets + first weights in shared memory, second weights streamed from L2; (4) everything from L2.
     const size_t budget = (size_t)g.max_smem_optin > 2048 ? (size_t)g.max_smem_optin - 1024 : 0;
     const bool no_smem = g.tune_arcs_in_global;   // test hooks (read once at Init): exercise the large-graph tiers
     bool w1_smem = backward && !g.tune_w1_in_global;
     size_t arc_bytes = (size_t)pass.max_tile_arcs * (backward && w1_smem ? 12 : sizeof(Arc));
     if (backward && w1_smem && fixed_smem + arc_bytes > budget) { w1_smem = false; arc_bytes = (size_t)pass.max_tile_arcs * sizeof(Arc); }
     const bool smem_arcs = fixed_smem + arc_bytes <= budget && !no_smem;
-    const size_t smem = fixed_smem + (smem_arcs ? arc_bytes : 0);
+    size_t smem = fixed_smem + (smem_arcs ? arc_bytes : 0);
     // utterances per lane: the widest row segment the batch allows, except that the backward pass (two accumulators per
     // utterance) runs out of registers at 4 -- it walks 64-utterance groups instead.
     int U = LaneWidth(p.Npad);
     if (backward && U == 4) U = kBwdMaxLaneWidth;
-    if (U == 1) return DispatchU<NT, 1>(backward, smem_arcs, w1_smem, p, g.n_ctas, smem, stream, err);
-    if (U == 2) return DispatchU<NT, 2>(backward, smem_arcs, w1_smem, p, g.n_ctas, smem, stream, err);
-    return DispatchU<NT, 4>(backward, smem_arcs, w1_smem, p, g.n_ctas, smem, stream, err);
+    // TMA tier: needs the full shared-memory stream, room for the rings, and a descriptor the driver accepts
+    bool tma = false;
+    p.use_tma = 0;
+    if (smem_arcs && (!backward || w1_smem) && !g.tune_no_tma) {
+        const size_t ring_off = (smem + 127) & ~(size_t)127;
+        const size_t bar_off = ring_off + (size_t)g.n_warps * TmaRingBytes(U);
+        const size_t total = bar_off + (size_t)g.n_warps * 2 * 8;
+        const float *table = backward ? p.bh : p.alpha;
+        const size_t rows = backward ? (size_t)2 * g.S : (size_t)(p.Tmax + 1 + (g.P > 0 ? 2 : 0)) * g.S;
+        if (total <= budget && rows < ((size_t)1 << 31) && EncodeRowTensorMap(&p.tmap, table, rows, p.Npad, 32 * U)) {
+            tma = true;
+            p.use_tma = 1; p.ring_off = (int)ring_off; p.bar_off = (int)bar_off;
+            smem = total;
+        }
+    }
+    if (U == 1) return DispatchU<NT, 1>(backward, tma, smem_arcs, w1_smem, p, g.n_ctas, smem, stream, err);
+    if (U == 2) return DispatchU<NT, 2>(backward, tma, smem_arcs, w1_smem, p, g.n_ctas, smem, stream, err);
+    return DispatchU<NT, 4>(backward, tma, smem_arcs, w1_smem, p, g.n_ctas, smem, stream, err);
 }
 
-int DispatchThreads(bool backward, const DeviceGraph &g, const DenParams &p, size_t fixed_smem, cudaStream_t stream,
+int DispatchThreads(bool backward, const DeviceGraph &g, DenParams &p, size_t fixed_smem, cudaStream_t stream,
                     std::string *err) {
     if (p.Npad > g.n_warps * 32) { *err = "batch too large for the den kernel's bookkeeping CTA (N <= " + std::to_string(g.n_warps * 32) + ")"; return 1; }
     if (g.n_warps == 16) return Dispatch<512>(backward, g, p, fixed_smem, stream, err);
@@ -988,7 +1213,31 @@ int LaunchLogitGrad(const void *z, int z_bf16, long sn, long st, int N, int T, i
     return (int)cudaGetLastError();
 }
 
-int LaunchDenForward(const DeviceGraph &g, DenParams p, cudaStream_t stream, std::string *err) {
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+bool EncodeRowTensorMap(CUtensorMap *tm, const float *base, size_t rows, int Npad, int box_cols) {
+    typedef CUresult (*EncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeTiled encode = []() -> EncodeTiled {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        return (EncodeTiled)fn;
+    }();
+    if (!encode || !base || rows == 0 || box_cols > 256 || (reinterpret_cast<uintptr_t>(base) & 15)) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)Npad, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)Npad * 4};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, 1};
+    cuuint32_t estr[2] = {1, 1};
+    return encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+int LaunchDenForward(const DeviceGraph &g, DenParams &p, cudaStream_t stream, std::string *err) {
     p.arcs = g.fwd.arcs; p.chunk_state = g.fwd.chunk_state; p.chunk_arc = g.fwd.chunk_arc;
     p.chunk_pair = g.fwd.chunk_pair; p.cta_labels = g.fwd.cta_labels;
     p.gacc_rows = 0;
@@ -997,7 +1246,7 @@ int LaunchDenForward(const DeviceGraph &g, DenParams p, cudaStream_t stream, std
     return DispatchThreads(false, g, p, fixed, stream, err);
 }
 
-int LaunchDenBackward(const DeviceGraph &g, DenParams p, cudaStream_t stream, std::string *err) {
+int LaunchDenBackward(const DeviceGraph &g, DenParams &p, cudaStream_t stream, std::string *err) {
     p.arcs = g.bwd.arcs; p.chunk_state = g.bwd.chunk_state; p.chunk_arc = g.bwd.chunk_arc;
     p.chunk_pair = g.bwd.chunk_pair; p.cta_labels = g.bwd.cta_labels; p.w1 = g.bwd.w1;
     // label accumulator in shared memory when the per-CTA label range is small enough

@@ -48,12 +48,42 @@ def select_utterances(labels: torch.Tensor, ly: torch.Tensor, idx: Sequence[int]
     return torch.cat(parts) if parts else labels[:0]
 
 
-def allreduce_cost(cost_sum: torch.Tensor, count: int, group=None) -> Tuple[torch.Tensor, int]:
-    """One all-reduce(SUM) of [sum cost, count]; returns the global pair."""
-    v = torch.stack([cost_sum.reshape(()).float(), torch.tensor(float(count), device=cost_sum.device)])
+def allreduce_cost_tensor(cost_sum: torch.Tensor, count: int, group=None) -> torch.Tensor:
+    """One all-reduce(SUM) of [sum cost, count]; returns the global pair as a 2-vector on the device of ``cost_sum``
+    (no host synchronisation)."""
+    v = torch.stack([cost_sum.reshape(()).float(), torch.full((), float(count), device=cost_sum.device)])
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(v, op=dist.ReduceOp.SUM, group=group)
+    return v
+
+
+def allreduce_cost(cost_sum: torch.Tensor, count: int, group=None) -> Tuple[torch.Tensor, int]:
+    """Same, with the count read back to the host."""
+    v = allreduce_cost_tensor(cost_sum, count, group)
     return v[0], int(round(float(v[1])))
+
+
+def local_shard(logits: torch.Tensor, labels: torch.Tensor, lx: torch.Tensor, ly: torch.Tensor, rank: int, world_size: int):
+    """This rank's share of a GLOBAL batch: (utterance indices, logits[idx], flattened labels, lx[idx], ly[idx]), longest
+    first.  In training the data loader does this (every rank reads its own utterances, cat/shared/data.py:471-585);
+    benchmarks call it once, outside the timed region."""
+    idx = shard_by_length(lx.tolist(), world_size)[rank]
+    sel = torch.tensor(idx, dtype=torch.long)
+    return idx, logits[sel.to(logits.device)].contiguous(), select_utterances(labels, ly, idx), lx[sel], ly[sel]
+
+
+def sharded_step(loss_fn: Callable[..., Tuple[torch.Tensor, torch.Tensor]], shard, size_average: bool = True, group=None):
+    """One step on an already sharded batch: the rank-local op, then the path's ONE collective -- all-reduce(SUM) of
+    [sum of costs, utterance count] -- and the normalisation by the GLOBAL count (cat/shared/manager.py:546 arrives at the
+    same factor from local_bs * world / global_bs).  Returns (global loss, local gradient of the global loss)."""
+    idx, logits, labels, lx, ly = shard
+    if idx:
+        cost, grad = loss_fn(logits, labels, lx, ly)
+    else:
+        cost, grad = torch.zeros((), device=logits.device), logits[:0]
+    v = allreduce_cost_tensor(cost, len(idx), group)          # the only exchange of the path; stays on the device
+    scale = 1.0 / v[1].clamp(min=1.0) if size_average else torch.ones((), device=v.device)
+    return v[0] * scale, grad * scale.to(grad.dtype)
 
 
 def sharded_loss(loss_fn: Callable[..., Tuple[torch.Tensor, torch.Tensor]],
@@ -64,13 +94,17 @@ def sharded_loss(loss_fn: Callable[..., Tuple[torch.Tensor, torch.Tensor]],
     ``loss_fn(logits_shard, labels_shard, lx_shard, ly_shard) -> (sum of per-utterance costs, grad of that
     sum w.r.t. logits_shard)`` is the rank-local op (size_average=False).  Returns
     (global loss, local utterance indices, local gradient of the global loss)."""
-    shards = shard_by_length(lx.tolist(), world_size)
-    idx = shards[rank]
-    sel = torch.tensor(idx, dtype=torch.long)
-    if idx:
-        cost, grad = loss_fn(logits[sel.to(logits.device)], select_utterances(labels, ly, idx), lx[sel], ly[sel])
-    else:
-        cost, grad = torch.zeros((), device=logits.device), logits[:0]
-    total, count = allreduce_cost(cost, len(idx), group)
-    scale = 1.0 / max(count, 1) if size_average else 1.0
-    return total * scale, idx, grad * scale
+    shard = local_shard(logits, labels, lx, ly, rank, world_size)
+    loss, grad = sharded_step(loss_fn, shard, size_average, group)
+    return loss, shard[0], grad
+
+
+def cuda_loss_fn(lamb: float):
+    """The rank-local op for ``sharded_loss`` / ``sharded_step``: this library's fused CUDA loss with size_average=False,
+    i.e. (sum of per-utterance costs, d sum / d logits)."""
+    from . import _C
+
+    def fn(logits, labels, lx, ly):
+        loss, grad, _ = _C.ctc_crf_loss_fwd(logits, labels.to(torch.int32), lx.to(torch.int32), ly.to(torch.int32), lamb, False)
+        return loss.reshape(()), grad
+    return fn

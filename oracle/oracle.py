@@ -25,6 +25,9 @@ def build(force: bool = False) -> None:
         subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
     if os.path.isdir("/root/reference/src/ctc_crf"):
         subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
+        # the reference's own binding.cpp linked against this repository's library (tests/test_ref_binding.py)
+        if os.path.exists(os.path.join(_HERE, "..", "cat_b200", "libctc_crf_b200.so")):
+            subprocess.check_call(["make", "-C", _HERE, "ref_binding"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
 
 
 def lib():
