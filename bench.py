@@ -332,14 +332,20 @@ def main():
     # measured DRAM traffic per launch: per-frame bytes from the committed ncu --set full capture (profiles/traffic.json,
     # taken at the same N/V/graph) x the frames of this launch; null for other workloads
     traffic = None
+    pipes = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath) and (N, V, args.H, args.d, args.dtype) == (64, 218, 20000, 24, "f32"):
         tj = json.load(open(tpath))
         if "den_forward_kernel" in tj and "den_backward_kernel" in tj:
             traffic = (tj["den_forward_kernel"]["dram_bytes_per_frame"] + tj["den_backward_kernel"]["dram_bytes_per_frame"]) * T
+            # instruction-pipe utilisation from the same committed ncu capture (report MUFU/FMA next to HBM)
+            pipes = {k: {"fma": tj[k].get("pipe_fma_pct"), "xu": tj[k].get("pipe_xu_pct"), "issue_active": tj[k].get("issue_active_pct")}
+                     for k in ("den_forward_kernel", "den_backward_kernel")}
+            pipes["unit"] = "% of peak sustained active (ncu sm__inst_executed_pipe_*), " + tj["den_forward_kernel"].get("capture", "")
     roofline = {
         "bound": "hbm", "kernel": "den_forward_kernel + den_backward_kernel (denominator forward-backward)",
-        "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
+        "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+        "traffic_ratio": (traffic / bytes_den) if traffic else None, "pipes": pipes, "peak_source": peak_src,
         "algorithmic_bytes": bytes_den,
         "algorithmic_bytes_per_frame": 2 * V * b_in + 4 * V + 8 * S_plan,
         "den_ms": ms_fb, "den_frames_per_s": frames_per_step / (ms_fb * 1e-3),

@@ -86,10 +86,13 @@ def gpu_den(logits: torch.Tensor, grad_net: torch.Tensor, input_lengths: torch.T
         stream = _stream(dev)
         S = den_num_states()
         # binding.cpp:77-79 sizes; alpha is padded to whole 32-lane groups here
-        alpha = torch.empty(max(int(L.ccb_den_alpha_floats(N, T)), (T + 1) * N * S), dtype=torch.float32, device=dev)
+        # the library states its need through ccb_den_alpha_floats (lane padding, parked pair rows); alpha_size is the
+        # per-(frame, utterance) row count binding.cpp would pass, rounded UP so that (T+1)*N*alpha_size covers the need
+        per = (T + 1) * N
+        alpha_states = max(S, -(-int(L.ccb_den_alpha_floats(N, T)) // per))
+        alpha = torch.empty(per * alpha_states, dtype=torch.float32, device=dev)
         beta = torch.empty(1, dtype=torch.float32, device=dev)
         grad_storage = torch.empty(1, dtype=torch.float32, device=dev)
-        alpha_states = alpha.numel() // ((T + 1) * N)
         L.compute_alpha(alpha.data_ptr(), logits.data_ptr(), N, T, alpha_states, V, input_lengths.data_ptr(),
                         costs_alpha.data_ptr(), stream)
         _raise_if_error("gpu_den/compute_alpha")

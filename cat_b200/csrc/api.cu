@@ -135,6 +135,14 @@ int InitImpl(const char *fst_name, int n_gpus, const int *gpus) {
         { const char *e = getenv("CCB_NO_TMA"); d.tune_no_tma = e && e[0] == '1'; }   // A/B: register gathers instead of TMA gather4
         if (d.tune_arcs_in_global || d.tune_w1_in_global)
             fprintf(stderr, "ctc_crf_b200: CCB_ARCS_IN_GLOBAL / CCB_W1_IN_GLOBAL set -- den arc tiles forced out of shared memory (test hook, slow)\n");
+        {   // small-batch kernels: both arc streams in shared memory next to 4 KB (8 KB) of rings per warp, no hub rows
+            const size_t budget = (size_t)d.max_smem_optin > 2048 ? (size_t)d.max_smem_optin - 1024 : 0;
+            const size_t ring = (size_t)d.n_warps * (4 * 16 * 64 + 64);
+            const size_t fwd_need = (size_t)d.fwd.max_tile_arcs * sizeof(Arc) + (size_t)(16 + d.fwd.max_tile_rows) * 4 + ring + 512;
+            const size_t bwd_need = (size_t)d.bwd.max_tile_arcs * 12 + ((size_t)(2 + d.bwd.max_tile_labels) * 16 + 2 * (size_t)d.bwd.max_tile_rows) * 4 + ring + 512;
+            d.small_ok = !d.tune_no_tma && !d.tune_arcs_in_global && !d.tune_w1_in_global && g_plan.hub_states.empty() &&
+                         fwd_need <= budget && bwd_need <= budget && getenv("CCB_NO_SMALL") == nullptr;
+        }
         d.n_start_arcs = (int)g_plan.start_arcs.size();
         d.n_hubs = (int)g_plan.hub_states.size();
         d.start_final = g_plan.final_lin[(size_t)g_plan.start];
@@ -196,8 +204,8 @@ int CheckDen(const DeviceGraph &g, int dtype, int N, int T, int V) {
     if (dtype != CCB_DTYPE_F32 && dtype != CCB_DTYPE_BF16) return Fail("den: unsupported logits dtype");
     if (V < g.num_labels)
         return Fail("den graph uses label " + std::to_string(g.num_labels - 1) + " but logits have only " + std::to_string(V) + " classes");
-    if ((size_t)(2 * (size_t)g.S + g.P) * (size_t)PadLanes(N) * 4 >= ((size_t)1 << 32)) return Fail("den: states x batch too large for 32-bit row offsets; split the batch");
-    if (PadLanes(N) > g.n_warps * 32) return Fail("den: batch larger than " + std::to_string(g.n_warps * 32) + " utterances per call; split the batch");
+    if ((size_t)(2 * (size_t)g.S + g.P) * (size_t)PadLanes(N, g.small_ok) * 4 >= ((size_t)1 << 32)) return Fail("den: states x batch too large for 32-bit row offsets; split the batch");
+    if (PadLanes(N, g.small_ok) > g.n_warps * 32) return Fail("den: batch larger than " + std::to_string(g.n_warps * 32) + " utterances per call; split the batch");
     return 0;
 }
 
@@ -205,7 +213,7 @@ int CheckDen(const DeviceGraph &g, int dtype, int N, int T, int V) {
 // raw: `y` holds unnormalised logits; the log-normalisers go to aux (lz, lnorm) and logZ comes out normalised
 int DenForward(const DeviceGraph &g, const void *y, int dtype, long sn, long st, int N, int T, int V, const int *len,
                float *alpha, void *aux, cudaStream_t stream, bool raw = false) {
-    const DenAuxLayout L = MakeDenAuxLayout(g.S, N, T);
+    const DenAuxLayout L = MakeDenAuxLayout(g.S, N, T, g.small_ok);
     char *a = reinterpret_cast<char *>(aux);
     CCB_CUDA(cudaMemsetAsync(a, 0, L.zero_bytes, stream));
     int rc = raw ? LaunchFrameLse(y, dtype == CCB_DTYPE_BF16, sn, st, N, T, V, len, reinterpret_cast<float *>(a + L.fmax),
@@ -225,7 +233,7 @@ int DenForward(const DeviceGraph &g, const void *y, int dtype, long sn, long st,
 int DenBackward(const DeviceGraph &g, const void *y, int dtype, long sn, long st, int N, int T, int V, const int *len,
                 float *alpha, void *aux, float *grad, long gsn, long gst, float grad_scale, cudaStream_t stream,
                 bool raw = false) {
-    const DenAuxLayout L = MakeDenAuxLayout(g.S, N, T);
+    const DenAuxLayout L = MakeDenAuxLayout(g.S, N, T, g.small_ok);
     char *a = reinterpret_cast<char *>(aux);
     DenParams p = BaseParams(g, y, dtype, sn, st, N, T, V, len, alpha, aux, L);
     if (raw) p.lnorm = reinterpret_cast<const double *>(a + L.lnorm);
@@ -257,7 +265,7 @@ int EnsureLegacy(int dev, const DeviceGraph &g, int N, int T, float *caller_alph
     LegacyScratch &ls = g_legacy[dev];
     if (ls.used && ls.stream != s) CCB_CUDA(cudaStreamSynchronize(ls.stream));
     ls.stream = s; ls.used = true;
-    const DenAuxLayout L = MakeDenAuxLayout(g.S, N, T);
+    const DenAuxLayout L = MakeDenAuxLayout(g.S, N, T, g.small_ok);
     if (GrowAsync(&ls.aux, &ls.aux_bytes, L.total, s)) return 1;
     const size_t need = ccb_den_alpha_floats(N, T);
     if (caller_alpha && caller_floats >= need) { *alpha_out = caller_alpha; return 0; }
@@ -300,25 +308,30 @@ void Release(int n_gpus, int *gpus) { ReleaseImpl(n_gpus, gpus); }
 
 // (S, P) of the graph on the CURRENT device when one is loaded there (devices may hold different graphs if Init was
 // called per device with different files), else of the last plan built
-static void CurrentSizes(int *S, int *P) {
+static void CurrentSizes(int *S, int *P, bool *small_ok) {
     int dev = -1;
-    if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < kMaxDevices && g_dev[dev].loaded) { *S = g_dev[dev].S; *P = g_dev[dev].P; return; }
+    if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < kMaxDevices && g_dev[dev].loaded) {
+        *S = g_dev[dev].S; *P = g_dev[dev].P; *small_ok = g_dev[dev].small_ok;
+        return;
+    }
     cudaGetLastError();
-    *S = g_plan_valid ? g_plan.num_states : 0; *P = g_plan_valid ? g_plan.num_pairs : 0;
+    *S = g_plan_valid ? g_plan.num_states : 0; *P = g_plan_valid ? g_plan.num_pairs : 0; *small_ok = false;
 }
 
 size_t ccb_den_alpha_floats(int N, int T) {
     int S, P;
-    CurrentSizes(&S, &P);
+    bool small_ok;
+    CurrentSizes(&S, &P, &small_ok);
     // T+1 frames of S real rows; the virtual pair-sum rows of a frame are parked two frames ahead (den_kernels.cu), so two
     // more frames at the end when the plan has pairs
-    return (size_t)(T + 1 + (P > 0 ? 2 : 0)) * (size_t)S * (size_t)PadLanes(N);
+    return (size_t)(T + 1 + (P > 0 ? 2 : 0)) * (size_t)S * (size_t)PadLanes(N, small_ok);
 }
 
 size_t ccb_den_aux_bytes(int N, int T) {
     int S, P;
-    CurrentSizes(&S, &P);
-    return S ? MakeDenAuxLayout(S, N, T).total : 0;
+    bool small_ok;
+    CurrentSizes(&S, &P, &small_ok);
+    return S ? MakeDenAuxLayout(S, N, T, small_ok).total : 0;
 }
 
 size_t ccb_ctc_workspace_bytes(int N, int T, int max_label_len) {
@@ -342,7 +355,7 @@ void compute_alpha(float *alpha, float *logits, const int batch_size, int T, con
     if (DenForward(*g, logits, CCB_DTYPE_F32, (long)T * logits_size, logits_size, batch_size, T, logits_size,
                    input_lengths, al, ls.aux, s)) return;
     ls.fwd_valid = true;
-    const DenAuxLayout L = MakeDenAuxLayout(g->S, batch_size, T);
+    const DenAuxLayout L = MakeDenAuxLayout(g->S, batch_size, T, g->small_ok);
     cudaError_t e = cudaMemcpyAsync(loglikelihood, (char *)ls.aux + L.logz_a, sizeof(float) * batch_size, cudaMemcpyDeviceToDevice, s);
     if (e != cudaSuccess) FailCuda("copy logZ", e);
 }
@@ -367,7 +380,7 @@ void compute_beta_and_grad(float *beta, const float *const alpha, const float *c
     if (DenBackward(*g, logits, CCB_DTYPE_F32, (long)T * logits_size, logits_size, batch_size, T, logits_size,
                     input_lengths, al, ls.aux, grad_net, (long)T * logits_size, logits_size, 1.f, s)) return;
     if (loglikelihood) {
-        const DenAuxLayout L = MakeDenAuxLayout(g->S, batch_size, T);
+        const DenAuxLayout L = MakeDenAuxLayout(g->S, batch_size, T, g->small_ok);
         cudaError_t e = cudaMemcpyAsync(loglikelihood, (char *)ls.aux + L.logz_b, sizeof(float) * batch_size, cudaMemcpyDeviceToDevice, s);
         if (e != cudaSuccess) FailCuda("copy logZ(beta)", e);
     }
@@ -383,7 +396,7 @@ int ccb_den_forward_backward(const void *logits, int dtype, long sn, long st, in
     if (!alpha_ws || !aux_ws) return Fail("den: workspace missing");
     cudaStream_t s = (cudaStream_t)stream;
     if (DenForward(*g, logits, dtype, sn, st, N, T, V, len_dev, alpha_ws, aux_ws, s)) return 1;
-    const DenAuxLayout L = MakeDenAuxLayout(g->S, N, T);
+    const DenAuxLayout L = MakeDenAuxLayout(g->S, N, T, g->small_ok);
     if (logz) CCB_CUDA(cudaMemcpyAsync(logz, (char *)aux_ws + L.logz_a, sizeof(float) * N, cudaMemcpyDeviceToDevice, s));
     if (grad) {
         if (DenBackward(*g, logits, dtype, sn, st, N, T, V, len_dev, alpha_ws, aux_ws, grad, gsn, gst, grad_scale, s)) return 1;
@@ -464,7 +477,7 @@ static int LossFwdImpl(bool raw, const void *logits, int dtype, int N, int T, in
     CCB_CUDA(cudaMemsetAsync(grad, 0, sizeof(float) * (size_t)N * T * V, s));
     if (DenForward(*g, logits, dtype, sn, st, N, Tmax, V, len_dev, alpha_ws, aux_ws, s, raw)) return 1;
     if (DenBackward(*g, logits, dtype, sn, st, N, Tmax, V, len_dev, alpha_ws, aux_ws, grad, sn, st, scale, s, raw)) return 1;
-    const DenAuxLayout L = MakeDenAuxLayout(g->S, N, Tmax);
+    const DenAuxLayout L = MakeDenAuxLayout(g->S, N, Tmax, g->small_ok);
     float *logz = reinterpret_cast<float *>((char *)aux_ws + L.logz_a);
     float *logp = reinterpret_cast<float *>((char *)aux_ws + L.logz_b);   // logZ(beta) no longer needed: reuse
     const double *lnorm = raw ? reinterpret_cast<const double *>((char *)aux_ws + L.lnorm) : nullptr;

@@ -45,6 +45,9 @@ struct DeviceGraph {
     int max_smem_optin = 0;
     // test hooks, read ONCE at Init (never on the per-call path): force the large-graph tiers on a small graph
     bool tune_arcs_in_global = false, tune_w1_in_global = false, tune_no_tma = false;
+    // batches of <= 16 utterances run the small-batch TMA kernels (rows of 8 / 16 floats): needs both arc streams in
+    // shared memory next to the rings, no hub rows, and a usable TMA descriptor -- decided once at Init
+    bool small_ok = false;
 };
 
 // Kernel parameter block shared by the two persistent den kernels (passed as a __grid_constant__ kernel parameter: the TMA
@@ -108,13 +111,18 @@ struct DenAuxLayout {
     size_t colsum_a = 0, colsum_b = 0, absum = 0, zsum = 0, b0 = 0, barrier = 0, zero_bytes = 0;
     size_t fmax = 0, bh = 0, logz_a = 0, logz_b = 0, lz = 0, lnorm = 0, total = 0;
 };
-DenAuxLayout MakeDenAuxLayout(int S, int N, int T);
-inline int PadLanes(int N) {
+// Lane padding of a batch: whole 32-lane groups carrying 1, 2 or 4 utterances per lane; batches of <= 16 utterances
+// on a graph that supports the small-batch kernels (DeviceGraph::small_ok) use 8- or 16-float rows instead, with the
+// lanes of a warp spread over (arc of the quad) x (utterance)  (den_kernels.cu, LPR template parameter).
+inline int PadLanes(int N, bool small_ok) {
+    if (small_ok && N <= 8) return 8;
+    if (small_ok && N <= 16) return 16;
     int g = (N + 31) / 32;
     if (g >= 3) g = (g + 3) / 4 * 4;   // lanes carry 1, 2 or 4 utterances each
     return g * 32;
 }
-inline int LaneWidth(int Npad) { int g = Npad / 32; return g >= 4 ? 4 : g; }
+DenAuxLayout MakeDenAuxLayout(int S, int N, int T, bool small_ok);
+inline int LaneWidth(int Npad) { int g = Npad / 32; return g >= 4 ? 4 : (g < 1 ? 1 : g); }
 
 // host launchers; return cudaError_t-compatible int (0 = ok) and fill *err
 int LaunchFrameMax(const void *y, int y_bf16, long sn, long st, int N, int T, int V, const int *len, float *fmax,

@@ -458,6 +458,56 @@ __device__ __forceinline__ void walk_arcs_tma(const uint4 *arcs, int n_batches, 
     }
 }
 
+// Small batches (Npad = LPR = 8 or 16 utterances): a row of the gather table is 32 / 64 bytes, and the lanes of a warp are
+// spread over (arc of the quad) x (utterance): the four rows of a quad lie back to back in the ring (4 * LPR floats), so
+// ONE `LDS.32` per lane reads 32 / LPR arcs x LPR utterances at once (LPR = 8: a whole quad per instruction; 16: two
+// instructions), each lane multiplies by the weight of ITS arc, and the partial sums of the 32 / LPR lane groups are
+// combined with one or two shuffles when a segment ends.  A warp thus spends 4x (2x) fewer instructions and rows of L2
+// traffic per utterance than with 24 (16) of 32 lanes idle -- the per-GPU share of a batch sharded over 8 GPUs is 8-32
+// utterances.  Rings: kSmallStages stages of 16 rows per warp.
+constexpr int kSmallStages = 4;
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float r;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(addr));
+    return r;
+}
+template <int LPR, int WPQ, typename Prologue, typename ConsumeQuad>
+__device__ __forceinline__ void walk_arcs_tma_small(const uint4 *arcs, int n_batches, const CUtensorMap *tm, int row_base,
+                                                    TmaRing &ring, int lane, Prologue &&prologue, ConsumeQuad &&consume_quad) {
+    constexpr int R = 16, QB = R / kQuad, STEPS = LPR / 8;      // LDS steps per quad: 1 (LPR = 8) or 2 (LPR = 16)
+    constexpr uint32_t ROWB = LPR * 4u;
+    auto issue = [&](int k, int s) {
+        const uint32_t bar = ring.bar + 8u * s;
+        if (lane == 0) mbar_expect_tx(bar, R * ROWB);
+        __syncwarp();
+        if (lane < QB) {
+            const uint4 pr = arcs[(size_t)WPQ * (k * QB + lane)];
+            tma_gather4(ring.buf + (uint32_t)(s * R + kQuad * lane) * ROWB, tm, 0, row_base + (int)pr.x, row_base + (int)pr.y,
+                        row_base + (int)pr.z, row_base + (int)pr.w, bar);
+        }
+    };
+    if (n_batches <= 0) { prologue(); return; }
+    for (int k = 0; k < kSmallStages && k < n_batches; ++k) issue(k, k);
+    prologue();
+    for (int k = 0; k < n_batches; ++k) {
+        const int s = k & (kSmallStages - 1);
+        mbar_wait(ring.bar + 8u * s, (ring.phase >> s) & 1u);
+        ring.phase ^= 1u << s;
+        const uint32_t base = ring.buf + (uint32_t)(s * R) * ROWB + (uint32_t)lane * 4u;
+#pragma unroll
+        for (int q = 0; q < QB; ++q) {
+            float v[STEPS];
+#pragma unroll
+            for (int st = 0; st < STEPS; ++st) v[st] = lds_f32(base + (uint32_t)q * (kQuad * ROWB) + (uint32_t)st * 128u);
+            consume_quad(arcs + (size_t)WPQ * (k * QB + q), v);
+        }
+        __syncwarp();
+        if (k + kSmallStages < n_batches) issue(k + kSmallStages, s);
+    }
+}
+// weight of arc j (0..3) of a quad's weight word
+__device__ __forceinline__ uint32_t quad_word(const uint4 &w, int j) { return j == 0 ? w.x : j == 1 ? w.y : j == 2 ? w.z : w.w; }
+
 __device__ __forceinline__ unsigned long long global_timer() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -505,15 +555,19 @@ __device__ __noinline__ void forward_partial_row(const int *state_label, const i
 // partial-row path out entirely so that it costs the hot row-end code nothing.
 // TMA: the gathered rows are staged in shared memory by gather4 copies (walk_arcs_tma) instead of register gathers; needs
 // the arc tile in shared memory (SMEM_ARCS) and DenParams::tmap.
-template <int NT, int U, int BATCH, bool SMEM_ARCS, bool HUBS, bool TMA = false>
+// LPR < 32 (8 or 16 lanes per row): the small-batch variant, see walk_arcs_tma_small (TMA, U = 1, no hub rows).
+template <int NT, int U, int BATCH, bool SMEM_ARCS, bool HUBS, bool TMA = false, int LPR = 32>
 __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const __grid_constant__ DenParams P) {
     static_assert(!TMA || SMEM_ARCS, "the TMA walk reads the arc tile from shared memory");
+    static_assert(LPR == 32 || (TMA && U == 1 && !HUBS && (LPR == 8 || LPR == 16)), "small-batch variant: TMA, one utterance per lane, no hubs");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *s_sum = reinterpret_cast<float *>(smem_raw);                                  // [Npad]
     int *s_label = reinterpret_cast<int *>(s_sum + P.Npad);                              // [tile_rows] label per row
     Arc *s_arcs = reinterpret_cast<Arc *>(smem_raw + (((size_t)(P.Npad + P.tile_rows) * 4 + 15) & ~(size_t)15));
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int sub = LPR == 32 ? 0 : lane / LPR;    // small batches: which arc(s) of a quad this lane multiplies
+    const int ul = LPR == 32 ? lane : lane % LPR;   // ... and which utterance(s) it carries
     const int cta = blockIdx.x;
     const int chunk = cta * P.n_warps + warp;
     const int n_chunks = gridDim.x * P.n_warps;
@@ -536,16 +590,18 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const __grid_constan
     int labp0 = -1, labp1 = -1;
     for (int q = se - 1; q >= sb; --q) { if (__ldg(P.state_pos + q)) labp1 = __ldg(P.state_label + q); else labp0 = __ldg(P.state_label + q); }
     unsigned epoch = 0;
-    const int n_batches = (ae - ab) / (TMA ? TmaShape<U>::R : BATCH);
+    const int n_batches = (ae - ab) / (TMA ? (LPR == 32 ? TmaShape<U>::R : 16) : BATCH);
     const uint4 *const arc4 = SMEM_ARCS ? reinterpret_cast<const uint4 *>(s_arcs + (ab - tile_a0))
                                         : reinterpret_cast<const uint4 *>(P.arcs + ab);
     TmaRing ring{0u, 0u, 0u};
     if (TMA) {
-        constexpr uint32_t kRingBytes = (uint32_t)TmaShape<U>::STAGES * TmaShape<U>::R * 32u * U * 4u;
+        constexpr int kStages = LPR == 32 ? TmaShape<U>::STAGES : kSmallStages;
+        constexpr uint32_t kRingBytes = LPR == 32 ? (uint32_t)TmaShape<U>::STAGES * TmaShape<U>::R * 32u * U * 4u
+                                                  : (uint32_t)kSmallStages * 16u * LPR * 4u;
         ring.buf = smem_u32(smem_raw + P.ring_off) + (uint32_t)warp * kRingBytes;
-        ring.bar = smem_u32(smem_raw + P.bar_off) + (uint32_t)warp * 8u * TmaShape<U>::STAGES;
+        ring.bar = smem_u32(smem_raw + P.bar_off) + (uint32_t)warp * 8u * kStages;
         if (lane == 0) {
-            for (int st = 0; st < TmaShape<U>::STAGES; ++st) mbar_init(ring.bar + 8u * st, 1);
+            for (int st = 0; st < kStages; ++st) mbar_init(ring.bar + 8u * st, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -591,7 +647,7 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const __grid_constan
     const int my_len = (cta == 0 && tid < P.N) ? __ldg(P.len + tid) : 0;   // CTA 0 keeps log-scale books
     int len0[U];   // lengths of this lane's utterances in lane group 0 (the only group for N <= 32*U)
 #pragma unroll
-    for (int u = 0; u < U; ++u) len0[u] = (lane * U + u < P.N) ? __ldg(P.len + lane * U + u) : 0;
+    for (int u = 0; u < U; ++u) len0[u] = (ul * U + u < P.N) ? __ldg(P.len + ul * U + u) : 0;
     double runlog = 0.0;
     if (TMA) fence_proxy_async_global();
     grid_barrier(P.barrier, (++epoch) * gridDim.x);
@@ -601,8 +657,8 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const __grid_constan
         if (TMA) fence_proxy_async_global();
         const float *a_prev = P.alpha + (size_t)(t - 1) * frame_elems;
         float *a_cur = P.alpha + (size_t)t * frame_elems;
-        for (int gc = 0; gc < Npad / (32 * U); ++gc) {
-            const int n0 = gc * 32 * U + lane * U;
+        for (int gc = 0; gc < (LPR == 32 ? Npad / (32 * U) : 1); ++gc) {
+            const int n0 = gc * 32 * U + ul * U;
             bool act[U];
             bool lane_act = false;
 #pragma unroll
@@ -667,18 +723,32 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const __grid_constan
                     sum[u] += out.v[u];
                     acc[u] = 0.f;
                 }
-                if (TMA || lane_act) out.stcg(row_ptr<U>(out_base, out_row, row_bytes));
+                if ((TMA || lane_act) && sub == 0) out.stcg(row_ptr<U>(out_base, out_row, row_bytes));
                 if (ev == kEvRowPos0) cacc = out;
                 else if (ev == kEvRowPos1) {   // the pair's virtual row: what the next frame gathers instead of both
 #pragma unroll
                     for (int u = 0; u < U; ++u) cacc.v[u] += out.v[u];
-                    if (TMA || lane_act) cacc.stcg(row_ptr<U>(out_base, virt_row, row_bytes));
+                    if ((TMA || lane_act) && sub == 0) cacc.stcg(row_ptr<U>(out_base, virt_row, row_bytes));
                     ++virt_row;
                 }
                 ++out_row;
                 ++ql;
             };
-            if (TMA) {
+            if (TMA && LPR < 32) {
+                float acc[1] = {0.f};
+                walk_arcs_tma_small<LPR, 2>(arc4, n_batches, &P.tmap, (t - 1) * S, ring, lane, frame_scalars,
+                                            [&](const uint4 *quad, const float *v) {
+                    const uint4 wq = quad[1];
+#pragma unroll
+                    for (int st = 0; st < LPR / 8; ++st)
+                        acc[0] = fmaf(fabsf(__uint_as_float(quad_word(wq, st * (32 / LPR) + sub))), v[st], acc[0]);
+                    if ((int)wq.w < 0) {   // warp-uniform: a segment ends at this quad -> combine the lane groups' partial sums
+                        acc[0] += __shfl_xor_sync(kFull, acc[0], 16);
+                        if (LPR == 8) acc[0] += __shfl_xor_sync(kFull, acc[0], 8);
+                        seg_end(acc, (int)(((wq.z >> 31) << 1) | (wq.y >> 31)), (int)wq.x < 0, quad);
+                    }
+                });
+            } else if (TMA) {
                 float acc[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) acc[u] = 0.f;
@@ -703,7 +773,7 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const __grid_constan
             }
 #pragma unroll
             for (int u = 0; u < U; ++u)
-                if (act[u] && sum[u] != 0.f) atomicAdd(&s_sum[n0 + u], sum[u]);
+                if (act[u] && sub == 0 && sum[u] != 0.f) atomicAdd(&s_sum[n0 + u], sum[u]);
         }
         tl_mark(P, t, chunk, n_chunks, 1, lane);
         if (HUBS && t < P.Tmax) zero_hub_rows(t + 1);
@@ -728,7 +798,7 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const __grid_constan
     }
 
     // logZ[n] = log sum_q alpha_len(q) final(q) + accumulated log scale      (den_calculate.cu:105-161)
-    for (int gc = 0; gc < Npad / 32; ++gc) {
+    for (int gc = 0; gc < (Npad + 31) / 32; ++gc) {
         const int n = gc * 32 + lane;
         const int ln = (n < P.N) ? __ldg(P.len + n) : -1;
         float zs = 0.f;
@@ -752,9 +822,10 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const __grid_constan
 // ------------------------------------------------------------------------------------------------
 // backward: beta recursion, occupancies, logZ from beta
 // ------------------------------------------------------------------------------------------------
-template <int NT, int U, int BATCH, bool SMEM_ARCS, bool W1_SMEM = SMEM_ARCS, bool TMA = false>
+template <int NT, int U, int BATCH, bool SMEM_ARCS, bool W1_SMEM = SMEM_ARCS, bool TMA = false, int LPR = 32>
 __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const __grid_constant__ DenParams P) {
     static_assert(!TMA || (SMEM_ARCS && W1_SMEM), "the TMA walk reads offsets and both weights from shared memory");
+    static_assert(LPR == 32 || (TMA && U == 1 && (LPR == 8 || LPR == 16)), "small-batch variant: TMA, one utterance per lane");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int Npad = P.Npad, S = P.S;
     float *s_sum = reinterpret_cast<float *>(smem_raw);            // [2][Npad]: colsum_b, absum
@@ -764,6 +835,8 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const __grid_consta
     Arc *s_arcs = reinterpret_cast<Arc *>(smem_raw + ((((size_t)(2 + P.gacc_rows) * Npad + 2 * (size_t)P.tile_rows) * 4 + 15) & ~(size_t)15));
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int sub = LPR == 32 ? 0 : lane / LPR;    // small batches: which arc(s) of a quad this lane multiplies
+    const int ul = LPR == 32 ? lane : lane % LPR;   // ... and which utterance it carries (lane groups sub > 0 are replicas at row ends)
     const int cta = blockIdx.x;
     const int chunk = cta * P.n_warps + warp;
     const int n_chunks = gridDim.x * P.n_warps;
@@ -778,7 +851,7 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const __grid_consta
     const int cl_lab1 = __ldg(P.cta_labels + cta * 4 + 2), cl_n1 = __ldg(P.cta_labels + cta * 4 + 3);
     int labp0 = -1, labp1 = -1;
     for (int q = se - 1; q >= sb; --q) { if (__ldg(P.state_pos + q)) labp1 = __ldg(P.state_label + q); else labp0 = __ldg(P.state_label + q); }
-    const int n_batches = (ae - ab) / (TMA ? TmaShape<U>::R : BATCH);
+    const int n_batches = (ae - ab) / (TMA ? (LPR == 32 ? TmaShape<U>::R : 16) : BATCH);
     // shared memory: 3 words of 16 bytes per quad {byte offsets}{w0}{w1}; global fallback: AoS arcs + w1 array
     constexpr int kW = W1_SMEM ? 3 : 2;   // 16-byte words per staged quad
     const uint4 *const arc4 = SMEM_ARCS ? reinterpret_cast<const uint4 *>(s_arcs) + kW * ((ab - tile_a0) / kQuad)
@@ -808,11 +881,13 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const __grid_consta
     }
     TmaRing ring{0u, 0u, 0u};
     if (TMA) {
-        constexpr uint32_t kRingBytes = (uint32_t)TmaShape<U>::STAGES * TmaShape<U>::R * 32u * U * 4u;
+        constexpr int kStages = LPR == 32 ? TmaShape<U>::STAGES : kSmallStages;
+        constexpr uint32_t kRingBytes = LPR == 32 ? (uint32_t)TmaShape<U>::STAGES * TmaShape<U>::R * 32u * U * 4u
+                                                  : (uint32_t)kSmallStages * 16u * LPR * 4u;
         ring.buf = smem_u32(smem_raw + P.ring_off) + (uint32_t)warp * kRingBytes;
-        ring.bar = smem_u32(smem_raw + P.bar_off) + (uint32_t)warp * 8u * TmaShape<U>::STAGES;
+        ring.bar = smem_u32(smem_raw + P.bar_off) + (uint32_t)warp * 8u * kStages;
         if (lane == 0) {
-            for (int st = 0; st < TmaShape<U>::STAGES; ++st) mbar_init(ring.bar + 8u * st, 1);
+            for (int st = 0; st < kStages; ++st) mbar_init(ring.bar + 8u * st, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -821,7 +896,7 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const __grid_consta
     const int my_len = (cta == 0 && tid < P.N) ? __ldg(P.len + tid) : 0;
     int len0[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) len0[u] = (lane * U + u < P.N) ? __ldg(P.len + lane * U + u) : 0;
+    for (int u = 0; u < U; ++u) len0[u] = (ul * U + u < P.N) ? __ldg(P.len + ul * U + u) : 0;
     double runlog = 0.0;
     __syncthreads();
 
@@ -836,8 +911,8 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const __grid_consta
             const size_t bytes = (size_t)(se - sb) * Npad * 4;
             for (size_t off = (size_t)lane * 128; off < bytes; off += 32 * 128) prefetch_l2(nb + off);
         }
-        for (int gc = 0; gc < Npad / (32 * U); ++gc) {
-            const int n0 = gc * 32 * U + lane * U;
+        for (int gc = 0; gc < (LPR == 32 ? Npad / (32 * U) : 1); ++gc) {
+            const int n0 = gc * 32 * U + ul * U;
             bool act[U], gat[U];
             bool lane_act = false, lane_gat = false;
 #pragma unroll
@@ -880,7 +955,7 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const __grid_consta
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const float g = k1 ? gsum1[u] : gsum0[u];
-                    if (g != 0.f) {
+                    if (g != 0.f && sub == 0) {
                         if (use_gacc) atomicAdd(&s_gacc[row * Npad + n0 + u], g);
                         else atomicAdd(P.grad + (n0 + u) * P.gsn + (long)(tau - 1) * P.gst + lab, g);
                     }
@@ -914,7 +989,7 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const __grid_consta
                     sum_b[u] += out.v[u];
                     acc[u] = 0.f;
                 }
-                if (TMA || lane_act) out.stcg(row_ptr<U>(out_base, out_row, row_bytes));   // (TMA: every lane reads the row later)
+                if ((TMA || lane_act) && sub == 0) out.stcg(row_ptr<U>(out_base, out_row, row_bytes));   // (TMA: every lane reads the row later)
                 ++out_row;
                 ++ql;
             };
@@ -931,7 +1006,25 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const __grid_consta
                 a_q = ((int)out_row < se && lane_act) ? gather_row<U>(a_base, out_row * row_bytes) : vec_zero<U>();
                 a_q1 = ((int)out_row + 1 < se && lane_act) ? gather_row<U>(a_base, (out_row + 1) * row_bytes) : vec_zero<U>();
             };
-            if (TMA) {
+            if (TMA && LPR < 32) {
+                float acc0[1] = {0.f}, acc1[1] = {0.f};
+                walk_arcs_tma_small<LPR, 3>(arc4, n_batches, &P.tmap, ((tau + 1) & 1) * S, ring, lane, frame_scalars,
+                                            [&](const uint4 *quad, const float *v) {
+                    const uint4 wq = quad[1], t1 = quad[2];
+#pragma unroll
+                    for (int st = 0; st < LPR / 8; ++st) {
+                        const int j = st * (32 / LPR) + sub;
+                        acc0[0] = fmaf(fabsf(__uint_as_float(quad_word(wq, j))), v[st], acc0[0]);
+                        acc1[0] = fmaf(__uint_as_float(quad_word(t1, j)), v[st], acc1[0]);
+                    }
+                    if ((int)wq.w < 0) {   // warp-uniform: the group ends at this quad -> combine the lane groups' partial sums
+                        acc0[0] += __shfl_xor_sync(kFull, acc0[0], 16);
+                        acc1[0] += __shfl_xor_sync(kFull, acc1[0], 16);
+                        if (LPR == 8) { acc0[0] += __shfl_xor_sync(kFull, acc0[0], 8); acc1[0] += __shfl_xor_sync(kFull, acc1[0], 8); }
+                        group_end(acc0, acc1, (int)wq.z < 0, (int)wq.x < 0, (int)wq.y < 0);
+                    }
+                });
+            } else if (TMA) {
                 float acc0[U], acc1[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) { acc0[u] = 0.f; acc1[u] = 0.f; }
@@ -961,7 +1054,7 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const __grid_consta
             if (curlab1 >= 0) flush_gsum(true);
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                if (act[u]) {
+                if (act[u] && sub == 0) {
                     if (sum_b[u] != 0.f) atomicAdd(&s_sum[n0 + u], sum_b[u]);
                     if (sum_ab[u] != 0.f) atomicAdd(&s_sum[Npad + n0 + u], sum_ab[u]);
                 }
@@ -1088,6 +1181,14 @@ int LaunchTma(bool backward, const DenParams &p, int n_ctas, size_t smem, cudaSt
     return LaunchCoop(fn, NT, p, n_ctas, smem, stream, err);
 }
 
+// small batches: rows of LPR = 8 / 16 floats (see walk_arcs_tma_small)
+template <int NT, int LPR>
+int LaunchTmaSmall(bool backward, const DenParams &p, int n_ctas, size_t smem, cudaStream_t stream, std::string *err) {
+    const void *fn = backward ? (const void *)den_backward_kernel<NT, 1, 16, true, true, true, LPR>
+                              : (const void *)den_forward_kernel<NT, 1, 16, true, false, true, LPR>;
+    return LaunchCoop(fn, NT, p, n_ctas, smem, stream, err);
+}
+
 constexpr int kBwdMaxLaneWidth = 2;   // N=256: bwd 163 ms at 2 vs 248 ms at 4 (profiles/r01_experiments.md)
 
 // Gathers per batch (two batches are in flight per warp), fixed per variant by the register budget at 512 threads
@@ -1129,6 +1230,22 @@ int Dispatch(bool backward, const DeviceGraph &g, DenParams &p, size_t fixed_sme
     // utterance) runs out of registers at 4 -- it walks 64-utterance groups instead.
     int U = LaneWidth(p.Npad);
     if (backward && U == 4) U = kBwdMaxLaneWidth;
+    if (p.Npad < 32) {   // small batch: the lane padding promised the small-batch TMA kernels (DeviceGraph::small_ok)
+        const int LPR = p.Npad;
+        const size_t ring_off = (smem + 127) & ~(size_t)127;
+        const size_t bar_off = ring_off + (size_t)g.n_warps * kSmallStages * 16 * LPR * 4;
+        const size_t total = bar_off + (size_t)g.n_warps * kSmallStages * 8;
+        const float *table = backward ? p.bh : p.alpha;
+        const size_t rows = backward ? (size_t)2 * g.S : (size_t)(p.Tmax + 1 + (g.P > 0 ? 2 : 0)) * g.S;
+        if (!g.small_ok || !smem_arcs || (backward && !w1_smem) || total > budget || p.n_hubs > 0 || (LPR != 8 && LPR != 16) ||
+            rows >= ((size_t)1 << 31) || !EncodeRowTensorMap(&p.tmap, table, rows, p.Npad, LPR)) {
+            *err = "den: small-batch kernels unavailable for this graph/device although the batch was padded for them";
+            return 1;
+        }
+        p.use_tma = 1; p.ring_off = (int)ring_off; p.bar_off = (int)bar_off;
+        return LPR == 8 ? LaunchTmaSmall<NT, 8>(backward, p, g.n_ctas, total, stream, err)
+                        : LaunchTmaSmall<NT, 16>(backward, p, g.n_ctas, total, stream, err);
+    }
     // TMA tier: needs the full shared-memory stream, room for the rings, and a descriptor the driver accepts
     bool tma = false;
     p.use_tma = 0;
@@ -1159,9 +1276,9 @@ int DispatchThreads(bool backward, const DeviceGraph &g, DenParams &p, size_t fi
 
 }  // namespace
 
-DenAuxLayout MakeDenAuxLayout(int S, int N, int T) {
+DenAuxLayout MakeDenAuxLayout(int S, int N, int T, bool small_ok) {
     DenAuxLayout L;
-    L.Npad = PadLanes(N);
+    L.Npad = PadLanes(N, small_ok);
     auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
     size_t off = 0;
     const size_t rows = (size_t)(T + 2) * L.Npad * 4;

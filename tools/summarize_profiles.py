@@ -30,6 +30,9 @@ want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum", "launch__registers_per_thread",
+        "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+        "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
         "launch__shared_mem_per_block_dynamic", "lts__t_sector_hit_rate.pct",
         "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
@@ -53,7 +56,13 @@ for r in rr[2:]:
     def val(m):
         i = hdr.index(m); v = float(r[i].replace(",", "")); u = units[i].lower()
         return v * (1e9 if u.startswith("gbyte") else 1e6 if u.startswith("mbyte") else 1e3 if u.startswith("kbyte") else 1)
+    def pct(m):
+        return float(r[hdr.index(m)].replace(",", "")) if m in hdr else None
     traffic[key] = {"dram_bytes_per_frame": (val("dram__bytes_read.sum") + val("dram__bytes_write.sum")) / 100.0,
+                    "l2_to_sm_bytes_per_frame": val("l1tex__m_xbar2l1tex_read_bytes.sum") / 100.0 if "l1tex__m_xbar2l1tex_read_bytes.sum" in hdr else None,
+                    "pipe_fma_pct": pct("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
+                    "pipe_xu_pct": pct("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"),
+                    "issue_active_pct": pct("smsp__issue_active.avg.pct_of_peak_sustained_active"),
                     "capture": f"{tag}: ncu --set full, bench.py --T 100 (N=64, V=218, 1M-arc graph)"}
 json.dump(traffic, open("profiles/traffic.json", "w"), indent=1)
 os.makedirs("profiles", exist_ok=True)
