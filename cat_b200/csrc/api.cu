@@ -137,10 +137,11 @@ int InitImpl(const char *fst_name, int n_gpus, const int *gpus) {
             fprintf(stderr, "ctc_crf_b200: CCB_ARCS_IN_GLOBAL / CCB_W1_IN_GLOBAL set -- den arc tiles forced out of shared memory (test hook, slow)\n");
         {   // small-batch kernels: both arc streams in shared memory next to 4 KB (8 KB) of rings per warp, no hub rows
             const size_t budget = (size_t)d.max_smem_optin > 2048 ? (size_t)d.max_smem_optin - 1024 : 0;
-            const size_t ring = (size_t)d.n_warps * (4 * 16 * 64 + 64);
+            // (the backward pass may keep only offsets + first weights resident, 8 bytes per slot, and stream the second weights)
+            const size_t ring = (size_t)d.n_warps * (4 * 16 * 64 + 4 * (8 + 64));
             const size_t fwd_need = (size_t)d.fwd.max_tile_arcs * sizeof(Arc) + (size_t)(16 + d.fwd.max_tile_rows) * 4 + ring + 512;
-            const size_t bwd_need = (size_t)d.bwd.max_tile_arcs * 12 + ((size_t)(2 + d.bwd.max_tile_labels) * 16 + 2 * (size_t)d.bwd.max_tile_rows) * 4 + ring + 512;
-            d.small_ok = !d.tune_no_tma && !d.tune_arcs_in_global && !d.tune_w1_in_global && g_plan.hub_states.empty() &&
+            const size_t bwd_need = (size_t)d.bwd.max_tile_arcs * 8 + ((size_t)(2 + d.bwd.max_tile_labels) * 16 + 2 * (size_t)d.bwd.max_tile_rows) * 4 + ring + 512;
+            d.small_ok = !d.tune_no_tma && !d.tune_arcs_in_global && g_plan.hub_states.empty() &&
                          fwd_need <= budget && bwd_need <= budget && getenv("CCB_NO_SMALL") == nullptr;
         }
         d.n_start_arcs = (int)g_plan.start_arcs.size();

@@ -382,6 +382,11 @@ __device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap *tm,
     asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
                  ::"r"(dst), "l"(tm), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar) : "memory");
 }
+// 1-D bulk copy global -> shared (SASS UBLKCP): sequential arc words of a batch, completing on the batch's mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, unsigned bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
 // rows written with ordinary stores by other CTAs are read through the async proxy (TMA) one frame later: order the two
 // proxies on both sides of the grid barrier
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
@@ -471,14 +476,21 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(addr));
     return r;
 }
-template <int LPR, int WPQ, typename Prologue, typename ConsumeQuad>
+// W1_STREAM (backward pass of graphs whose 12-byte slots do not fit shared memory): the SECOND weights of a batch -- 16
+// consecutive floats of DenPlan::bwd.w1 -- are not resident; they ride along with the batch's rows as one 64-byte bulk copy
+// into `w1buf` (one 64-byte slot per stage) on the same mbarrier, and `consume_quad` receives their shared-memory address.
+template <int LPR, int WPQ, bool W1_STREAM = false, typename Prologue, typename ConsumeQuad>
 __device__ __forceinline__ void walk_arcs_tma_small(const uint4 *arcs, int n_batches, const CUtensorMap *tm, int row_base,
-                                                    TmaRing &ring, int lane, Prologue &&prologue, ConsumeQuad &&consume_quad) {
+                                                    TmaRing &ring, int lane, Prologue &&prologue, ConsumeQuad &&consume_quad,
+                                                    const float *w1g = nullptr, uint32_t w1buf = 0u) {
     constexpr int R = 16, QB = R / kQuad, STEPS = LPR / 8;      // LDS steps per quad: 1 (LPR = 8) or 2 (LPR = 16)
     constexpr uint32_t ROWB = LPR * 4u;
     auto issue = [&](int k, int s) {
         const uint32_t bar = ring.bar + 8u * s;
-        if (lane == 0) mbar_expect_tx(bar, R * ROWB);
+        if (lane == 0) {
+            mbar_expect_tx(bar, R * ROWB + (W1_STREAM ? R * 4u : 0u));
+            if (W1_STREAM) bulk_g2s(w1buf + 64u * s, w1g + (size_t)k * R, R * 4u, bar);
+        }
         __syncwarp();
         if (lane < QB) {
             const uint4 pr = arcs[(size_t)WPQ * (k * QB + lane)];
@@ -499,7 +511,7 @@ __device__ __forceinline__ void walk_arcs_tma_small(const uint4 *arcs, int n_bat
             float v[STEPS];
 #pragma unroll
             for (int st = 0; st < STEPS; ++st) v[st] = lds_f32(base + (uint32_t)q * (kQuad * ROWB) + (uint32_t)st * 128u);
-            consume_quad(arcs + (size_t)WPQ * (k * QB + q), v);
+            consume_quad(arcs + (size_t)WPQ * (k * QB + q), v, w1buf + 64u * s + 16u * q);
         }
         __syncwarp();
         if (k + kSmallStages < n_batches) issue(k + kSmallStages, s);
@@ -737,7 +749,7 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const __grid_constan
             if (TMA && LPR < 32) {
                 float acc[1] = {0.f};
                 walk_arcs_tma_small<LPR, 2>(arc4, n_batches, &P.tmap, (t - 1) * S, ring, lane, frame_scalars,
-                                            [&](const uint4 *quad, const float *v) {
+                                            [&](const uint4 *quad, const float *v, uint32_t) {
                     const uint4 wq = quad[1];
 #pragma unroll
                     for (int st = 0; st < LPR / 8; ++st)
@@ -824,7 +836,7 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const __grid_constan
 // ------------------------------------------------------------------------------------------------
 template <int NT, int U, int BATCH, bool SMEM_ARCS, bool W1_SMEM = SMEM_ARCS, bool TMA = false, int LPR = 32>
 __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const __grid_constant__ DenParams P) {
-    static_assert(!TMA || (SMEM_ARCS && W1_SMEM), "the TMA walk reads offsets and both weights from shared memory");
+    static_assert(!TMA || (SMEM_ARCS && (W1_SMEM || LPR < 32)), "the TMA walk reads the offsets (and, at full width, both weights) from shared memory");
     static_assert(LPR == 32 || (TMA && U == 1 && (LPR == 8 || LPR == 16)), "small-batch variant: TMA, one utterance per lane");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int Npad = P.Npad, S = P.S;
@@ -1008,9 +1020,13 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const __grid_consta
             };
             if (TMA && LPR < 32) {
                 float acc0[1] = {0.f}, acc1[1] = {0.f};
-                walk_arcs_tma_small<LPR, 3>(arc4, n_batches, &P.tmap, ((tau + 1) & 1) * S, ring, lane, frame_scalars,
-                                            [&](const uint4 *quad, const float *v) {
-                    const uint4 wq = quad[1], t1 = quad[2];
+                const uint32_t w1buf = smem_u32(smem_raw + P.bar_off) + (uint32_t)P.n_warps * 8u * kSmallStages + (uint32_t)warp * 64u * kSmallStages;
+                walk_arcs_tma_small<LPR, W1_SMEM ? 3 : 2, !W1_SMEM>(arc4, n_batches, &P.tmap, ((tau + 1) & 1) * S, ring, lane, frame_scalars,
+                                            [&](const uint4 *quad, const float *v, uint32_t w1s) {
+                    const uint4 wq = quad[1];
+                    uint4 t1;
+                    if (W1_SMEM) t1 = quad[2];
+                    else asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(t1.x), "=r"(t1.y), "=r"(t1.z), "=r"(t1.w) : "r"(w1s));
 #pragma unroll
                     for (int st = 0; st < LPR / 8; ++st) {
                         const int j = st * (32 / LPR) + sub;
@@ -1023,7 +1039,7 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const __grid_consta
                         if (LPR == 8) { acc0[0] += __shfl_xor_sync(kFull, acc0[0], 8); acc1[0] += __shfl_xor_sync(kFull, acc1[0], 8); }
                         group_end(acc0, acc1, (int)wq.z < 0, (int)wq.x < 0, (int)wq.y < 0);
                     }
-                });
+                }, reinterpret_cast<const float *>(w1g), w1buf);
             } else if (TMA) {
                 float acc0[U], acc1[U];
 #pragma unroll
@@ -1183,9 +1199,10 @@ int LaunchTma(bool backward, const DenParams &p, int n_ctas, size_t smem, cudaSt
 
 // small batches: rows of LPR = 8 / 16 floats (see walk_arcs_tma_small)
 template <int NT, int LPR>
-int LaunchTmaSmall(bool backward, const DenParams &p, int n_ctas, size_t smem, cudaStream_t stream, std::string *err) {
-    const void *fn = backward ? (const void *)den_backward_kernel<NT, 1, 16, true, true, true, LPR>
-                              : (const void *)den_forward_kernel<NT, 1, 16, true, false, true, LPR>;
+int LaunchTmaSmall(bool backward, bool w1_smem, const DenParams &p, int n_ctas, size_t smem, cudaStream_t stream, std::string *err) {
+    const void *fn = !backward ? (const void *)den_forward_kernel<NT, 1, 16, true, false, true, LPR>
+                     : w1_smem ? (const void *)den_backward_kernel<NT, 1, 16, true, true, true, LPR>
+                               : (const void *)den_backward_kernel<NT, 1, 16, true, false, true, LPR>;
     return LaunchCoop(fn, NT, p, n_ctas, smem, stream, err);
 }
 
@@ -1234,17 +1251,18 @@ int Dispatch(bool backward, const DeviceGraph &g, DenParams &p, size_t fixed_sme
         const int LPR = p.Npad;
         const size_t ring_off = (smem + 127) & ~(size_t)127;
         const size_t bar_off = ring_off + (size_t)g.n_warps * kSmallStages * 16 * LPR * 4;
-        const size_t total = bar_off + (size_t)g.n_warps * kSmallStages * 8;
+        // mbarriers, then (backward, second weights streamed) one 64-byte slot per stage and warp for the bulk-copied w1 words
+        const size_t total = bar_off + (size_t)g.n_warps * kSmallStages * (8 + 64);
         const float *table = backward ? p.bh : p.alpha;
         const size_t rows = backward ? (size_t)2 * g.S : (size_t)(p.Tmax + 1 + (g.P > 0 ? 2 : 0)) * g.S;
-        if (!g.small_ok || !smem_arcs || (backward && !w1_smem) || total > budget || p.n_hubs > 0 || (LPR != 8 && LPR != 16) ||
+        if (!g.small_ok || !smem_arcs || total > budget || p.n_hubs > 0 || (LPR != 8 && LPR != 16) ||
             rows >= ((size_t)1 << 31) || !EncodeRowTensorMap(&p.tmap, table, rows, p.Npad, LPR)) {
             *err = "den: small-batch kernels unavailable for this graph/device although the batch was padded for them";
             return 1;
         }
         p.use_tma = 1; p.ring_off = (int)ring_off; p.bar_off = (int)bar_off;
-        return LPR == 8 ? LaunchTmaSmall<NT, 8>(backward, p, g.n_ctas, total, stream, err)
-                        : LaunchTmaSmall<NT, 16>(backward, p, g.n_ctas, total, stream, err);
+        return LPR == 8 ? LaunchTmaSmall<NT, 8>(backward, w1_smem, p, g.n_ctas, total, stream, err)
+                        : LaunchTmaSmall<NT, 16>(backward, w1_smem, p, g.n_ctas, total, stream, err);
     }
     // TMA tier: needs the full shared-memory stream, room for the rings, and a descriptor the driver accepts
     bool tma = false;

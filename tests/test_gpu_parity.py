@@ -128,7 +128,9 @@ def test_fallback_paths(tmp_graphs, monkeypatch, env):
     path, g, V = tmp_graphs["tlm_mid"]
     ctx = _ctx(path)
     T = 30
-    for N in ((40, 20) if "W1" in env else (40,)):      # 20: one utterance per lane (second weights prefetched with the gathers)
+    # 20: one utterance per lane (second weights prefetched with the gathers); 12 / 5: the small-batch kernels (16- / 8-float
+    # rows), whose backward pass then streams the second weights with bulk copies next to the TMA row gathers
+    for N in ((40, 20, 12, 5) if "W1" in env else (40,)):
         lens = np.maximum(1, T - (np.arange(N) * 5) % T).astype(np.int32)
         y, _, lens, _ = oracle.synth_batch(N, T, V, seed=8, lens=lens)
         logits = torch.tensor(y, device="cuda")
