@@ -115,7 +115,8 @@ struct DenAuxLayout {
 // on a graph that supports the small-batch kernels (DeviceGraph::small_ok) use 8- or 16-float rows instead, with the
 // lanes of a warp spread over (arc of the quad) x (utterance)  (den_kernels.cu, LPR template parameter).
 inline int PadLanes(int N, bool small_ok) {
-    if (small_ok && N <= 8) return 8;
+    // (8-float rows were measured slower than 16-float rows with half the lanes idle -- N=8, T=600: 11.1 + 14.2 ms against
+    // 8.1 + 8.7 ms -- because the gather4 copies are bound by their count, not by their bytes: profiles/r02_experiments.md)
     if (small_ok && N <= 16) return 16;
     int g = (N + 31) / 32;
     if (g >= 3) g = (g + 3) / 4 * 4;   // lanes carry 1, 2 or 4 utterances each

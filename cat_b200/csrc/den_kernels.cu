@@ -392,6 +392,7 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, unsigned
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
 // per-warp ring state: shared-memory address of the ring, of its first mbarrier, and the parity to wait for per stage
+constexpr uint32_t kOobRow = 0x40000000u;   // a row coordinate no gather table reaches (tables are limited to 2^30 rows)
 struct TmaRing {
     uint32_t buf, bar, phase;
 };
@@ -629,7 +630,16 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const __grid_constan
         for (int i = tid; i < (tile_a1 - tile_a0) / kQuad; i += NT) {
             const uint4 m0 = __ldg(src + 2 * i), m1 = __ldg(src + 2 * i + 1);
             const uint32_t mul = TMA ? 1u : row_bytes;   // TMA: row coordinates; register gathers: byte offsets
-            sq[2 * i] = make_uint4(fwd_row(m0.x, S) * mul, fwd_row(m0.z, S) * mul, fwd_row(m1.x, S) * mul, fwd_row(m1.z, S) * mul);
+            uint4 pr = make_uint4(fwd_row(m0.x, S) * mul, fwd_row(m0.z, S) * mul, fwd_row(m1.x, S) * mul, fwd_row(m1.z, S) * mul);
+            if (TMA && !HUBS) {
+                // zero-weight padding slots name a row coordinate beyond the tensor: the TMA unit zero-fills them in shared
+                // memory without touching L2 (17 % of the forward stream; the register path gets these from L1 instead)
+                if ((m0.y & 0x7fffffffu) == 0u) pr.x = kOobRow;
+                if ((m0.w & 0x7fffffffu) == 0u) pr.y = kOobRow;
+                if ((m1.y & 0x7fffffffu) == 0u) pr.z = kOobRow;
+                if ((m1.w & 0x7fffffffu) == 0u) pr.w = kOobRow;
+            }
+            sq[2 * i] = pr;
             sq[2 * i + 1] = make_uint4(m0.y, m0.w, m1.y, m1.w);
         }
     }
@@ -886,9 +896,17 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const __grid_consta
         for (int i = tid; i < (tile_a1 - tile_a0) / kQuad; i += NT) {
             const uint4 m0 = __ldg(src + 2 * i), m1 = __ldg(src + 2 * i + 1);
             const uint32_t mul = TMA ? 1u : row_bytes;   // TMA: row coordinates; register gathers: byte offsets
-            sq[kW * i] = make_uint4(m0.x * mul, m0.z * mul, m1.x * mul, m1.z * mul);
+            uint4 pr = make_uint4(m0.x * mul, m0.z * mul, m1.x * mul, m1.z * mul);
+            const uint4 w1q = __ldg(src1 + i);
+            if (TMA) {   // padding slots (both weights zero): out-of-bounds row coordinate, zero-filled by the TMA unit
+                if ((m0.y & 0x7fffffffu) == 0u && w1q.x == 0u) pr.x = kOobRow;
+                if ((m0.w & 0x7fffffffu) == 0u && w1q.y == 0u) pr.y = kOobRow;
+                if ((m1.y & 0x7fffffffu) == 0u && w1q.z == 0u) pr.z = kOobRow;
+                if ((m1.w & 0x7fffffffu) == 0u && w1q.w == 0u) pr.w = kOobRow;
+            }
+            sq[kW * i] = pr;
             sq[kW * i + 1] = make_uint4(m0.y, m0.w, m1.y, m1.w);
-            if (W1_SMEM) sq[kW * i + 2] = __ldg(src1 + i);
+            if (W1_SMEM) sq[kW * i + 2] = w1q;
         }
     }
     TmaRing ring{0u, 0u, 0u};
@@ -1256,7 +1274,7 @@ int Dispatch(bool backward, const DeviceGraph &g, DenParams &p, size_t fixed_sme
         const float *table = backward ? p.bh : p.alpha;
         const size_t rows = backward ? (size_t)2 * g.S : (size_t)(p.Tmax + 1 + (g.P > 0 ? 2 : 0)) * g.S;
         if (!g.small_ok || !smem_arcs || total > budget || p.n_hubs > 0 || (LPR != 8 && LPR != 16) ||
-            rows >= ((size_t)1 << 31) || !EncodeRowTensorMap(&p.tmap, table, rows, p.Npad, LPR)) {
+            rows >= ((size_t)1 << 30) || !EncodeRowTensorMap(&p.tmap, table, rows, p.Npad, LPR)) {
             *err = "den: small-batch kernels unavailable for this graph/device although the batch was padded for them";
             return 1;
         }
@@ -1273,7 +1291,7 @@ int Dispatch(bool backward, const DeviceGraph &g, DenParams &p, size_t fixed_sme
         const size_t total = bar_off + (size_t)g.n_warps * 2 * 8;
         const float *table = backward ? p.bh : p.alpha;
         const size_t rows = backward ? (size_t)2 * g.S : (size_t)(p.Tmax + 1 + (g.P > 0 ? 2 : 0)) * g.S;
-        if (total <= budget && rows < ((size_t)1 << 31) && EncodeRowTensorMap(&p.tmap, table, rows, p.Npad, 32 * U)) {
+        if (total <= budget && rows < ((size_t)1 << 30) && EncodeRowTensorMap(&p.tmap, table, rows, p.Npad, 32 * U)) {
             tma = true;
             p.use_tma = 1; p.ring_off = (int)ring_off; p.bar_off = (int)bar_off;
             smem = total;
