@@ -21,6 +21,7 @@ struct DevicePass {
     int *chunk_pair = nullptr;
     int *cta_labels = nullptr;
     float *w1 = nullptr;      // backward pass: second weight per slot
+    float *own_c = nullptr;   // [2S] own-row coefficients of this pass (DenPlan::own_fwd / own_bwd)
     int num_arcs = 0;
     int max_tile_arcs = 0;
     int max_tile_labels = 0;
@@ -35,6 +36,7 @@ struct DeviceGraph {
     int n_ctas = 0, n_warps = 0;
     int *state_label = nullptr;
     int *state_pos = nullptr;
+    int *state_flags = nullptr;
     float *final_lin = nullptr;
     DevicePass fwd, bwd;
     Arc *start_arcs = nullptr;   // out-arcs of the start state
@@ -45,6 +47,7 @@ struct DeviceGraph {
     int max_smem_optin = 0;
     // test hooks, read ONCE at Init (never on the per-call path): force the large-graph tiers on a small graph
     bool tune_arcs_in_global = false, tune_w1_in_global = false, tune_no_tma = false;
+    int tune_ring_rows = 0;    // > 0: force this many rows per TMA ring stage (A/B runs)
     // batches of <= 16 utterances run the small-batch TMA kernels (rows of 8 / 16 floats): needs both arc streams in
     // shared memory next to the rings, no hub rows, and a usable TMA descriptor -- decided once at Init
     bool small_ok = false;
@@ -68,6 +71,11 @@ struct alignas(64) DenParams {
     const int *cta_labels;
     const int *state_label;
     const int *state_pos;
+    const int *state_flags;   // bit 0: first member of a pair whose forward row has own terms only (den_graph.h)
+    const float *own_c;       // [2S] own-row coefficients of this pass
+    int ownc_off;             // byte offset in dynamic shared memory of the tile's coefficients [tile_rows][2]
+    int own_off;              // ... of the tile's own rows [tile_rows][Npad] (valid when own_smem)
+    int own_smem;             // 1: the previous frame's own rows are kept in shared memory; 0: re-read from the gather table
     const float *final_lin;
     const Arc *start_arcs;
     int n_start_arcs;

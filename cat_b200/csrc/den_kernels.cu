@@ -396,10 +396,11 @@ constexpr uint32_t kOobRow = 0x40000000u;   // a row coordinate no gather table 
 struct TmaRing {
     uint32_t buf, bar, phase;
 };
-template <int U> struct TmaShape;   // rows per batch / stages per warp: 8 KB (4 KB at U=1) of rows in flight per warp
-template <> struct TmaShape<1> { static constexpr int R = 16, STAGES = 2; };
-template <> struct TmaShape<2> { static constexpr int R = 16, STAGES = 2; };
-template <> struct TmaShape<4> { static constexpr int R = 8, STAGES = 2; };
+// rows per ring stage (two stages per warp): the default, and the shallower ring that makes room for the own rows
+template <int U> struct TmaShape;
+template <> struct TmaShape<1> { static constexpr int R = 16, R_SMALL = 16; };
+template <> struct TmaShape<2> { static constexpr int R = 16, R_SMALL = 8; };
+template <> struct TmaShape<4> { static constexpr int R = 8, R_SMALL = 8; };
 
 template <int U> __device__ __forceinline__ Vec<U> lds_row(uint32_t addr);
 template <> __device__ __forceinline__ Vec<1> lds_row<1>(uint32_t addr) {
@@ -421,12 +422,12 @@ template <> __device__ __forceinline__ Vec<4> lds_row<4>(uint32_t addr) {
 // The arc walk with TMA-staged rows.  `arcs`: the chunk's quads in shared memory, WPQ 16-byte words per quad
 // {row index 0..3}{w0..3}[{w1 0..3}]; n_batches = chunk arcs / R.  One batch = R/4 quads, issued by lanes 0..R/4-1 (one
 // gather4 each).  `consume_quad(words of the quad, rows v[4])` does the FMAs and the segment-end work.
-template <int U, int WPQ, typename Prologue, typename ConsumeQuad>
+template <int U, int R, int WPQ, typename Prologue, typename ConsumeQuad>
 __device__ __forceinline__ void walk_arcs_tma(const uint4 *arcs, int n_batches, const CUtensorMap *tm, int col, int row_base,
                                               TmaRing &ring, int lane, Prologue &&prologue, ConsumeQuad &&consume_quad) {
-    constexpr int R = TmaShape<U>::R, STAGES = TmaShape<U>::STAGES, QB = R / kQuad;
+    constexpr int QB = R / kQuad;   // (two stages)
     constexpr uint32_t ROWB = 32u * U * 4u;
-    static_assert(STAGES == 2, "the loop below is unrolled for two stages");
+    static_assert(R % kQuad == 0 && kChunkArcPad % R == 0, "a batch is whole quads and divides the chunk padding");
     auto issue = [&](int k, int s) {
         const uint32_t bar = ring.bar + 8u * s;
         if (lane == 0) mbar_expect_tx(bar, R * ROWB);
@@ -537,6 +538,10 @@ __device__ __forceinline__ void tl_mark(const DenParams &P, int step_index, int 
     else rec[slot + 1] = clock64();
 }
 
+// The per-row metadata word staged in shared memory: label | kRowPos0 (first member of a pair) | kRowOwnOnly (its forward row
+// has own terms only and no segment: finalised by its twin's segment end, den_graph.h DenPlan::state_flags)
+constexpr int kRowLabelMask = 0x1fffffff, kRowPos0 = 1 << 29, kRowOwnOnly = 1 << 30;
+
 // One PART of a high in-degree forward row (den_graph.h kEvPartial): scale the partial sum like a row end and add it
 // into the target row with atomics (the row was zeroed one frame ahead).  Deliberately out of line and self-contained:
 // it recomputes the few per-frame scalars it needs so that the hot row-end path keeps its registers.
@@ -603,14 +608,13 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const __grid_constan
     int labp0 = -1, labp1 = -1;
     for (int q = se - 1; q >= sb; --q) { if (__ldg(P.state_pos + q)) labp1 = __ldg(P.state_label + q); else labp0 = __ldg(P.state_label + q); }
     unsigned epoch = 0;
-    const int n_batches = (ae - ab) / (TMA ? (LPR == 32 ? TmaShape<U>::R : 16) : BATCH);
+    const int n_batches = (ae - ab) / (TMA && LPR < 32 ? 16 : BATCH);   // (TMA: BATCH = rows per ring stage)
     const uint4 *const arc4 = SMEM_ARCS ? reinterpret_cast<const uint4 *>(s_arcs + (ab - tile_a0))
                                         : reinterpret_cast<const uint4 *>(P.arcs + ab);
     TmaRing ring{0u, 0u, 0u};
     if (TMA) {
-        constexpr int kStages = LPR == 32 ? TmaShape<U>::STAGES : kSmallStages;
-        constexpr uint32_t kRingBytes = LPR == 32 ? (uint32_t)TmaShape<U>::STAGES * TmaShape<U>::R * 32u * U * 4u
-                                                  : (uint32_t)kSmallStages * 16u * LPR * 4u;
+        constexpr int kStages = LPR == 32 ? 2 : kSmallStages;
+        constexpr uint32_t kRingBytes = LPR == 32 ? 2u * BATCH * 32u * U * 4u : (uint32_t)kSmallStages * 16u * LPR * 4u;
         ring.buf = smem_u32(smem_raw + P.ring_off) + (uint32_t)warp * kRingBytes;
         ring.bar = smem_u32(smem_raw + P.bar_off) + (uint32_t)warp * 8u * kStages;
         if (lane == 0) {
@@ -622,7 +626,15 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const __grid_constan
 
     // per-row metadata lives in shared memory: L1 is invalidated at every grid barrier, and a global load on the
     // row-end path would cost an L2 round trip per row
-    for (int i = tid; i < tile_s1 - tile_s0; i += NT) s_label[i] = __ldg(P.state_label + tile_s0 + i);
+    float2 *const s_ownc = reinterpret_cast<float2 *>(smem_raw + P.ownc_off);   // [tile_rows] own-row coefficients (ca, cb)
+    float *const s_own = reinterpret_cast<float *>(smem_raw + P.own_off);        // [tile_rows][Npad] previous frame's own rows
+    for (int i = tid; i < tile_s1 - tile_s0; i += NT) {
+        s_label[i] = __ldg(P.state_label + tile_s0 + i) | (__ldg(P.state_pos + tile_s0 + i) == 0 ? kRowPos0 : 0) |
+                     ((__ldg(P.state_flags + tile_s0 + i) & 1) ? kRowOwnOnly : 0);
+        s_ownc[i] = make_float2(__ldg(P.own_c + 2 * (size_t)(tile_s0 + i)), __ldg(P.own_c + 2 * (size_t)(tile_s0 + i) + 1));
+    }
+    if (P.own_smem)   // alpha_0 of the tile's rows
+        for (int i = tid; i < (tile_s1 - tile_s0) * Npad; i += NT) s_own[i] = (tile_s0 + i / Npad == P.start) ? 1.f : 0.f;
     const uint32_t row_bytes = (uint32_t)Npad * 4u;
     if (SMEM_ARCS) {   // stage the tile once, quad-wise transposed: {byte offset 0..3}{w0..3}
         uint4 *sq = reinterpret_cast<uint4 *>(s_arcs);
@@ -710,22 +722,19 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const __grid_constan
             uint32_t virt_row = virt0 + (uint32_t)vj0;           // the next virtual row (parked two frames ahead)
             float *const out_base = a_cur + n0;
             Vec<U> cacc = vec_zero<U>();
-            auto seg_end = [&](float *acc, int ev, bool new_label, const uint4 *quad) {
-                const bool k1 = ev != kEvRowPos0;
-                if (P.debug & 1) { sum[0] += acc[0]; acc[0] = 0.f; return; }
-                if (HUBS && ev == kEvPartial) {   // high in-degree rows only: handled out of line, nothing hot is captured
-                    Vec<U> part;
+            // own rows of the previous frame (this group's): from shared memory, or re-read from the gather table
+            auto load_own = [&](int tile_row, float *x) {
 #pragma unroll
-                    for (int u = 0; u < U; ++u) { part.v[u] = acc[u]; acc[u] = 0.f; }
-                    // byte offset of the target row (last slot of the segment)
-                    const uint32_t tgt_off = TMA ? quad[0].w * row_bytes : load_quad_peers<SMEM_ARCS>(quad, row_bytes, (uint32_t)S).w;
-                    forward_partial_row<U>(P.state_label, P.len, P.colsum_a + (size_t)(t - 1) * Npad, P.fmax + (size_t)(t - 1) * Npad,
-                                           P.y, P.y_bf16, P.sn, (long)(t - 1) * P.st, P.N, t, n0, part, tgt_off, row_bytes, a_cur, s_sum, P.scale_exp);
-                    if (tgt_off == out_row * row_bytes) { ++out_row; ++ql; }   // the part that lives in the row's own group
-                    return;
-                }
+                for (int u = 0; u < U; ++u)
+                    x[u] = P.own_smem ? s_own[(size_t)tile_row * Npad + n0 + u] : __ldcg(a_prev + (size_t)(tile_s0 + tile_row) * Npad + n0 + u);
+            };
+            float xa[U], xb[U];   // previous-frame alpha of the current pair's first / second row
+#pragma unroll
+            for (int u = 0; u < U; ++u) { xa[u] = 0.f; xb[u] = 0.f; }
+            // one row ends: acc (gathered sum + own terms) -> alpha_t(row); kind 0 = unpaired, 1 = pair first, 2 = pair second
+            auto row_end = [&](bool k1, bool new_label, float *acc, int kind) {
                 if (new_label) {   // rare: a new label for this row position -> refresh its emission
-                    const int lab = s_label[ql];
+                    const int lab = s_label[ql] & kRowLabelMask;
                     const int lp = k1 ? labp1 : labp0;
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
@@ -739,15 +748,19 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const __grid_constan
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     out.v[u] = acc[u] * (k1 ? ec1[u] : ec0[u]) * r[u];   // ec is 0 for inactive utterances
-                    // TMA rows are read by every lane, whatever its utterances do: inactive columns are kept at a clean 0
-                    // (the register path never loads them)
-                    if (TMA && !act[u]) out.v[u] = 0.f;
+                    // rows are read back by every lane (TMA gathers, own rows), whatever its utterances do: inactive columns
+                    // are kept at a clean 0
+                    if (!act[u]) out.v[u] = 0.f;
                     sum[u] += out.v[u];
                     acc[u] = 0.f;
                 }
                 if ((TMA || lane_act) && sub == 0) out.stcg(row_ptr<U>(out_base, out_row, row_bytes));
-                if (ev == kEvRowPos0) cacc = out;
-                else if (ev == kEvRowPos1) {   // the pair's virtual row: what the next frame gathers instead of both
+                if (P.own_smem && sub == 0) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) s_own[(size_t)ql * Npad + n0 + u] = out.v[u];
+                }
+                if (kind == 1) cacc = out;
+                else if (kind == 2) {   // the pair's virtual row: what the next frame gathers instead of both
 #pragma unroll
                     for (int u = 0; u < U; ++u) cacc.v[u] += out.v[u];
                     if ((TMA || lane_act) && sub == 0) cacc.stcg(row_ptr<U>(out_base, virt_row, row_bytes));
@@ -755,6 +768,54 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const __grid_constan
                 }
                 ++out_row;
                 ++ql;
+            };
+            auto seg_end = [&](float *acc, int ev, bool new_label, const uint4 *quad) {
+                if (P.debug & 1) { sum[0] += acc[0]; acc[0] = 0.f; return; }
+                const int meta = s_label[ql];
+                if (!HUBS && (meta & kRowOwnOnly)) {
+                    // the pair's first member has own terms only (T o LM: the blank twin = emission x pair sum): it has no
+                    // segment; this one is its twin's.  Flags: new_label = first member's, ev & 1 = the twin's.
+                    load_own(ql, xa); load_own(ql + 1, xb);
+                    float a0[U];
+                    const float2 c0 = s_ownc[ql], c1 = s_ownc[ql + 1];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        a0[u] = fmaf(c0.x, xa[u], c0.y * xb[u]);
+                        acc[u] += fmaf(c1.x, xa[u], c1.y * xb[u]);
+                    }
+                    row_end(false, new_label, a0, 1);
+                    row_end(true, (ev & 1) != 0, acc, 2);
+                    return;
+                }
+                if (HUBS && ev == kEvPartial) {   // high in-degree rows only: handled out of line, nothing hot is captured
+                    Vec<U> part;
+#pragma unroll
+                    for (int u = 0; u < U; ++u) { part.v[u] = acc[u]; acc[u] = 0.f; }
+                    // byte offset of the target row (last slot of the segment)
+                    const uint32_t tgt_off = TMA ? quad[0].w * row_bytes : load_quad_peers<SMEM_ARCS>(quad, row_bytes, (uint32_t)S).w;
+                    forward_partial_row<U>(P.state_label, P.len, P.colsum_a + (size_t)(t - 1) * Npad, P.fmax + (size_t)(t - 1) * Npad,
+                                           P.y, P.y_bf16, P.sn, (long)(t - 1) * P.st, P.N, t, n0, part, tgt_off, row_bytes, a_cur, s_sum, P.scale_exp);
+                    if (tgt_off == out_row * row_bytes) { ++out_row; ++ql; }   // the part that lives in the row's own group
+                    return;
+                }
+                const float2 c = s_ownc[ql];
+                if (ev == kEvRowPos0) {          // first member of a pair: fetch the pair's own rows, keep them for the twin
+                    load_own(ql, xa); load_own(ql + 1, xb);
+#pragma unroll
+                    for (int u = 0; u < U; ++u) acc[u] += fmaf(c.x, xa[u], c.y * xb[u]);
+                    row_end(false, new_label, acc, 1);
+                } else if (ev == kEvRowPos1) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) acc[u] += fmaf(c.x, xa[u], c.y * xb[u]);
+                    row_end(true, new_label, acc, 2);
+                } else {                         // unpaired row: its own previous value (self loop)
+                    if (c.y != 0.f) {
+                        load_own(ql, xb);
+#pragma unroll
+                        for (int u = 0; u < U; ++u) acc[u] = fmaf(c.y, xb[u], acc[u]);
+                    }
+                    row_end(true, new_label, acc, 0);
+                }
             };
             if (TMA && LPR < 32) {
                 float acc[1] = {0.f};
@@ -774,7 +835,7 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const __grid_constan
                 float acc[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) acc[u] = 0.f;
-                walk_arcs_tma<U, 2>(arc4, n_batches, &P.tmap, gc * 32 * U, (t - 1) * S, ring, lane, frame_scalars,
+                walk_arcs_tma<U, BATCH, 2>(arc4, n_batches, &P.tmap, gc * 32 * U, (t - 1) * S, ring, lane, frame_scalars,
                                     [&](const uint4 *quad, const Vec<U> *v) {
                     const uint4 wq = quad[1];
                     const float w0 = fabsf(__uint_as_float(wq.x)), w1 = fabsf(__uint_as_float(wq.y));
@@ -873,7 +934,7 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const __grid_consta
     const int cl_lab1 = __ldg(P.cta_labels + cta * 4 + 2), cl_n1 = __ldg(P.cta_labels + cta * 4 + 3);
     int labp0 = -1, labp1 = -1;
     for (int q = se - 1; q >= sb; --q) { if (__ldg(P.state_pos + q)) labp1 = __ldg(P.state_label + q); else labp0 = __ldg(P.state_label + q); }
-    const int n_batches = (ae - ab) / (TMA ? (LPR == 32 ? TmaShape<U>::R : 16) : BATCH);
+    const int n_batches = (ae - ab) / (TMA && LPR < 32 ? 16 : BATCH);   // (TMA: BATCH = rows per ring stage)
     // shared memory: 3 words of 16 bytes per quad {byte offsets}{w0}{w1}; global fallback: AoS arcs + w1 array
     constexpr int kW = W1_SMEM ? 3 : 2;   // 16-byte words per staged quad
     const uint4 *const arc4 = SMEM_ARCS ? reinterpret_cast<const uint4 *>(s_arcs) + kW * ((ab - tile_a0) / kQuad)
@@ -884,10 +945,15 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const __grid_consta
     const size_t alpha_frame = (size_t)S * Npad;                          // alpha spill: real rows only (see den_forward_kernel)
     unsigned epoch = 0;
 
+    float2 *const s_ownc = reinterpret_cast<float2 *>(smem_raw + P.ownc_off);   // [tile_rows] own-row coefficients (da, db)
+    float *const s_own = reinterpret_cast<float *>(smem_raw + P.own_off);        // [tile_rows][Npad] next frame's own beta-hat rows
     for (int i = tid; i < tile_s1 - tile_s0; i += NT) {
         s_label[i] = __ldg(P.state_label + tile_s0 + i);
         s_final[i] = __ldg(P.final_lin + tile_s0 + i);
+        s_ownc[i] = make_float2(__ldg(P.own_c + 2 * (size_t)(tile_s0 + i)), __ldg(P.own_c + 2 * (size_t)(tile_s0 + i) + 1));
     }
+    if (P.own_smem)
+        for (int i = tid; i < (tile_s1 - tile_s0) * Npad; i += NT) s_own[i] = 0.f;
     const uint32_t row_bytes = (uint32_t)Npad * 4u;
     if (SMEM_ARCS) {   // stage the tile once, quad-wise transposed: {byte offset 0..3}{w0 0..3}[{w1 0..3}]
         uint4 *sq = reinterpret_cast<uint4 *>(s_arcs);
@@ -911,9 +977,8 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const __grid_consta
     }
     TmaRing ring{0u, 0u, 0u};
     if (TMA) {
-        constexpr int kStages = LPR == 32 ? TmaShape<U>::STAGES : kSmallStages;
-        constexpr uint32_t kRingBytes = LPR == 32 ? (uint32_t)TmaShape<U>::STAGES * TmaShape<U>::R * 32u * U * 4u
-                                                  : (uint32_t)kSmallStages * 16u * LPR * 4u;
+        constexpr int kStages = LPR == 32 ? 2 : kSmallStages;
+        constexpr uint32_t kRingBytes = LPR == 32 ? 2u * BATCH * 32u * U * 4u : (uint32_t)kSmallStages * 16u * LPR * 4u;
         ring.buf = smem_u32(smem_raw + P.ring_off) + (uint32_t)warp * kRingBytes;
         ring.bar = smem_u32(smem_raw + P.bar_off) + (uint32_t)warp * 8u * kStages;
         if (lane == 0) {
@@ -1020,15 +1085,40 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const __grid_consta
                     acc[u] = 0.f;
                 }
                 if ((TMA || lane_act) && sub == 0) out.stcg(row_ptr<U>(out_base, out_row, row_bytes));   // (TMA: every lane reads the row later)
+                if (P.own_smem && sub == 0) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) s_own[(size_t)ql * Npad + n0 + u] = out.v[u];
+                }
                 ++out_row;
                 ++ql;
             };
+            // own rows of the next frame (this group's beta-hat): from shared memory, or re-read from the ping-pong table
+            auto load_own = [&](int tile_row, float *x) {
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    x[u] = P.own_smem ? s_own[(size_t)tile_row * Npad + n0 + u] : __ldcg(bh_next + (size_t)(tile_s0 + tile_row) * Npad + n0 + u);
+            };
             auto group_end = [&](float *acc0, float *acc1, bool pair, bool new0, bool new1) {
                 if (P.debug & 1) { sum_b[0] += acc0[0] + acc1[0]; acc0[0] = 0.f; acc1[0] = 0.f; return; }
+                float xa[U], xb[U];
                 if (pair) {
+                    load_own(ql, xa); load_own(ql + 1, xb);
+                    const float2 d0 = s_ownc[ql], d1 = s_ownc[ql + 1];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        // (gat false: beta comes from the final weights, whatever the ring / own rows hold is not selected)
+                        acc0[u] += fmaf(d0.x, xa[u], d0.y * xb[u]);
+                        acc1[u] += fmaf(d1.x, xa[u], d1.y * xb[u]);
+                    }
                     do_row(false, new0, acc0, a_q);
                     do_row(true, new1, acc1, a_q1);
                 } else {
+                    const float2 d0 = s_ownc[ql];
+                    if (d0.y != 0.f) {
+                        load_own(ql, xb);
+#pragma unroll
+                        for (int u = 0; u < U; ++u) acc0[u] = fmaf(d0.y, xb[u], acc0[u]);
+                    }
                     do_row(true, new0, acc0, a_q);
 #pragma unroll
                     for (int u = 0; u < U; ++u) acc1[u] = 0.f;
@@ -1064,7 +1154,7 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const __grid_consta
                 for (int u = 0; u < U; ++u) { acc0[u] = 0.f; acc1[u] = 0.f; }
                 // (the first backward frame of an utterance takes beta from the final weights, not from these sums: whatever
                 // the ring holds then is never selected, see do_row)
-                walk_arcs_tma<U, 3>(arc4, n_batches, &P.tmap, gc * 32 * U, ((tau + 1) & 1) * S, ring, lane, frame_scalars,
+                walk_arcs_tma<U, BATCH, 3>(arc4, n_batches, &P.tmap, gc * 32 * U, ((tau + 1) & 1) * S, ring, lane, frame_scalars,
                                     [&](const uint4 *quad, const Vec<U> *v) {
                     const uint4 wq = quad[1], t1 = quad[2];
                     const float a0 = fabsf(__uint_as_float(wq.x)), a1 = fabsf(__uint_as_float(wq.y));
@@ -1205,10 +1295,9 @@ int LaunchBwd(bool w1_smem, const DenParams &p, int n_ctas, size_t smem, cudaStr
     return LaunchCoop(fn, NT, p, n_ctas, smem, stream, err);
 }
 
-// TMA gather4 variants (arc tile and, backward, both weights in shared memory)
-template <int NT, int U>
+// TMA gather4 variants (arc tile and, backward, both weights in shared memory); R = rows per ring stage
+template <int NT, int U, int R>
 int LaunchTma(bool backward, const DenParams &p, int n_ctas, size_t smem, cudaStream_t stream, std::string *err) {
-    constexpr int R = TmaShape<U>::R;
     const void *fn = backward ? (const void *)den_backward_kernel<NT, U, R, true, true, true>
                      : p.n_hubs > 0 ? (const void *)den_forward_kernel<NT, U, R, true, true, true>
                                     : (const void *)den_forward_kernel<NT, U, R, true, false, true>;
@@ -1232,9 +1321,10 @@ template <int U> struct FwdBatch { static constexpr int value = U == 4 ? 8 : 16;
 constexpr int kBwdBatch = 8;
 
 template <int NT, int U>
-int DispatchU(bool backward, bool tma, bool smem_arcs, bool w1_smem, const DenParams &p, int n_ctas, size_t smem, cudaStream_t stream,
-              std::string *err) {
-    if (tma) return LaunchTma<NT, U>(backward, p, n_ctas, smem, stream, err);
+int DispatchU(bool backward, bool tma, int ring_rows, bool smem_arcs, bool w1_smem, const DenParams &p, int n_ctas, size_t smem,
+              cudaStream_t stream, std::string *err) {
+    if (tma) return ring_rows == TmaShape<U>::R ? LaunchTma<NT, U, TmaShape<U>::R>(backward, p, n_ctas, smem, stream, err)
+                                                : LaunchTma<NT, U, TmaShape<U>::R_SMALL>(backward, p, n_ctas, smem, stream, err);
     if (backward)
         return smem_arcs ? LaunchBwd<NT, U, kBwdBatch, true>(w1_smem, p, n_ctas, smem, stream, err)
                          : LaunchBwd<NT, U, kBwdBatch, false>(w1_smem, p, n_ctas, smem, stream, err);
@@ -1242,37 +1332,46 @@ int DispatchU(bool backward, bool tma, bool smem_arcs, bool w1_smem, const DenPa
                      : LaunchFwd<NT, U, FwdBatch<U>::value, false>(p, n_ctas, smem, stream, err);
 }
 
-size_t TmaRingBytes(int U) {   // per warp
-    return U == 1 ? (size_t)TmaShape<1>::STAGES * TmaShape<1>::R * 128 : U == 2 ? (size_t)TmaShape<2>::STAGES * TmaShape<2>::R * 256
-                                                                               : (size_t)TmaShape<4>::STAGES * TmaShape<4>::R * 512;
+// Shared-memory tail of every variant: the tile's own-row coefficients [tile_rows][2] and, when they fit, the tile's own
+// rows of the previous frame [tile_rows][Npad].  Returns the new total; sets the DenParams offsets.
+size_t PlaceOwnRows(DenParams &p, size_t smem, size_t budget) {
+    const size_t ownc_off = (smem + 15) & ~(size_t)15;
+    const size_t own_off = (ownc_off + (size_t)p.tile_rows * 8 + 15) & ~(size_t)15;
+    const size_t with_rows = own_off + (size_t)p.tile_rows * p.Npad * 4;
+    p.ownc_off = (int)ownc_off; p.own_off = (int)own_off;
+    p.own_smem = with_rows <= budget ? 1 : 0;
+    return p.own_smem ? with_rows : own_off;
 }
 
 template <int NT>
 int Dispatch(bool backward, const DeviceGraph &g, DenParams &p, size_t fixed_smem, cudaStream_t stream,
              std::string *err) {
     const DevicePass &pass = backward ? g.bwd : g.fwd;
+    p.own_c = pass.own_c;
     // Tiers by graph size.  (1) TMA: the whole arc stream in shared memory (8 bytes per forward slot, 12 per backward slot)
     // next to the per-warp row rings the gather4 copies fill; (2) the same stream with register gathers (no ring);
     // (3) backward only: offsets + first weights in shared memory, second weights streamed from L2; (4) everything from L2.
+    // Every tier ends with the own-row coefficients and, if there is room, the own rows themselves (PlaceOwnRows).
     const size_t budget = (size_t)g.max_smem_optin > 2048 ? (size_t)g.max_smem_optin - 1024 : 0;
     const bool no_smem = g.tune_arcs_in_global;   // test hooks (read once at Init): exercise the large-graph tiers
+    const size_t coef_bytes = (size_t)p.tile_rows * 8 + 32;
     bool w1_smem = backward && !g.tune_w1_in_global;
     size_t arc_bytes = (size_t)pass.max_tile_arcs * (backward && w1_smem ? 12 : sizeof(Arc));
-    if (backward && w1_smem && fixed_smem + arc_bytes > budget) { w1_smem = false; arc_bytes = (size_t)pass.max_tile_arcs * sizeof(Arc); }
-    const bool smem_arcs = fixed_smem + arc_bytes <= budget && !no_smem;
+    if (backward && w1_smem && fixed_smem + arc_bytes + coef_bytes > budget) { w1_smem = false; arc_bytes = (size_t)pass.max_tile_arcs * sizeof(Arc); }
+    const bool smem_arcs = fixed_smem + arc_bytes + coef_bytes <= budget && !no_smem;
     size_t smem = fixed_smem + (smem_arcs ? arc_bytes : 0);
     // utterances per lane: the widest row segment the batch allows, except that the backward pass (two accumulators per
     // utterance) runs out of registers at 4 -- it walks 64-utterance groups instead.
     int U = LaneWidth(p.Npad);
     if (backward && U == 4) U = kBwdMaxLaneWidth;
+    const float *table = backward ? p.bh : p.alpha;
+    const size_t rows = backward ? (size_t)2 * g.S : (size_t)(p.Tmax + 1 + (g.P > 0 ? 2 : 0)) * g.S;
     if (p.Npad < 32) {   // small batch: the lane padding promised the small-batch TMA kernels (DeviceGraph::small_ok)
         const int LPR = p.Npad;
         const size_t ring_off = (smem + 127) & ~(size_t)127;
         const size_t bar_off = ring_off + (size_t)g.n_warps * kSmallStages * 16 * LPR * 4;
         // mbarriers, then (backward, second weights streamed) one 64-byte slot per stage and warp for the bulk-copied w1 words
-        const size_t total = bar_off + (size_t)g.n_warps * kSmallStages * (8 + 64);
-        const float *table = backward ? p.bh : p.alpha;
-        const size_t rows = backward ? (size_t)2 * g.S : (size_t)(p.Tmax + 1 + (g.P > 0 ? 2 : 0)) * g.S;
+        const size_t total = PlaceOwnRows(p, bar_off + (size_t)g.n_warps * kSmallStages * (8 + 64), budget);
         if (!g.small_ok || !smem_arcs || total > budget || p.n_hubs > 0 || (LPR != 8 && LPR != 16) ||
             rows >= ((size_t)1 << 30) || !EncodeRowTensorMap(&p.tmap, table, rows, p.Npad, LPR)) {
             *err = "den: small-batch kernels unavailable for this graph/device although the batch was padded for them";
@@ -1282,24 +1381,33 @@ int Dispatch(bool backward, const DeviceGraph &g, DenParams &p, size_t fixed_sme
         return LPR == 8 ? LaunchTmaSmall<NT, 8>(backward, w1_smem, p, g.n_ctas, total, stream, err)
                         : LaunchTmaSmall<NT, 16>(backward, w1_smem, p, g.n_ctas, total, stream, err);
     }
-    // TMA tier: needs the full shared-memory stream, room for the rings, and a descriptor the driver accepts
+    // TMA tier: needs the full shared-memory stream, room for the rings, and a descriptor the driver accepts.  Ring depth:
+    // the default stage (16 rows) if the own rows still fit next to it, else the shallow stage if that makes them fit (the
+    // stream is bound by the number of gather operations, not by rows in flight -- profiles/r02_experiments.md), else the
+    // default stage with the own rows re-read from the gather table.
     bool tma = false;
+    int ring_rows = 0;
     p.use_tma = 0;
-    if (smem_arcs && (!backward || w1_smem) && !g.tune_no_tma) {
+    if (smem_arcs && (!backward || w1_smem) && !g.tune_no_tma && rows < ((size_t)1 << 30) &&
+        EncodeRowTensorMap(&p.tmap, table, rows, p.Npad, 32 * U)) {
+        const int r_def = U == 4 ? TmaShape<4>::R : 16, r_small = U == 2 ? TmaShape<2>::R_SMALL : r_def;
         const size_t ring_off = (smem + 127) & ~(size_t)127;
-        const size_t bar_off = ring_off + (size_t)g.n_warps * TmaRingBytes(U);
-        const size_t total = bar_off + (size_t)g.n_warps * 2 * 8;
-        const float *table = backward ? p.bh : p.alpha;
-        const size_t rows = backward ? (size_t)2 * g.S : (size_t)(p.Tmax + 1 + (g.P > 0 ? 2 : 0)) * g.S;
-        if (total <= budget && rows < ((size_t)1 << 30) && EncodeRowTensorMap(&p.tmap, table, rows, p.Npad, 32 * U)) {
-            tma = true;
+        for (int pass_i = 0; pass_i < 3 && !tma; ++pass_i) {
+            const int R = pass_i == 1 ? r_small : r_def;
+            if (g.tune_ring_rows > 0 && pass_i < 2 && R != g.tune_ring_rows) continue;   // A/B: force a ring depth
+            const size_t bar_off = ring_off + (size_t)g.n_warps * 2 * R * 32 * U * 4;
+            const size_t total = PlaceOwnRows(p, bar_off + (size_t)g.n_warps * 2 * 8, budget);
+            if (total > budget) continue;
+            if (pass_i < 2 && !p.own_smem) continue;      // first two passes insist on the own rows in shared memory
+            tma = true; ring_rows = R;
             p.use_tma = 1; p.ring_off = (int)ring_off; p.bar_off = (int)bar_off;
             smem = total;
         }
     }
-    if (U == 1) return DispatchU<NT, 1>(backward, tma, smem_arcs, w1_smem, p, g.n_ctas, smem, stream, err);
-    if (U == 2) return DispatchU<NT, 2>(backward, tma, smem_arcs, w1_smem, p, g.n_ctas, smem, stream, err);
-    return DispatchU<NT, 4>(backward, tma, smem_arcs, w1_smem, p, g.n_ctas, smem, stream, err);
+    if (!tma) smem = PlaceOwnRows(p, smem, budget);
+    if (U == 1) return DispatchU<NT, 1>(backward, tma, ring_rows, smem_arcs, w1_smem, p, g.n_ctas, smem, stream, err);
+    if (U == 2) return DispatchU<NT, 2>(backward, tma, ring_rows, smem_arcs, w1_smem, p, g.n_ctas, smem, stream, err);
+    return DispatchU<NT, 4>(backward, tma, ring_rows, smem_arcs, w1_smem, p, g.n_ctas, smem, stream, err);
 }
 
 int DispatchThreads(bool backward, const DeviceGraph &g, DenParams &p, size_t fixed_smem, cudaStream_t stream,

@@ -79,9 +79,12 @@ def test_plan_invariants(tmp_graphs, n_ctas, n_warps):
         for pv, is_fwd in ((P.fwd, True), (P.bwd, False)):
             segs = list(pv.segments())
             if is_fwd:
-                assert len(segs) == S                                    # one row-end event per state
-                assert sum(1 for x in segs if x[2] == plan.EV_ROW_POS1) == NP == sum(1 for x in segs if x[2] == plan.EV_ROW_POS0)
-                assert not any(x[2] == plan.EV_COMMON for x in segs)
+                fsegs = list(P.forward_segments())
+                n_fused = sum(1 for x in fsegs if x[2] == "fused")
+                assert n_fused == int((P.state_flags & 1).sum())
+                assert len(fsegs) == S - n_fused and sum(len(x[3]) for x in fsegs) == S      # every state ends exactly once
+                assert sum(1 for x in fsegs if x[2] == "pos1") + n_fused == NP == sum(1 for x in fsegs if x[2] == "pos0") + n_fused
+                assert not any(x[2] == "partial" for x in fsegs)
                 assert (pv.arcs["peer"] < S + NP).all() and pv.w1 is None
             else:
                 assert len(segs) == S - NP                               # one group-end event per group
@@ -103,10 +106,10 @@ def test_plan_invariants(tmp_graphs, n_ctas, n_warps):
             q = 0
             prev = {}
             chunk_of = np.searchsorted(pv.chunk_arc, np.arange(0, len(pv.arcs), plan.QUAD), side="right") - 1
-            for a0, a1, ev, chg in segs:
+            for si, (a0, a1, ev, chg) in enumerate(segs):
                 c = int(chunk_of[(a1 - 1) // plan.QUAD])
                 if is_fwd:
-                    rows = [(0 if ev == plan.EV_ROW_POS0 else 1, chg)]
+                    rows = [(pos, flag) for _, pos, flag in fsegs[si][3]]
                 else:
                     rows = [(0, chg[0]), (1, chg[1])] if ev == plan.EV_ROW_POS1 else [(1, chg[0])]
                     if ev != plan.EV_ROW_POS1:
@@ -134,15 +137,23 @@ def test_plan_invariants(tmp_graphs, n_ctas, n_warps):
 
 
 def test_pairing_halves_tlm_arcs_and_can_be_disabled(tmp_path, monkeypatch):
+    monkeypatch.setenv("CCB_OWN", "1")
     g = fst.make_synthetic_den(400, 12, 40, seed=11)
     p = str(tmp_path / "g.fst")
     fst.write_fst(p, g)
     P = plan.load_plan(p, 8, 4)
     assert P.num_pairs == 399                                           # every (h,B),(h,L) twin
     assert int((P.fwd.weights() > 0).sum()) < 0.56 * g.num_arcs
+    # own-row terms: the blank twin's row (1 arc on the pair-sum row) and the token self loop left the gather stream
+    assert int((P.state_flags & 1).sum()) == 399 and (P.own_fwd[P.state_pos == 0] == [1.0, 1.0]).all()
     monkeypatch.setenv("CCB_NO_PAIRS", "1")
     Q = plan.load_plan(p, 8, 4)
-    assert Q.num_pairs == 0 and int((Q.fwd.weights() > 0).sum()) == g.num_arcs
+    n_self = int((np.asarray(g.src) == np.asarray(g.dst)).sum())          # without pairs only the self loops are own-row arcs
+    assert Q.num_pairs == 0 and int((Q.fwd.weights() > 0).sum()) == g.num_arcs - n_self
+    assert np.count_nonzero(Q.own_fwd) == n_self == np.count_nonzero(Q.own_bwd)
+    monkeypatch.setenv("CCB_NO_OWN", "1")
+    R = plan.load_plan(p, 8, 4)
+    assert int((R.fwd.weights() > 0).sum()) == g.num_arcs and not R.own_fwd.any() and not R.own_bwd.any()
 
 
 def test_plan_balance(tmp_path):
@@ -158,8 +169,10 @@ def test_plan_balance(tmp_path):
     assert P.max_tile_arcs * 8 < 200 * 1024
 
 
+@pytest.mark.parametrize("own", [True, False])
 @pytest.mark.parametrize("name,lens", [("tlm_small", [30, 22, 9, 1]), ("random_split", [20, 13, 7, 2])])
-def test_kernel_arithmetic_emulation_matches_oracle(tmp_graphs, name, lens):
+def test_kernel_arithmetic_emulation_matches_oracle(tmp_graphs, name, lens, monkeypatch, own):
+    monkeypatch.setenv("CCB_OWN" if own else "CCB_NO_OWN", "1")
     """The scaled-linear / hoisted-emission / state-product algorithm the kernels implement, emulated in numpy on
     the product's own plan arrays, equals the arc-based log-domain reference semantics."""
     path, g, V = tmp_graphs[name]
