@@ -136,6 +136,7 @@ int InitImpl(const char *fst_name, int n_gpus, const int *gpus) {
         { const char *e = getenv("CCB_W1_IN_GLOBAL"); d.tune_w1_in_global = e && e[0] == '1'; }
         { const char *e = getenv("CCB_NO_TMA"); d.tune_no_tma = e && e[0] == '1'; }   // A/B: register gathers instead of TMA gather4
         { const char *e = getenv("CCB_RING_ROWS"); d.tune_ring_rows = e ? atoi(e) : 0; }   // A/B: rows per TMA ring stage (16 / 8)
+        { const char *e = getenv("CCB_OWN_GLOBAL"); d.tune_own_global = e && e[0] == '1'; }   // test hook: own rows not in shared memory
         if (d.tune_arcs_in_global || d.tune_w1_in_global)
             fprintf(stderr, "ctc_crf_b200: CCB_ARCS_IN_GLOBAL / CCB_W1_IN_GLOBAL set -- den arc tiles forced out of shared memory (test hook, slow)\n");
         {   // small-batch kernels: both arc streams in shared memory next to 4 KB (8 KB) of rings per warp, no hub rows

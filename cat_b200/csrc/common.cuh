@@ -48,6 +48,7 @@ struct DeviceGraph {
     // test hooks, read ONCE at Init (never on the per-call path): force the large-graph tiers on a small graph
     bool tune_arcs_in_global = false, tune_w1_in_global = false, tune_no_tma = false;
     int tune_ring_rows = 0;    // > 0: force this many rows per TMA ring stage (A/B runs)
+    bool tune_own_global = false;   // test hook: re-read the own rows from the gather table instead of shared memory
     // batches of <= 16 utterances run the small-batch TMA kernels (rows of 8 / 16 floats): needs both arc streams in
     // shared memory next to the rings, no hub rows, and a usable TMA descriptor -- decided once at Init
     bool small_ok = false;

@@ -1334,12 +1334,12 @@ int DispatchU(bool backward, bool tma, int ring_rows, bool smem_arcs, bool w1_sm
 
 // Shared-memory tail of every variant: the tile's own-row coefficients [tile_rows][2] and, when they fit, the tile's own
 // rows of the previous frame [tile_rows][Npad].  Returns the new total; sets the DenParams offsets.
-size_t PlaceOwnRows(DenParams &p, size_t smem, size_t budget) {
+size_t PlaceOwnRows(DenParams &p, size_t smem, size_t budget, bool allow_rows = true) {
     const size_t ownc_off = (smem + 15) & ~(size_t)15;
     const size_t own_off = (ownc_off + (size_t)p.tile_rows * 8 + 15) & ~(size_t)15;
     const size_t with_rows = own_off + (size_t)p.tile_rows * p.Npad * 4;
     p.ownc_off = (int)ownc_off; p.own_off = (int)own_off;
-    p.own_smem = with_rows <= budget ? 1 : 0;
+    p.own_smem = (allow_rows && with_rows <= budget) ? 1 : 0;
     return p.own_smem ? with_rows : own_off;
 }
 
@@ -1371,7 +1371,7 @@ int Dispatch(bool backward, const DeviceGraph &g, DenParams &p, size_t fixed_sme
         const size_t ring_off = (smem + 127) & ~(size_t)127;
         const size_t bar_off = ring_off + (size_t)g.n_warps * kSmallStages * 16 * LPR * 4;
         // mbarriers, then (backward, second weights streamed) one 64-byte slot per stage and warp for the bulk-copied w1 words
-        const size_t total = PlaceOwnRows(p, bar_off + (size_t)g.n_warps * kSmallStages * (8 + 64), budget);
+        const size_t total = PlaceOwnRows(p, bar_off + (size_t)g.n_warps * kSmallStages * (8 + 64), budget, !g.tune_own_global);
         if (!g.small_ok || !smem_arcs || total > budget || p.n_hubs > 0 || (LPR != 8 && LPR != 16) ||
             rows >= ((size_t)1 << 30) || !EncodeRowTensorMap(&p.tmap, table, rows, p.Npad, LPR)) {
             *err = "den: small-batch kernels unavailable for this graph/device although the batch was padded for them";
@@ -1396,7 +1396,7 @@ int Dispatch(bool backward, const DeviceGraph &g, DenParams &p, size_t fixed_sme
             const int R = pass_i == 1 ? r_small : r_def;
             if (g.tune_ring_rows > 0 && pass_i < 2 && R != g.tune_ring_rows) continue;   // A/B: force a ring depth
             const size_t bar_off = ring_off + (size_t)g.n_warps * 2 * R * 32 * U * 4;
-            const size_t total = PlaceOwnRows(p, bar_off + (size_t)g.n_warps * 2 * 8, budget);
+            const size_t total = PlaceOwnRows(p, bar_off + (size_t)g.n_warps * 2 * 8, budget, !g.tune_own_global);
             if (total > budget) continue;
             if (pass_i < 2 && !p.own_smem) continue;      // first two passes insist on the own rows in shared memory
             tma = true; ring_rows = R;
@@ -1404,7 +1404,7 @@ int Dispatch(bool backward, const DeviceGraph &g, DenParams &p, size_t fixed_sme
             smem = total;
         }
     }
-    if (!tma) smem = PlaceOwnRows(p, smem, budget);
+    if (!tma) smem = PlaceOwnRows(p, smem, budget, !g.tune_own_global);
     if (U == 1) return DispatchU<NT, 1>(backward, tma, ring_rows, smem_arcs, w1_smem, p, g.n_ctas, smem, stream, err);
     if (U == 2) return DispatchU<NT, 2>(backward, tma, ring_rows, smem_arcs, w1_smem, p, g.n_ctas, smem, stream, err);
     return DispatchU<NT, 4>(backward, tma, ring_rows, smem_arcs, w1_smem, p, g.n_ctas, smem, stream, err);

@@ -51,8 +51,9 @@ def test_bad_files_raise_not_exit(tmp_path, fixture_fst, bad):
             fst.read_fst(str(p))
 
 
-@pytest.mark.parametrize("n_ctas,n_warps", [(1, 1), (4, 2), (148, 16), (148, 32)])
-def test_plan_invariants(tmp_graphs, n_ctas, n_warps):
+@pytest.mark.parametrize("n_ctas,n_warps,own", [(1, 1, False), (4, 2, True), (148, 16, False), (148, 16, True), (148, 32, False)])
+def test_plan_invariants(tmp_graphs, n_ctas, n_warps, own, monkeypatch):
+    monkeypatch.setenv("CCB_OWN" if own else "CCB_NO_OWN", "1")
     for name in ("tlm_small", "random_split", "tlm_mid"):
         path, g, V = tmp_graphs[name]
         P = plan.load_plan(path, n_ctas, n_warps)
@@ -132,8 +133,19 @@ def test_plan_invariants(tmp_graphs, n_ctas, n_warps):
             assert S > g.num_states
         else:
             assert S == g.num_states and NP > 0
-            assert nz_f < g.num_arcs and nz_b < g.num_arcs and nz_f == nz_b    # pairing removed the shared arcs
+            assert nz_f < g.num_arcs and nz_b < g.num_arcs                     # pairing removed the shared arcs
+            if not own:
+                assert nz_f == nz_b and not P.own_fwd.any() and not P.own_bwd.any()
+            else:   # every pair: the blank twin's arc + the token self loop (forward), B->B, L->B, L->L (backward)
+                assert (P.own_fwd[P.state_pos == 0] == [1.0, 1.0]).all() and int((P.state_flags & 1).sum()) == NP
+                # (an LM arc h -> h adds more own terms; in these small graphs a few exist)
+                assert np.count_nonzero(P.own_bwd) >= 3 * NP + np.count_nonzero(P.own_bwd[_unpaired(P)])
         assert len(P.start_arcs) == int((np.asarray(g.src) == g.start).sum()) or name == "random_split"
+
+
+def _unpaired(P):
+    ids = np.arange(P.num_states)
+    return (P.state_pos == 1) & ~((ids > 0) & (np.roll(P.state_pos, 1) == 0))
 
 
 def test_pairing_halves_tlm_arcs_and_can_be_disabled(tmp_path, monkeypatch):
