@@ -14,6 +14,11 @@ namespace ccb {
 // ------------------------------------------------------------------------------------------------
 // Device copy of the den plan (one per GPU listed in Init()).
 // ------------------------------------------------------------------------------------------------
+constexpr uint32_t kOobRow = 0x40000000u;   // a TMA row coordinate no gather table reaches (tables are limited to 2^30 rows)
+// backward arc bytes per CTA tile (12 per slot) above which a graph also gets the streamed-arc copy of its quads: below it
+// the stream fits shared memory next to the deepest rings at every batch width
+constexpr size_t kStreamTierArcBytes = 72 * 1024;
+
 struct DevicePass {
     Arc *arcs = nullptr;
     int *chunk_state = nullptr;
@@ -22,6 +27,10 @@ struct DevicePass {
     int *cta_labels = nullptr;
     float *w1 = nullptr;      // backward pass: second weight per slot
     float *own_c = nullptr;   // [2S] own-row coefficients of this pass (DenPlan::own_fwd / own_bwd)
+    // Streamed-arc tier (graphs whose arc stream does not fit shared memory): the pass's quads as the TMA kernels stage them,
+    // 2 (forward) / 3 (backward) 16-byte words per quad {row coordinate 0..3}{w0 0..3}[{w1 0..3}]; built at Init when the
+    // graph is large enough to need it, else null
+    uint4 *tq = nullptr;
     int num_arcs = 0;
     int max_tile_arcs = 0;
     int max_tile_labels = 0;
@@ -49,6 +58,7 @@ struct DeviceGraph {
     bool tune_arcs_in_global = false, tune_w1_in_global = false, tune_no_tma = false;
     int tune_ring_rows = 0;    // > 0: force this many rows per TMA ring stage (A/B runs)
     bool tune_own_global = false;   // test hook: re-read the own rows from the gather table instead of shared memory
+    bool own_any = false;           // the plan moved arcs out of the streams into own-row coefficients (DenPlan::own_fwd/own_bwd)
     // batches of <= 16 utterances run the small-batch TMA kernels (rows of 8 / 16 floats): needs both arc streams in
     // shared memory next to the rings, no hub rows, and a usable TMA descriptor -- decided once at Init
     bool small_ok = false;
@@ -74,6 +84,8 @@ struct alignas(64) DenParams {
     const int *state_pos;
     const int *state_flags;   // bit 0: first member of a pair whose forward row has own terms only (den_graph.h)
     const float *own_c;       // [2S] own-row coefficients of this pass
+    const uint4 *tq;          // streamed-arc tier: the pass's transposed quads in global memory (DevicePass::tq)
+    int aring_off, abar_off;  // ... byte offsets in dynamic shared memory of the per-warp arc rings and their mbarriers
     int ownc_off;             // byte offset in dynamic shared memory of the tile's coefficients [tile_rows][2]
     int own_off;              // ... of the tile's own rows [tile_rows][Npad] (valid when own_smem)
     int own_smem;             // 1: the previous frame's own rows are kept in shared memory; 0: re-read from the gather table

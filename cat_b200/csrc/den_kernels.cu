@@ -392,7 +392,6 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, unsigned
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
 // per-warp ring state: shared-memory address of the ring, of its first mbarrier, and the parity to wait for per stage
-constexpr uint32_t kOobRow = 0x40000000u;   // a row coordinate no gather table reaches (tables are limited to 2^30 rows)
 struct TmaRing {
     uint32_t buf, bar, phase;
 };
@@ -455,6 +454,88 @@ __device__ __forceinline__ void walk_arcs_tma(const uint4 *arcs, int n_batches, 
     issue(0, 0);
     if (n_batches > 1) issue(1, 1);
     prologue();   // per-frame scalars are fetched while the first rows are in flight
+    for (int k = 0; k < n_batches; k += 2) {
+        consume(k, 0);
+        if (k + 2 < n_batches) issue(k + 2, 0);
+        if (k + 1 < n_batches) {
+            consume(k + 1, 1);
+            if (k + 3 < n_batches) issue(k + 3, 1);
+        }
+    }
+}
+
+// Streamed arcs (graphs whose arc stream does not fit shared memory, BASELINE config 4: 5 M arcs): the chunk's quads are
+// not resident; they flow through a per-warp ring of kArcStages batches, filled by 1-D bulk copies (`cp.async.bulk`, SASS
+// UBLKCP: the stream is sequential and the same every frame) from DevicePass::tq, each stage completing its own mbarrier.
+// The ring is topped up after every consumed batch and runs across frames and lane groups: the first kArcStages batches
+// of the NEXT walk are requested at the end of this one, so they are in shared memory before the grid barrier opens.
+// Batches are counted from the start of the kernel (stage = count % kArcStages, parity = count / kArcStages & 1).
+constexpr int kArcStages = 8;
+struct ArcRing {
+    const uint4 *buf;        // this warp's ring in shared memory ...
+    uint32_t buf_s, bar;     // ... its shared-memory address, and its first mbarrier
+    uint32_t issued, done;   // batches requested / consumed so far
+    uint32_t src_k, n;       // next batch of the chunk to request (wraps at n = batches per walk)
+    const uint4 *src;        // the chunk's quads in global memory
+};
+template <int AW>   // AW = 16-byte words per batch
+__device__ __forceinline__ void arc_ring_fill(ArcRing &ar, int lane) {
+    if (ar.n == 0) return;
+    while (ar.issued != ar.done + kArcStages) {
+        if (lane == 0) {
+            const uint32_t st = ar.issued % kArcStages, bar = ar.bar + 8u * st;
+            mbar_expect_tx(bar, AW * 16u);
+            bulk_g2s(ar.buf_s + st * (AW * 16u), ar.src + (size_t)ar.src_k * AW, AW * 16u, bar);
+        }
+        ++ar.issued;
+        if (++ar.src_k == ar.n) ar.src_k = 0;
+    }
+}
+// before the kernel ends: no bulk copy may still be in flight into this CTA's shared memory
+__device__ __forceinline__ void arc_ring_drain(ArcRing &ar) {
+    while (ar.done != ar.issued) {
+        mbar_wait(ar.bar + 8u * (ar.done % kArcStages), (ar.done / kArcStages) & 1u);
+        ++ar.done;
+    }
+}
+template <int U, int R, int WPQ, typename Prologue, typename ConsumeQuad>
+__device__ __forceinline__ void walk_arcs_tma_stream(ArcRing &ar, int n_batches, const CUtensorMap *tm, int col, int row_base,
+                                                     TmaRing &ring, int lane, Prologue &&prologue, ConsumeQuad &&consume_quad) {
+    constexpr int QB = R / kQuad, AW = QB * WPQ;
+    constexpr uint32_t ROWB = 32u * U * 4u;
+    const uint32_t g0 = ar.done;
+    auto issue = [&](int k, int s) {
+        const uint32_t g = g0 + (uint32_t)k, st = g % kArcStages;
+        mbar_wait(ar.bar + 8u * st, (g / kArcStages) & 1u);   // every lane: the batch's arc words have landed
+        const uint32_t bar = ring.bar + 8u * s;
+        if (lane == 0) mbar_expect_tx(bar, R * ROWB);
+        __syncwarp();
+        if (lane < QB) {
+            const uint4 pr = ar.buf[st * AW + WPQ * lane];
+            tma_gather4(ring.buf + (uint32_t)(s * R + kQuad * lane) * ROWB, tm, col, row_base + (int)pr.x, row_base + (int)pr.y,
+                        row_base + (int)pr.z, row_base + (int)pr.w, bar);
+        }
+    };
+    auto consume = [&](int k, int s) {
+        mbar_wait(ring.bar + 8u * s, (ring.phase >> s) & 1u);
+        ring.phase ^= 1u << s;
+        const uint32_t base = ring.buf + (uint32_t)(s * R) * ROWB + (uint32_t)lane * (U * 4u);
+        const uint4 *quads = ar.buf + ((g0 + (uint32_t)k) % kArcStages) * AW;
+#pragma unroll
+        for (int q = 0; q < QB; ++q) {
+            Vec<U> v[kQuad];
+#pragma unroll
+            for (int j = 0; j < kQuad; ++j) v[j] = lds_row<U>(base + (uint32_t)(q * kQuad + j) * ROWB);
+            consume_quad(quads + WPQ * q, v);
+        }
+        __syncwarp();   // every lane is done with the row stage and the arc stage before they are refilled
+        ar.done = g0 + (uint32_t)k + 1u;
+        arc_ring_fill<AW>(ar, lane);
+    };
+    if (n_batches <= 0) { prologue(); return; }
+    issue(0, 0);
+    if (n_batches > 1) issue(1, 1);
+    prologue();
     for (int k = 0; k < n_batches; k += 2) {
         consume(k, 0);
         if (k + 2 < n_batches) issue(k + 2, 0);
@@ -574,9 +655,11 @@ __device__ __noinline__ void forward_partial_row(const int *state_label, const i
 // TMA: the gathered rows are staged in shared memory by gather4 copies (walk_arcs_tma) instead of register gathers; needs
 // the arc tile in shared memory (SMEM_ARCS) and DenParams::tmap.
 // LPR < 32 (8 or 16 lanes per row): the small-batch variant, see walk_arcs_tma_small (TMA, U = 1, no hub rows).
-template <int NT, int U, int BATCH, bool SMEM_ARCS, bool HUBS, bool TMA = false, int LPR = 32>
+// STREAM: the arc stream is not resident (walk_arcs_tma_stream); TMA, full-width rows, no hub rows.
+template <int NT, int U, int BATCH, bool SMEM_ARCS, bool HUBS, bool TMA = false, int LPR = 32, bool STREAM = false>
 __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const __grid_constant__ DenParams P) {
-    static_assert(!TMA || SMEM_ARCS, "the TMA walk reads the arc tile from shared memory");
+    static_assert(!TMA || SMEM_ARCS || STREAM, "the TMA walk reads the arc tile from shared memory or from the streamed ring");
+    static_assert(!STREAM || (TMA && !SMEM_ARCS && !HUBS && LPR == 32), "streamed arcs: TMA, full-width rows, no hub rows");
     static_assert(LPR == 32 || (TMA && U == 1 && !HUBS && (LPR == 8 || LPR == 16)), "small-batch variant: TMA, one utterance per lane, no hubs");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *s_sum = reinterpret_cast<float *>(smem_raw);                                  // [Npad]
@@ -619,9 +702,20 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const __grid_constan
         ring.bar = smem_u32(smem_raw + P.bar_off) + (uint32_t)warp * 8u * kStages;
         if (lane == 0) {
             for (int st = 0; st < kStages; ++st) mbar_init(ring.bar + 8u * st, 1);
+            if (STREAM) for (int st = 0; st < kArcStages; ++st) mbar_init(smem_u32(smem_raw + P.abar_off) + (uint32_t)(warp * kArcStages + st) * 8u, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
+    }
+    ArcRing aring{nullptr, 0u, 0u, 0u, 0u, 0u, 0u, nullptr};
+    if (STREAM) {
+        constexpr int kAW = BATCH / kQuad * 2;   // 16-byte words per batch
+        aring.buf = reinterpret_cast<const uint4 *>(smem_raw + P.aring_off) + (size_t)warp * kArcStages * kAW;
+        aring.buf_s = smem_u32(aring.buf);
+        aring.bar = smem_u32(smem_raw + P.abar_off) + (uint32_t)warp * kArcStages * 8u;
+        aring.n = (uint32_t)n_batches;
+        aring.src = P.tq + (size_t)2 * (ab / kQuad);
+        arc_ring_fill<kAW>(aring, lane);
     }
 
     // per-row metadata lives in shared memory: L1 is invalidated at every grid barrier, and a global load on the
@@ -800,7 +894,13 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const __grid_constan
                 }
                 const float2 c = s_ownc[ql];
                 if (ev == kEvRowPos0) {          // first member of a pair: fetch the pair's own rows, keep them for the twin
-                    load_own(ql, xa); load_own(ql + 1, xb);
+                    const float2 c1 = s_ownc[ql + 1];
+                    if (c.x != 0.f || c.y != 0.f || c1.x != 0.f || c1.y != 0.f) {   // (warp-uniform; all zero when the plan keeps own arcs in the stream)
+                        load_own(ql, xa); load_own(ql + 1, xb);
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < U; ++u) { xa[u] = 0.f; xb[u] = 0.f; }
+                    }
 #pragma unroll
                     for (int u = 0; u < U; ++u) acc[u] += fmaf(c.x, xa[u], c.y * xb[u]);
                     row_end(false, new_label, acc, 1);
@@ -835,8 +935,7 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const __grid_constan
                 float acc[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) acc[u] = 0.f;
-                walk_arcs_tma<U, BATCH, 2>(arc4, n_batches, &P.tmap, gc * 32 * U, (t - 1) * S, ring, lane, frame_scalars,
-                                    [&](const uint4 *quad, const Vec<U> *v) {
+                auto consume_quad = [&](const uint4 *quad, const Vec<U> *v) {
                     const uint4 wq = quad[1];
                     const float w0 = fabsf(__uint_as_float(wq.x)), w1 = fabsf(__uint_as_float(wq.y));
                     const float w2 = fabsf(__uint_as_float(wq.z)), w3 = fabsf(__uint_as_float(wq.w));
@@ -849,7 +948,9 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const __grid_constan
                     }
                     if ((int)wq.w < 0)   // warp-uniform: a segment ends at this quad
                         seg_end(acc, (int)(((wq.z >> 31) << 1) | (wq.y >> 31)), (int)wq.x < 0, quad);
-                });
+                };
+                if (STREAM) walk_arcs_tma_stream<U, BATCH, 2>(aring, n_batches, &P.tmap, gc * 32 * U, (t - 1) * S, ring, lane, frame_scalars, consume_quad);
+                else walk_arcs_tma<U, BATCH, 2>(arc4, n_batches, &P.tmap, gc * 32 * U, (t - 1) * S, ring, lane, frame_scalars, consume_quad);
             } else {
                 walk_arcs<U, BATCH, SMEM_ARCS>(arc4, n_batches, row_bytes, (uint32_t)S, reinterpret_cast<const char *>(a_prev + n0), lane_act,
                                                frame_scalars, seg_end);
@@ -880,6 +981,7 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const __grid_constan
         tl_mark(P, t, chunk, n_chunks, 2, lane);
     }
 
+    if (STREAM) arc_ring_drain(aring);
     // logZ[n] = log sum_q alpha_len(q) final(q) + accumulated log scale      (den_calculate.cu:105-161)
     for (int gc = 0; gc < (Npad + 31) / 32; ++gc) {
         const int n = gc * 32 + lane;
@@ -905,9 +1007,10 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const __grid_constan
 // ------------------------------------------------------------------------------------------------
 // backward: beta recursion, occupancies, logZ from beta
 // ------------------------------------------------------------------------------------------------
-template <int NT, int U, int BATCH, bool SMEM_ARCS, bool W1_SMEM = SMEM_ARCS, bool TMA = false, int LPR = 32>
+template <int NT, int U, int BATCH, bool SMEM_ARCS, bool W1_SMEM = SMEM_ARCS, bool TMA = false, int LPR = 32, bool STREAM = false>
 __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const __grid_constant__ DenParams P) {
-    static_assert(!TMA || (SMEM_ARCS && (W1_SMEM || LPR < 32)), "the TMA walk reads the offsets (and, at full width, both weights) from shared memory");
+    static_assert(!TMA || STREAM || (SMEM_ARCS && (W1_SMEM || LPR < 32)), "the TMA walk reads the offsets (and, at full width, both weights) from shared memory");
+    static_assert(!STREAM || (TMA && !SMEM_ARCS && LPR == 32), "streamed arcs: TMA, full-width rows");
     static_assert(LPR == 32 || (TMA && U == 1 && (LPR == 8 || LPR == 16)), "small-batch variant: TMA, one utterance per lane");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int Npad = P.Npad, S = P.S;
@@ -983,9 +1086,20 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const __grid_consta
         ring.bar = smem_u32(smem_raw + P.bar_off) + (uint32_t)warp * 8u * kStages;
         if (lane == 0) {
             for (int st = 0; st < kStages; ++st) mbar_init(ring.bar + 8u * st, 1);
+            if (STREAM) for (int st = 0; st < kArcStages; ++st) mbar_init(smem_u32(smem_raw + P.abar_off) + (uint32_t)(warp * kArcStages + st) * 8u, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
+    }
+    ArcRing aring{nullptr, 0u, 0u, 0u, 0u, 0u, 0u, nullptr};
+    if (STREAM) {
+        constexpr int kAW = BATCH / kQuad * 3;   // 16-byte words per batch
+        aring.buf = reinterpret_cast<const uint4 *>(smem_raw + P.aring_off) + (size_t)warp * kArcStages * kAW;
+        aring.buf_s = smem_u32(aring.buf);
+        aring.bar = smem_u32(smem_raw + P.abar_off) + (uint32_t)warp * kArcStages * 8u;
+        aring.n = (uint32_t)n_batches;
+        aring.src = P.tq + (size_t)3 * (ab / kQuad);
+        arc_ring_fill<kAW>(aring, lane);
     }
     for (int i = tid; i < (2 + P.gacc_rows) * Npad; i += NT) s_sum[i] = 0.f;
     const int my_len = (cta == 0 && tid < P.N) ? __ldg(P.len + tid) : 0;
@@ -1102,8 +1216,13 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const __grid_consta
                 if (P.debug & 1) { sum_b[0] += acc0[0] + acc1[0]; acc0[0] = 0.f; acc1[0] = 0.f; return; }
                 float xa[U], xb[U];
                 if (pair) {
-                    load_own(ql, xa); load_own(ql + 1, xb);
                     const float2 d0 = s_ownc[ql], d1 = s_ownc[ql + 1];
+                    if (d0.x != 0.f || d0.y != 0.f || d1.x != 0.f || d1.y != 0.f) {   // (warp-uniform)
+                        load_own(ql, xa); load_own(ql + 1, xb);
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < U; ++u) { xa[u] = 0.f; xb[u] = 0.f; }
+                    }
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
                         // (gat false: beta comes from the final weights, whatever the ring / own rows hold is not selected)
@@ -1154,8 +1273,7 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const __grid_consta
                 for (int u = 0; u < U; ++u) { acc0[u] = 0.f; acc1[u] = 0.f; }
                 // (the first backward frame of an utterance takes beta from the final weights, not from these sums: whatever
                 // the ring holds then is never selected, see do_row)
-                walk_arcs_tma<U, BATCH, 3>(arc4, n_batches, &P.tmap, gc * 32 * U, ((tau + 1) & 1) * S, ring, lane, frame_scalars,
-                                    [&](const uint4 *quad, const Vec<U> *v) {
+                auto consume_quad = [&](const uint4 *quad, const Vec<U> *v) {
                     const uint4 wq = quad[1], t1 = quad[2];
                     const float a0 = fabsf(__uint_as_float(wq.x)), a1 = fabsf(__uint_as_float(wq.y));
                     const float a2 = fabsf(__uint_as_float(wq.z)), a3 = fabsf(__uint_as_float(wq.w));
@@ -1169,7 +1287,9 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const __grid_consta
                     }
                     if ((int)wq.w < 0)   // warp-uniform: the group ends at this quad
                         group_end(acc0, acc1, (int)wq.z < 0, (int)wq.x < 0, (int)wq.y < 0);
-                });
+                };
+                if (STREAM) walk_arcs_tma_stream<U, BATCH, 3>(aring, n_batches, &P.tmap, gc * 32 * U, ((tau + 1) & 1) * S, ring, lane, frame_scalars, consume_quad);
+                else walk_arcs_tma<U, BATCH, 3>(arc4, n_batches, &P.tmap, gc * 32 * U, ((tau + 1) & 1) * S, ring, lane, frame_scalars, consume_quad);
             } else {
                 walk_arcs_dual<U, BATCH, SMEM_ARCS, W1_SMEM>(arc4, w1g, n_batches, row_bytes, reinterpret_cast<const char *>(bh_next + n0),
                                                              lane_gat, frame_scalars, group_end);
@@ -1222,6 +1342,7 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const __grid_consta
         tl_mark(P, P.Tmax - tau, chunk, n_chunks, 2, lane);
     }
 
+    if (STREAM) arc_ring_drain(aring);
     // tau = 0: beta_0(start) only -> logZ recomputed from the backward pass (den_calculate.cu:177-187,255-261)
     if (cta == 0 && warp == 0) {
         const float *bh1 = P.bh + (size_t)(1 & 1) * frame_elems;
@@ -1303,6 +1424,13 @@ int LaunchTma(bool backward, const DenParams &p, int n_ctas, size_t smem, cudaSt
                                     : (const void *)den_forward_kernel<NT, U, R, true, false, true>;
     return LaunchCoop(fn, NT, p, n_ctas, smem, stream, err);
 }
+// ... with the arc stream flowing through per-warp rings instead of being resident (walk_arcs_tma_stream)
+template <int NT, int U, int R>
+int LaunchTmaStream(bool backward, const DenParams &p, int n_ctas, size_t smem, cudaStream_t stream, std::string *err) {
+    const void *fn = backward ? (const void *)den_backward_kernel<NT, U, R, false, true, true, 32, true>
+                              : (const void *)den_forward_kernel<NT, U, R, false, false, true, 32, true>;
+    return LaunchCoop(fn, NT, p, n_ctas, smem, stream, err);
+}
 
 // small batches: rows of LPR = 8 / 16 floats (see walk_arcs_tma_small)
 template <int NT, int LPR>
@@ -1323,6 +1451,7 @@ constexpr int kBwdBatch = 8;
 template <int NT, int U>
 int DispatchU(bool backward, bool tma, int ring_rows, bool smem_arcs, bool w1_smem, const DenParams &p, int n_ctas, size_t smem,
               cudaStream_t stream, std::string *err) {
+    if (tma && !smem_arcs) return LaunchTmaStream<NT, U, TmaShape<U>::R>(backward, p, n_ctas, smem, stream, err);
     if (tma) return ring_rows == TmaShape<U>::R ? LaunchTma<NT, U, TmaShape<U>::R>(backward, p, n_ctas, smem, stream, err)
                                                 : LaunchTma<NT, U, TmaShape<U>::R_SMALL>(backward, p, n_ctas, smem, stream, err);
     if (backward)
@@ -1353,6 +1482,7 @@ int Dispatch(bool backward, const DeviceGraph &g, DenParams &p, size_t fixed_sme
     // (3) backward only: offsets + first weights in shared memory, second weights streamed from L2; (4) everything from L2.
     // Every tier ends with the own-row coefficients and, if there is room, the own rows themselves (PlaceOwnRows).
     const size_t budget = (size_t)g.max_smem_optin > 2048 ? (size_t)g.max_smem_optin - 1024 : 0;
+    const bool own_rows_ok = g.own_any && !g.tune_own_global;   // keep the tile's own rows in shared memory when they fit
     const bool no_smem = g.tune_arcs_in_global;   // test hooks (read once at Init): exercise the large-graph tiers
     const size_t coef_bytes = (size_t)p.tile_rows * 8 + 32;
     bool w1_smem = backward && !g.tune_w1_in_global;
@@ -1371,7 +1501,7 @@ int Dispatch(bool backward, const DeviceGraph &g, DenParams &p, size_t fixed_sme
         const size_t ring_off = (smem + 127) & ~(size_t)127;
         const size_t bar_off = ring_off + (size_t)g.n_warps * kSmallStages * 16 * LPR * 4;
         // mbarriers, then (backward, second weights streamed) one 64-byte slot per stage and warp for the bulk-copied w1 words
-        const size_t total = PlaceOwnRows(p, bar_off + (size_t)g.n_warps * kSmallStages * (8 + 64), budget, !g.tune_own_global);
+        const size_t total = PlaceOwnRows(p, bar_off + (size_t)g.n_warps * kSmallStages * (8 + 64), budget, own_rows_ok);
         if (!g.small_ok || !smem_arcs || total > budget || p.n_hubs > 0 || (LPR != 8 && LPR != 16) ||
             rows >= ((size_t)1 << 30) || !EncodeRowTensorMap(&p.tmap, table, rows, p.Npad, LPR)) {
             *err = "den: small-batch kernels unavailable for this graph/device although the batch was padded for them";
@@ -1392,22 +1522,42 @@ int Dispatch(bool backward, const DeviceGraph &g, DenParams &p, size_t fixed_sme
         EncodeRowTensorMap(&p.tmap, table, rows, p.Npad, 32 * U)) {
         const int r_def = U == 4 ? TmaShape<4>::R : 16, r_small = U == 2 ? TmaShape<2>::R_SMALL : r_def;
         const size_t ring_off = (smem + 127) & ~(size_t)127;
-        for (int pass_i = 0; pass_i < 3 && !tma; ++pass_i) {
-            const int R = pass_i == 1 ? r_small : r_def;
-            if (g.tune_ring_rows > 0 && pass_i < 2 && R != g.tune_ring_rows) continue;   // A/B: force a ring depth
+        const int forced = (g.tune_ring_rows == r_def || g.tune_ring_rows == r_small) ? g.tune_ring_rows : 0;   // A/B hook
+        for (int pass_i = 0; pass_i < 4 && !tma; ++pass_i) {
+            // passes 0, 1: default / shallow stage with the own rows in shared memory; 2, 3: the same, own rows from the table
+            const int R = (pass_i & 1) ? r_small : r_def;
+            if ((forced && R != forced) || ((pass_i & 1) && r_small == r_def)) continue;
+            if (pass_i < 2 && !own_rows_ok) continue;
             const size_t bar_off = ring_off + (size_t)g.n_warps * 2 * R * 32 * U * 4;
-            const size_t total = PlaceOwnRows(p, bar_off + (size_t)g.n_warps * 2 * 8, budget, !g.tune_own_global);
-            if (total > budget) continue;
-            if (pass_i < 2 && !p.own_smem) continue;      // first two passes insist on the own rows in shared memory
+            const size_t total = PlaceOwnRows(p, bar_off + (size_t)g.n_warps * 2 * 8, budget, pass_i < 2);
+            if (total > budget || (pass_i < 2 && !p.own_smem)) continue;
             tma = true; ring_rows = R;
             p.use_tma = 1; p.ring_off = (int)ring_off; p.bar_off = (int)bar_off;
             smem = total;
         }
     }
-    if (!tma) smem = PlaceOwnRows(p, smem, budget, !g.tune_own_global);
-    if (U == 1) return DispatchU<NT, 1>(backward, tma, ring_rows, smem_arcs, w1_smem, p, g.n_ctas, smem, stream, err);
-    if (U == 2) return DispatchU<NT, 2>(backward, tma, ring_rows, smem_arcs, w1_smem, p, g.n_ctas, smem, stream, err);
-    return DispatchU<NT, 4>(backward, tma, ring_rows, smem_arcs, w1_smem, p, g.n_ctas, smem, stream, err);
+    // Streamed-arc TMA tier: the stream does not fit (or the test hook says so) but the graph carries the transposed copy.
+    bool smem_arcs_eff = smem_arcs;
+    if (!tma && pass.tq != nullptr && p.n_hubs == 0 && !g.tune_no_tma && rows < ((size_t)1 << 30) && p.Npad >= 32 &&
+        EncodeRowTensorMap(&p.tmap, table, rows, p.Npad, 32 * U)) {
+        const int R = U == 4 ? TmaShape<4>::R : 16;
+        const size_t ring_off = (fixed_smem + 127) & ~(size_t)127;
+        const size_t bar_off = ring_off + (size_t)g.n_warps * 2 * R * 32 * U * 4;
+        const size_t abar_off = bar_off + (size_t)g.n_warps * 2 * 8;
+        const size_t aring_off = (abar_off + (size_t)g.n_warps * kArcStages * 8 + 127) & ~(size_t)127;
+        const size_t arc_ring = (size_t)g.n_warps * kArcStages * (R / kQuad) * (backward ? 3 : 2) * 16;
+        const size_t total = PlaceOwnRows(p, aring_off + arc_ring, budget, own_rows_ok);
+        if (total <= budget) {
+            tma = true; ring_rows = R; smem_arcs_eff = false;
+            p.use_tma = 1; p.ring_off = (int)ring_off; p.bar_off = (int)bar_off;
+            p.abar_off = (int)abar_off; p.aring_off = (int)aring_off; p.tq = pass.tq;
+            smem = total;
+        }
+    }
+    if (!tma) smem = PlaceOwnRows(p, smem, budget, own_rows_ok);
+    if (U == 1) return DispatchU<NT, 1>(backward, tma, ring_rows, smem_arcs_eff, w1_smem, p, g.n_ctas, smem, stream, err);
+    if (U == 2) return DispatchU<NT, 2>(backward, tma, ring_rows, smem_arcs_eff, w1_smem, p, g.n_ctas, smem, stream, err);
+    return DispatchU<NT, 4>(backward, tma, ring_rows, smem_arcs_eff, w1_smem, p, g.n_ctas, smem, stream, err);
 }
 
 int DispatchThreads(bool backward, const DeviceGraph &g, DenParams &p, size_t fixed_smem, cudaStream_t stream,

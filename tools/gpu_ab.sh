@@ -1,12 +1,19 @@
 #!/bin/bash
-# A/B harness: tools/gpu_ab.sh "name:ENV=1 ENV2=x" ...   (bench.py kernel times per configuration)
+# A/B of the den kernels under gpurun: usage  bash tools/gpu_ab.sh <tag> "ENV=.. ENV=.." "ENV=.." ...   (one bench per env set)
+tag=$1; shift
 mkdir -p gpurun_out
-show() { python -c "
-import json,sys
-j=json.load(open('$1')); r=j['roofline']
-print('$2', round(j['value']), round(j['ms_per_step'],2), {k:round(v['ms'],2) for k,v in r['kernels'].items()}, round(r['frac'],4), 'e2e', round(j['e2e']['ms_per_step'],2))"; }
-for cfg in "$@"; do
-  name=${cfg%%:*}; envs=${cfg#*:}
-  env $envs timeout 600 python bench.py --steps 8 --warmup 3 --no-cpu-baseline --no-ref-cuda > gpurun_out/ab_$name.json 2> gpurun_out/ab_$name.err || tail -3 gpurun_out/ab_$name.err
-  show gpurun_out/ab_$name.json $name
+i=0
+for envs in "$@"; do
+  i=$((i+1))
+  echo "== [$i] $envs"
+  env $envs timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-ref-cuda --no-strong > gpurun_out/${tag}_ab$i.json 2> gpurun_out/${tag}_ab$i.err
+  python - <<PY
+import json
+try:
+    d = json.load(open("gpurun_out/${tag}_ab$i.json"))
+    k = d["roofline"]["kernels"]
+    print("   step %.2f ms  den %.2f ms  " % (d["ms_per_step"], d["roofline"]["den_ms"]) + "  ".join("%s %.2f" % (n.replace("den_", "").replace("_kernel", ""), v["ms"]) for n, v in k.items()))
+except Exception as e:
+    print("   failed:", e); print(open("gpurun_out/${tag}_ab$i.err").read()[-800:])
+PY
 done
