@@ -64,8 +64,8 @@ int Upload(T **dst, const std::vector<T> &src) {
 
 void FreeDevice(DeviceGraph &d) {
     if (!d.loaded) return;
-    cudaFree(d.state_label); cudaFree(d.state_pos); cudaFree(d.state_flags); cudaFree(d.final_lin); cudaFree(d.start_arcs); cudaFree(d.hub_states);
-    for (DevicePass *p : {&d.fwd, &d.bwd}) { cudaFree(p->arcs); cudaFree(p->chunk_state); cudaFree(p->chunk_arc); cudaFree(p->chunk_pair); cudaFree(p->cta_labels); cudaFree(p->w1); cudaFree(p->own_c); cudaFree(p->tq); }
+    cudaFree(d.state_label); cudaFree(d.state_pos); cudaFree(d.final_lin); cudaFree(d.start_arcs); cudaFree(d.hub_states);
+    for (DevicePass *p : {&d.fwd, &d.bwd}) { cudaFree(p->arcs); cudaFree(p->chunk_state); cudaFree(p->chunk_arc); cudaFree(p->chunk_pair); cudaFree(p->cta_labels); cudaFree(p->w1); cudaFree(p->tq); }
     d = DeviceGraph();
 }
 
@@ -152,18 +152,13 @@ int InitImpl(const char *fst_name, int n_gpus, const int *gpus) {
         d.n_ctas = g_plan.n_ctas; d.n_warps = g_plan.n_warps;
         d.max_smem_optin = (int)p2.sharedMemPerBlockOptin;
         rc = Upload(&d.state_label, g_plan.state_label) || Upload(&d.state_pos, g_plan.state_pos) ||
-             Upload(&d.state_flags, g_plan.state_flags) ||
              Upload(&d.final_lin, g_plan.final_lin) || Upload(&d.start_arcs, g_plan.start_arcs) ||
              Upload(&d.hub_states, g_plan.hub_states) ||
-             UploadPass(g_plan.fwd, &d.fwd) || UploadPass(g_plan.bwd, &d.bwd) ||
-             Upload(&d.fwd.own_c, g_plan.own_fwd) || Upload(&d.bwd.own_c, g_plan.own_bwd);
+             UploadPass(g_plan.fwd, &d.fwd) || UploadPass(g_plan.bwd, &d.bwd);
         { const char *e = getenv("CCB_ARCS_IN_GLOBAL"); d.tune_arcs_in_global = e && e[0] == '1'; }
         { const char *e = getenv("CCB_W1_IN_GLOBAL"); d.tune_w1_in_global = e && e[0] == '1'; }
         { const char *e = getenv("CCB_NO_TMA"); d.tune_no_tma = e && e[0] == '1'; }   // A/B: register gathers instead of TMA gather4
         { const char *e = getenv("CCB_RING_ROWS"); d.tune_ring_rows = e ? atoi(e) : 0; }   // A/B: rows per TMA ring stage (16 / 8)
-        { const char *e = getenv("CCB_OWN_GLOBAL"); d.tune_own_global = e && e[0] == '1'; }   // test hook: own rows not in shared memory
-        for (size_t k = 0; k < g_plan.own_fwd.size() && !d.own_any; ++k) d.own_any = g_plan.own_fwd[k] != 0.f;
-        for (size_t k = 0; k < g_plan.own_bwd.size() && !d.own_any; ++k) d.own_any = g_plan.own_bwd[k] != 0.f;
         // streamed-arc tier: only graphs whose arc stream may not fit shared memory next to the TMA rings carry the copy
         if (rc == 0 && g_plan.hub_states.empty() && !d.tune_no_tma &&
             (d.tune_arcs_in_global || (size_t)d.bwd.max_tile_arcs * 12 > kStreamTierArcBytes))
@@ -173,7 +168,7 @@ int InitImpl(const char *fst_name, int n_gpus, const int *gpus) {
         {   // small-batch kernels: both arc streams in shared memory next to 4 KB (8 KB) of rings per warp, no hub rows
             const size_t budget = (size_t)d.max_smem_optin > 2048 ? (size_t)d.max_smem_optin - 1024 : 0;
             // (the backward pass may keep only offsets + first weights resident, 8 bytes per slot, and stream the second weights)
-            const size_t ring = (size_t)d.n_warps * (4 * 16 * 64 + 4 * (8 + 64)) + (size_t)std::max(d.fwd.max_tile_rows, d.bwd.max_tile_rows) * 8 + 64;
+            const size_t ring = (size_t)d.n_warps * (4 * 16 * 64 + 4 * (8 + 64));
             const size_t fwd_need = (size_t)d.fwd.max_tile_arcs * sizeof(Arc) + (size_t)(16 + d.fwd.max_tile_rows) * 4 + ring + 512;
             const size_t bwd_need = (size_t)d.bwd.max_tile_arcs * 8 + ((size_t)(2 + d.bwd.max_tile_labels) * 16 + 2 * (size_t)d.bwd.max_tile_rows) * 4 + ring + 512;
             d.small_ok = !d.tune_no_tma && !d.tune_arcs_in_global && g_plan.hub_states.empty() &&
@@ -212,7 +207,7 @@ DenParams BaseParams(const DeviceGraph &g, const void *y, int dtype, long sn, lo
     DenParams p;
     memset(&p, 0, sizeof(p));
     char *a = reinterpret_cast<char *>(aux);
-    p.state_label = g.state_label; p.state_pos = g.state_pos; p.state_flags = g.state_flags; p.final_lin = g.final_lin;
+    p.state_label = g.state_label; p.state_pos = g.state_pos; p.final_lin = g.final_lin;
     p.start_arcs = g.start_arcs; p.n_start_arcs = g.n_start_arcs;
     p.hub_states = g.hub_states; p.n_hubs = g.n_hubs;
     p.S = g.S; p.num_pairs = g.P; p.start = g.start; p.n_warps = g.n_warps;
@@ -668,9 +663,6 @@ int ccb_plan_copy(void *plan, int which, void *dst, size_t dst_bytes) {
         case 14: src = p->bwd.cta_labels.data(); bytes = p->bwd.cta_labels.size() * 4; break;
         case 15: src = p->bwd.w1.data(); bytes = p->bwd.w1.size() * 4; break;
         case 16: src = p->hub_states.data(); bytes = p->hub_states.size() * 4; break;
-        case 17: src = p->own_fwd.data(); bytes = p->own_fwd.size() * 4; break;
-        case 18: src = p->own_bwd.data(); bytes = p->own_bwd.size() * 4; break;
-        case 19: src = p->state_flags.data(); bytes = p->state_flags.size() * 4; break;
         default: return 1;
     }
     if (bytes > dst_bytes) return 2;

@@ -26,7 +26,6 @@ struct DevicePass {
     int *chunk_pair = nullptr;
     int *cta_labels = nullptr;
     float *w1 = nullptr;      // backward pass: second weight per slot
-    float *own_c = nullptr;   // [2S] own-row coefficients of this pass (DenPlan::own_fwd / own_bwd)
     // Streamed-arc tier (graphs whose arc stream does not fit shared memory): the pass's quads as the TMA kernels stage them,
     // 2 (forward) / 3 (backward) 16-byte words per quad {row coordinate 0..3}{w0 0..3}[{w1 0..3}]; built at Init when the
     // graph is large enough to need it, else null
@@ -45,7 +44,6 @@ struct DeviceGraph {
     int n_ctas = 0, n_warps = 0;
     int *state_label = nullptr;
     int *state_pos = nullptr;
-    int *state_flags = nullptr;
     float *final_lin = nullptr;
     DevicePass fwd, bwd;
     Arc *start_arcs = nullptr;   // out-arcs of the start state
@@ -57,8 +55,6 @@ struct DeviceGraph {
     // test hooks, read ONCE at Init (never on the per-call path): force the large-graph tiers on a small graph
     bool tune_arcs_in_global = false, tune_w1_in_global = false, tune_no_tma = false;
     int tune_ring_rows = 0;    // > 0: force this many rows per TMA ring stage (A/B runs)
-    bool tune_own_global = false;   // test hook: re-read the own rows from the gather table instead of shared memory
-    bool own_any = false;           // the plan moved arcs out of the streams into own-row coefficients (DenPlan::own_fwd/own_bwd)
     // batches of <= 16 utterances run the small-batch TMA kernels (rows of 8 / 16 floats): needs both arc streams in
     // shared memory next to the rings, no hub rows, and a usable TMA descriptor -- decided once at Init
     bool small_ok = false;
@@ -82,13 +78,8 @@ struct alignas(64) DenParams {
     const int *cta_labels;
     const int *state_label;
     const int *state_pos;
-    const int *state_flags;   // bit 0: first member of a pair whose forward row has own terms only (den_graph.h)
-    const float *own_c;       // [2S] own-row coefficients of this pass
     const uint4 *tq;          // streamed-arc tier: the pass's transposed quads in global memory (DevicePass::tq)
     int aring_off, abar_off;  // ... byte offsets in dynamic shared memory of the per-warp arc rings and their mbarriers
-    int ownc_off;             // byte offset in dynamic shared memory of the tile's coefficients [tile_rows][2]
-    int own_off;              // ... of the tile's own rows [tile_rows][Npad] (valid when own_smem)
-    int own_smem;             // 1: the previous frame's own rows are kept in shared memory; 0: re-read from the gather table
     const float *final_lin;
     const Arc *start_arcs;
     int n_start_arcs;

@@ -94,9 +94,6 @@ bool ReadFstFile(const char *path, HostFst *out, std::string *err) {
 
 namespace {
 
-// (flipped to false once the kernels' own-row path is verified on the GPU in this round)
-constexpr bool kOwnRowsDefaultOff = true;
-
 inline uint32_t Bits(float w) { uint32_t b; memcpy(&b, &w, 4); return b; }
 inline float WithSign(float w) { uint32_t b = Bits(w) | 0x80000000u; float r; memcpy(&r, &b, 4); return r; }
 
@@ -339,9 +336,6 @@ bool BuildDenPlan(const HostFst &fst, int n_ctas, int n_warps, DenPlan *plan, st
         if (x.s1 != y.s1) return x.s1 < y.s1;
         return x.part < y.part;
     });
-    // own-row terms: ON unless CCB_NO_OWN is set (test hook: keep the own-row arcs in the gather streams)
-    const bool no_own = getenv("CCB_NO_OWN") != nullptr || (kOwnRowsDefaultOff && getenv("CCB_OWN") == nullptr);
-    const bool any_hub = std::find(is_hub.begin(), is_hub.end(), (char)1) != is_hub.end();
     std::vector<int> fid(S, -1), pair_of(S, -1);
     std::vector<Group> fgroups, bgroups;
     auto by_peer = [](const Arc &a, const Arc &b) { return a.peer < b.peer; };
@@ -353,7 +347,6 @@ bool BuildDenPlan(const HostFst &fst, int n_ctas, int n_warps, DenPlan *plan, st
     // (re)number the states for a given group order and build both passes' segments
     auto build = [&](const std::vector<GroupKey> &order) {
         plan->state_label.assign(S, 0); plan->state_pos.assign(S, 1); plan->orig_state.assign(S, 0); plan->final_lin.assign(S, 0.f);
-        plan->own_fwd.assign(2 * S, 0.f); plan->own_bwd.assign(2 * S, 0.f); plan->state_flags.assign(S, 0);
         int next = 0, n_pairs = 0;
         for (auto &g : order) {
             if (g.part > 0) continue;   // floating part of a hub row: no state of its own
@@ -404,34 +397,6 @@ bool BuildDenPlan(const HostFst &fst, int n_ctas, int n_warps, DenPlan *plan, st
             }
             std::sort(row->begin(), row->end(), by_peer);
         };
-        // move the arcs of `row` (forward row of sid s) whose source is one of its group's own rows -- real rows f0 / f1 or the
-        // group's virtual pair-sum row -- into the own-row coefficients
-        auto extract_own_fwd = [&](int s, int s0, int s1, std::vector<Arc> *row) {
-            if (no_own) return;
-            const int f = fid[(size_t)s];
-            const uint32_t f0 = s0 >= 0 ? (uint32_t)fid[(size_t)s0] : 0xffffffffu, f1 = (uint32_t)fid[(size_t)s1];
-            const uint32_t vr = s0 >= 0 ? (uint32_t)(S + (size_t)pair_of[(size_t)s0]) : 0xffffffffu;
-            size_t k = 0;
-            for (auto &a : *row) {
-                if (a.peer == f0) plan->own_fwd[2 * (size_t)f] += a.w;
-                else if (a.peer == f1) plan->own_fwd[2 * (size_t)f + 1] += a.w;
-                else if (a.peer == vr) { plan->own_fwd[2 * (size_t)f] += a.w; plan->own_fwd[2 * (size_t)f + 1] += a.w; }
-                else (*row)[k++] = a;
-            }
-            row->resize(k);
-        };
-        auto extract_own_bwd = [&](int s, int s0, int s1, std::vector<OEnt> *l) {
-            if (no_own) return;
-            const int f = fid[(size_t)s];
-            const int f0 = s0 >= 0 ? fid[(size_t)s0] : -1, f1 = fid[(size_t)s1];
-            size_t k = 0;
-            for (auto &e : *l) {
-                if (e.q == f0) plan->own_bwd[2 * (size_t)f] += e.w;
-                else if (e.q == f1) plan->own_bwd[2 * (size_t)f + 1] += e.w;
-                else (*l)[k++] = e;
-            }
-            l->resize(k);
-        };
         auto out_list = [&](int s, std::vector<OEnt> *l) {
             l->clear();
             for (auto &a : out_s[(size_t)s]) l->push_back(OEnt{fid[(size_t)a.peer], Bits(a.w), a.w});
@@ -477,10 +442,8 @@ bool BuildDenPlan(const HostFst &fst, int n_ctas, int n_warps, DenPlan *plan, st
             if (g.s0 < 0) {
                 Segment f, b;
                 forward_row(g.s1, &f.arcs);
-                extract_own_fwd(g.s1, -1, g.s1, &f.arcs);
                 f.event = kEvRow;
                 out_list(g.s1, &l1);
-                extract_own_bwd(g.s1, -1, g.s1, &l1);
                 for (auto &e : l1) { b.arcs.push_back(Arc{(uint32_t)e.q, e.w}); b.w1.push_back(0.f); }
                 b.event = kEvRow;
                 b.rows = 1;
@@ -490,13 +453,9 @@ bool BuildDenPlan(const HostFst &fst, int n_ctas, int n_warps, DenPlan *plan, st
                 Segment f0, f1, b;
                 forward_row(g.s0, &f0.arcs); f0.event = kEvRowPos0;
                 forward_row(g.s1, &f1.arcs); f1.event = kEvRowPos1;
-                extract_own_fwd(g.s0, g.s0, g.s1, &f0.arcs);
-                extract_own_fwd(g.s1, g.s0, g.s1, &f1.arcs);
                 // backward: ONE segment for the pair; slot weights (w for p0, w1 for p1): shared arcs carry both
                 out_list(g.s0, &l0);
                 out_list(g.s1, &l1);
-                extract_own_bwd(g.s0, g.s0, g.s1, &l0);
-                extract_own_bwd(g.s1, g.s0, g.s1, &l1);
                 size_t i = 0, j = 0;
                 while (i < l0.size() || j < l1.size()) {
                     if (i < l0.size() && j < l1.size() && l0[i].q == l1[j].q && l0[i].wb == l1[j].wb) {
@@ -509,15 +468,7 @@ bool BuildDenPlan(const HostFst &fst, int n_ctas, int n_warps, DenPlan *plan, st
                 }
                 b.event = kEvRowPos1;
                 b.rows = 2;
-                if (f0.arcs.empty() && !no_own && !any_hub) {   // (a fused segment's flags would be ambiguous with kEvPartial)
-                    // the first member's forward row has own terms only: no segment (no gather operation) of its own; its
-                    // twin's segment end finalises both rows (flags: sign(w[0]) / sign(w[1]) = label changed of p0 / p1)
-                    plan->state_flags[(size_t)fid[(size_t)g.s0]] |= 1;
-                    f1.rows = 2;
-                    fg.segs.push_back(std::move(f1));
-                } else {
-                    fg.segs.push_back(std::move(f0)); fg.segs.push_back(std::move(f1));
-                }
+                fg.segs.push_back(std::move(f0)); fg.segs.push_back(std::move(f1));
                 bg.segs.push_back(std::move(b));
             }
             fgroups.push_back(std::move(fg));

@@ -72,14 +72,6 @@ struct DenPlan {
     std::vector<int> state_pos;         // [S] 0 = first member of a pair, 1 = second member or unpaired
     std::vector<float> final_lin;       // [S] exp(final_logw) (0 for non-final)
     std::vector<int> orig_state;        // [S] state id in the file
-    // OWN-ROW terms (T-compose-LM: the blank twin's row, the token self loop): arcs whose source row belongs to the
-    // destination's own group were produced by the same warp one frame earlier -- the kernels keep those rows in shared
-    // memory and the arcs leave the gather streams.  own_fwd[2q], own_fwd[2q+1] = (ca, cb): row q of the forward pass
-    // receives ca * X0 + cb * X1 on top of its gathered sum, X0 / X1 = previous-frame alpha of the group's first / second
-    // row (an unpaired row is its group's second row: ca = 0).  own_bwd likewise with the next-frame beta-hat rows.
-    std::vector<float> own_fwd, own_bwd;   // [2S]
-    std::vector<int> state_flags;          // [S] bit 0: first member of a pair whose forward row has own terms only -- it has
-                                           //     no segment of its own and is finalised by its twin's segment end
     std::vector<Arc> start_arcs;        // out-arcs of the start state (plain), for logZ recomputed from beta
     std::vector<int> hub_states;        // states whose forward row is accumulated from parts (rows zeroed before each frame)
     // fwd: one segment per state (its in-arcs; peers may be virtual pair rows), events kEvRow / kEvRowPos0 / kEvRowPos1;

@@ -395,7 +395,7 @@ __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence
 struct TmaRing {
     uint32_t buf, bar, phase;
 };
-// rows per ring stage (two stages per warp): the default, and the shallower ring that makes room for the own rows
+// rows per ring stage (two stages per warp): the default, and a shallower ring (A/B hook CCB_RING_ROWS)
 template <int U> struct TmaShape;
 template <> struct TmaShape<1> { static constexpr int R = 16, R_SMALL = 16; };
 template <> struct TmaShape<2> { static constexpr int R = 16, R_SMALL = 8; };
@@ -619,10 +619,6 @@ __device__ __forceinline__ void tl_mark(const DenParams &P, int step_index, int 
     else rec[slot + 1] = clock64();
 }
 
-// The per-row metadata word staged in shared memory: label | kRowPos0 (first member of a pair) | kRowOwnOnly (its forward row
-// has own terms only and no segment: finalised by its twin's segment end, den_graph.h DenPlan::state_flags)
-constexpr int kRowLabelMask = 0x1fffffff, kRowPos0 = 1 << 29, kRowOwnOnly = 1 << 30;
-
 // One PART of a high in-degree forward row (den_graph.h kEvPartial): scale the partial sum like a row end and add it
 // into the target row with atomics (the row was zeroed one frame ahead).  Deliberately out of line and self-contained:
 // it recomputes the few per-frame scalars it needs so that the hot row-end path keeps its registers.
@@ -720,15 +716,7 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const __grid_constan
 
     // per-row metadata lives in shared memory: L1 is invalidated at every grid barrier, and a global load on the
     // row-end path would cost an L2 round trip per row
-    float2 *const s_ownc = reinterpret_cast<float2 *>(smem_raw + P.ownc_off);   // [tile_rows] own-row coefficients (ca, cb)
-    float *const s_own = reinterpret_cast<float *>(smem_raw + P.own_off);        // [tile_rows][Npad] previous frame's own rows
-    for (int i = tid; i < tile_s1 - tile_s0; i += NT) {
-        s_label[i] = __ldg(P.state_label + tile_s0 + i) | (__ldg(P.state_pos + tile_s0 + i) == 0 ? kRowPos0 : 0) |
-                     ((__ldg(P.state_flags + tile_s0 + i) & 1) ? kRowOwnOnly : 0);
-        s_ownc[i] = make_float2(__ldg(P.own_c + 2 * (size_t)(tile_s0 + i)), __ldg(P.own_c + 2 * (size_t)(tile_s0 + i) + 1));
-    }
-    if (P.own_smem)   // alpha_0 of the tile's rows
-        for (int i = tid; i < (tile_s1 - tile_s0) * Npad; i += NT) s_own[i] = (tile_s0 + i / Npad == P.start) ? 1.f : 0.f;
+    for (int i = tid; i < tile_s1 - tile_s0; i += NT) s_label[i] = __ldg(P.state_label + tile_s0 + i);
     const uint32_t row_bytes = (uint32_t)Npad * 4u;
     if (SMEM_ARCS) {   // stage the tile once, quad-wise transposed: {byte offset 0..3}{w0..3}
         uint4 *sq = reinterpret_cast<uint4 *>(s_arcs);
@@ -816,19 +804,22 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const __grid_constan
             uint32_t virt_row = virt0 + (uint32_t)vj0;           // the next virtual row (parked two frames ahead)
             float *const out_base = a_cur + n0;
             Vec<U> cacc = vec_zero<U>();
-            // own rows of the previous frame (this group's): from shared memory, or re-read from the gather table
-            auto load_own = [&](int tile_row, float *x) {
+            auto seg_end = [&](float *acc, int ev, bool new_label, const uint4 *quad) {
+                const bool k1 = ev != kEvRowPos0;
+                if (P.debug & 1) { sum[0] += acc[0]; acc[0] = 0.f; return; }
+                if (HUBS && ev == kEvPartial) {   // high in-degree rows only: handled out of line, nothing hot is captured
+                    Vec<U> part;
 #pragma unroll
-                for (int u = 0; u < U; ++u)
-                    x[u] = P.own_smem ? s_own[(size_t)tile_row * Npad + n0 + u] : __ldcg(a_prev + (size_t)(tile_s0 + tile_row) * Npad + n0 + u);
-            };
-            float xa[U], xb[U];   // previous-frame alpha of the current pair's first / second row
-#pragma unroll
-            for (int u = 0; u < U; ++u) { xa[u] = 0.f; xb[u] = 0.f; }
-            // one row ends: acc (gathered sum + own terms) -> alpha_t(row); kind 0 = unpaired, 1 = pair first, 2 = pair second
-            auto row_end = [&](bool k1, bool new_label, float *acc, int kind) {
+                    for (int u = 0; u < U; ++u) { part.v[u] = acc[u]; acc[u] = 0.f; }
+                    // byte offset of the target row (last slot of the segment)
+                    const uint32_t tgt_off = TMA ? quad[0].w * row_bytes : load_quad_peers<SMEM_ARCS>(quad, row_bytes, (uint32_t)S).w;
+                    forward_partial_row<U>(P.state_label, P.len, P.colsum_a + (size_t)(t - 1) * Npad, P.fmax + (size_t)(t - 1) * Npad,
+                                           P.y, P.y_bf16, P.sn, (long)(t - 1) * P.st, P.N, t, n0, part, tgt_off, row_bytes, a_cur, s_sum, P.scale_exp);
+                    if (tgt_off == out_row * row_bytes) { ++out_row; ++ql; }   // the part that lives in the row's own group
+                    return;
+                }
                 if (new_label) {   // rare: a new label for this row position -> refresh its emission
-                    const int lab = s_label[ql] & kRowLabelMask;
+                    const int lab = s_label[ql];
                     const int lp = k1 ? labp1 : labp0;
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
@@ -842,19 +833,15 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const __grid_constan
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     out.v[u] = acc[u] * (k1 ? ec1[u] : ec0[u]) * r[u];   // ec is 0 for inactive utterances
-                    // rows are read back by every lane (TMA gathers, own rows), whatever its utterances do: inactive columns
-                    // are kept at a clean 0
-                    if (!act[u]) out.v[u] = 0.f;
+                    // TMA rows are read by every lane, whatever its utterances do: inactive columns are kept at a clean 0
+                    // (the register path never loads them)
+                    if (TMA && !act[u]) out.v[u] = 0.f;
                     sum[u] += out.v[u];
                     acc[u] = 0.f;
                 }
                 if ((TMA || lane_act) && sub == 0) out.stcg(row_ptr<U>(out_base, out_row, row_bytes));
-                if (P.own_smem && sub == 0) {
-#pragma unroll
-                    for (int u = 0; u < U; ++u) s_own[(size_t)ql * Npad + n0 + u] = out.v[u];
-                }
-                if (kind == 1) cacc = out;
-                else if (kind == 2) {   // the pair's virtual row: what the next frame gathers instead of both
+                if (ev == kEvRowPos0) cacc = out;
+                else if (ev == kEvRowPos1) {   // the pair's virtual row: what the next frame gathers instead of both
 #pragma unroll
                     for (int u = 0; u < U; ++u) cacc.v[u] += out.v[u];
                     if ((TMA || lane_act) && sub == 0) cacc.stcg(row_ptr<U>(out_base, virt_row, row_bytes));
@@ -862,60 +849,6 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const __grid_constan
                 }
                 ++out_row;
                 ++ql;
-            };
-            auto seg_end = [&](float *acc, int ev, bool new_label, const uint4 *quad) {
-                if (P.debug & 1) { sum[0] += acc[0]; acc[0] = 0.f; return; }
-                const int meta = s_label[ql];
-                if (!HUBS && (meta & kRowOwnOnly)) {
-                    // the pair's first member has own terms only (T o LM: the blank twin = emission x pair sum): it has no
-                    // segment; this one is its twin's.  Flags: new_label = first member's, ev & 1 = the twin's.
-                    load_own(ql, xa); load_own(ql + 1, xb);
-                    float a0[U];
-                    const float2 c0 = s_ownc[ql], c1 = s_ownc[ql + 1];
-#pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        a0[u] = fmaf(c0.x, xa[u], c0.y * xb[u]);
-                        acc[u] += fmaf(c1.x, xa[u], c1.y * xb[u]);
-                    }
-                    row_end(false, new_label, a0, 1);
-                    row_end(true, (ev & 1) != 0, acc, 2);
-                    return;
-                }
-                if (HUBS && ev == kEvPartial) {   // high in-degree rows only: handled out of line, nothing hot is captured
-                    Vec<U> part;
-#pragma unroll
-                    for (int u = 0; u < U; ++u) { part.v[u] = acc[u]; acc[u] = 0.f; }
-                    // byte offset of the target row (last slot of the segment)
-                    const uint32_t tgt_off = TMA ? quad[0].w * row_bytes : load_quad_peers<SMEM_ARCS>(quad, row_bytes, (uint32_t)S).w;
-                    forward_partial_row<U>(P.state_label, P.len, P.colsum_a + (size_t)(t - 1) * Npad, P.fmax + (size_t)(t - 1) * Npad,
-                                           P.y, P.y_bf16, P.sn, (long)(t - 1) * P.st, P.N, t, n0, part, tgt_off, row_bytes, a_cur, s_sum, P.scale_exp);
-                    if (tgt_off == out_row * row_bytes) { ++out_row; ++ql; }   // the part that lives in the row's own group
-                    return;
-                }
-                const float2 c = s_ownc[ql];
-                if (ev == kEvRowPos0) {          // first member of a pair: fetch the pair's own rows, keep them for the twin
-                    const float2 c1 = s_ownc[ql + 1];
-                    if (c.x != 0.f || c.y != 0.f || c1.x != 0.f || c1.y != 0.f) {   // (warp-uniform; all zero when the plan keeps own arcs in the stream)
-                        load_own(ql, xa); load_own(ql + 1, xb);
-                    } else {
-#pragma unroll
-                        for (int u = 0; u < U; ++u) { xa[u] = 0.f; xb[u] = 0.f; }
-                    }
-#pragma unroll
-                    for (int u = 0; u < U; ++u) acc[u] += fmaf(c.x, xa[u], c.y * xb[u]);
-                    row_end(false, new_label, acc, 1);
-                } else if (ev == kEvRowPos1) {
-#pragma unroll
-                    for (int u = 0; u < U; ++u) acc[u] += fmaf(c.x, xa[u], c.y * xb[u]);
-                    row_end(true, new_label, acc, 2);
-                } else {                         // unpaired row: its own previous value (self loop)
-                    if (c.y != 0.f) {
-                        load_own(ql, xb);
-#pragma unroll
-                        for (int u = 0; u < U; ++u) acc[u] = fmaf(c.y, xb[u], acc[u]);
-                    }
-                    row_end(true, new_label, acc, 0);
-                }
             };
             if (TMA && LPR < 32) {
                 float acc[1] = {0.f};
@@ -1048,15 +981,10 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const __grid_consta
     const size_t alpha_frame = (size_t)S * Npad;                          // alpha spill: real rows only (see den_forward_kernel)
     unsigned epoch = 0;
 
-    float2 *const s_ownc = reinterpret_cast<float2 *>(smem_raw + P.ownc_off);   // [tile_rows] own-row coefficients (da, db)
-    float *const s_own = reinterpret_cast<float *>(smem_raw + P.own_off);        // [tile_rows][Npad] next frame's own beta-hat rows
     for (int i = tid; i < tile_s1 - tile_s0; i += NT) {
         s_label[i] = __ldg(P.state_label + tile_s0 + i);
         s_final[i] = __ldg(P.final_lin + tile_s0 + i);
-        s_ownc[i] = make_float2(__ldg(P.own_c + 2 * (size_t)(tile_s0 + i)), __ldg(P.own_c + 2 * (size_t)(tile_s0 + i) + 1));
     }
-    if (P.own_smem)
-        for (int i = tid; i < (tile_s1 - tile_s0) * Npad; i += NT) s_own[i] = 0.f;
     const uint32_t row_bytes = (uint32_t)Npad * 4u;
     if (SMEM_ARCS) {   // stage the tile once, quad-wise transposed: {byte offset 0..3}{w0 0..3}[{w1 0..3}]
         uint4 *sq = reinterpret_cast<uint4 *>(s_arcs);
@@ -1199,45 +1127,15 @@ __global__ void __launch_bounds__(NT, 1) den_backward_kernel(const __grid_consta
                     acc[u] = 0.f;
                 }
                 if ((TMA || lane_act) && sub == 0) out.stcg(row_ptr<U>(out_base, out_row, row_bytes));   // (TMA: every lane reads the row later)
-                if (P.own_smem && sub == 0) {
-#pragma unroll
-                    for (int u = 0; u < U; ++u) s_own[(size_t)ql * Npad + n0 + u] = out.v[u];
-                }
                 ++out_row;
                 ++ql;
             };
-            // own rows of the next frame (this group's beta-hat): from shared memory, or re-read from the ping-pong table
-            auto load_own = [&](int tile_row, float *x) {
-#pragma unroll
-                for (int u = 0; u < U; ++u)
-                    x[u] = P.own_smem ? s_own[(size_t)tile_row * Npad + n0 + u] : __ldcg(bh_next + (size_t)(tile_s0 + tile_row) * Npad + n0 + u);
-            };
             auto group_end = [&](float *acc0, float *acc1, bool pair, bool new0, bool new1) {
                 if (P.debug & 1) { sum_b[0] += acc0[0] + acc1[0]; acc0[0] = 0.f; acc1[0] = 0.f; return; }
-                float xa[U], xb[U];
                 if (pair) {
-                    const float2 d0 = s_ownc[ql], d1 = s_ownc[ql + 1];
-                    if (d0.x != 0.f || d0.y != 0.f || d1.x != 0.f || d1.y != 0.f) {   // (warp-uniform)
-                        load_own(ql, xa); load_own(ql + 1, xb);
-                    } else {
-#pragma unroll
-                        for (int u = 0; u < U; ++u) { xa[u] = 0.f; xb[u] = 0.f; }
-                    }
-#pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        // (gat false: beta comes from the final weights, whatever the ring / own rows hold is not selected)
-                        acc0[u] += fmaf(d0.x, xa[u], d0.y * xb[u]);
-                        acc1[u] += fmaf(d1.x, xa[u], d1.y * xb[u]);
-                    }
                     do_row(false, new0, acc0, a_q);
                     do_row(true, new1, acc1, a_q1);
                 } else {
-                    const float2 d0 = s_ownc[ql];
-                    if (d0.y != 0.f) {
-                        load_own(ql, xb);
-#pragma unroll
-                        for (int u = 0; u < U; ++u) acc0[u] = fmaf(d0.y, xb[u], acc0[u]);
-                    }
                     do_row(true, new0, acc0, a_q);
 #pragma unroll
                     for (int u = 0; u < U; ++u) acc1[u] = 0.f;
@@ -1461,34 +1359,19 @@ int DispatchU(bool backward, bool tma, int ring_rows, bool smem_arcs, bool w1_sm
                      : LaunchFwd<NT, U, FwdBatch<U>::value, false>(p, n_ctas, smem, stream, err);
 }
 
-// Shared-memory tail of every variant: the tile's own-row coefficients [tile_rows][2] and, when they fit, the tile's own
-// rows of the previous frame [tile_rows][Npad].  Returns the new total; sets the DenParams offsets.
-size_t PlaceOwnRows(DenParams &p, size_t smem, size_t budget, bool allow_rows = true) {
-    const size_t ownc_off = (smem + 15) & ~(size_t)15;
-    const size_t own_off = (ownc_off + (size_t)p.tile_rows * 8 + 15) & ~(size_t)15;
-    const size_t with_rows = own_off + (size_t)p.tile_rows * p.Npad * 4;
-    p.ownc_off = (int)ownc_off; p.own_off = (int)own_off;
-    p.own_smem = (allow_rows && with_rows <= budget) ? 1 : 0;
-    return p.own_smem ? with_rows : own_off;
-}
-
 template <int NT>
 int Dispatch(bool backward, const DeviceGraph &g, DenParams &p, size_t fixed_smem, cudaStream_t stream,
              std::string *err) {
     const DevicePass &pass = backward ? g.bwd : g.fwd;
-    p.own_c = pass.own_c;
     // Tiers by graph size.  (1) TMA: the whole arc stream in shared memory (8 bytes per forward slot, 12 per backward slot)
     // next to the per-warp row rings the gather4 copies fill; (2) the same stream with register gathers (no ring);
     // (3) backward only: offsets + first weights in shared memory, second weights streamed from L2; (4) everything from L2.
-    // Every tier ends with the own-row coefficients and, if there is room, the own rows themselves (PlaceOwnRows).
     const size_t budget = (size_t)g.max_smem_optin > 2048 ? (size_t)g.max_smem_optin - 1024 : 0;
-    const bool own_rows_ok = g.own_any && !g.tune_own_global;   // keep the tile's own rows in shared memory when they fit
     const bool no_smem = g.tune_arcs_in_global;   // test hooks (read once at Init): exercise the large-graph tiers
-    const size_t coef_bytes = (size_t)p.tile_rows * 8 + 32;
     bool w1_smem = backward && !g.tune_w1_in_global;
     size_t arc_bytes = (size_t)pass.max_tile_arcs * (backward && w1_smem ? 12 : sizeof(Arc));
-    if (backward && w1_smem && fixed_smem + arc_bytes + coef_bytes > budget) { w1_smem = false; arc_bytes = (size_t)pass.max_tile_arcs * sizeof(Arc); }
-    const bool smem_arcs = fixed_smem + arc_bytes + coef_bytes <= budget && !no_smem;
+    if (backward && w1_smem && fixed_smem + arc_bytes > budget) { w1_smem = false; arc_bytes = (size_t)pass.max_tile_arcs * sizeof(Arc); }
+    const bool smem_arcs = fixed_smem + arc_bytes <= budget && !no_smem;
     size_t smem = fixed_smem + (smem_arcs ? arc_bytes : 0);
     // utterances per lane: the widest row segment the batch allows, except that the backward pass (two accumulators per
     // utterance) runs out of registers at 4 -- it walks 64-utterance groups instead.
@@ -1501,36 +1384,32 @@ int Dispatch(bool backward, const DeviceGraph &g, DenParams &p, size_t fixed_sme
         const size_t ring_off = (smem + 127) & ~(size_t)127;
         const size_t bar_off = ring_off + (size_t)g.n_warps * kSmallStages * 16 * LPR * 4;
         // mbarriers, then (backward, second weights streamed) one 64-byte slot per stage and warp for the bulk-copied w1 words
-        const size_t total = PlaceOwnRows(p, bar_off + (size_t)g.n_warps * kSmallStages * (8 + 64), budget, own_rows_ok);
-        if (!g.small_ok || !smem_arcs || total > budget || p.n_hubs > 0 || (LPR != 8 && LPR != 16) ||
-            rows >= ((size_t)1 << 30) || !EncodeRowTensorMap(&p.tmap, table, rows, p.Npad, LPR)) {
-            *err = "den: small-batch kernels unavailable for this graph/device although the batch was padded for them";
+        const size_t total = bar_off + (size_t)g.n_warps * kSmallStages * (8 + 64);
+        const bool fits = g.small_ok && smem_arcs && total <= budget && p.n_hubs == 0 && (LPR == 8 || LPR == 16) && rows < ((size_t)1 << 30);
+        if (!fits || !EncodeRowTensorMap(&p.tmap, table, rows, p.Npad, LPR)) {
+            *err = "den: small-batch kernels unavailable for this graph/device although the batch was padded for them (" +
+                   std::string(backward ? "backward" : "forward") + ": small_ok=" + std::to_string((int)g.small_ok) + " smem_arcs=" + std::to_string((int)smem_arcs) +
+                   " smem=" + std::to_string(total) + "/" + std::to_string(budget) + " hubs=" + std::to_string(p.n_hubs) + " rows=" + std::to_string(rows) +
+                   (fits ? " tensor map rejected)" : ")");
             return 1;
         }
         p.use_tma = 1; p.ring_off = (int)ring_off; p.bar_off = (int)bar_off;
         return LPR == 8 ? LaunchTmaSmall<NT, 8>(backward, w1_smem, p, g.n_ctas, total, stream, err)
                         : LaunchTmaSmall<NT, 16>(backward, w1_smem, p, g.n_ctas, total, stream, err);
     }
-    // TMA tier: needs the full shared-memory stream, room for the rings, and a descriptor the driver accepts.  Ring depth:
-    // the default stage (16 rows) if the own rows still fit next to it, else the shallow stage if that makes them fit (the
-    // stream is bound by the number of gather operations, not by rows in flight -- profiles/r02_experiments.md), else the
-    // default stage with the own rows re-read from the gather table.
+    // TMA tier: needs the full shared-memory stream, room for the rings (two stages of R rows per warp), and a descriptor the
+    // driver accepts.
     bool tma = false;
     int ring_rows = 0;
     p.use_tma = 0;
     if (smem_arcs && (!backward || w1_smem) && !g.tune_no_tma && rows < ((size_t)1 << 30) &&
         EncodeRowTensorMap(&p.tmap, table, rows, p.Npad, 32 * U)) {
         const int r_def = U == 4 ? TmaShape<4>::R : 16, r_small = U == 2 ? TmaShape<2>::R_SMALL : r_def;
+        const int R = g.tune_ring_rows == r_small ? r_small : r_def;   // (A/B hook: the shallow ring)
         const size_t ring_off = (smem + 127) & ~(size_t)127;
-        const int forced = (g.tune_ring_rows == r_def || g.tune_ring_rows == r_small) ? g.tune_ring_rows : 0;   // A/B hook
-        for (int pass_i = 0; pass_i < 4 && !tma; ++pass_i) {
-            // passes 0, 1: default / shallow stage with the own rows in shared memory; 2, 3: the same, own rows from the table
-            const int R = (pass_i & 1) ? r_small : r_def;
-            if ((forced && R != forced) || ((pass_i & 1) && r_small == r_def)) continue;
-            if (pass_i < 2 && !own_rows_ok) continue;
-            const size_t bar_off = ring_off + (size_t)g.n_warps * 2 * R * 32 * U * 4;
-            const size_t total = PlaceOwnRows(p, bar_off + (size_t)g.n_warps * 2 * 8, budget, pass_i < 2);
-            if (total > budget || (pass_i < 2 && !p.own_smem)) continue;
+        const size_t bar_off = ring_off + (size_t)g.n_warps * 2 * R * 32 * U * 4;
+        const size_t total = bar_off + (size_t)g.n_warps * 2 * 8;
+        if (total <= budget) {
             tma = true; ring_rows = R;
             p.use_tma = 1; p.ring_off = (int)ring_off; p.bar_off = (int)bar_off;
             smem = total;
@@ -1546,7 +1425,7 @@ int Dispatch(bool backward, const DeviceGraph &g, DenParams &p, size_t fixed_sme
         const size_t abar_off = bar_off + (size_t)g.n_warps * 2 * 8;
         const size_t aring_off = (abar_off + (size_t)g.n_warps * kArcStages * 8 + 127) & ~(size_t)127;
         const size_t arc_ring = (size_t)g.n_warps * kArcStages * (R / kQuad) * (backward ? 3 : 2) * 16;
-        const size_t total = PlaceOwnRows(p, aring_off + arc_ring, budget, own_rows_ok);
+        const size_t total = aring_off + arc_ring;
         if (total <= budget) {
             tma = true; ring_rows = R; smem_arcs_eff = false;
             p.use_tma = 1; p.ring_off = (int)ring_off; p.bar_off = (int)bar_off;
@@ -1554,7 +1433,6 @@ int Dispatch(bool backward, const DeviceGraph &g, DenParams &p, size_t fixed_sme
             smem = total;
         }
     }
-    if (!tma) smem = PlaceOwnRows(p, smem, budget, own_rows_ok);
     if (U == 1) return DispatchU<NT, 1>(backward, tma, ring_rows, smem_arcs_eff, w1_smem, p, g.n_ctas, smem, stream, err);
     if (U == 2) return DispatchU<NT, 2>(backward, tma, ring_rows, smem_arcs_eff, w1_smem, p, g.n_ctas, smem, stream, err);
     return DispatchU<NT, 4>(backward, tma, ring_rows, smem_arcs_eff, w1_smem, p, g.n_ctas, smem, stream, err);

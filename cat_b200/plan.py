@@ -69,32 +69,6 @@ class PlanView:
     hub_states: np.ndarray
     fwd: PassView
     bwd: PassView
-    own_fwd: np.ndarray = None      # float32 [S, 2]: own-row coefficients of the forward pass (den_graph.h DenPlan::own_fwd)
-    own_bwd: np.ndarray = None      # float32 [S, 2]
-    state_flags: np.ndarray = None  # int32 [S] bit 0: first member of a pair with own terms only (no forward segment)
-
-
-    def forward_segments(self):
-        """The forward stream as the kernels walk it, own-only first members resolved: yields
-        (arc_begin, arc_end, kind, rows) with kind in {"row", "pos0", "pos1", "fused", "partial"} and rows = the list of
-        (state, position 0/1, label_changed) that END with the segment ("fused": the pair's first member -- own terms only,
-        no segment of its own -- and its twin; "partial": a part of a hub row, rows = [] unless it is the row's own part)."""
-        q = 0
-        hubs = set(int(h) for h in self.hub_states)
-        for a0, a1, ev, chg in self.fwd.segments():
-            if q < self.num_states and (self.state_flags[q] & 1):
-                w_last = self.fwd.arcs["w"][a1 - QUAD:a1]
-                yield a0, a1, "fused", [(q, 0, bool(np.signbit(w_last[0]))), (q + 1, 1, bool(np.signbit(w_last[1])))]
-                q += 2
-            elif ev == EV_PARTIAL:
-                tgt = int(self.fwd.arcs["peer"][a1 - 1])
-                own = tgt == q and tgt in hubs
-                yield a0, a1, "partial", ([(q, 1, False)] if own else [])
-                q += 1 if own else 0
-            else:
-                kind = {EV_ROW: "row", EV_ROW_POS0: "pos0", EV_ROW_POS1: "pos1"}[ev]
-                yield a0, a1, kind, [(q, 0 if ev == EV_ROW_POS0 else 1, chg)]
-                q += 1
 
 
 def load_plan(path: str, n_ctas: int = 148, n_warps: int = 16) -> PlanView:
@@ -121,7 +95,6 @@ def load_plan(path: str, n_ctas: int = 148, n_warps: int = 16) -> PlanView:
                                  get(10, np.int32, n_chunks + 1), get(13, np.int32, nc * 4).reshape(nc, 4)),
                         PassView(get(6, ARC_DTYPE, Ab), get(7, np.int32, n_chunks + 1), get(8, np.int32, n_chunks + 1),
                                  get(11, np.int32, n_chunks + 1), get(14, np.int32, nc * 4).reshape(nc, 4),
-                                 get(15, np.float32, Ab)),
-                        get(17, np.float32, 2 * S).reshape(S, 2), get(18, np.float32, 2 * S).reshape(S, 2), get(19, np.int32, S))
+                                 get(15, np.float32, Ab)))
     finally:
         L.ccb_plan_destroy(h)

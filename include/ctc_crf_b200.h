@@ -176,8 +176,7 @@ int ccb_plan_info(void *plan, long *info);
  *        3 fwd_arcs[A_fwd] {u32 peer, f32 w (sign bits = segment events)}, 4 fwd_chunk_state[n_ctas*n_warps+1] i32,
  *        5 fwd_chunk_arc[n_ctas*n_warps+1] i32, 6 bwd_arcs[A_bwd], 7 bwd_chunk_state, 8 bwd_chunk_arc,
  *        9 state_pos[S] i32, 10 fwd_chunk_pair, 11 bwd_chunk_pair, 12 start_arcs[n_start_arcs],
- *        13 fwd_cta_labels[n_ctas*4] i32, 14 bwd_cta_labels, 15 bwd second weights f32[A_bwd], 16 hub_states[n_hubs] i32,
- *        17 own_fwd[2S] f32, 18 own_bwd[2S] f32 (own-row coefficients, den_graph.h), 19 state_flags[S] i32 */
+ *        13 fwd_cta_labels[n_ctas*4] i32, 14 bwd_cta_labels, 15 bwd second weights f32[A_bwd], 16 hub_states[n_hubs] i32 */
 int ccb_plan_copy(void *plan, int which, void *dst, size_t dst_bytes);
 
 #ifdef __cplusplus

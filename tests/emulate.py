@@ -23,34 +23,31 @@ def _decode_forward(plan):
     S = plan.num_states
     row, peer, w = [], [], []
     pairs = []
+    q = 0
     arcs = plan.fwd.arcs
     hubs = set(int(h) for h in plan.hub_states)
-    ended = 0
-    for a0, a1, kind, rows in plan.forward_segments():
+    for a0, a1, ev, _chg in plan.fwd.segments():
         n = a1 - a0
-        if kind == "partial":     # a part of a high in-degree row: the last slot names the target row (weight 0)
+        if ev == 3:     # a part of a high in-degree row: the last slot names the target row (weight 0)
             tgt = int(arcs["peer"][a1 - 1])
             assert tgt in hubs and arcs["w"][a1 - 1] == 0
             row.append(np.full(n - 1, tgt)); peer.append(arcs["peer"][a0:a1 - 1].astype(np.int64)); w.append(np.abs(arcs["w"][a0:a1 - 1]).astype(np.float64))
-            for q, pos, _ in rows:
+            if tgt == q:
                 assert plan.state_pos[q] == 1
-            ended += len(rows)
+                q += 1
             continue
-        q = rows[-1][0]           # the gathered arcs of a segment belong to the LAST row it ends
         assert q not in hubs
         row.append(np.full(n, q)); peer.append(arcs["peer"][a0:a1].astype(np.int64)); w.append(np.abs(arcs["w"][a0:a1]).astype(np.float64))
-        for qq, pos, _ in rows:
-            assert plan.state_pos[qq] == pos
-        if kind == "pos0":
+        if ev == 1:
+            assert plan.state_pos[q] == 0
             pos0 = q
-        elif kind == "pos1":
-            assert pos0 == q - 1
-            pairs.append((pos0, q))
-        elif kind == "fused":
-            assert rows[0][0] == q - 1
-            pairs.append((q - 1, q))
-        ended += len(rows)
-    assert ended == S and len(pairs) == plan.num_pairs
+        else:
+            assert plan.state_pos[q] == 1
+            if ev == 2:
+                assert pos0 == q - 1
+                pairs.append((pos0, q))
+        q += 1
+    assert q == S and len(pairs) == plan.num_pairs
     return np.concatenate(row), np.concatenate(peer), np.concatenate(w), np.array(pairs, dtype=np.int64).reshape(-1, 2)
 
 
@@ -87,15 +84,6 @@ def den_emulate(plan, y, lens):
     fin = plan.final_lin.astype(np.float64)
     frow, fpeer, fw, pairs = _decode_forward(plan)
     brow, bpeer, bw = _decode_backward(plan)
-    # own-row terms: row q receives c[q,0] * X(first row of its group) + c[q,1] * X(second row of its group)
-    pos = plan.state_pos.astype(np.int64)
-    ids = np.arange(S)
-    g0 = np.where(pos == 0, ids, np.where((ids > 0) & (np.roll(pos, 1) == 0), ids - 1, ids))   # first row of the group
-    g1 = np.where(pos == 0, ids + 1, ids)                                                        # second row (or the row itself)
-    g1 = np.minimum(g1, S - 1)
-    cf, cb = plan.own_fwd.astype(np.float64), plan.own_bwd.astype(np.float64)
-    unp = (pos == 1) & ~((ids > 0) & (np.roll(pos, 1) == 0))        # unpaired rows: only the second coefficient may be set
-    assert not cf[unp, 0].any() and not cb[unp, 0].any()
     P = plan.num_pairs
     sa = plan.start_arcs
     logz_a = np.zeros(N)
@@ -114,7 +102,6 @@ def den_emulate(plan, y, lens):
         for t in range(1, Tn + 1):
             r, sh = _scale(colsum)
             acc = np.bincount(frow, weights=fw * alpha[t - 1, fpeer], minlength=S)
-            acc = acc + cf[:, 0] * alpha[t - 1, g0] + cf[:, 1] * alpha[t - 1, g1]
             e = np.exp(yn[t - 1, lab] - fmax[t - 1])
             alpha[t, :S] = acc * e * r
             if P:
@@ -132,7 +119,7 @@ def den_emulate(plan, y, lens):
                 b = fin.copy()
             else:
                 rb, sh = _scale(colsum_b)
-                b = rb * (np.bincount(brow, weights=bw * bh_next[bpeer], minlength=S) + cb[:, 0] * bh_next[g0] + cb[:, 1] * bh_next[g1])
+                b = rb * np.bincount(brow, weights=bw * bh_next[bpeer], minlength=S)
                 runlog += fmax[tau] - sh * np.log(2.0)
             ab = alpha[tau, :S] * b
             tot = ab.sum()

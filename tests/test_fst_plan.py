@@ -51,9 +51,8 @@ def test_bad_files_raise_not_exit(tmp_path, fixture_fst, bad):
             fst.read_fst(str(p))
 
 
-@pytest.mark.parametrize("n_ctas,n_warps,own", [(1, 1, False), (4, 2, True), (148, 16, False), (148, 16, True), (148, 32, False)])
-def test_plan_invariants(tmp_graphs, n_ctas, n_warps, own, monkeypatch):
-    monkeypatch.setenv("CCB_OWN" if own else "CCB_NO_OWN", "1")
+@pytest.mark.parametrize("n_ctas,n_warps", [(1, 1), (4, 2), (148, 16), (148, 32)])
+def test_plan_invariants(tmp_graphs, n_ctas, n_warps):
     for name in ("tlm_small", "random_split", "tlm_mid"):
         path, g, V = tmp_graphs[name]
         P = plan.load_plan(path, n_ctas, n_warps)
@@ -80,12 +79,9 @@ def test_plan_invariants(tmp_graphs, n_ctas, n_warps, own, monkeypatch):
         for pv, is_fwd in ((P.fwd, True), (P.bwd, False)):
             segs = list(pv.segments())
             if is_fwd:
-                fsegs = list(P.forward_segments())
-                n_fused = sum(1 for x in fsegs if x[2] == "fused")
-                assert n_fused == int((P.state_flags & 1).sum())
-                assert len(fsegs) == S - n_fused and sum(len(x[3]) for x in fsegs) == S      # every state ends exactly once
-                assert sum(1 for x in fsegs if x[2] == "pos1") + n_fused == NP == sum(1 for x in fsegs if x[2] == "pos0") + n_fused
-                assert not any(x[2] == "partial" for x in fsegs)
+                assert len(segs) == S                                    # one row-end event per state
+                assert sum(1 for x in segs if x[2] == plan.EV_ROW_POS1) == NP == sum(1 for x in segs if x[2] == plan.EV_ROW_POS0)
+                assert not any(x[2] == plan.EV_COMMON for x in segs)
                 assert (pv.arcs["peer"] < S + NP).all() and pv.w1 is None
             else:
                 assert len(segs) == S - NP                               # one group-end event per group
@@ -107,10 +103,10 @@ def test_plan_invariants(tmp_graphs, n_ctas, n_warps, own, monkeypatch):
             q = 0
             prev = {}
             chunk_of = np.searchsorted(pv.chunk_arc, np.arange(0, len(pv.arcs), plan.QUAD), side="right") - 1
-            for si, (a0, a1, ev, chg) in enumerate(segs):
+            for a0, a1, ev, chg in segs:
                 c = int(chunk_of[(a1 - 1) // plan.QUAD])
                 if is_fwd:
-                    rows = [(pos, flag) for _, pos, flag in fsegs[si][3]]
+                    rows = [(0 if ev == plan.EV_ROW_POS0 else 1, chg)]
                 else:
                     rows = [(0, chg[0]), (1, chg[1])] if ev == plan.EV_ROW_POS1 else [(1, chg[0])]
                     if ev != plan.EV_ROW_POS1:
@@ -133,39 +129,20 @@ def test_plan_invariants(tmp_graphs, n_ctas, n_warps, own, monkeypatch):
             assert S > g.num_states
         else:
             assert S == g.num_states and NP > 0
-            assert nz_f < g.num_arcs and nz_b < g.num_arcs                     # pairing removed the shared arcs
-            if not own:
-                assert nz_f == nz_b and not P.own_fwd.any() and not P.own_bwd.any()
-            else:   # every pair: the blank twin's arc + the token self loop (forward), B->B, L->B, L->L (backward)
-                assert (P.own_fwd[P.state_pos == 0] == [1.0, 1.0]).all() and int((P.state_flags & 1).sum()) == NP
-                # (an LM arc h -> h adds more own terms; in these small graphs a few exist)
-                assert np.count_nonzero(P.own_bwd) >= 3 * NP + np.count_nonzero(P.own_bwd[_unpaired(P)])
+            assert nz_f < g.num_arcs and nz_b < g.num_arcs and nz_f == nz_b    # pairing removed the shared arcs
         assert len(P.start_arcs) == int((np.asarray(g.src) == g.start).sum()) or name == "random_split"
 
 
-def _unpaired(P):
-    ids = np.arange(P.num_states)
-    return (P.state_pos == 1) & ~((ids > 0) & (np.roll(P.state_pos, 1) == 0))
-
-
 def test_pairing_halves_tlm_arcs_and_can_be_disabled(tmp_path, monkeypatch):
-    monkeypatch.setenv("CCB_OWN", "1")
     g = fst.make_synthetic_den(400, 12, 40, seed=11)
     p = str(tmp_path / "g.fst")
     fst.write_fst(p, g)
     P = plan.load_plan(p, 8, 4)
     assert P.num_pairs == 399                                           # every (h,B),(h,L) twin
     assert int((P.fwd.weights() > 0).sum()) < 0.56 * g.num_arcs
-    # own-row terms: the blank twin's row (1 arc on the pair-sum row) and the token self loop left the gather stream
-    assert int((P.state_flags & 1).sum()) == 399 and (P.own_fwd[P.state_pos == 0] == [1.0, 1.0]).all()
     monkeypatch.setenv("CCB_NO_PAIRS", "1")
     Q = plan.load_plan(p, 8, 4)
-    n_self = int((np.asarray(g.src) == np.asarray(g.dst)).sum())          # without pairs only the self loops are own-row arcs
-    assert Q.num_pairs == 0 and int((Q.fwd.weights() > 0).sum()) == g.num_arcs - n_self
-    assert np.count_nonzero(Q.own_fwd) == n_self == np.count_nonzero(Q.own_bwd)
-    monkeypatch.setenv("CCB_NO_OWN", "1")
-    R = plan.load_plan(p, 8, 4)
-    assert int((R.fwd.weights() > 0).sum()) == g.num_arcs and not R.own_fwd.any() and not R.own_bwd.any()
+    assert Q.num_pairs == 0 and int((Q.fwd.weights() > 0).sum()) == g.num_arcs
 
 
 def test_plan_balance(tmp_path):
@@ -181,10 +158,8 @@ def test_plan_balance(tmp_path):
     assert P.max_tile_arcs * 8 < 200 * 1024
 
 
-@pytest.mark.parametrize("own", [True, False])
 @pytest.mark.parametrize("name,lens", [("tlm_small", [30, 22, 9, 1]), ("random_split", [20, 13, 7, 2])])
-def test_kernel_arithmetic_emulation_matches_oracle(tmp_graphs, name, lens, monkeypatch, own):
-    monkeypatch.setenv("CCB_OWN" if own else "CCB_NO_OWN", "1")
+def test_kernel_arithmetic_emulation_matches_oracle(tmp_graphs, name, lens):
     """The scaled-linear / hoisted-emission / state-product algorithm the kernels implement, emulated in numpy on
     the product's own plan arrays, equals the arc-based log-domain reference semantics."""
     path, g, V = tmp_graphs[name]
