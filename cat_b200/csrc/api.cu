@@ -117,7 +117,14 @@ int CurrentGraph(DeviceGraph **out) {
     return 0;
 }
 
-int DenWarps() { return 16; }   // warps per CTA of the persistent den kernels (512 threads, one CTA per SM)
+// warps per CTA of the persistent den kernels (512 threads, one CTA per SM); tuning builds: CCB_DEN_WARPS=8 for experiments
+int DenWarps() {
+#ifdef CCB_TUNING
+    const char *e = getenv("CCB_DEN_WARPS");
+    if (e && atoi(e) == 8) return 8;
+#endif
+    return 16;
+}
 
 int InitImpl(const char *fst_name, int n_gpus, const int *gpus) {
     std::lock_guard<std::mutex> lk(g_mu);
@@ -271,6 +278,11 @@ int DenBackward(const DeviceGraph &g, const void *y, int dtype, long sn, long st
     p.barrier = reinterpret_cast<unsigned *>(a + L.barrier + 128);
     p.logz = reinterpret_cast<float *>(a + L.logz_b);
     p.grad = grad; p.gsn = gsn; p.gst = gst;
+    // the pass accumulates into colsum_b / absum / b0 and counts on its own barrier word: zero them here, so that a second
+    // backward pass over the same forward pass (or a reused aux buffer) starts clean instead of relying on DenForward's memset
+    CCB_CUDA(cudaMemsetAsync(a + L.colsum_b, 0, L.zsum - L.colsum_b, stream));
+    CCB_CUDA(cudaMemsetAsync(a + L.b0, 0, (size_t)L.Npad * 4, stream));
+    CCB_CUDA(cudaMemsetAsync(a + L.barrier + 128, 0, 128, stream));
     std::string err;
     int rc = LaunchDenBackward(g, p, stream, &err);
     if (rc) return Fail(err);
@@ -435,6 +447,17 @@ int ccb_den_forward_backward(const void *logits, int dtype, long sn, long st, in
     }
     return 0;
 }
+
+#ifdef CCB_TUNING
+/* tuning builds only: the backward pass alone over the spill of an earlier forward pass (overlap experiments) */
+int ccb_debug_den_backward(const void *logits, int dtype, long sn, long st, int N, int T, int V, const int *len_dev,
+                           float *alpha_ws, void *aux_ws, float *grad, long gsn, long gst, void *stream) {
+    g_err.clear();
+    DeviceGraph *g;
+    if (CurrentGraph(&g)) return 1;
+    return DenBackward(*g, logits, dtype, sn, st, N, T, V, len_dev, alpha_ws, aux_ws, grad, gsn, gst, 1.f, (cudaStream_t)stream);
+}
+#endif
 
 int ccb_ctc_forward_backward(const void *logits, int dtype, long sn, long st, int N, int T, int V,
                              const int *labels_dev, const int *label_off_dev, const int *label_len_dev,

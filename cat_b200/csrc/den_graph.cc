@@ -55,9 +55,11 @@ bool ReadFstFile(const char *path, HostFst *out, std::string *err) {
         *err = "unsupported fst/arc type '" + fst_type + "'/'" + arc_type + "' (need vector/standard)";
         return false;
     }
-    (void)r.get<int32_t>();  // version
-    int32_t flags = r.get<int32_t>();
+    const int32_t version = r.get<int32_t>();
+    const int32_t flags = r.get<int32_t>();
+    if (r.ok && version != 2) { *err = "unsupported VectorFst file version " + std::to_string(version) + " (need 2)"; return false; }
     if (flags & 0x3) { *err = "den graph carries embedded symbol tables; strip them (fstsymbols --clear_*)"; return false; }
+    if (flags & 0x4) { *err = "den graph was written with aligned fields (FstHeader::IS_ALIGNED); rewrite it with --fst_align=false"; return false; }
     (void)r.get<uint64_t>();  // properties
     int64_t start = r.get<int64_t>();
     int64_t ns = r.get<int64_t>();

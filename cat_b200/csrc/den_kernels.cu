@@ -653,7 +653,7 @@ __device__ __noinline__ void forward_partial_row(const int *state_label, const i
 // LPR < 32 (8 or 16 lanes per row): the small-batch variant, see walk_arcs_tma_small (TMA, U = 1, no hub rows).
 // STREAM: the arc stream is not resident (walk_arcs_tma_stream); TMA, full-width rows, no hub rows.
 template <int NT, int U, int BATCH, bool SMEM_ARCS, bool HUBS, bool TMA = false, int LPR = 32, bool STREAM = false>
-__global__ void __launch_bounds__(NT, 1) den_forward_kernel(const __grid_constant__ DenParams P) {
+__global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) den_forward_kernel(const __grid_constant__ DenParams P) {
     static_assert(!TMA || SMEM_ARCS || STREAM, "the TMA walk reads the arc tile from shared memory or from the streamed ring");
     static_assert(!STREAM || (TMA && !SMEM_ARCS && !HUBS && LPR == 32), "streamed arcs: TMA, full-width rows, no hub rows");
     static_assert(LPR == 32 || (TMA && U == 1 && !HUBS && (LPR == 8 || LPR == 16)), "small-batch variant: TMA, one utterance per lane, no hubs");
@@ -941,7 +941,7 @@ __global__ void __launch_bounds__(NT, 1) den_forward_kernel(const __grid_constan
 // backward: beta recursion, occupancies, logZ from beta
 // ------------------------------------------------------------------------------------------------
 template <int NT, int U, int BATCH, bool SMEM_ARCS, bool W1_SMEM = SMEM_ARCS, bool TMA = false, int LPR = 32, bool STREAM = false>
-__global__ void __launch_bounds__(NT, 1) den_backward_kernel(const __grid_constant__ DenParams P) {
+__global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) den_backward_kernel(const __grid_constant__ DenParams P) {
     static_assert(!TMA || STREAM || (SMEM_ARCS && (W1_SMEM || LPR < 32)), "the TMA walk reads the offsets (and, at full width, both weights) from shared memory");
     static_assert(!STREAM || (TMA && !SMEM_ARCS && LPR == 32), "streamed arcs: TMA, full-width rows");
     static_assert(LPR == 32 || (TMA && U == 1 && (LPR == 8 || LPR == 16)), "small-batch variant: TMA, one utterance per lane");
@@ -1442,6 +1442,9 @@ int DispatchThreads(bool backward, const DeviceGraph &g, DenParams &p, size_t fi
                     std::string *err) {
     if (p.Npad > g.n_warps * 32) { *err = "batch too large for the den kernel's bookkeeping CTA (N <= " + std::to_string(g.n_warps * 32) + ")"; return 1; }
     if (g.n_warps == 16) return Dispatch<512>(backward, g, p, fixed_smem, stream, err);
+#ifdef CCB_TUNING
+    if (g.n_warps == 8) return Dispatch<256>(backward, g, p, fixed_smem, stream, err);   // two co-resident CTAs per SM (experiments)
+#endif
     *err = "unsupported warps per CTA for den kernels (16)";
     return 1;
 }

@@ -33,20 +33,29 @@ def test_roundtrip_and_cxx_reader_agree(tmp_path):
     np.testing.assert_allclose(P.final_lin, np.exp(g.end_weight()[P.orig_state]), rtol=1e-6)
 
 
-@pytest.mark.parametrize("bad", ["missing", "garbage", "truncated", "wrongtype"])
+@pytest.mark.parametrize("bad", ["missing", "garbage", "truncated", "wrongtype", "version1", "aligned"])
 def test_bad_files_raise_not_exit(tmp_path, fixture_fst, bad):
     p = tmp_path / "x.fst"
     raw = open(fixture_fst, "rb").read()
+    hdr = 4 + (4 + 6) + (4 + 8)     # magic, "vector", "standard": then int32 version, int32 flags
     if bad == "garbage":
         p.write_bytes(b"\x00" * 64)
     elif bad == "truncated":
         p.write_bytes(raw[:200])
     elif bad == "wrongtype":
         p.write_bytes(raw.replace(b"standard", b"log64xyz"))
+    elif bad == "version1":
+        p.write_bytes(raw[:hdr] + (1).to_bytes(4, "little") + raw[hdr + 4:])
+    elif bad == "aligned":
+        p.write_bytes(raw[:hdr + 4] + (4).to_bytes(4, "little") + raw[hdr + 8:])
     with pytest.raises(RuntimeError):
         plan.load_plan(str(p), 4, 2)
     assert _lib.last_error()
-    if bad != "missing":
+    if bad == "version1":
+        assert "version" in _lib.last_error()
+    if bad == "aligned":
+        assert "aligned" in _lib.last_error()
+    if bad not in ("missing", "version1", "aligned"):
         with pytest.raises(ValueError):
             fst.read_fst(str(p))
 
