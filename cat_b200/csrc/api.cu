@@ -83,27 +83,23 @@ int UploadPass(const PassPlan &h, DevicePass *d) {
     return 0;
 }
 
-// The pass's quads as the streamed-arc TMA kernels read them (DevicePass::tq): per quad {row coordinate of slot 0..3}
-// {first-weight bits 0..3} and, backward, {second-weight bits 0..3}.  Forward peers beyond the S real rows are pair-sum rows,
-// parked at row 2S + j of the frame (den_kernels.cu); padding slots (all weights zero) name an out-of-bounds row, which the
+// The backward pass's quads as the streamed-arc TMA kernel reads them (DevicePass::tq): per quad {row coordinate of slot 0..3}
+// {first-weight bits 0..3}{second-weight bits 0..3}; padding slots (both weights zero) name an out-of-bounds row, which the
 // TMA unit zero-fills without a fetch.
-int UploadTransposedQuads(const PassPlan &h, bool backward, int S, DevicePass *d) {
-    const size_t nq = h.arcs.size() / kQuad, wpq = backward ? 3 : 2;
-    std::vector<uint4> tq(nq * wpq);
+int UploadTransposedQuads(const PassPlan &h, DevicePass *d) {
+    const size_t nq = h.arcs.size() / kQuad;
+    std::vector<uint4> tq(nq * 3);
     for (size_t i = 0; i < nq; ++i) {
         uint32_t c[kQuad], w0[kQuad], w1[kQuad];
         for (int j = 0; j < kQuad; ++j) {
             const Arc &a = h.arcs[i * kQuad + j];
             memcpy(&w0[j], &a.w, 4);
-            w1[j] = 0;
-            if (backward) memcpy(&w1[j], &h.w1[i * kQuad + j], 4);
-            const uint32_t peer = (uint32_t)a.peer;
-            c[j] = (!backward && peer >= (uint32_t)S) ? peer + (uint32_t)S : peer;
-            if ((w0[j] & 0x7fffffffu) == 0u && w1[j] == 0u) c[j] = kOobRow;
+            memcpy(&w1[j], &h.w1[i * kQuad + j], 4);
+            c[j] = ((w0[j] & 0x7fffffffu) == 0u && w1[j] == 0u) ? kOobRow : (uint32_t)a.peer;
         }
-        tq[wpq * i] = make_uint4(c[0], c[1], c[2], c[3]);
-        tq[wpq * i + 1] = make_uint4(w0[0], w0[1], w0[2], w0[3]);
-        if (backward) tq[wpq * i + 2] = make_uint4(w1[0], w1[1], w1[2], w1[3]);
+        tq[3 * i] = make_uint4(c[0], c[1], c[2], c[3]);
+        tq[3 * i + 1] = make_uint4(w0[0], w0[1], w0[2], w0[3]);
+        tq[3 * i + 2] = make_uint4(w1[0], w1[1], w1[2], w1[3]);
     }
     return Upload(&d->tq, tq);
 }
@@ -121,7 +117,7 @@ int CurrentGraph(DeviceGraph **out) {
 int DenWarps() {
 #ifdef CCB_TUNING
     const char *e = getenv("CCB_DEN_WARPS");
-    if (e && atoi(e) == 8) return 8;
+    if (e && (atoi(e) == 8 || atoi(e) == 24)) return atoi(e);
 #endif
     return 16;
 }
@@ -169,7 +165,7 @@ int InitImpl(const char *fst_name, int n_gpus, const int *gpus) {
         // streamed-arc tier: only graphs whose arc stream may not fit shared memory next to the TMA rings carry the copy
         if (rc == 0 && g_plan.hub_states.empty() && !d.tune_no_tma &&
             (d.tune_arcs_in_global || (size_t)d.bwd.max_tile_arcs * 12 > kStreamTierArcBytes))
-            rc = UploadTransposedQuads(g_plan.fwd, false, d.S, &d.fwd) || UploadTransposedQuads(g_plan.bwd, true, d.S, &d.bwd);
+            rc = UploadTransposedQuads(g_plan.bwd, &d.bwd);   // (the forward pass of such graphs keeps register gathers)
         if (d.tune_arcs_in_global || d.tune_w1_in_global)
             fprintf(stderr, "ctc_crf_b200: CCB_ARCS_IN_GLOBAL / CCB_W1_IN_GLOBAL set -- den arc tiles forced out of shared memory (test hook, slow)\n");
         {   // small-batch kernels: both arc streams in shared memory next to 4 KB (8 KB) of rings per warp, no hub rows

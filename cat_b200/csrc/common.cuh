@@ -26,9 +26,9 @@ struct DevicePass {
     int *chunk_pair = nullptr;
     int *cta_labels = nullptr;
     float *w1 = nullptr;      // backward pass: second weight per slot
-    // Streamed-arc tier (graphs whose arc stream does not fit shared memory): the pass's quads as the TMA kernels stage them,
-    // 2 (forward) / 3 (backward) 16-byte words per quad {row coordinate 0..3}{w0 0..3}[{w1 0..3}]; built at Init when the
-    // graph is large enough to need it, else null
+    // Streamed-arc tier (backward pass of graphs whose arc stream does not fit shared memory): the pass's quads as the TMA
+    // kernel stages them, 3 16-byte words per quad {row coordinate 0..3}{w0 0..3}{w1 0..3}; built at Init when the graph is
+    // large enough to need it, else null
     uint4 *tq = nullptr;
     int num_arcs = 0;
     int max_tile_arcs = 0;

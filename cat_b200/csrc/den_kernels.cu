@@ -651,18 +651,17 @@ __device__ __noinline__ void forward_partial_row(const int *state_label, const i
 // TMA: the gathered rows are staged in shared memory by gather4 copies (walk_arcs_tma) instead of register gathers; needs
 // the arc tile in shared memory (SMEM_ARCS) and DenParams::tmap.
 // LPR < 32 (8 or 16 lanes per row): the small-batch variant, see walk_arcs_tma_small (TMA, U = 1, no hub rows).
-// STREAM: the arc stream is not resident (walk_arcs_tma_stream); TMA, full-width rows, no hub rows.
-template <int NT, int U, int BATCH, bool SMEM_ARCS, bool HUBS, bool TMA = false, int LPR = 32, bool STREAM = false>
+template <int NT, int U, int BATCH, bool SMEM_ARCS, bool HUBS, bool TMA = false, int LPR = 32>
 __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) den_forward_kernel(const __grid_constant__ DenParams P) {
-    static_assert(!TMA || SMEM_ARCS || STREAM, "the TMA walk reads the arc tile from shared memory or from the streamed ring");
-    static_assert(!STREAM || (TMA && !SMEM_ARCS && !HUBS && LPR == 32), "streamed arcs: TMA, full-width rows, no hub rows");
+    static_assert(!TMA || SMEM_ARCS, "the TMA walk reads the arc tile from shared memory");
     static_assert(LPR == 32 || (TMA && U == 1 && !HUBS && (LPR == 8 || LPR == 16)), "small-batch variant: TMA, one utterance per lane, no hubs");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *s_sum = reinterpret_cast<float *>(smem_raw);                                  // [Npad]
     int *s_label = reinterpret_cast<int *>(s_sum + P.Npad);                              // [tile_rows] label per row
     Arc *s_arcs = reinterpret_cast<Arc *>(smem_raw + (((size_t)(P.Npad + P.tile_rows) * 4 + 15) & ~(size_t)15));
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(kFull, tid >> 5, 0);   // (through a shuffle: lets ptxas keep warp-derived addresses in uniform registers)
     const int sub = LPR == 32 ? 0 : lane / LPR;    // small batches: which arc(s) of a quad this lane multiplies
     const int ul = LPR == 32 ? lane : lane % LPR;   // ... and which utterance(s) it carries
     const int cta = blockIdx.x;
@@ -698,20 +697,9 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) den_forward_kernel(cons
         ring.bar = smem_u32(smem_raw + P.bar_off) + (uint32_t)warp * 8u * kStages;
         if (lane == 0) {
             for (int st = 0; st < kStages; ++st) mbar_init(ring.bar + 8u * st, 1);
-            if (STREAM) for (int st = 0; st < kArcStages; ++st) mbar_init(smem_u32(smem_raw + P.abar_off) + (uint32_t)(warp * kArcStages + st) * 8u, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
-    }
-    ArcRing aring{nullptr, 0u, 0u, 0u, 0u, 0u, 0u, nullptr};
-    if (STREAM) {
-        constexpr int kAW = BATCH / kQuad * 2;   // 16-byte words per batch
-        aring.buf = reinterpret_cast<const uint4 *>(smem_raw + P.aring_off) + (size_t)warp * kArcStages * kAW;
-        aring.buf_s = smem_u32(aring.buf);
-        aring.bar = smem_u32(smem_raw + P.abar_off) + (uint32_t)warp * kArcStages * 8u;
-        aring.n = (uint32_t)n_batches;
-        aring.src = P.tq + (size_t)2 * (ab / kQuad);
-        arc_ring_fill<kAW>(aring, lane);
     }
 
     // per-row metadata lives in shared memory: L1 is invalidated at every grid barrier, and a global load on the
@@ -882,8 +870,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) den_forward_kernel(cons
                     if ((int)wq.w < 0)   // warp-uniform: a segment ends at this quad
                         seg_end(acc, (int)(((wq.z >> 31) << 1) | (wq.y >> 31)), (int)wq.x < 0, quad);
                 };
-                if (STREAM) walk_arcs_tma_stream<U, BATCH, 2>(aring, n_batches, &P.tmap, gc * 32 * U, (t - 1) * S, ring, lane, frame_scalars, consume_quad);
-                else walk_arcs_tma<U, BATCH, 2>(arc4, n_batches, &P.tmap, gc * 32 * U, (t - 1) * S, ring, lane, frame_scalars, consume_quad);
+                walk_arcs_tma<U, BATCH, 2>(arc4, n_batches, &P.tmap, gc * 32 * U, (t - 1) * S, ring, lane, frame_scalars, consume_quad);
             } else {
                 walk_arcs<U, BATCH, SMEM_ARCS>(arc4, n_batches, row_bytes, (uint32_t)S, reinterpret_cast<const char *>(a_prev + n0), lane_act,
                                                frame_scalars, seg_end);
@@ -914,7 +901,6 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) den_forward_kernel(cons
         tl_mark(P, t, chunk, n_chunks, 2, lane);
     }
 
-    if (STREAM) arc_ring_drain(aring);
     // logZ[n] = log sum_q alpha_len(q) final(q) + accumulated log scale      (den_calculate.cu:105-161)
     for (int gc = 0; gc < (Npad + 31) / 32; ++gc) {
         const int n = gc * 32 + lane;
@@ -953,7 +939,8 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) den_backward_kernel(con
     float *s_final = reinterpret_cast<float *>(s_label + P.tile_rows);             // [tile_rows]
     Arc *s_arcs = reinterpret_cast<Arc *>(smem_raw + ((((size_t)(2 + P.gacc_rows) * Npad + 2 * (size_t)P.tile_rows) * 4 + 15) & ~(size_t)15));
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(kFull, tid >> 5, 0);   // (through a shuffle: lets ptxas keep warp-derived addresses in uniform registers)
     const int sub = LPR == 32 ? 0 : lane / LPR;    // small batches: which arc(s) of a quad this lane multiplies
     const int ul = LPR == 32 ? lane : lane % LPR;   // ... and which utterance it carries (lane groups sub > 0 are replicas at row ends)
     const int cta = blockIdx.x;
@@ -1322,12 +1309,10 @@ int LaunchTma(bool backward, const DenParams &p, int n_ctas, size_t smem, cudaSt
                                     : (const void *)den_forward_kernel<NT, U, R, true, false, true>;
     return LaunchCoop(fn, NT, p, n_ctas, smem, stream, err);
 }
-// ... with the arc stream flowing through per-warp rings instead of being resident (walk_arcs_tma_stream)
+// backward pass with the arc stream flowing through per-warp rings instead of being resident (walk_arcs_tma_stream)
 template <int NT, int U, int R>
-int LaunchTmaStream(bool backward, const DenParams &p, int n_ctas, size_t smem, cudaStream_t stream, std::string *err) {
-    const void *fn = backward ? (const void *)den_backward_kernel<NT, U, R, false, true, true, 32, true>
-                              : (const void *)den_forward_kernel<NT, U, R, false, false, true, 32, true>;
-    return LaunchCoop(fn, NT, p, n_ctas, smem, stream, err);
+int LaunchTmaStreamBwd(const DenParams &p, int n_ctas, size_t smem, cudaStream_t stream, std::string *err) {
+    return LaunchCoop((const void *)den_backward_kernel<NT, U, R, false, true, true, 32, true>, NT, p, n_ctas, smem, stream, err);
 }
 
 // small batches: rows of LPR = 8 / 16 floats (see walk_arcs_tma_small)
@@ -1349,7 +1334,7 @@ constexpr int kBwdBatch = 8;
 template <int NT, int U>
 int DispatchU(bool backward, bool tma, int ring_rows, bool smem_arcs, bool w1_smem, const DenParams &p, int n_ctas, size_t smem,
               cudaStream_t stream, std::string *err) {
-    if (tma && !smem_arcs) return LaunchTmaStream<NT, U, TmaShape<U>::R>(backward, p, n_ctas, smem, stream, err);
+    if (tma && !smem_arcs) return LaunchTmaStreamBwd<NT, U, TmaShape<U>::R>(p, n_ctas, smem, stream, err);
     if (tma) return ring_rows == TmaShape<U>::R ? LaunchTma<NT, U, TmaShape<U>::R>(backward, p, n_ctas, smem, stream, err)
                                                 : LaunchTma<NT, U, TmaShape<U>::R_SMALL>(backward, p, n_ctas, smem, stream, err);
     if (backward)
@@ -1415,16 +1400,19 @@ int Dispatch(bool backward, const DeviceGraph &g, DenParams &p, size_t fixed_sme
             smem = total;
         }
     }
-    // Streamed-arc TMA tier: the stream does not fit (or the test hook says so) but the graph carries the transposed copy.
+    // Streamed-arc TMA tier, BACKWARD pass only: the stream does not fit (or the test hook says so) but the graph carries the
+    // transposed copy.  The forward pass of such graphs keeps the register gathers with the arcs read from L2: measured
+    // on the 5.1 M-arc graph (N=16, T=2000) forward 97.9 ms against 138.8 ms streamed -- its 8-byte slots make 128-byte
+    // bulk copies, one per 16 rows -- while the backward pass gains (151.4 against 156.4 ms; profiles/r02_experiments.md).
     bool smem_arcs_eff = smem_arcs;
-    if (!tma && pass.tq != nullptr && p.n_hubs == 0 && !g.tune_no_tma && rows < ((size_t)1 << 30) && p.Npad >= 32 &&
+    if (!tma && backward && pass.tq != nullptr && p.n_hubs == 0 && !g.tune_no_tma && rows < ((size_t)1 << 30) && p.Npad >= 32 &&
         EncodeRowTensorMap(&p.tmap, table, rows, p.Npad, 32 * U)) {
         const int R = U == 4 ? TmaShape<4>::R : 16;
         const size_t ring_off = (fixed_smem + 127) & ~(size_t)127;
         const size_t bar_off = ring_off + (size_t)g.n_warps * 2 * R * 32 * U * 4;
         const size_t abar_off = bar_off + (size_t)g.n_warps * 2 * 8;
         const size_t aring_off = (abar_off + (size_t)g.n_warps * kArcStages * 8 + 127) & ~(size_t)127;
-        const size_t arc_ring = (size_t)g.n_warps * kArcStages * (R / kQuad) * (backward ? 3 : 2) * 16;
+        const size_t arc_ring = (size_t)g.n_warps * kArcStages * (R / kQuad) * 3 * 16;
         const size_t total = aring_off + arc_ring;
         if (total <= budget) {
             tma = true; ring_rows = R; smem_arcs_eff = false;
@@ -1444,6 +1432,7 @@ int DispatchThreads(bool backward, const DeviceGraph &g, DenParams &p, size_t fi
     if (g.n_warps == 16) return Dispatch<512>(backward, g, p, fixed_smem, stream, err);
 #ifdef CCB_TUNING
     if (g.n_warps == 8) return Dispatch<256>(backward, g, p, fixed_smem, stream, err);   // two co-resident CTAs per SM (experiments)
+    if (g.n_warps == 24) return Dispatch<768>(backward, g, p, fixed_smem, stream, err);
 #endif
     *err = "unsupported warps per CTA for den kernels (16)";
     return 1;

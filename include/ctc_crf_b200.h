@@ -39,9 +39,13 @@ void Init(const char *fst_name, int n_gpus, int *gpus);
 void Release(int n_gpus, int *gpus);
 
 /* replaces compute_alpha (binding.cpp:26-34, den_calculate.cu:427-451).
- *   alpha      : scratch, >= ccb_den_alpha_floats(batch_size, T) floats (OPAQUE layout: [t][state][lane]);
- *                binding.cpp's (T+1)*N*DEN_NUM_STATES suffices whenever N is a multiple of 32, otherwise the
- *                library falls back to an internal stream-ordered allocation.
+ *   alpha      : scratch, >= ccb_den_alpha_floats(batch_size, T) floats (OPAQUE layout: [t][state][lane]).
+ *                The need is (T+3) frames of DEN_NUM_STATES-P rows of PadLanes(N) floats (lanes padded to 32, 64 or a multiple
+ *                of 128; 16 for batches of <= 16 utterances on small graphs): binding.cpp's (T+1)*N*DEN_NUM_STATES covers it
+ *                for N = 32, 64, 128, 256 ... but NOT for every other N (e.g. 96 -> 128 lanes).  When the caller's buffer is
+ *                too small the library takes its own from the device's default memory pool, stream-ordered
+ *                (cudaMallocAsync on `stream`: no device synchronisation), keeps it between calls and returns it in Release().
+ *                Size the buffer with ccb_den_alpha_floats() to avoid the second allocation.
  *   logits     : (N,T,V) fp32 log-probs, contiguous
  *   input_lengths : (N,) int32 DEVICE
  *   loglikelihood : (N,) fp32 DEVICE out, logZ_den per utterance */
