@@ -155,6 +155,14 @@ int LaunchCtc(const void *y, int y_bf16, long sn, long st, int N, int T, int V, 
               const int *label_off, const int *label_len, const int *len, int max_label_len, int blank,
               float *alpha_ws, float *grad, long gsn, long gst, float grad_scale, float *logp,
               const double *lnorm, cudaStream_t stream, std::string *err, int overwrite = 0, int Tfull = 0);
+int LaunchCtcAlphaBeta(const void *y, int y_bf16, long sn, long st, int N, int T, int V, const int *labels,
+                       const int *label_off, const int *label_len, const int *len, int max_label_len, int blank,
+                       float *alpha_ws, bool want_beta, float *logp, const double *lnorm, cudaStream_t stream,
+                       std::string *err, bool share_sm);
+int LaunchCtcGamma(const void *y, int y_bf16, long sn, long st, int N, int T, int V, const int *labels,
+                   const int *label_off, const int *label_len, const int *len, int max_label_len, int blank,
+                   float *alpha_ws, float *grad, long gsn, long gst, float grad_scale, cudaStream_t stream,
+                   std::string *err, int overwrite = 0, int Tfull = 0);
 int LaunchSumScale(const float *logp, int N, float scale, float *loss, cudaStream_t stream);
 int LaunchCtcViterbi(const void *y, int y_bf16, long sn, long st, int N, int T, int V, const int *labels,
                      const int *label_off, const int *label_len, const int *len, int max_label_len, int blank,

@@ -29,19 +29,31 @@ namespace {
 constexpr unsigned kFull = 0xffffffffu;
 
 // Precision: lattice cells are carried in DOUBLE, the log-add's transcendental part in float:
-//     log_add(a, b) = max(a, b) + (double) log1pf(expf((float)(min(a, b) - max(a, b))))
-// The float part is a number in (0, ln 2] with ~1e-7 absolute error whatever the magnitude of the cells, and the double
+//     log_add(a, b[, c]) = m + (double) log(sum_i exp((float)(x_i - m))),   m = max_i x_i
+// The float part is a number in [0, ln 3] with ~2e-7 absolute error whatever the magnitude of the cells, and the double
 // sum does not quantise.  fp32 cells (round 1, relative to a per-frame offset) were not enough: at the cells that carry
 // the occupancy mass, alpha lies ~ln C(t, t/2) - ln C(t, t/6) ~ 700 nats below the frame's alpha maximum at t = 3000
 // (most alpha mass sits on paths that are ahead of the alignment), so |a_rel| ~ 700, ulp = 6e-5 per frame, and the
 // occupancies came out 1.3e-3 (GPU) / 5e-3 (numpy float32 emulation) off the fp64 oracle at T = 3000.  With double cells
 // the emulation gives 4e-7 at T = 3000.  (the reference's plain fp32 log domain: ~1e-2 at T ~ 1000.)
+// Latency: a frame of the recursion is ONE dependent chain per thread (barrier -> neighbours' cells -> log-add -> cell), T of
+// them in a row, so the chain length is the kernel's run time.  The 3-way log-sum of a label cell is therefore evaluated with
+// one logarithm over the sum of the three exponentials (not two nested 2-way log-adds), and the exponentials / logarithm are
+// the hardware ex2 / lg2 approximations: their arguments are differences to the maximum (|x| small, sum in [1, 3]), where
+// they are as accurate in ABSOLUTE terms (ex2: 2 ulp of a number <= 1; lg2: 2^-22) as the libm versions.
 // per-utterance workspace: alpha [T][ScMax] | beta [T][ScMax] doubles, then log p
 __device__ __forceinline__ double log_add_d(double a, double b) {
     const double m = fmax(a, b);
     if (m == -INFINITY) return m;
-    const float d = (float)(fmin(a, b) - m);          // <= 0; -inf when one side is empty: exp -> 0, log1p -> 0
-    return m + (double)log1pf(expf(d));
+    const float d = (float)(fmin(a, b) - m);          // <= 0; -inf when one side is empty: exp -> 0, log 1 -> 0
+    return m + (double)__logf(1.f + __expf(d));
+}
+// c may be -inf ("no skip transition"): its exponential is then 0
+__device__ __forceinline__ double log_add3_d(double a, double b, double c) {
+    const double m = fmax(fmax(a, b), c);
+    if (m == -INFINITY) return m;
+    const float s = __expf((float)(a - m)) + __expf((float)(b - m)) + __expf((float)(c - m));   // one term is exp(0) = 1
+    return m + (double)__logf(s);
 }
 
 struct CtcWorkspace {
@@ -134,8 +146,8 @@ __global__ void ctc_alpha_beta_kernel(const void *y, int y_bf16, long sn, long s
             if (i < L) {   // label cell 2i+1
                 const int sl = sb + 1;
                 const int li = s_lab[i];
-                double vl = log_add_d(prev[sl], prev[sb]);
-                if (i > 0 && li != s_lab[i - 1]) vl = log_add_d(vl, prev[sl - 2]);
+                const bool skip = i > 0 && li != s_lab[i - 1];
+                double vl = log_add3_d(prev[sl], prev[sb], skip ? prev[sl - 2] : -INFINITY);
                 vl += (double)yc[li];
                 cur[sl] = vl;
                 ws[(size_t)t * ScMax + sl] = vl;
@@ -192,8 +204,8 @@ __global__ void ctc_alpha_beta_kernel(const void *y, int y_bf16, long sn, long s
                 if (t == Tn - 1) {
                     vl = (sl == Sc - 2) ? (double)yc[li] : -INFINITY;
                 } else {
-                    vl = log_add_d(nxt[sl], nxt[sl + 1]);
-                    if (i + 1 < L && li != s_lab[i + 1]) vl = log_add_d(vl, nxt[sl + 2]);
+                    const bool skip = i + 1 < L && li != s_lab[i + 1];
+                    vl = log_add3_d(nxt[sl], nxt[sl + 1], skip ? nxt[sl + 2] : -INFINITY);
                     vl += (double)yc[li];
                 }
                 cur[sl] = vl;
@@ -357,10 +369,13 @@ __global__ void assemble_loss_kernel(const float *logz, const float *logp, int N
 
 }  // namespace
 
-int LaunchCtc(const void *y, int y_bf16, long sn, long st, int N, int T, int V, const int *labels,
-              const int *label_off, const int *label_len, const int *len, int max_label_len, int blank,
-              float *alpha_ws, float *grad, long gsn, long gst, float grad_scale, float *logp,
-              const double *lnorm, cudaStream_t stream, std::string *err, int overwrite, int Tfull) {
+// The two halves of the numerator, separately launchable: the alpha || beta chains read only y and the labels and write
+// the cell workspace + logp, so the fused loss runs them on a side stream next to the den forward pass (api.cu); the
+// occupancy kernel accumulates into the gradient and therefore follows the den normalisation pass.
+int LaunchCtcAlphaBeta(const void *y, int y_bf16, long sn, long st, int N, int T, int V, const int *labels,
+                       const int *label_off, const int *label_len, const int *len, int max_label_len, int blank,
+                       float *alpha_ws, bool want_beta, float *logp, const double *lnorm, cudaStream_t stream,
+                       std::string *err, bool share_sm) {
     if (N == 0) return 0;
     const int ScMax = 2 * max_label_len + 1;
     int threads = ((max_label_len + 1 + 31) / 32) * 32;
@@ -369,24 +384,49 @@ int LaunchCtc(const void *y, int y_bf16, long sn, long st, int N, int T, int V, 
     if (smem > 200 * 1024 || (size_t)V * 4 > 200 * 1024) { *err = "label sequence too long for the numerator kernel's shared memory"; return 1; }
     cudaError_t e = cudaFuncSetAttribute(ctc_alpha_beta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { *err = std::string("cudaFuncSetAttribute(ctc): ") + cudaGetErrorString(e); return (int)e; }
+    // share_sm: these CTAs are meant to sit NEXT to a persistent den CTA (166-182 KB of shared memory) on the same SM.  An SM
+    // cannot change its L1 / shared-memory split while a CTA is resident, so both kernels must ask for the same split or the
+    // later one waits for the earlier one to drain: prefer the maximum carve-out here as the den kernels need it anyway.
+    e = cudaFuncSetAttribute(ctc_alpha_beta_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             share_sm ? (int)cudaSharedmemCarveoutMaxShared : (int)cudaSharedmemCarveoutDefault);
+    if (e != cudaSuccess) { *err = std::string("cudaFuncSetAttribute(ctc carve-out): ") + cudaGetErrorString(e); return (int)e; }
     ctc_alpha_beta_kernel<<<2 * N, threads, smem, stream>>>(y, y_bf16, sn, st, T, V, labels, label_off, label_len, len,
-                                                            max_label_len, blank, alpha_ws, grad != nullptr, logp, lnorm);
+                                                            max_label_len, blank, alpha_ws, want_beta, logp, lnorm);
     CountLaunch();
-    if (grad != nullptr) {
-        int wpb = 8;   // warps (= frames) per CTA of the occupancy kernel, bounded by the [V] accumulators
-        while (wpb > 1 && (size_t)wpb * V * 4 > 48 * 1024) wpb >>= 1;
-        const size_t gsm = (size_t)wpb * V * 4;
-        e = cudaFuncSetAttribute(ctc_gamma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm);
-        if (e != cudaSuccess) { *err = std::string("cudaFuncSetAttribute(ctc gamma): ") + cudaGetErrorString(e); return (int)e; }
-        const long rows = (long)N * (overwrite ? Tfull : T);
-        ctc_gamma_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, gsm, stream>>>(
-            y, y_bf16, sn, st, N, T, V, labels, label_off, label_len, len, max_label_len, blank, alpha_ws, grad, gsn, gst, grad_scale,
-            overwrite, Tfull);
-        CountLaunch();
-    }
     e = cudaGetLastError();
     if (e != cudaSuccess) { *err = std::string("ctc launch: ") + cudaGetErrorString(e); return (int)e; }
     return 0;
+}
+
+int LaunchCtcGamma(const void *y, int y_bf16, long sn, long st, int N, int T, int V, const int *labels,
+                   const int *label_off, const int *label_len, const int *len, int max_label_len, int blank,
+                   float *alpha_ws, float *grad, long gsn, long gst, float grad_scale, cudaStream_t stream,
+                   std::string *err, int overwrite, int Tfull) {
+    if (N == 0) return 0;
+    int wpb = 8;   // warps (= frames) per CTA of the occupancy kernel, bounded by the [V] accumulators
+    while (wpb > 1 && (size_t)wpb * V * 4 > 48 * 1024) wpb >>= 1;
+    const size_t gsm = (size_t)wpb * V * 4;
+    cudaError_t e = cudaFuncSetAttribute(ctc_gamma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm);
+    if (e != cudaSuccess) { *err = std::string("cudaFuncSetAttribute(ctc gamma): ") + cudaGetErrorString(e); return (int)e; }
+    const long rows = (long)N * (overwrite ? Tfull : T);
+    ctc_gamma_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, gsm, stream>>>(
+        y, y_bf16, sn, st, N, T, V, labels, label_off, label_len, len, max_label_len, blank, alpha_ws, grad, gsn, gst, grad_scale,
+        overwrite, Tfull);
+    CountLaunch();
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { *err = std::string("ctc gamma launch: ") + cudaGetErrorString(e); return (int)e; }
+    return 0;
+}
+
+int LaunchCtc(const void *y, int y_bf16, long sn, long st, int N, int T, int V, const int *labels,
+              const int *label_off, const int *label_len, const int *len, int max_label_len, int blank,
+              float *alpha_ws, float *grad, long gsn, long gst, float grad_scale, float *logp,
+              const double *lnorm, cudaStream_t stream, std::string *err, int overwrite, int Tfull) {
+    int rc = LaunchCtcAlphaBeta(y, y_bf16, sn, st, N, T, V, labels, label_off, label_len, len, max_label_len, blank, alpha_ws,
+                                grad != nullptr, logp, lnorm, stream, err, false);
+    if (rc || grad == nullptr) return rc;
+    return LaunchCtcGamma(y, y_bf16, sn, st, N, T, V, labels, label_off, label_len, len, max_label_len, blank, alpha_ws, grad, gsn,
+                          gst, grad_scale, stream, err, overwrite, Tfull);
 }
 
 int LaunchSumScale(const float *logp, int N, float scale, float *loss, cudaStream_t stream) {
