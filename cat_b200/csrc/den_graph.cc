@@ -103,7 +103,8 @@ struct Segment {
     std::vector<Arc> arcs;
     std::vector<float> w1;   // backward group segments only (same length as arcs)
     int event = kEvRow;
-    int rows = 1;            // rows that end with this segment (0 for kEvCommon, 2 for a backward pair group)
+    int rows = 1;            // rows that end with this segment (0 for kEvCommon, 2 for a backward pair group / a merged forward pair)
+    bool merged = false;     // forward kEvPairMerged: arcs = the second member's in-arcs + (last) the first member's single arc
 };
 struct Group {
     std::vector<Segment> segs;
@@ -143,7 +144,11 @@ void Layout(const std::vector<Group> &groups, int S, const std::vector<int> &sta
                 // the kernels then skip the label lookup / emission refresh on the common path.
                 // one-row segments: sign(w[0]); two-row (backward pair) segments: sign(w[0]) for p0, sign(w[1]) for p1.
                 bool chg0 = false, chg1 = false;
-                if (sg.rows == 1 && sg.event != kEvPartial) {   // (partial rows bypass the kernels' emission cache)
+                if (sg.merged) {   // one flag: the SECOND member's label (first members all carry one label, checked by the builder)
+                    prev_label[0] = state_label[(size_t)row];
+                    chg0 = state_label[(size_t)row + 1] != prev_label[1];
+                    prev_label[1] = state_label[(size_t)row + 1];
+                } else if (sg.rows == 1 && sg.event != kEvPartial) {   // (partial rows bypass the kernels' emission cache)
                     const int k = sg.event == kEvRowPos0 ? 0 : 1;
                     chg0 = state_label[(size_t)row] != prev_label[k];
                     prev_label[k] = state_label[(size_t)row];
@@ -159,9 +164,12 @@ void Layout(const std::vector<Group> &groups, int S, const std::vector<int> &sta
                 // Pointing them all at one fixed row makes every warp of the grid hammer a single L2 line
                 // (measured: 2x frame time from that hot spot alone).
                 const uint32_t pad_peer = sg.arcs.empty() ? (uint32_t)gr.first_state : sg.arcs.back().peer;
-                const bool dual = !sg.w1.empty() || sg.rows == 2;
+                const bool dual = !sg.merged && (!sg.w1.empty() || sg.rows == 2);
+                const size_t n_lead = sg.merged ? sg.arcs.size() - 1 : sg.arcs.size();   // merged: the last arc sits in the last slot
+                const uint32_t pad_peer_m = sg.merged ? (n_lead ? sg.arcs[n_lead - 1].peer : sg.arcs.back().peer) : pad_peer;
                 for (size_t i = 0; i < padded; ++i) {
-                    Arc a = i < sg.arcs.size() ? sg.arcs[i] : Arc{pad_peer, 0.f};
+                    Arc a = i < n_lead ? sg.arcs[i] : Arc{pad_peer_m, 0.f};
+                    if (sg.merged && i + 1 == padded) a = sg.arcs.back();
                     if (i + 1 == padded) a.w = WithSign(a.w);
                     if (i + 2 == padded && (sg.event & 2)) a.w = WithSign(a.w);
                     if (dual) {
@@ -407,6 +415,24 @@ bool BuildDenPlan(const HostFst &fst, int n_ctas, int n_warps, DenPlan *plan, st
         fgroups.clear(); bgroups.clear();
         fgroups.reserve(order.size()); bgroups.reserve(order.size());
         std::vector<Arc> hub_row;
+        // merged forward pairs (den_graph.h DenPlan::fwd_merged): all or nothing -- no hub rows anywhere, every first member
+        // has exactly one in-arc, all first members carry the same label (the kernels refresh that emission once per frame)
+        bool merge = plan->hub_states.empty() && plan->num_pairs > 0;
+        {
+            const char *e = getenv("CCB_NO_MERGE");   // test hook / A-B switch
+            if (e && e[0] == '1') merge = false;
+            int lab0 = -1;
+            std::vector<Arc> probe;
+            for (auto &g : order) {
+                if (!merge) break;
+                if (g.part > 0) { merge = false; break; }
+                if (g.s0 < 0) continue;
+                forward_row(g.s0, &probe);
+                if (probe.size() != 1 || !(probe[0].w > 0.f)) merge = false;
+                if (lab0 < 0) lab0 = g.lab0; else if (g.lab0 != lab0) merge = false;
+            }
+        }
+        plan->fwd_merged = merge;
         int next_state = 0;
         for (auto &g : order) {
             Group fg, bg;
@@ -470,7 +496,15 @@ bool BuildDenPlan(const HostFst &fst, int n_ctas, int n_warps, DenPlan *plan, st
                 }
                 b.event = kEvRowPos1;
                 b.rows = 2;
-                fg.segs.push_back(std::move(f0)); fg.segs.push_back(std::move(f1));
+                if (merge) {   // one segment for the pair: p1's in-arcs, then p0's single arc (emitted in the last slot)
+                    f1.arcs.push_back(f0.arcs[0]);
+                    f1.event = kEvPairMerged;
+                    f1.rows = 2;
+                    f1.merged = true;
+                    fg.segs.push_back(std::move(f1));
+                } else {
+                    fg.segs.push_back(std::move(f0)); fg.segs.push_back(std::move(f1));
+                }
                 bg.segs.push_back(std::move(b));
             }
             fgroups.push_back(std::move(fg));

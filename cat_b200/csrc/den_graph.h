@@ -29,6 +29,9 @@ static constexpr int kEvRowPos0 = 1;     // end of the row of the first member o
 static constexpr int kEvRowPos1 = 2;     // end of the row of the second member of a pair
 static constexpr int kEvPartial = 3;     // forward only: a PART of a high in-degree row; the last slot of the segment carries
                                          // the target row (weight 0) and the result is added to it atomically
+static constexpr int kEvPairMerged = 3;  // forward only, plans WITHOUT high in-degree rows (same code as kEvPartial, which such plans never
+                                         // contain): the segment ends BOTH rows of a pair.  Slots 0 .. n-2 are the in-arcs of the second
+                                         // member, the LAST slot is the single in-arc of the first member (DenPlan::fwd_merged)
 static constexpr int kHubInArcs = 384;   // rows with more in-arcs than this are split into parts of kPartArcs arcs that
 static constexpr int kPartArcs = 191;    // any warp of the grid can own (real n-gram den graphs have such states)
 
@@ -76,6 +79,12 @@ struct DenPlan {
     std::vector<int> hub_states;        // states whose forward row is accumulated from parts (rows zeroed before each frame)
     // fwd: one segment per state (its in-arcs; peers may be virtual pair rows), events kEvRow / kEvRowPos0 / kEvRowPos1;
     //      a high in-degree state has several kEvPartial segments instead (one in its own group, the others floating).
+    //      fwd_merged (T-compose-LM graphs: the blank twin (h,B) of every pair has ONE in-arc, the pair's own virtual row):
+    //      every pair is ONE segment, event kEvPairMerged -- the second member's in-arcs, then zero-weight padding, then the
+    //      first member's arc in the last slot of the last quad.  28 instead of 28 + 4 padded slots per pair of a 24-successor
+    //      LM and one row-end event instead of two: -12.5 % forward slots, forward pass 23.4 -> 20.5 ms at the headline size.
+    //      The label-changed flag (sign of w[0] of the last quad) is the SECOND member's; all first members share one label.
+    bool fwd_merged = false;
     // bwd: one segment per GROUP (an unpaired state, or a pair p0,p1): every slot carries two weights, arcs[i].w for the
     //      group's first row and w1[i] for its second row (0 when the arc does not belong to that row), so the arcs the
     //      two members share are gathered once.  Event kEvRow = one-row group, kEvRowPos1 = two-row group; the

@@ -246,15 +246,17 @@ __device__ __forceinline__ void walk_arcs(const uint4 *arcs, int n_batches, uint
             const uint4 wq = load_quad_weights<SMEM_ARCS>(p + 2 * g4);
             const float w0 = fabsf(__uint_as_float(wq.x)), w1 = fabsf(__uint_as_float(wq.y));
             const float w2 = fabsf(__uint_as_float(wq.z)), w3 = fabsf(__uint_as_float(wq.w));
+            float a2[U];   // the sums WITHOUT the quad's last slot (kEvPairMerged: that slot belongs to the pair's other row)
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 acc[u] = fmaf(w0, v[g4 * kQuad + 0].v[u], acc[u]);
                 acc[u] = fmaf(w1, v[g4 * kQuad + 1].v[u], acc[u]);
                 acc[u] = fmaf(w2, v[g4 * kQuad + 2].v[u], acc[u]);
+                a2[u] = acc[u];
                 acc[u] = fmaf(w3, v[g4 * kQuad + 3].v[u], acc[u]);
             }
             if ((int)wq.w < 0)   // warp-uniform: a segment ends at this quad; the callback owns the accumulators
-                seg_end(acc, (int)(((wq.z >> 31) << 1) | (wq.y >> 31)), (int)wq.x < 0, p + 2 * g4);
+                seg_end(acc, (int)(((wq.z >> 31) << 1) | (wq.y >> 31)), (int)wq.x < 0, p + 2 * g4, a2, v[g4 * kQuad + 3], w3);
         }
     };
 
@@ -792,9 +794,48 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) den_forward_kernel(cons
             uint32_t virt_row = virt0 + (uint32_t)vj0;           // the next virtual row (parked two frames ahead)
             float *const out_base = a_cur + n0;
             Vec<U> cacc = vec_zero<U>();
-            auto seg_end = [&](float *acc, int ev, bool new_label, const uint4 *quad) {
+            bool ec0_fresh = false;   // merged pairs: the first members' common emission, refreshed at the frame's first pair
+            auto seg_end = [&](float *acc, int ev, bool new_label, const uint4 *quad, const float *a2, const Vec<U> &v3, float w3) {
                 const bool k1 = ev != kEvRowPos0;
                 if (P.debug & 1) { sum[0] += acc[0]; acc[0] = 0.f; return; }
+                if (!HUBS && ev == kEvPairMerged) {
+                    // BOTH rows of a pair (den_graph.h DenPlan::fwd_merged): the second member's sum is everything but the last
+                    // slot (a2), the first member's single arc is the last slot (w3 * v3); rows out_row, out_row + 1
+                    if (new_label) {
+                        const int lab = s_label[ql + 1];
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            const float yv = (lab == labp1) ? ypre1[u]
+                                             : (act[u] ? load_y(P.y, P.y_bf16, (n0 + u) * P.sn + (long)(t - 1) * P.st + lab) : 0.f);
+                            ec1[u] = act[u] ? expf(yv - fm[u]) : 0.f;
+                        }
+                    }
+                    if (!ec0_fresh) {
+#pragma unroll
+                        for (int u = 0; u < U; ++u) ec0[u] = act[u] ? expf(ypre0[u] - fm[u]) : 0.f;
+                        ec0_fresh = true;
+                    }
+                    Vec<U> o0, o1, ov;
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        o0.v[u] = (w3 * v3.v[u]) * ec0[u] * r[u];   // (same operation order as a one-arc row: fma(w, v, 0) * e * r)
+                        o1.v[u] = a2[u] * ec1[u] * r[u];
+                        if (TMA && !act[u]) { o0.v[u] = 0.f; o1.v[u] = 0.f; }
+                        ov.v[u] = o0.v[u] + o1.v[u];
+                        sum[u] += o0.v[u];
+                        sum[u] += o1.v[u];
+                        acc[u] = 0.f;
+                    }
+                    if ((TMA || lane_act) && sub == 0) {
+                        o0.stcg(row_ptr<U>(out_base, out_row, row_bytes));
+                        o1.stcg(row_ptr<U>(out_base, out_row + 1u, row_bytes));
+                        ov.stcg(row_ptr<U>(out_base, virt_row, row_bytes));
+                    }
+                    ++virt_row;
+                    out_row += 2u;
+                    ql += 2;
+                    return;
+                }
                 if (HUBS && ev == kEvPartial) {   // high in-degree rows only: handled out of line, nothing hot is captured
                     Vec<U> part;
 #pragma unroll
@@ -843,13 +884,29 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) den_forward_kernel(cons
                 walk_arcs_tma_small<LPR, 2>(arc4, n_batches, &P.tmap, (t - 1) * S, ring, lane, frame_scalars,
                                             [&](const uint4 *quad, const float *v, uint32_t) {
                     const uint4 wq = quad[1];
+                    constexpr int STEPS = LPR / 8, SUBS = 32 / LPR;
+                    float before = acc[0];   // the lane's sum before the quad's last LDS step (slot 3 = last step of the last lane group)
 #pragma unroll
-                    for (int st = 0; st < LPR / 8; ++st)
-                        acc[0] = fmaf(fabsf(__uint_as_float(quad_word(wq, st * (32 / LPR) + sub))), v[st], acc[0]);
+                    for (int st = 0; st < STEPS; ++st) {
+                        if (st == STEPS - 1) before = acc[0];
+                        acc[0] = fmaf(fabsf(__uint_as_float(quad_word(wq, st * SUBS + sub))), v[st], acc[0]);
+                    }
                     if ((int)wq.w < 0) {   // warp-uniform: a segment ends at this quad -> combine the lane groups' partial sums
-                        acc[0] += __shfl_xor_sync(kFull, acc[0], 16);
-                        if (LPR == 8) acc[0] += __shfl_xor_sync(kFull, acc[0], 8);
-                        seg_end(acc, (int)(((wq.z >> 31) << 1) | (wq.y >> 31)), (int)wq.x < 0, quad);
+                        const int ev = (int)(((wq.z >> 31) << 1) | (wq.y >> 31));
+                        float a2[1] = {0.f};
+                        Vec<U> v3 = vec_zero<U>();   // (U == 1 on this path)
+                        if (ev == kEvPairMerged) {   // slot 3 (the pair's first member) apart from the rest (its second member)
+                            const bool last = sub == SUBS - 1;
+                            a2[0] = last ? before : acc[0];
+                            v3.v[0] = last ? fabsf(__uint_as_float(wq.w)) * v[STEPS - 1] : 0.f;
+                            a2[0] += __shfl_xor_sync(kFull, a2[0], 16);
+                            v3.v[0] += __shfl_xor_sync(kFull, v3.v[0], 16);
+                            if (LPR == 8) { a2[0] += __shfl_xor_sync(kFull, a2[0], 8); v3.v[0] += __shfl_xor_sync(kFull, v3.v[0], 8); }
+                        } else {
+                            acc[0] += __shfl_xor_sync(kFull, acc[0], 16);
+                            if (LPR == 8) acc[0] += __shfl_xor_sync(kFull, acc[0], 8);
+                        }
+                        seg_end(acc, ev, (int)wq.x < 0, quad, a2, v3, 1.f);
                     }
                 });
             } else if (TMA) {
@@ -860,15 +917,17 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) den_forward_kernel(cons
                     const uint4 wq = quad[1];
                     const float w0 = fabsf(__uint_as_float(wq.x)), w1 = fabsf(__uint_as_float(wq.y));
                     const float w2 = fabsf(__uint_as_float(wq.z)), w3 = fabsf(__uint_as_float(wq.w));
+                    float a2[U];   // the sums without the quad's last slot (kEvPairMerged)
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
                         acc[u] = fmaf(w0, v[0].v[u], acc[u]);
                         acc[u] = fmaf(w1, v[1].v[u], acc[u]);
                         acc[u] = fmaf(w2, v[2].v[u], acc[u]);
+                        a2[u] = acc[u];
                         acc[u] = fmaf(w3, v[3].v[u], acc[u]);
                     }
                     if ((int)wq.w < 0)   // warp-uniform: a segment ends at this quad
-                        seg_end(acc, (int)(((wq.z >> 31) << 1) | (wq.y >> 31)), (int)wq.x < 0, quad);
+                        seg_end(acc, (int)(((wq.z >> 31) << 1) | (wq.y >> 31)), (int)wq.x < 0, quad, a2, v[3], w3);
                 };
                 walk_arcs_tma<U, BATCH, 2>(arc4, n_batches, &P.tmap, gc * 32 * U, (t - 1) * S, ring, lane, frame_scalars, consume_quad);
             } else {

@@ -16,6 +16,7 @@ QUAD = 4            # arc segments are padded to whole quads (den_graph.h kQuad)
 CHUNK_ARC_PAD = 16  # chunk arc counts are padded to a multiple of this (kChunkArcPad)
 EV_ROW, EV_ROW_POS0, EV_ROW_POS1, EV_PARTIAL = 0, 1, 2, 3   # den_graph.h kEv*
 EV_COMMON = EV_PARTIAL   # (old name)
+EV_PAIR_MERGED = 3        # forward, plans without hub rows: ONE segment ends both rows of a pair (kEvPairMerged)
 ARC_DTYPE = np.dtype([("peer", "<u4"), ("w", "<f4")])
 
 
@@ -69,6 +70,15 @@ class PlanView:
     hub_states: np.ndarray
     fwd: PassView
     bwd: PassView
+
+    @property
+    def fwd_merged(self) -> bool:
+        """DenPlan::fwd_merged: every pair is one forward segment (its second member's in-arcs, padding, then the first
+        member's single arc in the last slot).  Event code 3 means kEvPairMerged in a plan without hub rows."""
+        if len(self.hub_states):
+            return False
+        sign = np.signbit(self.fwd.arcs["w"].reshape(-1, QUAD))
+        return bool((sign[:, 3] & sign[:, 2] & sign[:, 1]).any())
 
 
 def load_plan(path: str, n_ctas: int = 148, n_warps: int = 16) -> PlanView:

@@ -26,8 +26,16 @@ def _decode_forward(plan):
     q = 0
     arcs = plan.fwd.arcs
     hubs = set(int(h) for h in plan.hub_states)
+    merged = plan.fwd_merged
     for a0, a1, ev, _chg in plan.fwd.segments():
         n = a1 - a0
+        if ev == 3 and merged:   # both rows of a pair: slots 0..n-2 -> second member (q+1), last slot -> first member (q)
+            assert plan.state_pos[q] == 0 and plan.state_pos[q + 1] == 1 and arcs["w"][a1 - 1] != 0
+            row.append(np.full(n - 1, q + 1)); peer.append(arcs["peer"][a0:a1 - 1].astype(np.int64)); w.append(np.abs(arcs["w"][a0:a1 - 1]).astype(np.float64))
+            row.append(np.full(1, q)); peer.append(arcs["peer"][a1 - 1:a1].astype(np.int64)); w.append(np.abs(arcs["w"][a1 - 1:a1]).astype(np.float64))
+            pairs.append((q, q + 1))
+            q += 2
+            continue
         if ev == 3:     # a part of a high in-degree row: the last slot names the target row (weight 0)
             tgt = int(arcs["peer"][a1 - 1])
             assert tgt in hubs and arcs["w"][a1 - 1] == 0

@@ -87,7 +87,14 @@ def test_plan_invariants(tmp_graphs, n_ctas, n_warps):
                 tile_max = last.max()
         for pv, is_fwd in ((P.fwd, True), (P.bwd, False)):
             segs = list(pv.segments())
-            if is_fwd:
+            merged = is_fwd and P.fwd_merged
+            if merged:
+                assert len(segs) == S - NP                               # one event per pair / unpaired state
+                assert sum(1 for x in segs if x[2] == plan.EV_PAIR_MERGED) == NP
+                assert not any(x[2] in (plan.EV_ROW_POS0, plan.EV_ROW_POS1) for x in segs)
+                assert len(set(P.state_label[P.state_pos == 0].tolist())) == 1      # first members share one label
+                assert (pv.arcs["peer"] < S + NP).all() and pv.w1 is None
+            elif is_fwd:
                 assert len(segs) == S                                    # one row-end event per state
                 assert sum(1 for x in segs if x[2] == plan.EV_ROW_POS1) == NP == sum(1 for x in segs if x[2] == plan.EV_ROW_POS0)
                 assert not any(x[2] == plan.EV_COMMON for x in segs)
@@ -114,7 +121,13 @@ def test_plan_invariants(tmp_graphs, n_ctas, n_warps):
             chunk_of = np.searchsorted(pv.chunk_arc, np.arange(0, len(pv.arcs), plan.QUAD), side="right") - 1
             for a0, a1, ev, chg in segs:
                 c = int(chunk_of[(a1 - 1) // plan.QUAD])
-                if is_fwd:
+                if merged and ev == plan.EV_PAIR_MERGED:
+                    prev[(c, 0)] = int(P.state_label[q])           # the first member: no flag of its own
+                    q += 1
+                    rows = [(1, chg)]
+                    # the last slot is the first member's arc (non-zero), everything between the second member's arcs and it is padding
+                    assert pv.arcs["w"][a1 - 1] != 0
+                elif is_fwd:
                     rows = [(0 if ev == plan.EV_ROW_POS0 else 1, chg)]
                 else:
                     rows = [(0, chg[0]), (1, chg[1])] if ev == plan.EV_ROW_POS1 else [(1, chg[0])]
@@ -152,6 +165,33 @@ def test_pairing_halves_tlm_arcs_and_can_be_disabled(tmp_path, monkeypatch):
     monkeypatch.setenv("CCB_NO_PAIRS", "1")
     Q = plan.load_plan(p, 8, 4)
     assert Q.num_pairs == 0 and int((Q.fwd.weights() > 0).sum()) == g.num_arcs
+
+
+def test_merged_forward_pairs_and_switch(tmp_path, monkeypatch):
+    """T-compose-LM graphs: every pair is ONE forward segment (kEvPairMerged: the label twin's in-arcs, padding, the blank
+    twin's single arc in the last slot) -- fewer padded slots, half the row-end events; CCB_NO_MERGE=1 restores one segment
+    per state.  Both layouts emulate to the oracle."""
+    g = fst.make_synthetic_den(600, 24, 40, seed=5)
+    p = str(tmp_path / "g.fst")
+    fst.write_fst(p, g)
+    P = plan.load_plan(p, 4, 4)
+    assert P.fwd_merged and P.num_pairs == 599
+    n_ends = int(np.signbit(P.fwd.arcs["w"].reshape(-1, plan.QUAD)[:, 3]).sum())
+    assert n_ends == P.num_states - P.num_pairs
+    monkeypatch.setenv("CCB_NO_MERGE", "1")
+    Q = plan.load_plan(p, 4, 4)
+    assert not Q.fwd_merged and Q.num_pairs == 599
+    assert len(P.fwd.arcs) <= 0.92 * len(Q.fwd.arcs)                     # 28 instead of 28 + 4 slots per pair
+    assert int((P.fwd.weights() > 0).sum()) == int((Q.fwd.weights() > 0).sum())
+    assert int(((P.bwd.weights() > 0) | (P.bwd.w1 > 0)).sum()) == int(((Q.bwd.weights() > 0) | (Q.bwd.w1 > 0)).sum())   # (the cut may differ)
+    lens = [25, 14, 3]
+    y, _, lens, _ = oracle.synth_batch(len(lens), max(lens), 40, seed=2, lens=lens)
+    la, lb, gd = oracle.den(g, y, lens)
+    for X in (P, Q):
+        ea, eb, eg = emulate.den_emulate(X, y, lens)
+        np.testing.assert_allclose(ea, la, rtol=1e-7)
+        np.testing.assert_allclose(eb, lb, rtol=1e-7)
+        assert np.abs(eg - gd).max() < 1e-6
 
 
 def test_plan_balance(tmp_path):
