@@ -19,6 +19,14 @@
 
 #include "common.cuh"
 
+// timing-experiment switches (DenParams::debug: skip row ends / barriers -- WRONG RESULTS) exist in tuning builds only; the
+// shipped kernels do not even test the word
+#ifdef CCB_TUNING
+#define CCB_DBG(P, bit) (((P).debug & (bit)) != 0)
+#else
+#define CCB_DBG(P, bit) false
+#endif
+
 namespace ccb {
 
 namespace {
@@ -797,7 +805,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) den_forward_kernel(cons
             bool ec0_fresh = false;   // merged pairs: the first members' common emission, refreshed at the frame's first pair
             auto seg_end = [&](float *acc, int ev, bool new_label, const uint4 *quad, const float *a2, const Vec<U> &v3, float w3) {
                 const bool k1 = ev != kEvRowPos0;
-                if (P.debug & 1) { sum[0] += acc[0]; acc[0] = 0.f; return; }
+                if (CCB_DBG(P, 1)) { sum[0] += acc[0]; acc[0] = 0.f; return; }
                 if (!HUBS && ev == kEvPairMerged) {
                     // BOTH rows of a pair (den_graph.h DenPlan::fwd_merged): the second member's sum is everything but the last
                     // slot (a2), the first member's single arc is the last slot (w3 * v3); rows out_row, out_row + 1
@@ -947,7 +955,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) den_forward_kernel(cons
             if (v != 0.f) { atomicAdd(P.colsum_a + (size_t)t * Npad + i, v); s_sum[i] = 0.f; }
         }
         // arrive first, then the log-scale books of CTA 0 (two L2 round trips nobody waits for) in the barrier's shadow
-        const bool split_barrier = !(P.debug & 2) && !(P.debug & 8);
+        const bool split_barrier = !CCB_DBG(P, 2) && !CCB_DBG(P, 8);
         if (split_barrier) grid_barrier_arrive(P.barrier);
         if (cta == 0 && tid < P.N && t <= my_len) {
             int sh;
@@ -955,7 +963,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) den_forward_kernel(cons
             runlog += (double)__ldg(P.fmax + (size_t)(t - 1) * Npad + tid) - (double)sh * 0.6931471805599453;
         }
         if (split_barrier) grid_barrier_wait(P.barrier, (++epoch) * gridDim.x);
-        else if (!(P.debug & 2)) grid_barrier(P.barrier, (++epoch) * gridDim.x);
+        else if (!CCB_DBG(P, 2)) grid_barrier(P.barrier, (++epoch) * gridDim.x);
         else __syncthreads();
         tl_mark(P, t, chunk, n_chunks, 2, lane);
     }
@@ -1177,7 +1185,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) den_backward_kernel(con
                 ++ql;
             };
             auto group_end = [&](float *acc0, float *acc1, bool pair, bool new0, bool new1) {
-                if (P.debug & 1) { sum_b[0] += acc0[0] + acc1[0]; acc0[0] = 0.f; acc1[0] = 0.f; return; }
+                if (CCB_DBG(P, 1)) { sum_b[0] += acc0[0] + acc1[0]; acc0[0] = 0.f; acc1[0] = 0.f; return; }
                 if (pair) {
                     do_row(false, new0, acc0, a_q);
                     do_row(true, new1, acc1, a_q1);
@@ -1257,7 +1265,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) den_backward_kernel(con
         }
         // Everything the next frame reads is written: arrive now, and flush what only the end of the kernel needs
         // (occupancy sums, the label accumulator) in the shadow of the barrier latency.
-        const bool split_barrier = !(P.debug & 2) && !(P.debug & 8);
+        const bool split_barrier = !CCB_DBG(P, 2) && !CCB_DBG(P, 8);
         if (split_barrier) grid_barrier_arrive(P.barrier);
         for (int i = tid; i < Npad; i += NT) {
             const float vab = s_sum[Npad + i];
@@ -1281,7 +1289,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) den_backward_kernel(con
             runlog += (double)__ldg(P.fmax + (size_t)tau * Npad + tid) - (double)sh * 0.6931471805599453;
         }
         if (split_barrier) grid_barrier_wait(P.barrier, (++epoch) * gridDim.x);
-        else if (!(P.debug & 2)) grid_barrier(P.barrier, (++epoch) * gridDim.x);
+        else if (!CCB_DBG(P, 2)) grid_barrier(P.barrier, (++epoch) * gridDim.x);
         else __syncthreads();
         tl_mark(P, P.Tmax - tau, chunk, n_chunks, 2, lane);
     }
