@@ -108,7 +108,7 @@ int Upload(T **dst, const std::vector<T> &src) {
 void FreeDevice(DeviceGraph &d) {
     if (!d.loaded) return;
     cudaFree(d.state_label); cudaFree(d.state_pos); cudaFree(d.final_lin); cudaFree(d.start_arcs); cudaFree(d.hub_states);
-    for (DevicePass *p : {&d.fwd, &d.bwd}) { cudaFree(p->arcs); cudaFree(p->chunk_state); cudaFree(p->chunk_arc); cudaFree(p->chunk_pair); cudaFree(p->cta_labels); cudaFree(p->w1); cudaFree(p->tq); }
+    for (DevicePass *p : {&d.fwd, &d.bwd}) { cudaFree(p->arcs); cudaFree(p->chunk_state); cudaFree(p->chunk_arc); cudaFree(p->chunk_pair); cudaFree(p->cta_labels); cudaFree(p->w1); cudaFree(p->tq); cudaFree(p->own_c); }
     d = DeviceGraph();
 }
 
@@ -200,7 +200,9 @@ int InitImpl(const char *fst_name, int n_gpus, const int *gpus) {
         rc = Upload(&d.state_label, g_plan.state_label) || Upload(&d.state_pos, g_plan.state_pos) ||
              Upload(&d.final_lin, g_plan.final_lin) || Upload(&d.start_arcs, g_plan.start_arcs) ||
              Upload(&d.hub_states, g_plan.hub_states) ||
-             UploadPass(g_plan.fwd, &d.fwd) || UploadPass(g_plan.bwd, &d.bwd);
+             UploadPass(g_plan.fwd, &d.fwd) || UploadPass(g_plan.bwd, &d.bwd) ||
+             Upload(&d.fwd.own_c, g_plan.own_fwd) || Upload(&d.bwd.own_c, g_plan.own_bwd);
+        d.own_rows = g_plan.own_rows;
         { const char *e = getenv("CCB_ARCS_IN_GLOBAL"); d.tune_arcs_in_global = e && e[0] == '1'; }
         { const char *e = getenv("CCB_W1_IN_GLOBAL"); d.tune_w1_in_global = e && e[0] == '1'; }
         { const char *e = getenv("CCB_NO_TMA"); d.tune_no_tma = e && e[0] == '1'; }   // A/B: register gathers instead of TMA gather4
@@ -776,6 +778,8 @@ int ccb_plan_copy(void *plan, int which, void *dst, size_t dst_bytes) {
         case 14: src = p->bwd.cta_labels.data(); bytes = p->bwd.cta_labels.size() * 4; break;
         case 15: src = p->bwd.w1.data(); bytes = p->bwd.w1.size() * 4; break;
         case 16: src = p->hub_states.data(); bytes = p->hub_states.size() * 4; break;
+        case 17: src = p->own_fwd.data(); bytes = (size_t)p->num_states * 2 * 4; break;   // (without the 4 floats of padding)
+        case 18: src = p->own_bwd.data(); bytes = (size_t)p->num_states * 2 * 4; break;
         default: return 1;
     }
     if (bytes > dst_bytes) return 2;

@@ -26,6 +26,7 @@ struct DevicePass {
     int *chunk_pair = nullptr;
     int *cta_labels = nullptr;
     float *w1 = nullptr;      // backward pass: second weight per slot
+    float *own_c = nullptr;   // [2S + 4] own-row coefficients of this pass (DenPlan::own_fwd / own_bwd)
     // Streamed-arc tier (backward pass of graphs whose arc stream does not fit shared memory): the pass's quads as the TMA
     // kernel stages them, 3 16-byte words per quad {row coordinate 0..3}{w0 0..3}{w1 0..3}; built at Init when the graph is
     // large enough to need it, else null
@@ -58,6 +59,7 @@ struct DeviceGraph {
     // batches of <= 16 utterances run the small-batch TMA kernels (rows of 8 / 16 floats): needs both arc streams in
     // shared memory next to the rings, no hub rows, and a usable TMA descriptor -- decided once at Init
     bool small_ok = false;
+    bool own_rows = false;     // DenPlan::own_rows: own-row coefficients instead of own-row arcs (DevicePass::own_c)
 };
 
 // Kernel parameter block shared by the two persistent den kernels (passed as a __grid_constant__ kernel parameter: the TMA
@@ -105,6 +107,8 @@ struct alignas(64) DenParams {
     const float *fmax;    // [Tmax][Npad]          per-frame max of y (emission shift)
     unsigned *barrier;    // grid barrier counter (zeroed before launch)
     float *logz;          // [N] out (forward: logZ from alpha; backward: logZ from beta)
+    const float *own_c;   // [2S + 4] own-row coefficients of this pass (den_graph.h DenPlan::own_rows), used when own != 0
+    int own;
     const double *lnorm;  // [N] or null: sum_t log-normaliser of raw logits, subtracted from logZ (raw-logit entry)
     // gradient (backward)
     float *grad;          // raw accumulation target, element (n,t,k) at n*gsn + t*gst + k

@@ -104,7 +104,8 @@ struct Segment {
     std::vector<float> w1;   // backward group segments only (same length as arcs)
     int event = kEvRow;
     int rows = 1;            // rows that end with this segment (0 for kEvCommon, 2 for a backward pair group / a merged forward pair)
-    bool merged = false;     // forward kEvPairMerged: arcs = the second member's in-arcs + (last) the first member's single arc
+    bool merged = false;     // forward kEvPairMerged: arcs = the second member's in-arcs [+ (last) the first member's single arc]
+    bool tail = false;       // ... whether that tail arc is there (no own-row terms) or not
 };
 struct Group {
     std::vector<Segment> segs;
@@ -165,11 +166,11 @@ void Layout(const std::vector<Group> &groups, int S, const std::vector<int> &sta
                 // (measured: 2x frame time from that hot spot alone).
                 const uint32_t pad_peer = sg.arcs.empty() ? (uint32_t)gr.first_state : sg.arcs.back().peer;
                 const bool dual = !sg.merged && (!sg.w1.empty() || sg.rows == 2);
-                const size_t n_lead = sg.merged ? sg.arcs.size() - 1 : sg.arcs.size();   // merged: the last arc sits in the last slot
-                const uint32_t pad_peer_m = sg.merged ? (n_lead ? sg.arcs[n_lead - 1].peer : sg.arcs.back().peer) : pad_peer;
+                const size_t n_lead = sg.tail ? sg.arcs.size() - 1 : sg.arcs.size();   // merged with a tail: the last arc sits in the last slot
+                const uint32_t pad_peer_m = sg.tail ? (n_lead ? sg.arcs[n_lead - 1].peer : sg.arcs.back().peer) : pad_peer;
                 for (size_t i = 0; i < padded; ++i) {
                     Arc a = i < n_lead ? sg.arcs[i] : Arc{pad_peer_m, 0.f};
-                    if (sg.merged && i + 1 == padded) a = sg.arcs.back();
+                    if (sg.tail && i + 1 == padded) a = sg.arcs.back();
                     if (i + 1 == padded) a.w = WithSign(a.w);
                     if (i + 2 == padded && (sg.event & 2)) a.w = WithSign(a.w);
                     if (dual) {
@@ -412,6 +413,35 @@ bool BuildDenPlan(const HostFst &fst, int n_ctas, int n_warps, DenPlan *plan, st
             for (auto &a : out_s[(size_t)s]) l->push_back(OEnt{fid[(size_t)a.peer], Bits(a.w), a.w});
             std::sort(l->begin(), l->end(), [](const OEnt &x, const OEnt &y) { return x.q != y.q ? x.q < y.q : x.wb < y.wb; });
         };
+        // own-row terms (den_graph.h DenPlan::own_rows): move the arcs of `row` (forward row of sid s, group s0|s1) whose source
+        // is one of the group's own rows -- real rows or the pair's virtual row -- into the coefficients; likewise backward
+        bool own = false;
+        auto extract_own_fwd = [&](int s, int s0, int s1, std::vector<Arc> *row, bool commit) {
+            const int f = fid[(size_t)s];
+            const uint32_t f0 = s0 >= 0 ? (uint32_t)fid[(size_t)s0] : 0xffffffffu, f1 = (uint32_t)fid[(size_t)s1];
+            const uint32_t vr = s0 >= 0 ? (uint32_t)(S + (size_t)pair_of[(size_t)s0]) : 0xffffffffu;
+            size_t k = 0;
+            for (auto &a : *row) {
+                float c0 = 0.f, c1 = 0.f;
+                if (a.peer == f0) c0 = a.w;
+                else if (a.peer == f1) c1 = a.w;
+                else if (a.peer == vr) { c0 = a.w; c1 = a.w; }
+                else { (*row)[k++] = a; continue; }
+                if (commit) { plan->own_fwd[2 * (size_t)f] += c0; plan->own_fwd[2 * (size_t)f + 1] += c1; }
+            }
+            row->resize(k);
+        };
+        auto extract_own_bwd = [&](int s, int s0, int s1, std::vector<OEnt> *l) {
+            const int f = fid[(size_t)s];
+            const int f0 = s0 >= 0 ? fid[(size_t)s0] : -1, f1 = fid[(size_t)s1];
+            size_t k = 0;
+            for (auto &e : *l) {
+                if (e.q == f0) plan->own_bwd[2 * (size_t)f] += e.w;
+                else if (e.q == f1) plan->own_bwd[2 * (size_t)f + 1] += e.w;
+                else (*l)[k++] = e;
+            }
+            l->resize(k);
+        };
         fgroups.clear(); bgroups.clear();
         fgroups.reserve(order.size()); bgroups.reserve(order.size());
         std::vector<Arc> hub_row;
@@ -432,6 +462,28 @@ bool BuildDenPlan(const HostFst &fst, int n_ctas, int n_warps, DenPlan *plan, st
                 if (lab0 < 0) lab0 = g.lab0; else if (g.lab0 != lab0) merge = false;
             }
         }
+        // own-row terms: all or nothing -- every pair's first member must be left without a gathered in-arc
+        {
+            const char *e1 = getenv("CCB_NO_OWN"), *e2 = getenv("CCB_NO_MERGE");   // test hooks / A-B switches
+            own = plan->hub_states.empty() && !(e1 && e1[0] == '1') && !(e2 && e2[0] == '1');
+        }
+        {
+            int lab0 = -1;
+            std::vector<Arc> probe;
+            for (auto &g : order) {
+                if (!own) break;
+                if (g.part > 0) { own = false; break; }
+                if (g.s0 < 0) continue;
+                forward_row(g.s0, &probe);
+                extract_own_fwd(g.s0, g.s0, g.s1, &probe, false);
+                if (!probe.empty()) own = false;
+                if (lab0 < 0) lab0 = g.lab0; else if (g.lab0 != lab0) own = false;
+            }
+        }
+        plan->own_fwd.assign(2 * S + 4, 0.f);
+        plan->own_bwd.assign(2 * S + 4, 0.f);
+        plan->own_rows = own;
+        if (own) merge = plan->num_pairs > 0;
         plan->fwd_merged = merge;
         int next_state = 0;
         for (auto &g : order) {
@@ -470,8 +522,10 @@ bool BuildDenPlan(const HostFst &fst, int n_ctas, int n_warps, DenPlan *plan, st
             if (g.s0 < 0) {
                 Segment f, b;
                 forward_row(g.s1, &f.arcs);
+                if (own) extract_own_fwd(g.s1, -1, g.s1, &f.arcs, true);
                 f.event = kEvRow;
                 out_list(g.s1, &l1);
+                if (own) extract_own_bwd(g.s1, -1, g.s1, &l1);
                 for (auto &e : l1) { b.arcs.push_back(Arc{(uint32_t)e.q, e.w}); b.w1.push_back(0.f); }
                 b.event = kEvRow;
                 b.rows = 1;
@@ -484,6 +538,12 @@ bool BuildDenPlan(const HostFst &fst, int n_ctas, int n_warps, DenPlan *plan, st
                 // backward: ONE segment for the pair; slot weights (w for p0, w1 for p1): shared arcs carry both
                 out_list(g.s0, &l0);
                 out_list(g.s1, &l1);
+                if (own) {
+                    extract_own_fwd(g.s0, g.s0, g.s1, &f0.arcs, true);   // (leaves f0 empty: checked above)
+                    extract_own_fwd(g.s1, g.s0, g.s1, &f1.arcs, true);
+                    extract_own_bwd(g.s0, g.s0, g.s1, &l0);
+                    extract_own_bwd(g.s1, g.s0, g.s1, &l1);
+                }
                 size_t i = 0, j = 0;
                 while (i < l0.size() || j < l1.size()) {
                     if (i < l0.size() && j < l1.size() && l0[i].q == l1[j].q && l0[i].wb == l1[j].wb) {
@@ -496,8 +556,8 @@ bool BuildDenPlan(const HostFst &fst, int n_ctas, int n_warps, DenPlan *plan, st
                 }
                 b.event = kEvRowPos1;
                 b.rows = 2;
-                if (merge) {   // one segment for the pair: p1's in-arcs, then p0's single arc (emitted in the last slot)
-                    f1.arcs.push_back(f0.arcs[0]);
+                if (merge) {   // one segment for the pair: p1's in-arcs, then (without own-row terms) p0's single arc in the last slot
+                    if (!own) { f1.arcs.push_back(f0.arcs[0]); f1.tail = true; }
                     f1.event = kEvPairMerged;
                     f1.rows = 2;
                     f1.merged = true;

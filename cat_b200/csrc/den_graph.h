@@ -31,7 +31,8 @@ static constexpr int kEvPartial = 3;     // forward only: a PART of a high in-de
                                          // the target row (weight 0) and the result is added to it atomically
 static constexpr int kEvPairMerged = 3;  // forward only, plans WITHOUT high in-degree rows (same code as kEvPartial, which such plans never
                                          // contain): the segment ends BOTH rows of a pair.  Slots 0 .. n-2 are the in-arcs of the second
-                                         // member, the LAST slot is the single in-arc of the first member (DenPlan::fwd_merged)
+                                         // member, the LAST slot is the single in-arc of the first member (DenPlan::fwd_merged);
+                                         // with own-row terms (DenPlan::own_rows) there is no such tail slot: all slots are the second member's
 static constexpr int kHubInArcs = 384;   // rows with more in-arcs than this are split into parts of kPartArcs arcs that
 static constexpr int kPartArcs = 191;    // any warp of the grid can own (real n-gram den graphs have such states)
 
@@ -85,6 +86,17 @@ struct DenPlan {
     //      LM and one row-end event instead of two: -12.5 % forward slots, forward pass 23.4 -> 20.5 ms at the headline size.
     //      The label-changed flag (sign of w[0] of the last quad) is the SECOND member's; all first members share one label.
     bool fwd_merged = false;
+    // OWN-ROW terms (own_rows): arcs whose SOURCE row belongs to the destination's own group -- in a T-compose-LM graph the
+    // blank arcs into (h,B), the token self loop of (h,L); in the backward pass the arcs from (h,B) / (h,L) to (h,B) / (h,L) --
+    // name rows the same warp wrote one frame earlier.  They leave the gather streams: row q receives
+    //     own[2q] * X(first row of its group) + own[2q+1] * X(second row of its group, or the row itself if unpaired)
+    // on top of its gathered sum, X = the previous frame's alpha rows (forward) / the next frame's beta-hat rows (backward),
+    // which the kernels fetch with two plain row loads per group, one group ahead of use.  Frame time follows the number of
+    // slots a warp walks through its TMA ring (profiles/r02_experiments.md section 15), so this is worth 554 k -> 514 k forward
+    // and 564 k -> 488 k backward slots per frame.  All or nothing: only plans without hub rows in which every pair's first
+    // member is left with NO gathered in-arc (then every pair is one merged forward segment without a tail slot).
+    bool own_rows = false;
+    std::vector<float> own_fwd, own_bwd;   // [2S + 4] (zero when !own_rows; padded so that a 4-float read at 2q stays inside)
     // bwd: one segment per GROUP (an unpaired state, or a pair p0,p1): every slot carries two weights, arcs[i].w for the
     //      group's first row and w1[i] for its second row (0 when the arc does not belong to that row), so the arcs the
     //      two members share are gathered once.  Event kEvRow = one-row group, kEvRowPos1 = two-row group; the

@@ -785,7 +785,23 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) den_forward_kernel(cons
             float r[U], fm[U], sum[U], ypre0[U], ypre1[U], ec0[U], ec1[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) { r[u] = 1.f; fm[u] = 0.f; ypre0[u] = 0.f; ypre1[u] = 0.f; ec0[u] = 0.f; ec1[u] = 0.f; sum[u] = 0.f; }
+            // own-row terms (den_graph.h DenPlan::own_rows): the previous frame's rows of the NEXT group to end (rows `row`,
+            // `row + 1`: this warp wrote them one frame ago) and their coefficients, fetched one group ahead of use
+            const bool own = P.own != 0;
+            const char *const x_base = reinterpret_cast<const char *>(a_prev + n0);
+            Vec<U> xa = vec_zero<U>(), xb = vec_zero<U>();
+            float2 c01 = make_float2(0.f, 0.f), c23 = make_float2(0.f, 0.f);
+            auto own_prefetch = [&](uint32_t row) {
+                if (!own || (int)row >= se) return;
+                c01 = __ldg(reinterpret_cast<const float2 *>(P.own_c) + row);
+                c23 = __ldg(reinterpret_cast<const float2 *>(P.own_c) + row + 1);
+                if (TMA || lane_act) {
+                    xa = gather_row<U>(x_base, row * row_bytes);
+                    if ((int)row + 1 < se) xb = gather_row<U>(x_base, (row + 1u) * row_bytes);
+                }
+            };
             auto frame_scalars = [&]() {
+                own_prefetch((uint32_t)sb);
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     int sh;
@@ -826,8 +842,11 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) den_forward_kernel(cons
                     Vec<U> o0, o1, ov;
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
-                        o0.v[u] = (w3 * v3.v[u]) * ec0[u] * r[u];   // (same operation order as a one-arc row: fma(w, v, 0) * e * r)
-                        o1.v[u] = a2[u] * ec1[u] * r[u];
+                        // with own-row terms the segment has no tail slot: both rows take their own-group part from xa / xb
+                        const float s0 = own ? fmaf(c01.x, xa.v[u], c01.y * xb.v[u]) : w3 * v3.v[u];
+                        const float s1 = own ? fmaf(c23.x, xa.v[u], fmaf(c23.y, xb.v[u], acc[u])) : a2[u];
+                        o0.v[u] = s0 * ec0[u] * r[u];   // (no own terms: same operation order as a one-arc row, fma(w, v, 0) * e * r)
+                        o1.v[u] = s1 * ec1[u] * r[u];
                         if (TMA && !act[u]) { o0.v[u] = 0.f; o1.v[u] = 0.f; }
                         ov.v[u] = o0.v[u] + o1.v[u];
                         sum[u] += o0.v[u];
@@ -842,6 +861,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) den_forward_kernel(cons
                     ++virt_row;
                     out_row += 2u;
                     ql += 2;
+                    own_prefetch(out_row);
                     return;
                 }
                 if (HUBS && ev == kEvPartial) {   // high in-degree rows only: handled out of line, nothing hot is captured
@@ -869,6 +889,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) den_forward_kernel(cons
                 Vec<U> out;
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
+                    if (own) acc[u] = fmaf(c01.y, xa.v[u], acc[u]);     // unpaired row: its own previous-frame value (self loop)
                     out.v[u] = acc[u] * (k1 ? ec1[u] : ec0[u]) * r[u];   // ec is 0 for inactive utterances
                     // TMA rows are read by every lane, whatever its utterances do: inactive columns are kept at a clean 0
                     // (the register path never loads them)
@@ -886,6 +907,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) den_forward_kernel(cons
                 }
                 ++out_row;
                 ++ql;
+                own_prefetch(out_row);
             };
             if (TMA && LPR < 32) {
                 float acc[1] = {0.f};
@@ -903,7 +925,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) den_forward_kernel(cons
                         const int ev = (int)(((wq.z >> 31) << 1) | (wq.y >> 31));
                         float a2[1] = {0.f};
                         Vec<U> v3 = vec_zero<U>();   // (U == 1 on this path)
-                        if (ev == kEvPairMerged) {   // slot 3 (the pair's first member) apart from the rest (its second member)
+                        if (ev == kEvPairMerged && !own) {   // slot 3 (the pair's first member) apart from the rest (its second member)
                             const bool last = sub == SUBS - 1;
                             a2[0] = last ? before : acc[0];
                             v3.v[0] = last ? fabsf(__uint_as_float(wq.w)) * v[STEPS - 1] : 0.f;
@@ -1140,6 +1162,22 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) den_backward_kernel(con
             // alpha rows of the next group (one or two states) are fetched one group ahead
             Vec<U> a_q = (se > sb && lane_act) ? gather_row<U>(a_base, out_row * row_bytes) : vec_zero<U>();
             Vec<U> a_q1 = (se > sb + 1 && lane_act) ? gather_row<U>(a_base, (out_row + 1) * row_bytes) : vec_zero<U>();
+            // own-row terms (den_graph.h DenPlan::own_rows): the next frame's beta-hat rows of the group about to end (this warp
+            // wrote them one frame ago) and their coefficients, fetched one group ahead like the alpha rows
+            const bool own = P.own != 0;
+            const char *const b_base = reinterpret_cast<const char *>(bh_next + n0);
+            Vec<U> xa = vec_zero<U>(), xb = vec_zero<U>();
+            float2 c01 = make_float2(0.f, 0.f), c23 = make_float2(0.f, 0.f);
+            auto own_prefetch = [&](uint32_t row) {
+                if (!own || (int)row >= se) return;
+                c01 = __ldg(reinterpret_cast<const float2 *>(P.own_c) + row);
+                c23 = __ldg(reinterpret_cast<const float2 *>(P.own_c) + row + 1);
+                if (TMA || lane_act) {
+                    xa = gather_row<U>(b_base, row * row_bytes);
+                    if ((int)row + 1 < se) xb = gather_row<U>(b_base, (row + 1u) * row_bytes);
+                }
+            };
+            own_prefetch(out_row);
             auto flush_gsum = [&](bool k1) {
                 const int lab = k1 ? curlab1 : curlab0;
                 const int row = k1 ? cl_n0 + lab - cl_lab1 : lab - cl_lab0;
@@ -1186,6 +1224,17 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) den_backward_kernel(con
             };
             auto group_end = [&](float *acc0, float *acc1, bool pair, bool new0, bool new1) {
                 if (CCB_DBG(P, 1)) { sum_b[0] += acc0[0] + acc1[0]; acc0[0] = 0.f; acc1[0] = 0.f; return; }
+                if (own) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        if (pair) {
+                            acc0[u] = fmaf(c01.x, xa.v[u], fmaf(c01.y, xb.v[u], acc0[u]));
+                            acc1[u] = fmaf(c23.x, xa.v[u], fmaf(c23.y, xb.v[u], acc1[u]));
+                        } else {
+                            acc0[u] = fmaf(c01.y, xa.v[u], acc0[u]);   // unpaired row: its own next-frame value (self loop)
+                        }
+                    }
+                }
                 if (pair) {
                     do_row(false, new0, acc0, a_q);
                     do_row(true, new1, acc1, a_q1);
@@ -1196,6 +1245,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) den_backward_kernel(con
                 }
                 a_q = ((int)out_row < se && lane_act) ? gather_row<U>(a_base, out_row * row_bytes) : vec_zero<U>();
                 a_q1 = ((int)out_row + 1 < se && lane_act) ? gather_row<U>(a_base, (out_row + 1) * row_bytes) : vec_zero<U>();
+                own_prefetch(out_row);
             };
             if (TMA && LPR < 32) {
                 float acc0[1] = {0.f}, acc1[1] = {0.f};
@@ -1589,6 +1639,7 @@ int LaunchDenForward(const DeviceGraph &g, DenParams &p, cudaStream_t stream, st
     p.arcs = g.fwd.arcs; p.chunk_state = g.fwd.chunk_state; p.chunk_arc = g.fwd.chunk_arc;
     p.chunk_pair = g.fwd.chunk_pair; p.cta_labels = g.fwd.cta_labels;
     p.gacc_rows = 0;
+    p.own_c = g.fwd.own_c; p.own = g.own_rows ? 1 : 0;
     p.tile_rows = g.fwd.max_tile_rows;
     const size_t fixed = (((size_t)(p.Npad + p.tile_rows) * 4 + 15) & ~(size_t)15);
     return DispatchThreads(false, g, p, fixed, stream, err);
@@ -1597,6 +1648,7 @@ int LaunchDenForward(const DeviceGraph &g, DenParams &p, cudaStream_t stream, st
 int LaunchDenBackward(const DeviceGraph &g, DenParams &p, cudaStream_t stream, std::string *err) {
     p.arcs = g.bwd.arcs; p.chunk_state = g.bwd.chunk_state; p.chunk_arc = g.bwd.chunk_arc;
     p.chunk_pair = g.bwd.chunk_pair; p.cta_labels = g.bwd.cta_labels; p.w1 = g.bwd.w1;
+    p.own_c = g.bwd.own_c; p.own = g.own_rows ? 1 : 0;
     // label accumulator in shared memory when the per-CTA label range is small enough
     size_t gacc_bytes = (size_t)g.bwd.max_tile_labels * p.Npad * 4;
     p.gacc_rows = gacc_bytes <= 64 * 1024 ? g.bwd.max_tile_labels : 0;

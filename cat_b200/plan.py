@@ -70,11 +70,19 @@ class PlanView:
     hub_states: np.ndarray
     fwd: PassView
     bwd: PassView
+    own_fwd: np.ndarray = None      # float32 [S, 2]: own-row coefficients of the forward pass (den_graph.h DenPlan::own_fwd)
+    own_bwd: np.ndarray = None      # float32 [S, 2]
+
+    @property
+    def own_rows(self) -> bool:
+        """DenPlan::own_rows: arcs from a group's own rows are coefficients (own_fwd / own_bwd), not gathered slots."""
+        return bool(self.own_fwd.any() or self.own_bwd.any())
 
     @property
     def fwd_merged(self) -> bool:
-        """DenPlan::fwd_merged: every pair is one forward segment (its second member's in-arcs, padding, then the first
-        member's single arc in the last slot).  Event code 3 means kEvPairMerged in a plan without hub rows."""
+        """DenPlan::fwd_merged: every pair is one forward segment (its second member's in-arcs, padding, then -- unless the plan
+        carries own-row terms -- the first member's single arc in the last slot).  Event code 3 means kEvPairMerged in a plan
+        without hub rows."""
         if len(self.hub_states):
             return False
         sign = np.signbit(self.fwd.arcs["w"].reshape(-1, QUAD))
@@ -105,6 +113,7 @@ def load_plan(path: str, n_ctas: int = 148, n_warps: int = 16) -> PlanView:
                                  get(10, np.int32, n_chunks + 1), get(13, np.int32, nc * 4).reshape(nc, 4)),
                         PassView(get(6, ARC_DTYPE, Ab), get(7, np.int32, n_chunks + 1), get(8, np.int32, n_chunks + 1),
                                  get(11, np.int32, n_chunks + 1), get(14, np.int32, nc * 4).reshape(nc, 4),
-                                 get(15, np.float32, Ab)))
+                                 get(15, np.float32, Ab)),
+                        get(17, np.float32, 2 * S).reshape(S, 2), get(18, np.float32, 2 * S).reshape(S, 2))
     finally:
         L.ccb_plan_destroy(h)

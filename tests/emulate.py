@@ -29,6 +29,12 @@ def _decode_forward(plan):
     merged = plan.fwd_merged
     for a0, a1, ev, _chg in plan.fwd.segments():
         n = a1 - a0
+        if ev == 3 and merged and plan.own_rows:   # both rows of a pair end; every slot belongs to the second member (q+1)
+            assert plan.state_pos[q] == 0 and plan.state_pos[q + 1] == 1
+            row.append(np.full(n, q + 1)); peer.append(arcs["peer"][a0:a1].astype(np.int64)); w.append(np.abs(arcs["w"][a0:a1]).astype(np.float64))
+            pairs.append((q, q + 1))
+            q += 2
+            continue
         if ev == 3 and merged:   # both rows of a pair: slots 0..n-2 -> second member (q+1), last slot -> first member (q)
             assert plan.state_pos[q] == 0 and plan.state_pos[q + 1] == 1 and arcs["w"][a1 - 1] != 0
             row.append(np.full(n - 1, q + 1)); peer.append(arcs["peer"][a0:a1 - 1].astype(np.int64)); w.append(np.abs(arcs["w"][a0:a1 - 1]).astype(np.float64))
@@ -93,6 +99,15 @@ def den_emulate(plan, y, lens):
     frow, fpeer, fw, pairs = _decode_forward(plan)
     brow, bpeer, bw = _decode_backward(plan)
     P = plan.num_pairs
+    # own-row terms: row q receives c[q,0] * X(first row of its group) + c[q,1] * X(second row of its group, or q itself)
+    pos = plan.state_pos.astype(np.int64)
+    ids = np.arange(S)
+    after_pos0 = np.concatenate([[False], pos[:-1] == 0])          # q is the second member of a pair
+    g0 = np.where(pos == 0, ids, np.where(after_pos0, ids - 1, ids))
+    g1 = np.minimum(np.where(pos == 0, ids + 1, ids), S - 1)
+    cf, cb = plan.own_fwd.astype(np.float64), plan.own_bwd.astype(np.float64)
+    unp = (pos == 1) & ~after_pos0                                   # unpaired rows: only the second coefficient may be set
+    assert not cf[unp, 0].any() and not cb[unp, 0].any()
     sa = plan.start_arcs
     logz_a = np.zeros(N)
     logz_b = np.zeros(N)
@@ -110,6 +125,7 @@ def den_emulate(plan, y, lens):
         for t in range(1, Tn + 1):
             r, sh = _scale(colsum)
             acc = np.bincount(frow, weights=fw * alpha[t - 1, fpeer], minlength=S)
+            acc = acc + cf[:, 0] * alpha[t - 1, g0] + cf[:, 1] * alpha[t - 1, g1]
             e = np.exp(yn[t - 1, lab] - fmax[t - 1])
             alpha[t, :S] = acc * e * r
             if P:
@@ -127,7 +143,7 @@ def den_emulate(plan, y, lens):
                 b = fin.copy()
             else:
                 rb, sh = _scale(colsum_b)
-                b = rb * np.bincount(brow, weights=bw * bh_next[bpeer], minlength=S)
+                b = rb * (np.bincount(brow, weights=bw * bh_next[bpeer], minlength=S) + cb[:, 0] * bh_next[g0] + cb[:, 1] * bh_next[g1])
                 runlog += fmax[tau] - sh * np.log(2.0)
             ab = alpha[tau, :S] * b
             tot = ab.sum()

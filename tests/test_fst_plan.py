@@ -126,7 +126,7 @@ def test_plan_invariants(tmp_graphs, n_ctas, n_warps):
                     q += 1
                     rows = [(1, chg)]
                     # the last slot is the first member's arc (non-zero), everything between the second member's arcs and it is padding
-                    assert pv.arcs["w"][a1 - 1] != 0
+                    assert P.own_rows or pv.arcs["w"][a1 - 1] != 0
                 elif is_fwd:
                     rows = [(0 if ev == plan.EV_ROW_POS0 else 1, chg)]
                 else:
@@ -151,7 +151,10 @@ def test_plan_invariants(tmp_graphs, n_ctas, n_warps):
             assert S > g.num_states
         else:
             assert S == g.num_states and NP > 0
-            assert nz_f < g.num_arcs and nz_b < g.num_arcs and nz_f == nz_b    # pairing removed the shared arcs
+            assert nz_f < g.num_arcs and nz_b < g.num_arcs                     # pairing removed the shared arcs
+            own_f, own_b = int((P.own_fwd != 0).sum()), int((P.own_bwd != 0).sum())
+            assert P.own_rows and own_f > 0 and own_b > 0                      # T-compose-LM: blank arcs / self loops are own-row terms
+            assert nz_f == nz_b and own_f == own_b
         assert len(P.start_arcs) == int((np.asarray(g.src) == g.start).sum()) or name == "random_split"
 
 
@@ -164,7 +167,8 @@ def test_pairing_halves_tlm_arcs_and_can_be_disabled(tmp_path, monkeypatch):
     assert int((P.fwd.weights() > 0).sum()) < 0.56 * g.num_arcs
     monkeypatch.setenv("CCB_NO_PAIRS", "1")
     Q = plan.load_plan(p, 8, 4)
-    assert Q.num_pairs == 0 and int((Q.fwd.weights() > 0).sum()) == g.num_arcs
+    # (self loops are own-row terms: coefficients, not slots)
+    assert Q.num_pairs == 0 and int((Q.fwd.weights() > 0).sum()) + int((Q.own_fwd != 0).sum()) == g.num_arcs
 
 
 def test_merged_forward_pairs_and_switch(tmp_path, monkeypatch):
@@ -174,20 +178,30 @@ def test_merged_forward_pairs_and_switch(tmp_path, monkeypatch):
     g = fst.make_synthetic_den(600, 24, 40, seed=5)
     p = str(tmp_path / "g.fst")
     fst.write_fst(p, g)
+    monkeypatch.setenv("CCB_NO_OWN", "1")
     P = plan.load_plan(p, 4, 4)
-    assert P.fwd_merged and P.num_pairs == 599
+    assert P.fwd_merged and not P.own_rows and P.num_pairs == 599
     n_ends = int(np.signbit(P.fwd.arcs["w"].reshape(-1, plan.QUAD)[:, 3]).sum())
     assert n_ends == P.num_states - P.num_pairs
     monkeypatch.setenv("CCB_NO_MERGE", "1")
     Q = plan.load_plan(p, 4, 4)
-    assert not Q.fwd_merged and Q.num_pairs == 599
+    assert not Q.fwd_merged and not Q.own_rows and Q.num_pairs == 599
     assert len(P.fwd.arcs) <= 0.92 * len(Q.fwd.arcs)                     # 28 instead of 28 + 4 slots per pair
     assert int((P.fwd.weights() > 0).sum()) == int((Q.fwd.weights() > 0).sum())
+    # default: own-row terms on top -- the blank arcs and the token self loops are coefficients, not slots
+    monkeypatch.delenv("CCB_NO_OWN"); monkeypatch.delenv("CCB_NO_MERGE")
+    R = plan.load_plan(p, 4, 4)
+    assert R.fwd_merged and R.own_rows
+    # blank arc + token self loop per pair (+ the few LM arcs from a history to itself)
+    assert int((P.fwd.weights() > 0).sum()) - 2 * 599 - 60 <= int((R.fwd.weights() > 0).sum()) <= int((P.fwd.weights() > 0).sum()) - 2 * 599
+    nzb = lambda X: int(((X.bwd.weights() > 0) | (X.bwd.w1 > 0)).sum())
+    assert nzb(P) - 2 * 599 - 60 <= nzb(R) <= nzb(P) - 2 * 599            # (h,B) and (h,L) rows leave the backward groups
+    assert len(R.bwd.arcs) <= 0.9 * len(P.bwd.arcs)                      # 24 instead of 26 -> 28 slots per pair
     assert int(((P.bwd.weights() > 0) | (P.bwd.w1 > 0)).sum()) == int(((Q.bwd.weights() > 0) | (Q.bwd.w1 > 0)).sum())   # (the cut may differ)
     lens = [25, 14, 3]
     y, _, lens, _ = oracle.synth_batch(len(lens), max(lens), 40, seed=2, lens=lens)
     la, lb, gd = oracle.den(g, y, lens)
-    for X in (P, Q):
+    for X in (P, Q, R):
         ea, eb, eg = emulate.den_emulate(X, y, lens)
         np.testing.assert_allclose(ea, la, rtol=1e-7)
         np.testing.assert_allclose(eb, lb, rtol=1e-7)

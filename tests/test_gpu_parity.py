@@ -114,12 +114,15 @@ def test_ctc_vs_oracle(N, T, V, lens, ly):
 
 
 @pytest.mark.parametrize("env", ["CCB_ARCS_IN_GLOBAL", "CCB_W1_IN_GLOBAL", "CCB_NO_PAIRS", "HUBS", "HUBS+CCB_ARCS_IN_GLOBAL",
-                                 "CCB_NO_TMA", "CCB_RING_ROWS=8", "CCB_ARCS_IN_GLOBAL+CCB_NO_TMA", "CCB_NO_MERGE", "CCB_NO_MERGE+CCB_NO_TMA"])
+                                 "CCB_NO_TMA", "CCB_RING_ROWS=8", "CCB_ARCS_IN_GLOBAL+CCB_NO_TMA", "CCB_NO_MERGE", "CCB_NO_MERGE+CCB_NO_TMA",
+                                 "CCB_NO_OWN", "CCB_NO_OWN+CCB_NO_TMA"])
 def test_fallback_paths(tmp_graphs, monkeypatch, env):
     """Arc tiles streamed from global memory (graphs too large for shared memory: through per-warp bulk-copy rings next to
     the TMA row gathers, or -- CCB_NO_TMA, hub rows -- with plain loads), the un-paired plan, rows split into parts and the
-    two-segments-per-pair forward stream (CCB_NO_MERGE; the default on these graphs is one merged segment per pair, which
-    the other variants therefore run through the register-gather and arcs-in-global walkers) give the same answers."""
+    forward stream with two segments per pair (CCB_NO_MERGE) or with the first member's arc in a tail slot (CCB_NO_OWN) give
+    the same answers.  The default on these graphs is own-row terms (blank arcs / self loops as coefficients on plainly
+    loaded rows) and one merged segment per pair, which the other variants therefore run through the register-gather and
+    arcs-in-global walkers."""
     from oracle import oracle
     from cat_b200 import _C
     for e in env.split("+"):
@@ -134,7 +137,7 @@ def test_fallback_paths(tmp_graphs, monkeypatch, env):
     # 20: one utterance per lane (second weights prefetched with the gathers); 12 / 5: the small-batch kernels (16- / 8-float
     # rows), whose backward pass then streams the second weights with bulk copies next to the TMA row gathers
     # ARCS_IN_GLOBAL: 1, 2 and 4 utterances per lane of the streamed-arc kernels (two lane groups in the backward pass at 130)
-    for N in ((40, 20, 12, 5) if "W1" in env else (40, 12, 130) if "ARCS" in env else (40, 64) if "RING" in env else (40, 12, 64) if "MERGE" in env else (40,)):
+    for N in ((40, 20, 12, 5) if "W1" in env else (40, 12, 130) if "ARCS" in env else (40, 64) if "RING" in env else (40, 12, 64) if ("MERGE" in env or "OWN" in env) else (40,)):
         lens = np.maximum(1, T - (np.arange(N) * 5) % T).astype(np.int32)
         y, _, lens, _ = oracle.synth_batch(N, T, V, seed=8, lens=lens)
         logits = torch.tensor(y, device="cuda")
