@@ -1472,8 +1472,12 @@ int Dispatch(bool backward, const DeviceGraph &g, DenParams &p, size_t fixed_sme
     const bool no_smem = g.tune_arcs_in_global;   // test hooks (read once at Init): exercise the large-graph tiers
     bool w1_smem = backward && !g.tune_w1_in_global;
     size_t arc_bytes = (size_t)pass.max_tile_arcs * (backward && w1_smem ? 12 : sizeof(Arc));
-    if (backward && w1_smem && fixed_smem + arc_bytes > budget) { w1_smem = false; arc_bytes = (size_t)pass.max_tile_arcs * sizeof(Arc); }
-    const bool smem_arcs = fixed_smem + arc_bytes <= budget && !no_smem;
+    // small batches: the arc stream must fit NEXT TO the small-batch rings (the same sum DeviceGraph::small_ok was decided on at
+    // Init: 8 bytes per backward slot with the second weights streamed) -- without this the 12-byte form could be kept although
+    // only the 8-byte form leaves room for the rings, and the launch below refused a batch that had been padded for it
+    const size_t small_extra = p.Npad < 32 ? 128 + (size_t)g.n_warps * kSmallStages * (16 * (size_t)p.Npad * 4 + 8 + 64) : 0;
+    if (backward && w1_smem && fixed_smem + arc_bytes + small_extra > budget) { w1_smem = false; arc_bytes = (size_t)pass.max_tile_arcs * sizeof(Arc); }
+    const bool smem_arcs = fixed_smem + arc_bytes + small_extra <= budget && !no_smem;
     size_t smem = fixed_smem + (smem_arcs ? arc_bytes : 0);
     // utterances per lane: the widest row segment the batch allows, except that the backward pass (two accumulators per
     // utterance) runs out of registers at 4 -- it walks 64-utterance groups instead.
