@@ -217,7 +217,22 @@ void Layout(const std::vector<Group> &groups, int S, const std::vector<int> &sta
 
 }  // namespace
 
+static bool BuildDenPlanImpl(const HostFst &fst, int n_ctas, int n_warps, bool allow_own, DenPlan *plan, std::string *err);
+
 bool BuildDenPlan(const HostFst &fst, int n_ctas, int n_warps, DenPlan *plan, std::string *err) {
+    if (!BuildDenPlanImpl(fst, n_ctas, n_warps, true, plan, err)) return false;
+    // Own-row terms are for graphs that run the main tier (arc streams resident in shared memory next to the TMA rings).  A
+    // graph whose backward stream exceeds kOwnRowsMaxTileBytes per CTA runs the large-graph tiers (register gathers forwards,
+    // streamed arcs backwards), where the extra row loads and registers cost more than the dropped padding returns
+    // (5.1 M-arc graph, N=128, T=2000: 615 ms per step with own-row terms against 575 ms without): build it without them.
+    if (plan->own_rows && (size_t)plan->bwd.max_tile_arcs * 12 > kOwnRowsMaxTileBytes) {
+        *plan = DenPlan();
+        return BuildDenPlanImpl(fst, n_ctas, n_warps, false, plan, err);
+    }
+    return true;
+}
+
+static bool BuildDenPlanImpl(const HostFst &fst, int n_ctas, int n_warps, bool allow_own, DenPlan *plan, std::string *err) {
     const int S0 = fst.num_states;
     const size_t A0 = fst.src.size();
     if (n_ctas < 1 || n_warps < 1) { *err = "bad grid for den plan"; return false; }
@@ -465,7 +480,7 @@ bool BuildDenPlan(const HostFst &fst, int n_ctas, int n_warps, DenPlan *plan, st
         // own-row terms: all or nothing -- every pair's first member must be left without a gathered in-arc
         {
             const char *e1 = getenv("CCB_NO_OWN"), *e2 = getenv("CCB_NO_MERGE");   // test hooks / A-B switches
-            own = plan->hub_states.empty() && !(e1 && e1[0] == '1') && !(e2 && e2[0] == '1');
+            own = allow_own && plan->hub_states.empty() && !(e1 && e1[0] == '1') && !(e2 && e2[0] == '1');
         }
         {
             int lab0 = -1;
