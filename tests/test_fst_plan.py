@@ -212,6 +212,39 @@ def test_merged_forward_pairs_and_switch(tmp_path, monkeypatch):
         assert np.abs(eg - gd).max() < 1e-6
 
 
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_plan_emulation_on_random_graph_families(tmp_path, monkeypatch, seed):
+    """The plan builder's rewrites (in-label split, pair factoring, merged pair segments, own-row terms, hub parts) are exact:
+    for several graph families and every switch setting, the kernels' arithmetic emulated on the plan arrays equals the
+    arc-based oracle.  Families: synthetic T-compose-LM (with LM arcs from a history to itself), a natively composed
+    CTC-topology x phone-LM graph, an unstructured random graph with self loops."""
+    rng = np.random.default_rng(seed)
+    V = int(rng.integers(5, 14))
+    graphs = {
+        "tlm": fst.make_synthetic_den(int(rng.integers(6, 40)), int(rng.integers(2, 6)), V, seed=seed),
+        "composed": fst.compose_ctc_lm(fst.make_random_lm(int(rng.integers(3, 12)), V - 1, int(rng.integers(1, 4)), seed=seed)),
+        "random": fst.make_random_den(int(rng.integers(8, 30)), int(rng.integers(40, 200)), V, seed=seed),
+    }
+    lens = [int(x) for x in rng.integers(1, 14, size=3)]
+    for name, g in graphs.items():
+        p = str(tmp_path / f"{name}.fst")
+        fst.write_fst(p, g)
+        y, _, ln, _ = oracle.synth_batch(len(lens), max(lens), V, seed=seed + 10, lens=lens)
+        la, lb, gd = oracle.den(g, y, ln)
+        for env in ({}, {"CCB_NO_OWN": "1"}, {"CCB_NO_MERGE": "1"}, {"CCB_NO_PAIRS": "1"}, {"CCB_HUB_IN_ARCS": "5", "CCB_PART_ARCS": "7"}):
+            with monkeypatch.context() as m:
+                for k, v in env.items():
+                    m.setenv(k, v)
+                P = plan.load_plan(p, int(rng.integers(1, 6)), int(rng.integers(1, 5)))
+            ea, eb, eg = emulate.den_emulate(P, y, ln)
+            fin = np.isfinite(la)
+            np.testing.assert_allclose(ea[fin], la[fin], rtol=1e-7, err_msg=f"{name} {env}")
+            np.testing.assert_allclose(eb[fin], lb[fin], rtol=1e-7, err_msg=f"{name} {env}")
+            assert (np.isinf(ea[~fin]) & (ea[~fin] < 0)).all(), (name, env)       # no path to a final state: -inf on both sides
+            if fin.any():
+                assert np.abs(eg[fin] - gd[fin]).max() < 1e-6, (name, env)
+
+
 def test_plan_balance(tmp_path):
     g = fst.make_synthetic_den(4000, 24, 60, seed=7)
     p = str(tmp_path / "g.fst")
