@@ -421,7 +421,7 @@ size_t ccb_den_aux_bytes(int N, int T) {
 
 size_t ccb_ctc_workspace_bytes(int N, int T, int max_label_len) {
     // per utterance: alpha and beta cells [T][2L+1] in double + the fp64 log-likelihood (ctc_kernels.cu)
-    // ... and, behind them, N floats for the log-likelihoods of the fused loss (CtcLogp below)
+    // ... and, behind them, N floats for the log-likelihoods of the fused loss (LossFwdImpl: `logp`)
     const size_t per_utt = 2 * (size_t)T * (2 * (size_t)max_label_len + 1) + 1;
     return ((size_t)N * per_utt + 32 + ((size_t)N + 1) / 2) * sizeof(double);
 }
