@@ -45,6 +45,19 @@ def test_status_strings_and_workspace_query():
     assert L.ccb_launch_count() == 0
 
 
+def test_ctc_workspace_holds_cells_and_loglikelihoods():
+    """ccb_ctc_workspace_bytes: per utterance the alpha and beta cells [T][2L+1] in double + the fp64 log-likelihood, then
+    32 doubles of slack, then N floats -- where the fused loss keeps log p(l|x) (api.cu LossFwdImpl places them at double
+    offset N * per_utt + 32; the numerator may run while the den aux block is busy, so they cannot live there)."""
+    from cat_b200 import _lib
+    L = _lib.lib()
+    L.ccb_ctc_workspace_bytes.restype = C.c_size_t
+    for N, T, maxl in [(1, 1, 0), (3, 7, 2), (64, 1500, 250), (17, 33, 5)]:
+        per_utt = 2 * T * (2 * maxl + 1) + 1
+        logp_off = (N * per_utt + 32) * 8
+        assert int(L.ccb_ctc_workspace_bytes(N, T, maxl)) >= logp_off + 4 * N
+
+
 def test_python_surface_mirrors_reference(tmp_path):
     import ctc_crf
     for name in ("CTC_CRF_LOSS", "WARP_CTC_LOSS", "CRFContext", "__version__", "_C"):
